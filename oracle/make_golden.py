@@ -1,0 +1,206 @@
+"""ORACLE / TEST INFRASTRUCTURE — golden-vector generator.
+
+Runs the reference's OWN, UNMODIFIED modules (imported from /root/reference behind
+`oracle/refshim`, which only stands in for the absent `lightning`, `omegaconf`
+and `pytorch_lightning` packages and holds no arithmetic) on small seeded inputs
+and writes inputs, parameters, outputs and gradients to `tests/golden/*.npz`.
+
+Run in the build container only (the GPU box has no /root/reference):
+
+    python oracle/make_golden.py
+
+The committed fixtures are what `tests/test_oracle_golden.py` pins the oracle
+restatement (`oracle/ref_path.py`) against, and what the `-m gpu` parity tests
+replay through the CUDA path.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+REF = os.environ.get("NRX_REFERENCE", "/root/reference")
+sys.path.insert(0, os.path.join(HERE, "refshim"))
+sys.path.insert(0, REF)
+
+import yaml  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+CFGS = os.path.join(GOLD, "configs")
+
+
+def synth_batch(cfg, B, gen, with_mask=True, label_p=0.5, id_dtype=torch.int64):
+    """Default-collated DataReader.__getitem__ layout (src/dataset/DataReader/data_reader.py:54-114):
+    sparse name -> int64[B]; array name -> int64[B,L] right-padded with 0 + `<name>_mask` float32[B,L];
+    label -> float32[B,2]."""
+    feats = cfg["features"]
+    emb = cfg["embeddings"]
+    share = emb.get("share_emb_table_features", {}) or {}
+    batch = {}
+    for f in feats["sparse_feature_names"]:
+        rows = emb["embedding_table_size"][share.get(f, f)]
+        batch[f] = torch.randint(0, rows, (B,), generator=gen).to(id_dtype)  # 0 (pad id) allowed
+    for f in feats.get("array_feature_names", []) or []:
+        rows = emb["embedding_table_size"][share.get(f, f)]
+        L = feats["array_max_length"][f]
+        lens = torch.randint(0, L + 1, (B,), generator=gen)
+        lens[0] = 0          # empty bag
+        lens[1] = L          # full bag
+        ids = torch.randint(1, rows, (B, L), generator=gen)
+        ids[2, :3] = torch.tensor([5, 5, 9])   # duplicate ids inside a bag
+        lens[2] = 3
+        ids[3, :2] = torch.tensor([0, 8])      # pad id 0 with mask 1
+        lens[3] = 2
+        mask = (torch.arange(L)[None, :] < lens[:, None]).float()
+        ids = ids * mask.long()
+        ids[3, 0] = 0
+        batch[f] = ids.to(id_dtype)
+        if with_mask:
+            batch[f + "_mask"] = mask
+    lab = (torch.rand(B, generator=gen) < label_p).float()
+    batch["label"] = torch.stack([lab, 1.0 - lab], dim=1)
+    return batch
+
+
+def np_sd(sd):
+    return {"sd__" + k: v.detach().cpu().numpy().copy() for k, v in sd.items()}
+
+
+def run_model(kind, cls, cfg_name, B=24, with_mask=True, tag=None, opt_steps=0):
+    path = os.path.join(CFGS, f"train_cf_{cfg_name}.yaml")
+    cfg = yaml.safe_load(open(path))
+    torch.manual_seed(42)
+    model = cls(path)
+    # make biases / cross terms non-trivial so the fixture exercises them
+    g = torch.Generator().manual_seed(7)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if n.endswith(".bias") or n.endswith(".b"):
+                p.copy_(0.1 * torch.randn(p.shape, generator=g))
+    gen = torch.Generator().manual_seed(1234)
+    batch = synth_batch(cfg, B, gen, with_mask=with_mask)
+    out = {"kind": np.array(kind), "cfg": np.array(cfg_name)}
+    out.update(np_sd(model.state_dict()))
+    for k, v in batch.items():
+        out["in__" + k] = v.numpy()
+    names = model.user_feature_names | model.item_feature_names
+    feats, dims, fnames = model.get_embeddings_from_batch(batch, names)
+    out["features"] = feats.detach().numpy()
+    out["dims"] = np.array(dims)
+    out["names"] = np.array(fnames)
+    prob = model(batch)
+    loss = model.bceLoss(prob, batch["label"][:, 0])
+    model.zero_grad()
+    loss.backward()
+    out["prob"] = prob.detach().numpy()
+    out["loss"] = loss.detach().numpy()
+    for n, p in model.named_parameters():
+        out["grad__" + n] = (p.grad if p.grad is not None else torch.zeros_like(p)).numpy()
+    with torch.no_grad():
+        out["inference"] = model.inference(batch).numpy()
+    if opt_steps:
+        # the reference's own optimizer + schedule (e.g. sort/deep/model.py:54-65), stepped like Lightning does
+        oc = model.configure_optimizers()
+        opt, sch = oc["optimizer"], oc["lr_scheduler"]["scheduler"]
+        lrs = []
+        for s in range(opt_steps):
+            b = synth_batch(cfg, B, torch.Generator().manual_seed(100 + s), with_mask=with_mask)
+            for k, v in b.items():
+                out[f"opt{s}_in__" + k] = v.numpy()
+            opt.zero_grad()
+            l = model.bceLoss(model(b), b["label"][:, 0])
+            l.backward()
+            lrs.append(opt.param_groups[0]["lr"])
+            opt.step()
+            sch.step()
+            out[f"opt{s}_loss"] = l.detach().numpy()
+        out["opt_lrs"] = np.array(lrs)
+        for k, v in model.state_dict().items():
+            out["sdopt__" + k] = v.detach().numpy().copy()
+    name = tag or cfg_name
+    np.savez_compressed(os.path.join(GOLD, f"{name}.npz"), **out)
+    print(f"wrote {name}.npz  prob[:3]={prob.detach().view(-1)[:3].tolist()} loss={float(loss):.6f}")
+
+
+def run_units():
+    """Known-answer / edge-case probes of single reference functions."""
+    from src.model.sort.dcn.dcn_arch import DCNLayer, DCNNet, DCNv2Net
+    from src.model.sort.fm.model import FMModel
+    from src.model.model_utils.utils import MLP
+    from src.model.model_utils.lr_schedule import CosinDecayLR
+    out = {}
+    torch.manual_seed(3)
+    # FM identity: F=2 => second order == v1.v2  (fm/model.py:20-24)
+    fm = FMModel()
+    w = torch.zeros(1, 2)
+    v = torch.tensor([[[.1, .2, .3], [.4, .5, .6]]])
+    out["fm_identity"] = torch.logit(fm(w, v)).detach().numpy()  # 0.32
+    w = torch.randn(9, 5)
+    v = torch.randn(9, 5, 15)
+    with torch.no_grad():
+        fm.bias.fill_(0.3)
+    out["fm_w"], out["fm_v"], out["fm_bias"] = w.numpy(), v.numpy(), fm.bias.detach().numpy()
+    out["fm_prob"] = fm(w, v).detach().numpy()
+    # DCN v1 / v2 nets
+    net = DCNNet(20, 3)
+    x = torch.randn(7, 20)
+    with torch.no_grad():
+        for l in net.cross_net:
+            l.b.copy_(0.1 * torch.randn_like(l.b))
+    out["dcn_x"] = x.numpy()
+    for i, l in enumerate(net.cross_net):
+        out[f"dcn_w{i}"], out[f"dcn_b{i}"] = l.w.detach().numpy(), l.b.detach().numpy()
+    out["dcn_y"] = net(x).detach().numpy()
+    net2 = DCNv2Net(20, 3)
+    j = 0
+    for l in net2.cross_net:
+        if hasattr(l, "linear"):
+            out[f"dcn2_W{j}"], out[f"dcn2_b{j}"] = l.linear.weight.detach().numpy(), l.linear.bias.detach().numpy()
+            j += 1
+    out["dcn2_y"] = net2(x).detach().numpy()
+    # MLP
+    m = MLP([20, 16, 8, 1])
+    for i in (0, 2, 4):
+        out[f"mlp_w{i}"], out[f"mlp_b{i}"] = m.network[i].weight.detach().numpy(), m.network[i].bias.detach().numpy()
+    out["mlp_y"] = m(x).detach().numpy()
+    # BCE saturation clamp (deep/model.py:33): bce(p=0,y=1)=100
+    import torch.nn.functional as F
+    out["bce_sat"] = F.binary_cross_entropy(torch.tensor([0.0, 1.0, 0.25]), torch.tensor([1.0, 0.0, 1.0]),
+                                            reduction="none").numpy()
+    # CosinDecayLR trajectory (lr_schedule.py:16-28)
+    p = torch.nn.Parameter(torch.zeros(1))
+    opt = torch.optim.AdamW([p], lr=1e-3)
+    sch = CosinDecayLR(opt, lrs=[1e-3, 5e-6], milestones=[3, 9])
+    lrs = []
+    for _ in range(12):
+        lrs.append(opt.param_groups[0]["lr"])
+        opt.step()
+        sch.step()
+    out["cos_lrs"] = np.array(lrs)
+    np.savez_compressed(os.path.join(GOLD, "units.npz"), **out)
+    print("wrote units.npz")
+
+
+def main():
+    from src.model.sort.fm.model import FM
+    from src.model.sort.deep.model import Deep
+    from src.model.sort.widedeep.model import WideDeep
+    from src.model.sort.dcn.model import DCN
+    from src.model.sort.lr.model import LR
+    run_model("lr", LR, "lr")
+    run_model("fm", FM, "fm", opt_steps=3)
+    run_model("fm", FM, "fm_hist")
+    run_model("deep", Deep, "deep", opt_steps=3)
+    run_model("deep", Deep, "deep_hist")
+    run_model("deep", Deep, "deep_hist", with_mask=False, tag="deep_hist_nomask")
+    run_model("widedeep", WideDeep, "widedeep")
+    run_model("widedeep", WideDeep, "widedeep_hist")
+    run_model("dcn", DCN, "dcn")
+    run_model("dcn", DCN, "dcn_hist")
+    run_units()
+
+
+if __name__ == "__main__":
+    main()
