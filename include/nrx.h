@@ -1,0 +1,210 @@
+/*
+ * nrx.h — C ABI of libnrx.so, the B200 (sm_100a) implementation of the
+ * News_Recsys embedding-and-interaction hot path.
+ *
+ * The reference (ZhangHaoyang493/News_Recsys) has no FFI seam of its own: the
+ * boundary is its Python object model.  Each entry point below
+ * names the reference function(s) it replaces (paths relative to the reference
+ * root) and is what a maintainer would bind from `src/model/BaseModel/base_model.py`
+ * and the `src/model/sort/<model>/model.py` heads (see INTEGRATION.md for the
+ * ctypes stub).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer valid on `stream`, unless the parameter
+ *     name starts with `h_` (host);
+ *   - return 0 on success, a negative NRX_E* code otherwise; nrx_last_error()
+ *     returns a thread-local message for the last failure on the calling thread;
+ *   - no call allocates or frees caller memory, synchronises the device or
+ *     changes the current device; scratch comes from the caller (`ws`, sized by
+ *     the matching *_workspace_bytes query);
+ *   - no C++ exception crosses the boundary; the library is re-entrant.
+ */
+#ifndef NRX_H_
+#define NRX_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NRX_VERSION 100 /* major*100 + minor */
+
+typedef void* nrx_stream_t; /* cudaStream_t */
+
+enum {
+  NRX_OK = 0,
+  NRX_EINVAL = -1,      /* bad argument */
+  NRX_EUNSUPPORTED = -2,/* shape / dtype outside what the kernels handle */
+  NRX_ELAUNCH = -3,     /* CUDA launch or runtime failure */
+  NRX_EWORKSPACE = -4   /* workspace too small */
+};
+
+enum { NRX_POOL_NONE = 0, NRX_POOL_MASKED_MEAN = 1, NRX_POOL_MEAN = 2 };
+enum { NRX_IDX_I64 = 0, NRX_IDX_I32 = 1 };
+enum { NRX_MAX_FEATS = 16, NRX_MAX_TABLES = 16, NRX_MAX_LAYERS = 8 };
+
+/* One feature of get_embeddings_from_batch (base_model.py:284-308). */
+typedef struct NrxFeat {
+  const float* table;   /* nn.Embedding weight [rows, row_stride] fp32 (base_model.py:164) */
+  int64_t rows;
+  int32_t dim;          /* logical D */
+  int32_t row_stride;   /* elements between rows, >= dim */
+  int32_t table_id;     /* 0..n_tables-1; features aliased by share_emb_table_features share an id */
+  int32_t idx_dtype;    /* NRX_IDX_* (the reference casts with .long(), base_model.py:271) */
+  const void* idx;      /* [B] (L == 1) or [B, L] row ids, 0 = padding row */
+  int32_t L;            /* 1 for sparse features, array_max_length for array features */
+  int32_t pool;         /* NRX_POOL_*: array_feature_pooling (base_model.py:273-282) */
+  const float* mask;    /* [B, L] fp32 or NULL (NRX_POOL_MEAN / NONE) */
+  float* inv_den;       /* optional out [B]: 1/(sum(mask)+1e-8), reused by the backward; may be NULL */
+  int32_t out_col;      /* first column of this feature in the concatenated output */
+  int32_t reserved;
+} NrxFeat;
+
+int nrx_version(void);
+const char* nrx_last_error(void);
+
+/* ---- K1: fused gather + masked-mean pooling + concat ----------------------
+ * Replaces BaseModel.get_feature_embedding / array_feature_pooling /
+ * get_embeddings_from_batch (base_model.py:262-308): out[b, out_col_f : +dim_f].
+ * `status` (optional int32[1]) is set non-zero if any id is outside [0, rows). */
+int nrx_embed_pool_fwd(const NrxFeat* h_feats, int n_feats, int64_t B,
+                       float* out, int64_t out_ld, int32_t* status, nrx_stream_t stream);
+
+/* ---- K3: deterministic sorted-index segment-reduce backward ----------------
+ * Replaces aten::embedding_dense_backward behind base_model.py:271 (padding_idx=0
+ * rows receive no gradient) plus the backward of the pooling at :278-282.
+ *
+ * nrx_embed_bwd_plan sorts the (table,row) keys of every (feature, sample,
+ * position) occurrence once per batch; nrx_embed_bwd_apply then reduces
+ * grad_out rows per unique table row in a fixed order (ascending occurrence)
+ * and either writes dense per-table gradients (mode DENSE, `grads[t]` is
+ * [rows_t, stride_t], zeroed by this call) or applies a fused sparse row update
+ * in place (SGD / AdamW on touched rows only). */
+enum { NRX_BWD_DENSE = 0, NRX_BWD_SGD = 1, NRX_BWD_ADAMW = 2 };
+
+typedef struct NrxRowOpt {
+  float lr, beta1, beta2, eps, weight_decay;
+  int32_t step;               /* 1-based, for Adam bias correction */
+  float* m[NRX_MAX_TABLES];   /* AdamW first moment per table (same shape as the table) */
+  float* v[NRX_MAX_TABLES];   /* AdamW second moment per table */
+} NrxRowOpt;
+
+size_t nrx_embed_bwd_workspace_bytes(const NrxFeat* h_feats, int n_feats, int64_t B);
+int nrx_embed_bwd_plan(const NrxFeat* h_feats, int n_feats, int64_t B,
+                       void* ws, size_t ws_bytes, nrx_stream_t stream);
+int nrx_embed_bwd_apply(const NrxFeat* h_feats, int n_feats, int64_t B,
+                        const float* grad_out, int64_t grad_ld,
+                        int mode, float* const* h_grads /* [n_tables] device ptrs, DENSE */,
+                        float* const* h_tables /* [n_tables] device ptrs, SGD/ADAMW */,
+                        const NrxRowOpt* h_opt,
+                        void* ws, size_t ws_bytes, nrx_stream_t stream);
+
+/* ---- K2: field logits on the concatenated features --------------------------
+ * FM    : fm/model.py:48-59 (w = col 0, v = cols 1..) + :18-25  -> first + second order
+ * WIDE  : widedeep/model.py:58-65 + :25                          -> sum of col 0 of the listed fields
+ * SUM   : lr/model.py:24-27                                      -> sum of every column of the listed fields
+ * logit[b] (+)= term; backward adds into grad_x. */
+enum { NRX_FIELD_FM = 0, NRX_FIELD_WIDE = 1, NRX_FIELD_SUM = 2 };
+int nrx_field_logit_fwd(const float* x, int64_t ld, int64_t B, const int32_t* h_cols,
+                        const int32_t* h_dims, int n_fields, int mode,
+                        float* logit, int accumulate, nrx_stream_t stream);
+int nrx_field_logit_bwd(const float* x, int64_t ld, int64_t B, const int32_t* h_cols,
+                        const int32_t* h_dims, int n_fields, int mode,
+                        const float* dlogit, float* grad_x, int64_t grad_ld, int accumulate,
+                        nrx_stream_t stream);
+
+/* Gather-fused FM for sparse-only fields of equal width (BASELINE config 2):
+ * gathers the rows, never materialises the concat, and emits prob (+ per-sample
+ * BCE and dL/dlogit when label != NULL).  fm/model.py:18-26,43-59 + bceLoss :39-40. */
+int nrx_fm_fused_fwd(const NrxFeat* h_feats, int n_feats, int64_t B, const float* bias,
+                     const float* label, int64_t label_stride,
+                     float* logit, float* prob, float* loss_per_sample, float* dlogit,
+                     int32_t* status, nrx_stream_t stream);
+/* grad_x[b, out_col_f + d] = dlogit[b] * (d == 0 ? 1 : S_d - v_fd)  (S re-gathered). */
+int nrx_fm_fused_bwd(const NrxFeat* h_feats, int n_feats, int64_t B, const float* dlogit,
+                     float* grad_x, int64_t grad_ld, nrx_stream_t stream);
+
+/* ---- sigmoid + BCE on probabilities (bceLoss, deep/model.py:32-33) ----------
+ * prob = sigmoid(sum_t terms[t][b] + bias[0]); loss_b = -[y log p + (1-y) log(1-p)]
+ * with log clamped at -100; dlogit_b = (p-y)/max(p(1-p),1e-12) * p(1-p) / B. */
+int nrx_logit_loss_fwd(const float* const* h_terms, int n_terms, const float* bias, int64_t B,
+                       const float* label, int64_t label_stride,
+                       float* prob, float* loss_per_sample, float* dlogit, nrx_stream_t stream);
+/* Un-fused pieces of the same chain, for the autograd route (loss.backward()):
+ *   loss_b = BCE(prob_b, y_b)                          (bceLoss forward)
+ *   grad_prob_b = (p-y)/max(p(1-p),1e-12) * upstream[0] / B   (its autograd)
+ *   grad_logit_b = grad_prob_b * p(1-p)               (torch.sigmoid autograd) */
+int nrx_bce_fwd(const float* prob, const float* label, int64_t label_stride, int64_t B,
+                float* loss_per_sample, nrx_stream_t stream);
+int nrx_bce_bwd(const float* prob, const float* label, int64_t label_stride, int64_t B,
+                const float* upstream, float* grad_prob, nrx_stream_t stream);
+int nrx_sigmoid_bwd(const float* prob, const float* grad_prob, int64_t B, float* grad_logit,
+                    nrx_stream_t stream);
+/* Deterministic mean/sum of n floats into out[0] (fixed reduction tree). */
+int nrx_reduce_f32(const float* x, int64_t n, float scale, float* out, nrx_stream_t stream);
+
+/* ---- dense AdamW exactly as torch.optim.AdamW (deep/model.py:55) ------------ */
+int nrx_adamw_dense(float* p, const float* g, float* m, float* v, int64_t n,
+                    float lr, float beta1, float beta2, float eps, float weight_decay,
+                    int32_t step, nrx_stream_t stream);
+
+/* ---- K4/K5: fused bf16 tower on tcgen05 (MLP utils.py:6-17, DSSM towers
+ * recall/DSSM/model.py:26-44, DCN cross dcn_arch.py:14-30,53-70) --------------- */
+enum { NRX_ACT_RELU = 0, NRX_ACT_LEAKY = 1 };
+typedef struct NrxTower {
+  int32_t n_layers;                   /* Linear layers */
+  int32_t dims[NRX_MAX_LAYERS + 1];   /* in, hidden..., out */
+  const float* w[NRX_MAX_LAYERS];     /* [out, in] fp32 (nn.Linear layout) */
+  const float* b[NRX_MAX_LAYERS];     /* [out] */
+  int32_t act;                        /* NRX_ACT_* between layers, none after the last */
+  float negative_slope;
+} NrxTower;
+
+size_t nrx_tower_workspace_bytes(const NrxTower* h_tower, int64_t B, int training);
+/* y[B, dims[n]] = tower(x[B, dims[0]]); with training != 0 the bf16 activations of
+ * every layer are kept in `ws` for nrx_tower_bwd. */
+int nrx_tower_fwd(const NrxTower* h_tower, const float* x, int64_t x_ld, int64_t B,
+                  float* y, int64_t y_ld, int training, void* ws, size_t ws_bytes,
+                  nrx_stream_t stream);
+/* grad_x (+)= d/dx, grad_w[l] / grad_b[l] = d/dW_l, d/db_l (overwritten). */
+int nrx_tower_bwd(const NrxTower* h_tower, const float* x, int64_t x_ld, int64_t B,
+                  const float* grad_y, int64_t gy_ld,
+                  float* grad_x, int64_t gx_ld, int accumulate_gx,
+                  float* const* h_grad_w, float* const* h_grad_b,
+                  void* ws, size_t ws_bytes, nrx_stream_t stream);
+
+/* DCN-v1 cross stack: x_{l+1} = x0 * (x_l . w_l) + b_l + x_l  (dcn_arch.py:14-30),
+ * writes out[B, 2d] = cat[x, x_L] (dcn/model.py:29).  dots[L, B] keeps x_l . w_l. */
+int nrx_dcn_cross_fwd(const float* x, int64_t ld, int64_t B, int d, int n_layers,
+                      const float* const* h_w, const float* const* h_b,
+                      float* out, int64_t out_ld, float* dots, nrx_stream_t stream);
+int nrx_dcn_cross_bwd(const float* x, int64_t ld, int64_t B, int d, int n_layers,
+                      const float* const* h_w, const float* const* h_b,
+                      const float* grad_out, int64_t go_ld, const float* dots,
+                      float* grad_x, int64_t gx_ld,
+                      float* const* h_grad_w, float* const* h_grad_b,
+                      void* ws, size_t ws_bytes, nrx_stream_t stream);
+size_t nrx_dcn_cross_workspace_bytes(int64_t B, int d, int n_layers);
+
+/* ---- K6: exact inner-product top-k -----------------------------------------
+ * Replaces faiss.IndexFlatIP.add/search (recall/DSSM/model.py:209,249-251;
+ * model_utils/TopKSearcher.py:34-47,73-77): out ordered by (score desc, id asc),
+ * ids are corpus positions + id_base, padding (k > N) is id -1 / score -FLT_MAX. */
+size_t nrx_topk_ip_workspace_bytes(int64_t Q, int64_t N, int D, int k);
+int nrx_topk_ip(const float* queries, int64_t q_ld, const float* corpus, int64_t c_ld,
+                int64_t Q, int64_t N, int D, int k, int64_t id_base,
+                float* out_scores, int64_t* out_ids, void* ws, size_t ws_bytes,
+                nrx_stream_t stream);
+/* Merge `n_lists` per-shard lists [n_lists][Q][k] into the global top-k. */
+int nrx_topk_merge(const float* scores, const int64_t* ids, int n_lists, int64_t Q, int k,
+                   float* out_scores, int64_t* out_ids, nrx_stream_t stream);
+/* Row-wise L2 normalisation (faiss.normalize_L2 / F.normalize, DSSM/model.py:69-71). */
+int nrx_l2_normalize(const float* x, int64_t ld, int64_t n, int d, float* y, int64_t y_ld,
+                     nrx_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NRX_H_ */

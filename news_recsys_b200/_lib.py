@@ -1,0 +1,150 @@
+"""ctypes binding of libnrx.so (the C ABI declared in include/nrx.h).
+
+There is no fallback: if the library is missing or a call fails, this raises.
+torch is used only for device memory and streams.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libnrx.so")
+
+NRX_MAX_FEATS = 16
+NRX_MAX_TABLES = 16
+NRX_MAX_LAYERS = 8
+
+POOL_NONE, POOL_MASKED_MEAN, POOL_MEAN = 0, 1, 2
+IDX_I64, IDX_I32 = 0, 1
+BWD_DENSE, BWD_SGD, BWD_ADAMW = 0, 1, 2
+FIELD_FM, FIELD_WIDE, FIELD_SUM = 0, 1, 2
+ACT_RELU, ACT_LEAKY = 0, 1
+
+
+class NrxError(RuntimeError):
+    pass
+
+
+class NrxFeat(C.Structure):
+    _fields_ = [
+        ("table", C.c_void_p), ("rows", C.c_int64), ("dim", C.c_int32), ("row_stride", C.c_int32),
+        ("table_id", C.c_int32), ("idx_dtype", C.c_int32), ("idx", C.c_void_p), ("L", C.c_int32),
+        ("pool", C.c_int32), ("mask", C.c_void_p), ("inv_den", C.c_void_p), ("out_col", C.c_int32),
+        ("reserved", C.c_int32),
+    ]
+
+
+class NrxRowOpt(C.Structure):
+    _fields_ = [
+        ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
+        ("weight_decay", C.c_float), ("step", C.c_int32),
+        ("m", C.c_void_p * NRX_MAX_TABLES), ("v", C.c_void_p * NRX_MAX_TABLES),
+    ]
+
+
+class NrxTower(C.Structure):
+    _fields_ = [
+        ("n_layers", C.c_int32), ("dims", C.c_int32 * (NRX_MAX_LAYERS + 1)),
+        ("w", C.c_void_p * NRX_MAX_LAYERS), ("b", C.c_void_p * NRX_MAX_LAYERS),
+        ("act", C.c_int32), ("negative_slope", C.c_float),
+    ]
+
+
+_P = C.c_void_p
+_I64 = C.c_int64
+_I32 = C.c_int32
+_F = C.c_float
+_SZ = C.c_size_t
+
+# name -> (restype, argtypes); mirrors include/nrx.h one to one
+SIGNATURES = {
+    "nrx_version": (C.c_int, []),
+    "nrx_last_error": (C.c_char_p, []),
+    "nrx_embed_pool_fwd": (C.c_int, [C.POINTER(NrxFeat), C.c_int, _I64, _P, _I64, _P, _P]),
+    "nrx_embed_bwd_workspace_bytes": (_SZ, [C.POINTER(NrxFeat), C.c_int, _I64]),
+    "nrx_embed_bwd_plan": (C.c_int, [C.POINTER(NrxFeat), C.c_int, _I64, _P, _SZ, _P]),
+    "nrx_embed_bwd_apply": (C.c_int, [C.POINTER(NrxFeat), C.c_int, _I64, _P, _I64, C.c_int,
+                                      C.POINTER(_P), C.POINTER(_P), C.POINTER(NrxRowOpt), _P, _SZ, _P]),
+    "nrx_field_logit_fwd": (C.c_int, [_P, _I64, _I64, C.POINTER(_I32), C.POINTER(_I32), C.c_int, C.c_int, _P, C.c_int, _P]),
+    "nrx_field_logit_bwd": (C.c_int, [_P, _I64, _I64, C.POINTER(_I32), C.POINTER(_I32), C.c_int, C.c_int, _P, _P, _I64, C.c_int, _P]),
+    "nrx_fm_fused_fwd": (C.c_int, [C.POINTER(NrxFeat), C.c_int, _I64, _P, _P, _I64, _P, _P, _P, _P, _P, _P]),
+    "nrx_fm_fused_bwd": (C.c_int, [C.POINTER(NrxFeat), C.c_int, _I64, _P, _P, _I64, _P]),
+    "nrx_logit_loss_fwd": (C.c_int, [C.POINTER(_P), C.c_int, _P, _I64, _P, _I64, _P, _P, _P, _P]),
+    "nrx_bce_fwd": (C.c_int, [_P, _P, _I64, _I64, _P, _P]),
+    "nrx_bce_bwd": (C.c_int, [_P, _P, _I64, _I64, _P, _P, _P]),
+    "nrx_sigmoid_bwd": (C.c_int, [_P, _P, _I64, _P, _P]),
+    "nrx_reduce_f32": (C.c_int, [_P, _I64, _F, _P, _P]),
+    "nrx_adamw_dense": (C.c_int, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _I32, _P]),
+    "nrx_tower_workspace_bytes": (_SZ, [C.POINTER(NrxTower), _I64, C.c_int]),
+    "nrx_tower_fwd": (C.c_int, [C.POINTER(NrxTower), _P, _I64, _I64, _P, _I64, C.c_int, _P, _SZ, _P]),
+    "nrx_tower_bwd": (C.c_int, [C.POINTER(NrxTower), _P, _I64, _I64, _P, _I64, _P, _I64, C.c_int,
+                                C.POINTER(_P), C.POINTER(_P), _P, _SZ, _P]),
+    "nrx_dcn_cross_fwd": (C.c_int, [_P, _I64, _I64, C.c_int, C.c_int, C.POINTER(_P), C.POINTER(_P), _P, _I64, _P, _P]),
+    "nrx_dcn_cross_bwd": (C.c_int, [_P, _I64, _I64, C.c_int, C.c_int, C.POINTER(_P), C.POINTER(_P), _P, _I64, _P,
+                                    _P, _I64, C.POINTER(_P), C.POINTER(_P), _P, _SZ, _P]),
+    "nrx_dcn_cross_workspace_bytes": (_SZ, [_I64, C.c_int, C.c_int]),
+    "nrx_topk_ip_workspace_bytes": (_SZ, [_I64, _I64, C.c_int, C.c_int]),
+    "nrx_topk_ip": (C.c_int, [_P, _I64, _P, _I64, _I64, _I64, C.c_int, C.c_int, _I64, _P, _P, _P, _SZ, _P]),
+    "nrx_topk_merge": (C.c_int, [_P, _P, C.c_int, _I64, C.c_int, _P, _P, _P]),
+    "nrx_l2_normalize": (C.c_int, [_P, _I64, _I64, C.c_int, _P, _I64, _P]),
+}
+
+_lock = threading.Lock()
+_lib = None
+MISSING = []  # header symbols the loaded library does not export
+
+
+def load() -> C.CDLL:
+    """Load libnrx.so (once).  Raises NrxError if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise NrxError(
+                f"{LIB_PATH} is missing — build it with `python -m news_recsys_b200.build` "
+                "(there is no CPU or PyTorch fallback for this path)")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            try:
+                fn = getattr(lib, name)
+            except AttributeError:
+                MISSING.append(name)  # tests/test_abi.py requires this list to be empty
+                continue
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().nrx_last_error()
+        raise NrxError(f"{what} failed (code {rc}): {msg.decode() if msg else ''}")
+
+
+def stream_ptr(device=None) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def ptr(t) -> int:
+    return 0 if t is None else t.data_ptr()
+
+
+def ptr_array(ts, n=None):
+    """Host array of device pointers (void*[n])."""
+    n = len(ts) if n is None else n
+    arr = (_P * n)()
+    for i, t in enumerate(ts):
+        arr[i] = 0 if t is None else (t if isinstance(t, int) else t.data_ptr())
+    return arr
+
+
+def i32_array(xs):
+    return (_I32 * len(xs))(*[int(x) for x in xs])

@@ -1,0 +1,103 @@
+// Shared device/host helpers for libnrx (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/nrx.h"
+
+#define NRX_FULL_MASK 0xffffffffu
+
+namespace nrx {
+
+// ---- error plumbing (thread-local message, no exceptions across the ABI) ----
+void set_error(const char* fmt, ...);
+int check_launch(const char* what);  // cudaGetLastError -> NRX_ELAUNCH
+
+#define NRX_REQUIRE(cond, code, ...)          \
+  do {                                        \
+    if (!(cond)) {                            \
+      ::nrx::set_error(__VA_ARGS__);          \
+      return (code);                          \
+    }                                         \
+  } while (0)
+
+int sm_count();  // cached per process for the current device
+
+// ---- device-side feature descriptors (kernel parameter, < 4 KB) --------------
+struct DFeat {
+  const float* table;
+  const void* idx;
+  const float* mask;
+  float* inv_den;
+  long long rows;
+  long long occ_off;  // first occurrence number of this feature in the backward plan
+  int dim, stride, L, pool, out_col, idx32, table_id, cstart;  // cstart: first vec column (sparse group)
+};
+
+struct DFeats {
+  DFeat f[NRX_MAX_FEATS];
+  int n;
+  int n_sparse, n_array;
+  int sparse_ids[NRX_MAX_FEATS];
+  int array_ids[NRX_MAX_FEATS];
+  int sparse_cols;  // total vec columns of the sparse group
+  int vec;          // 4 or 1
+  int max_dim;
+  int n_tables;
+  long long n_occ;
+};
+
+// Validates and converts host NrxFeat[] -> DFeats.  `out_ld`/`out` only used for the vector-width decision.
+int make_dfeats(const NrxFeat* feats, int n, long long B, const void* out, long long out_ld, DFeats* d);
+
+__device__ __forceinline__ long long load_idx(const void* p, long long i, int idx32) {
+  return idx32 ? (long long)__ldg(reinterpret_cast<const int*>(p) + i)
+               : __ldg(reinterpret_cast<const long long*>(p) + i);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(NRX_FULL_MASK, v, o);
+  return v;
+}
+
+template <int V>
+struct VecT;
+template <>
+struct VecT<4> {
+  using type = float4;
+  static __device__ __forceinline__ float4 zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+  static __device__ __forceinline__ float4 load(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+  static __device__ __forceinline__ void store(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+  static __device__ __forceinline__ void fma(float4& a, float m, float4 v) {
+    a.x = fmaf(m, v.x, a.x); a.y = fmaf(m, v.y, a.y); a.z = fmaf(m, v.z, a.z); a.w = fmaf(m, v.w, a.w);
+  }
+  static __device__ __forceinline__ float4 shfl_xor(float4 v, int o) {
+    v.x = __shfl_xor_sync(NRX_FULL_MASK, v.x, o); v.y = __shfl_xor_sync(NRX_FULL_MASK, v.y, o);
+    v.z = __shfl_xor_sync(NRX_FULL_MASK, v.z, o); v.w = __shfl_xor_sync(NRX_FULL_MASK, v.w, o);
+    return v;
+  }
+  static __device__ __forceinline__ void add(float4& a, float4 b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+  static __device__ __forceinline__ float4 div(float4 a, float d) { return make_float4(a.x / d, a.y / d, a.z / d, a.w / d); }
+};
+template <>
+struct VecT<1> {
+  using type = float;
+  static __device__ __forceinline__ float zero() { return 0.f; }
+  static __device__ __forceinline__ float load(const float* p) { return __ldg(p); }
+  static __device__ __forceinline__ void store(float* p, float v) { *p = v; }
+  static __device__ __forceinline__ void fma(float& a, float m, float v) { a = fmaf(m, v, a); }
+  static __device__ __forceinline__ float shfl_xor(float v, int o) { return __shfl_xor_sync(NRX_FULL_MASK, v, o); }
+  static __device__ __forceinline__ void add(float& a, float b) { a += b; }
+  static __device__ __forceinline__ float div(float a, float d) { return a / d; }
+};
+
+static inline int pow2_ceil(int x) {
+  int p = 1;
+  while (p < x) p <<= 1;
+  return p;
+}
+
+}  // namespace nrx

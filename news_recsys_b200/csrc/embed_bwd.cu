@@ -1,0 +1,371 @@
+// K3 — deterministic sorted-index segment-reduce backward of the embedding gather/pool,
+// with optional fused sparse row update (SGD / AdamW).
+//
+// Replaces aten::embedding_dense_backward behind nn.Embedding(..., padding_idx=0)
+// (reference src/model/BaseModel/base_model.py:164,271) and the autograd of the masked
+// mean pooling (base_model.py:278-282).
+//
+//   plan : one key per (feature, sample, position) occurrence, key = table_id << row_bits | row,
+//          invalid occurrences (row 0 = padding_idx, mask == 0, out-of-range id) get a sentinel
+//          key that sorts last; stable LSD radix sort (cub::DeviceRadixSort) of (key, occurrence).
+//   apply: phase A, one warp per tile of sorted occurrences: lanes own gradient columns, the
+//          warp walks its tile in sorted order and sums grad_out rows per run of equal keys.
+//          Runs inside a tile are final; runs crossing tile borders leave a partial per tile.
+//          phase B, one warp per run that crosses a tile border: adds the partials in tile order.
+//          Every unique row is finalised by exactly one warp in a fixed order => bitwise
+//          reproducible, no float atomics.
+#include <cub/device/device_radix_sort.cuh>
+
+#include "common.cuh"
+
+namespace nrx {
+
+static constexpr int kTile = 64;  // sorted occurrences per warp in phase A
+
+struct DTables {
+  float* g[NRX_MAX_TABLES];   // dense grads
+  float* w[NRX_MAX_TABLES];   // tables (row update modes)
+  float* m[NRX_MAX_TABLES];
+  float* v[NRX_MAX_TABLES];
+  int dim[NRX_MAX_TABLES];
+  int stride[NRX_MAX_TABLES];
+  int mode;
+  int row_bits;
+  float lr, beta1, beta2, eps, wd, bc1, bc2_sqrt;
+};
+
+struct PlanLayout {
+  size_t keys_in, vals_in, keys_out, vals_out, head, tail, cub, total;
+  size_t cub_bytes;
+  long long n_tiles;
+  int row_bits, key_bits, nc;
+};
+
+static int plan_layout(const DFeats& d, PlanLayout* L) {
+  long long max_rows = 1;
+  for (int i = 0; i < d.n; ++i) max_rows = d.f[i].rows > max_rows ? d.f[i].rows : max_rows;
+  int row_bits = 1;
+  while ((1ll << row_bits) < max_rows) ++row_bits;
+  int tbits = 0;
+  while ((1 << tbits) < d.n_tables) ++tbits;
+  L->row_bits = row_bits;
+  L->key_bits = row_bits + tbits;
+  NRX_REQUIRE(L->key_bits + 1 <= 32, NRX_EUNSUPPORTED, "table_bits+row_bits=%d does not fit 31-bit keys", L->key_bits);
+  NRX_REQUIRE(d.n_occ < (1ll << 31), NRX_EUNSUPPORTED, "too many occurrences (%lld)", d.n_occ);
+  NRX_REQUIRE(d.max_dim <= 128, NRX_EUNSUPPORTED, "backward supports dim <= 128 (got %d)", d.max_dim);
+  L->nc = (d.max_dim + 31) / 32;
+  if (L->nc == 3) L->nc = 4;
+  const size_t n = (size_t)d.n_occ;
+  L->n_tiles = (d.n_occ + kTile - 1) / kTile;
+  auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  size_t off = 0;
+  L->keys_in = off;  off += al(n * 4);
+  L->vals_in = off;  off += al(n * 4);
+  L->keys_out = off; off += al(n * 4);
+  L->vals_out = off; off += al(n * 4);
+  const size_t part = al((size_t)L->n_tiles * 32 * L->nc * 4);
+  L->head = off; off += part;
+  L->tail = off; off += part;
+  size_t cub_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr,
+                                  (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)(n ? n : 1), 0, L->key_bits + 1);
+  L->cub_bytes = cub_bytes;
+  L->cub = off; off += al(cub_bytes);
+  L->total = off;
+  return NRX_OK;
+}
+
+__global__ void __launch_bounds__(256)
+build_keys_kernel(const __grid_constant__ DFeats P, int row_bits, uint32_t sentinel,
+                  uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P.n_occ) return;
+  int f = 0;
+  for (int i = 1; i < P.n; ++i)
+    if (p >= P.f[i].occ_off) f = i;
+  const DFeat& F = P.f[f];
+  const long long r = p - F.occ_off;  // == b * L + l
+  const long long id = load_idx(F.idx, r, F.idx32);
+  bool valid = id > 0 && id < F.rows;  // row 0 is padding_idx: never receives gradient
+  if (valid && F.pool == NRX_POOL_MASKED_MEAN) valid = __ldg(F.mask + r) != 0.f;
+  keys[p] = valid ? (((uint32_t)F.table_id << row_bits) | (uint32_t)id) : sentinel;
+  vals[p] = (uint32_t)p;
+}
+
+// ---- finalise one unique row (lanes own columns c = lane + 32*k) -------------------------
+template <int NC>
+__device__ __forceinline__ void finalize_row(const DTables& T, uint32_t key, const float (&acc)[NC], int lane) {
+  const int t = (int)(key >> T.row_bits);
+  const long long row = (long long)(key & ((1u << T.row_bits) - 1u));
+  const int dim = T.dim[t];
+  const long long base = row * T.stride[t];
+#pragma unroll
+  for (int k = 0; k < NC; ++k) {
+    const int c = lane + 32 * k;
+    if (c >= dim) continue;
+    const float g = acc[k];
+    if (T.mode == NRX_BWD_DENSE) {
+      T.g[t][base + c] = g;
+    } else if (T.mode == NRX_BWD_SGD) {
+      float p = T.w[t][base + c];
+      T.w[t][base + c] = p - T.lr * (g + T.wd * p);
+    } else {  // AdamW on the touched row (torch.optim.AdamW update rule)
+      float p = T.w[t][base + c];
+      float m = T.m[t][base + c], v = T.v[t][base + c];
+      p *= (1.f - T.lr * T.wd);
+      m = T.beta1 * m + (1.f - T.beta1) * g;
+      v = T.beta2 * v + (1.f - T.beta2) * g * g;
+      const float denom = sqrtf(v) / T.bc2_sqrt + T.eps;
+      p -= (T.lr / T.bc1) * (m / denom);
+      T.w[t][base + c] = p;
+      T.m[t][base + c] = m;
+      T.v[t][base + c] = v;
+    }
+  }
+}
+
+// Phase A.
+template <int NC>
+__global__ void __launch_bounds__(128)
+segment_reduce_kernel(const __grid_constant__ DFeats P, const __grid_constant__ DTables T,
+                      const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
+                      const float* __restrict__ grad, long long gld, long long n_occ, uint32_t sentinel,
+                      float* __restrict__ head, float* __restrict__ tail) {
+  const long long tile = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long ts = tile * kTile;
+  if (ts >= n_occ) return;
+  const long long te = min(ts + (long long)kTile, n_occ);
+  const uint32_t prev_key = ts > 0 ? keys[ts - 1] : 0xffffffffu;
+  const uint32_t next_key = te < n_occ ? keys[te] : 0xffffffffu;
+
+  float acc[NC];
+#pragma unroll
+  for (int k = 0; k < NC; ++k) acc[k] = 0.f;
+  uint32_t run_key = 0xffffffffu;
+  bool run_from_prev = false;
+
+  for (long long i0 = ts; i0 < te; i0 += 32) {
+    // lane-private decode of occurrence i0+lane
+    const long long i = i0 + lane;
+    uint32_t my_key = sentinel;
+    long long my_off = 0;
+    float my_scale = 0.f;
+    int my_dim = 0;
+    if (i < te) {
+      my_key = keys[i];
+      if (my_key != sentinel) {
+        const long long p = vals[i];
+        int f = 0;
+        for (int q = 1; q < P.n; ++q)
+          if (p >= P.f[q].occ_off) f = q;
+        const DFeat& F = P.f[f];
+        const long long r = p - F.occ_off;
+        const long long b = (F.L == 1) ? r : r / F.L;
+        my_off = b * gld + F.out_col;
+        my_dim = F.dim;
+        if (F.pool == NRX_POOL_NONE) my_scale = 1.f;
+        else if (F.pool == NRX_POOL_MEAN) my_scale = 1.f / (float)F.L;
+        else my_scale = __ldg(F.mask + r) * __ldg(F.inv_den + b);
+      }
+    }
+    const int n = (int)min(32ll, te - i0);
+    for (int j0 = 0; j0 < n; j0 += 8) {
+      float g[8][NC];
+      uint32_t kj[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int j = j0 + u;  // j < 32 always
+        kj[u] = __shfl_sync(NRX_FULL_MASK, my_key, j);
+        const long long off = __shfl_sync(NRX_FULL_MASK, my_off, j);
+        const float sc = __shfl_sync(NRX_FULL_MASK, my_scale, j);
+        const int dm = __shfl_sync(NRX_FULL_MASK, my_dim, j);
+#pragma unroll
+        for (int k = 0; k < NC; ++k) {
+          const int c = lane + 32 * k;
+          g[u][k] = (j < n && kj[u] != sentinel && c < dm) ? sc * __ldg(grad + off + c) : 0.f;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int j = j0 + u;
+        if (j >= n) break;
+        const uint32_t k_cur = kj[u];
+        const long long pos = i0 + j;
+        if (k_cur != run_key) {  // a new run starts at pos
+          run_key = k_cur;
+          run_from_prev = (pos == ts) && (k_cur == prev_key);
+#pragma unroll
+          for (int k = 0; k < NC; ++k) acc[k] = 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < NC; ++k) acc[k] += g[u][k];
+        // does the run end at pos?
+        uint32_t k_next;
+        if (pos + 1 < te) k_next = (j + 1 < 32) ? __shfl_sync(NRX_FULL_MASK, my_key, (j + 1) & 31) : keys[pos + 1];
+        else k_next = 0xfffffffeu;  // forces "ends here" handling below
+        const bool last_in_tile = (pos + 1 == te);
+        if (last_in_tile || k_next != k_cur) {
+          if (k_cur != sentinel) {
+            const bool to_next = last_in_tile && (k_cur == next_key);
+            if (!run_from_prev && !to_next) {
+              finalize_row<NC>(T, k_cur, acc, lane);
+            } else {
+              float* dst = (run_from_prev ? head : tail) + (tile * 32 + lane) * NC;
+#pragma unroll
+              for (int k = 0; k < NC; ++k) dst[k] = acc[k];
+            }
+          }
+          run_key = 0xffffffffu;  // next element opens a new run
+        }
+      }
+    }
+  }
+}
+
+// Phase B: tile `t` owns a run iff its last run starts in t and continues into t+1.
+template <int NC>
+__global__ void __launch_bounds__(128)
+segment_fixup_kernel(const __grid_constant__ DTables T, const uint32_t* __restrict__ keys, long long n_occ,
+                     long long n_tiles, uint32_t sentinel, const float* __restrict__ head,
+                     const float* __restrict__ tail) {
+  const long long t = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (t + 1 >= n_tiles) return;
+  const long long ts = t * kTile, te = ts + kTile;  // full tile (not the last one)
+  const uint32_t K = keys[te - 1];
+  if (K == sentinel || keys[te] != K) return;                       // does not continue
+  const bool started_here = (keys[ts] != K) || ts == 0 || keys[ts - 1] != K;
+  if (!started_here) return;                                        // an earlier tile owns it
+  float acc[NC];
+  const float* src = tail + (t * 32 + lane) * NC;
+#pragma unroll
+  for (int k = 0; k < NC; ++k) acc[k] = src[k];
+  for (long long u = t + 1; u < n_tiles && keys[u * kTile] == K; ++u) {
+    const float* h = head + (u * 32 + lane) * NC;
+#pragma unroll
+    for (int k = 0; k < NC; ++k) acc[k] += h[k];
+    const long long ue = min((u + 1) * (long long)kTile, n_occ);
+    if (keys[ue - 1] != K) break;  // run ended inside tile u
+  }
+  finalize_row<NC>(T, K, acc, lane);
+}
+
+template <int NC>
+static int launch_apply(const DFeats& d, const DTables& T, const PlanLayout& L, char* ws, const float* grad,
+                        long long gld, cudaStream_t st) {
+  const uint32_t sentinel = 1u << L.key_bits;
+  const uint32_t* keys = (const uint32_t*)(ws + L.keys_out);
+  const uint32_t* vals = (const uint32_t*)(ws + L.vals_out);
+  float* head = (float*)(ws + L.head);
+  float* tail = (float*)(ws + L.tail);
+  const int wpb = 4;
+  const unsigned blocks = (unsigned)((L.n_tiles + wpb - 1) / wpb);
+  segment_reduce_kernel<NC><<<blocks, wpb * 32, 0, st>>>(d, T, keys, vals, grad, gld, d.n_occ, sentinel, head, tail);
+  int rc = check_launch("segment_reduce");
+  if (rc != NRX_OK) return rc;
+  if (L.n_tiles > 1) {
+    segment_fixup_kernel<NC><<<blocks, wpb * 32, 0, st>>>(T, keys, d.n_occ, L.n_tiles, sentinel, head, tail);
+    rc = check_launch("segment_fixup");
+  }
+  return rc;
+}
+
+}  // namespace nrx
+
+extern "C" size_t nrx_embed_bwd_workspace_bytes(const NrxFeat* h_feats, int n_feats, int64_t B) {
+  using namespace nrx;
+  DFeats d;
+  if (make_dfeats(h_feats, n_feats, B, nullptr, 0, &d) != NRX_OK) return 0;
+  PlanLayout L;
+  if (plan_layout(d, &L) != NRX_OK) return 0;
+  return L.total;
+}
+
+extern "C" int nrx_embed_bwd_plan(const NrxFeat* h_feats, int n_feats, int64_t B, void* ws, size_t ws_bytes,
+                                  nrx_stream_t stream) {
+  using namespace nrx;
+  DFeats d;
+  int rc = make_dfeats(h_feats, n_feats, B, nullptr, 0, &d);
+  if (rc != NRX_OK) return rc;
+  PlanLayout L;
+  rc = plan_layout(d, &L);
+  if (rc != NRX_OK) return rc;
+  NRX_REQUIRE(ws != nullptr && ws_bytes >= L.total, NRX_EWORKSPACE, "workspace %zu < %zu", ws_bytes, L.total);
+  if (d.n_occ == 0) return NRX_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  char* w = (char*)ws;
+  const uint32_t sentinel = 1u << L.key_bits;
+  const unsigned blocks = (unsigned)((d.n_occ + 255) / 256);
+  build_keys_kernel<<<blocks, 256, 0, st>>>(d, L.row_bits, sentinel, (uint32_t*)(w + L.keys_in), (uint32_t*)(w + L.vals_in));
+  rc = check_launch("build_keys");
+  if (rc != NRX_OK) return rc;
+  size_t cub_bytes = L.cub_bytes;
+  cudaError_t e = cub::DeviceRadixSort::SortPairs(w + L.cub, cub_bytes, (const uint32_t*)(w + L.keys_in),
+                                                  (uint32_t*)(w + L.keys_out), (const uint32_t*)(w + L.vals_in),
+                                                  (uint32_t*)(w + L.vals_out), (int)d.n_occ, 0, L.key_bits + 1, st);
+  NRX_REQUIRE(e == cudaSuccess, NRX_ELAUNCH, "radix sort: %s", cudaGetErrorString(e));
+  return NRX_OK;
+}
+
+extern "C" int nrx_embed_bwd_apply(const NrxFeat* h_feats, int n_feats, int64_t B, const float* grad_out,
+                                   int64_t grad_ld, int mode, float* const* h_grads, float* const* h_tables,
+                                   const NrxRowOpt* h_opt, void* ws, size_t ws_bytes, nrx_stream_t stream) {
+  using namespace nrx;
+  DFeats d;
+  int rc = make_dfeats(h_feats, n_feats, B, nullptr, 0, &d);
+  if (rc != NRX_OK) return rc;
+  PlanLayout L;
+  rc = plan_layout(d, &L);
+  if (rc != NRX_OK) return rc;
+  NRX_REQUIRE(ws != nullptr && ws_bytes >= L.total, NRX_EWORKSPACE, "workspace %zu < %zu", ws_bytes, L.total);
+  NRX_REQUIRE(mode == NRX_BWD_DENSE || mode == NRX_BWD_SGD || mode == NRX_BWD_ADAMW, NRX_EINVAL, "bad mode %d", mode);
+  NRX_REQUIRE(grad_out != nullptr || B == 0, NRX_EINVAL, "null grad_out");
+  cudaStream_t st = (cudaStream_t)stream;
+
+  DTables T;
+  memset(&T, 0, sizeof(T));
+  T.mode = mode;
+  T.row_bits = L.row_bits;
+  long long trows[NRX_MAX_TABLES] = {0};
+  for (int i = 0; i < d.n; ++i) {
+    const DFeat& F = d.f[i];
+    const int t = F.table_id;
+    if (T.dim[t] != 0)
+      NRX_REQUIRE(T.dim[t] == F.dim && T.stride[t] == F.stride && trows[t] == F.rows, NRX_EINVAL,
+                  "features sharing table %d disagree on its shape", t);
+    T.dim[t] = F.dim; T.stride[t] = F.stride; trows[t] = F.rows;
+    NRX_REQUIRE(F.pool != NRX_POOL_MASKED_MEAN || F.inv_den != nullptr, NRX_EINVAL,
+                "feature %d: masked-mean backward needs inv_den from the forward", i);
+    NRX_REQUIRE(F.out_col + F.dim <= grad_ld, NRX_EINVAL, "feature %d overruns grad_ld", i);
+  }
+  for (int t = 0; t < d.n_tables; ++t) {
+    if (T.dim[t] == 0) continue;
+    if (mode == NRX_BWD_DENSE) {
+      NRX_REQUIRE(h_grads && h_grads[t], NRX_EINVAL, "dense mode: missing grad buffer for table %d", t);
+      T.g[t] = h_grads[t];
+      cudaError_t e = cudaMemsetAsync(T.g[t], 0, (size_t)trows[t] * T.stride[t] * sizeof(float), st);
+      NRX_REQUIRE(e == cudaSuccess, NRX_ELAUNCH, "memset: %s", cudaGetErrorString(e));
+    } else {
+      NRX_REQUIRE(h_tables && h_tables[t] && h_opt, NRX_EINVAL, "row-update mode: missing table %d / options", t);
+      T.w[t] = h_tables[t];
+      if (mode == NRX_BWD_ADAMW) {
+        NRX_REQUIRE(h_opt->m[t] && h_opt->v[t], NRX_EINVAL, "AdamW: missing moments for table %d", t);
+        T.m[t] = h_opt->m[t]; T.v[t] = h_opt->v[t];
+      }
+    }
+  }
+  if (mode != NRX_BWD_DENSE) {
+    T.lr = h_opt->lr; T.beta1 = h_opt->beta1; T.beta2 = h_opt->beta2; T.eps = h_opt->eps; T.wd = h_opt->weight_decay;
+    const int step = h_opt->step > 0 ? h_opt->step : 1;
+    T.bc1 = 1.f - powf(T.beta1, (float)step);
+    T.bc2_sqrt = sqrtf(1.f - powf(T.beta2, (float)step));
+  }
+  if (d.n_occ == 0) return NRX_OK;
+  char* w = (char*)ws;
+  switch (L.nc) {
+    case 1: return launch_apply<1>(d, T, L, w, grad_out, grad_ld, st);
+    case 2: return launch_apply<2>(d, T, L, w, grad_out, grad_ld, st);
+    default: return launch_apply<4>(d, T, L, w, grad_out, grad_ld, st);
+  }
+}

@@ -1,0 +1,439 @@
+// K2 — feature-interaction logits, sigmoid+BCE, deterministic reduction, dense AdamW, L2 normalise.
+//
+//   nrx_field_logit_*  : FM (fm/model.py:18-25,48-59), wide sum (widedeep/model.py:25,58-65),
+//                        LR sum (lr/model.py:24-27) on the concatenated feature buffer.
+//   nrx_fm_fused_*     : gather-fused FM for sparse-only equal-width fields (never materialises the concat).
+//   nrx_logit_loss_fwd : sigmoid + F.binary_cross_entropy on probabilities (deep/model.py:32-33), with
+//                        torch's log clamp (-100) and the exact autograd chain for dL/dlogit.
+//   nrx_adamw_dense    : torch.optim.AdamW update (deep/model.py:55).
+// All HBM/L2-bandwidth bound, warp-per-sample with lanes on contiguous columns.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace nrx {
+
+static constexpr int kMaxFields = 32;
+struct Fields {
+  int col[kMaxFields];
+  int dim[kMaxFields];
+  int n;
+  int mode;
+};
+
+// S_d accumulators: lane owns columns d = lane + 32*k, k < 4 (field width <= 128).
+__global__ void __launch_bounds__(256)
+field_logit_fwd_kernel(const float* __restrict__ x, long long ld, long long B, const __grid_constant__ Fields F,
+                       float* __restrict__ logit, int accumulate) {
+  const long long b = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (b >= B) return;
+  const float* xr = x + b * ld;
+  float first = 0.f, second = 0.f;
+  if (F.mode == NRX_FIELD_FM) {
+    float S[4] = {0.f, 0.f, 0.f, 0.f};
+    float sq = 0.f;
+    for (int f = 0; f < F.n; ++f) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int d = lane + 32 * k;
+        if (d < F.dim[f]) {
+          const float v = __ldg(xr + F.col[f] + d);
+          if (d == 0) first += v;
+          else { S[k] += v; sq = fmaf(v, v, sq); }
+        }
+      }
+    }
+    second = 0.5f * (S[0] * S[0] + S[1] * S[1] + S[2] * S[2] + S[3] * S[3] - sq);
+  } else if (F.mode == NRX_FIELD_WIDE) {
+    for (int f = lane; f < F.n; f += 32) first += __ldg(xr + F.col[f]);
+  } else {
+    for (int f = 0; f < F.n; ++f)
+      for (int d = lane; d < F.dim[f]; d += 32) first += __ldg(xr + F.col[f] + d);
+  }
+  const float tot = warp_sum(first + second);
+  if (lane == 0) logit[b] = accumulate ? logit[b] + tot : tot;
+}
+
+__global__ void __launch_bounds__(256)
+field_logit_bwd_kernel(const float* __restrict__ x, long long ld, long long B, const __grid_constant__ Fields F,
+                       const float* __restrict__ dlogit, float* __restrict__ gx, long long gld, int accumulate) {
+  const long long b = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (b >= B) return;
+  const float* xr = x + b * ld;
+  float* gr = gx + b * gld;
+  const float g = __ldg(dlogit + b);
+  if (F.mode == NRX_FIELD_FM) {
+    float S[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int f = 0; f < F.n; ++f) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int d = lane + 32 * k;
+        if (d > 0 && d < F.dim[f]) S[k] += __ldg(xr + F.col[f] + d);
+      }
+    }
+    for (int f = 0; f < F.n; ++f) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int d = lane + 32 * k;
+        if (d < F.dim[f]) {
+          const float v = __ldg(xr + F.col[f] + d);
+          const float gv = (d == 0) ? g : g * (S[k] - v);
+          float* p = gr + F.col[f] + d;
+          *p = accumulate ? *p + gv : gv;
+        }
+      }
+    }
+  } else if (F.mode == NRX_FIELD_WIDE) {
+    for (int f = lane; f < F.n; f += 32) {
+      float* p = gr + F.col[f];
+      *p = accumulate ? *p + g : g;
+    }
+  } else {
+    for (int f = 0; f < F.n; ++f)
+      for (int d = lane; d < F.dim[f]; d += 32) {
+        float* p = gr + F.col[f] + d;
+        *p = accumulate ? *p + g : g;
+      }
+  }
+}
+
+static int make_fields(const int32_t* cols, const int32_t* dims, int n, int mode, long long ld, Fields* F) {
+  NRX_REQUIRE(cols && dims && n > 0 && n <= kMaxFields, NRX_EINVAL, "n_fields=%d outside [1,%d]", n, kMaxFields);
+  NRX_REQUIRE(mode == NRX_FIELD_FM || mode == NRX_FIELD_WIDE || mode == NRX_FIELD_SUM, NRX_EINVAL, "bad field mode");
+  F->n = n;
+  F->mode = mode;
+  for (int i = 0; i < n; ++i) {
+    NRX_REQUIRE(cols[i] >= 0 && dims[i] >= 1 && cols[i] + dims[i] <= ld, NRX_EINVAL, "field %d outside the row", i);
+    if (mode == NRX_FIELD_FM) {
+      NRX_REQUIRE(dims[i] == dims[0], NRX_EINVAL, "FM needs equal field widths (fm/model.py:58 torch.stack)");
+      NRX_REQUIRE(dims[i] <= 128, NRX_EUNSUPPORTED, "FM field width %d > 128", dims[i]);
+    }
+    F->col[i] = cols[i];
+    F->dim[i] = dims[i];
+  }
+  return NRX_OK;
+}
+
+// ---- gather-fused FM (vec4 path: D % 4 == 0, D/4 a power of two <= 32) ---------------------
+__device__ __forceinline__ float sigmoid_f(float z) { return 1.f / (1.f + expf(-z)); }
+
+__device__ __forceinline__ void bce_terms(float p, float y, float invB, float* loss, float* dlogit) {
+  // F.binary_cross_entropy: log clamped at -100; autograd: (p-y)/max(p(1-p),1e-12) then sigmoid' = p(1-p)
+  const float lp = fmaxf(logf(p), -100.f), l1p = fmaxf(logf(1.f - p), -100.f);
+  if (loss) *loss = -(y * lp + (1.f - y) * l1p);
+  if (dlogit) {
+    const float pq = p * (1.f - p);
+    *dlogit = ((p - y) / fmaxf(pq, 1e-12f)) * pq * invB;
+  }
+}
+
+template <int SPW, bool BWD>
+__global__ void __launch_bounds__(256)
+fm_fused_kernel(const __grid_constant__ DFeats P, long long B, int LPF, const float* __restrict__ bias,
+                const float* __restrict__ label, long long lstride, float* __restrict__ logit,
+                float* __restrict__ prob, float* __restrict__ loss, float* __restrict__ dlogit,
+                const float* __restrict__ dlogit_in, float* __restrict__ gx, long long gld,
+                int* __restrict__ status) {
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long b0 = warp * SPW;
+  if (b0 >= B) return;
+  const int C = P.n * LPF;             // 16-byte columns per sample
+  const int off4 = (lane % LPF) * 4;   // same for every pass because 32 % LPF == 0
+  float4 S[SPW];
+  float first[SPW], sq[SPW];
+#pragma unroll
+  for (int s = 0; s < SPW; ++s) { S[s] = make_float4(0.f, 0.f, 0.f, 0.f); first[s] = 0.f; sq[s] = 0.f; }
+  bool bad = false;
+  for (int c = lane; c < ((C + 31) & ~31); c += 32) {
+    const bool act = c < C;
+    const DFeat& F = P.f[act ? c / LPF : 0];
+    long long id[SPW];
+#pragma unroll
+    for (int s = 0; s < SPW; ++s) id[s] = (act && b0 + s < B) ? load_idx(F.idx, b0 + s, F.idx32) : 0;
+#pragma unroll
+    for (int s = 0; s < SPW; ++s) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (act && b0 + s < B) {
+        if ((unsigned long long)id[s] < (unsigned long long)F.rows) v = __ldg(reinterpret_cast<const float4*>(F.table + id[s] * F.stride + off4));
+        else bad = true;
+      }
+      if (off4 == 0) { first[s] += v.x; v.x = 0.f; }   // column 0 is the first-order weight
+      S[s].x += v.x; S[s].y += v.y; S[s].z += v.z; S[s].w += v.w;
+      sq[s] += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+  }
+  // sum S over fields: lanes with equal lane % LPF
+#pragma unroll
+  for (int s = 0; s < SPW; ++s)
+    for (int o = LPF; o < 32; o <<= 1) {
+      S[s].x += __shfl_xor_sync(NRX_FULL_MASK, S[s].x, o); S[s].y += __shfl_xor_sync(NRX_FULL_MASK, S[s].y, o);
+      S[s].z += __shfl_xor_sync(NRX_FULL_MASK, S[s].z, o); S[s].w += __shfl_xor_sync(NRX_FULL_MASK, S[s].w, o);
+    }
+  if (!BWD) {
+    const float bz = bias ? __ldg(bias) : 0.f;
+    const float invB = 1.f / (float)B;
+#pragma unroll
+    for (int s = 0; s < SPW; ++s) {
+      const float ss = (lane < LPF) ? (S[s].x * S[s].x + S[s].y * S[s].y + S[s].z * S[s].z + S[s].w * S[s].w) : 0.f;
+      const float z = bz + warp_sum(first[s] + 0.5f * (ss - sq[s]));
+      const long long b = b0 + s;
+      if (lane == 0 && b < B) {
+        if (logit) logit[b] = z;
+        const float p = sigmoid_f(z);
+        if (prob) prob[b] = p;
+        if (label) bce_terms(p, __ldg(label + b * lstride), invB, loss ? loss + b : nullptr, dlogit ? dlogit + b : nullptr);
+      }
+    }
+    if (bad && status) atomicOr(status, 1);
+  } else {
+    // second pass: re-read the rows (L1/L2 hits) and emit grad_x
+    for (int c = lane; c < C; c += 32) {
+      const DFeat& F = P.f[c / LPF];
+#pragma unroll
+      for (int s = 0; s < SPW; ++s) {
+        const long long b = b0 + s;
+        if (b >= B) continue;
+        const long long id = load_idx(F.idx, b, F.idx32);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if ((unsigned long long)id < (unsigned long long)F.rows) v = __ldg(reinterpret_cast<const float4*>(F.table + id * F.stride + off4));
+        const float g = __ldg(dlogit_in + b);
+        float4 o;
+        o.x = (off4 == 0) ? g : g * (S[s].x - v.x);
+        o.y = g * (S[s].y - v.y); o.z = g * (S[s].z - v.z); o.w = g * (S[s].w - v.w);
+        *reinterpret_cast<float4*>(gx + b * gld + F.out_col + off4) = o;
+      }
+    }
+  }
+}
+
+static int fm_fused_check(const DFeats& d, int* LPF) {
+  NRX_REQUIRE(d.n_array == 0, NRX_EUNSUPPORTED, "fm_fused: array features go through embed_pool + field_logit");
+  const int D = d.f[0].dim;
+  for (int i = 0; i < d.n; ++i) {
+    NRX_REQUIRE(d.f[i].dim == D, NRX_EINVAL, "FM needs equal field widths (fm/model.py:58)");
+    NRX_REQUIRE((uintptr_t)d.f[i].table % 16 == 0 && d.f[i].stride % 4 == 0, NRX_EUNSUPPORTED, "fm_fused: table %d not 16B aligned", i);
+  }
+  NRX_REQUIRE(D % 4 == 0 && D <= 128 && (D / 4 & (D / 4 - 1)) == 0, NRX_EUNSUPPORTED,
+              "fm_fused: width %d (needs D/4 a power of two <= 32)", D);
+  *LPF = D / 4;
+  return NRX_OK;
+}
+
+// ---- sigmoid + BCE ----------------------------------------------------------------------------
+struct Terms { const float* t[8]; int n; };
+__global__ void __launch_bounds__(256)
+logit_loss_kernel(const __grid_constant__ Terms T, const float* __restrict__ bias, long long B,
+                  const float* __restrict__ label, long long lstride, float* __restrict__ prob,
+                  float* __restrict__ loss, float* __restrict__ dlogit) {
+  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float z = 0.f;
+  for (int i = 0; i < T.n; ++i) z += __ldg(T.t[i] + b);
+  if (bias) z += __ldg(bias);
+  const float p = sigmoid_f(z);
+  if (prob) prob[b] = p;
+  if (label) bce_terms(p, __ldg(label + b * lstride), 1.f / (float)B, loss ? loss + b : nullptr, dlogit ? dlogit + b : nullptr);
+}
+
+__global__ void __launch_bounds__(256)
+bce_fwd_kernel(const float* __restrict__ prob, const float* __restrict__ label, long long lstride, long long B,
+               float* __restrict__ loss) {
+  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) bce_terms(__ldg(prob + b), __ldg(label + b * lstride), 0.f, loss + b, nullptr);
+}
+__global__ void __launch_bounds__(256)
+bce_bwd_kernel(const float* __restrict__ prob, const float* __restrict__ label, long long lstride, long long B,
+               const float* __restrict__ upstream, float* __restrict__ gp) {
+  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const float p = __ldg(prob + b), y = __ldg(label + b * lstride);
+  gp[b] = ((p - y) / fmaxf(p * (1.f - p), 1e-12f)) * (__ldg(upstream) / (float)B);
+}
+__global__ void __launch_bounds__(256)
+sigmoid_bwd_kernel(const float* __restrict__ prob, const float* __restrict__ gp, long long B, float* __restrict__ gz) {
+  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const float p = __ldg(prob + b);
+  gz[b] = __ldg(gp + b) * (p * (1.f - p));
+}
+
+// ---- deterministic reduction (fixed tree: 1 block, 1024 threads) -------------------------------
+__global__ void __launch_bounds__(1024)
+reduce_kernel(const float* __restrict__ x, long long n, float scale, float* __restrict__ out) {
+  __shared__ float sm[32];
+  float a = 0.f;
+  for (long long i = threadIdx.x; i < n; i += 1024) a += __ldg(x + i);
+  a = warp_sum(a);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = a;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    a = warp_sum(sm[threadIdx.x]);
+    if (threadIdx.x == 0) out[0] = a * scale;
+  }
+}
+
+// ---- dense AdamW -------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+             long long n, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2s) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float pi = p[i] * (1.f - lr * wd);
+    const float gi = g[i];
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    pi -= (lr / bc1) * (mi / (sqrtf(vi) / bc2s + eps));
+    p[i] = pi; m[i] = mi; v[i] = vi;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+l2norm_kernel(const float* __restrict__ x, long long ld, long long n, int d, float* __restrict__ y, long long yld) {
+  const long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= n) return;
+  float ss = 0.f;
+  for (int c = lane; c < d; c += 32) { const float t = __ldg(x + r * ld + c); ss = fmaf(t, t, ss); }
+  ss = warp_sum(ss);
+  const float den = fmaxf(sqrtf(ss), 1e-12f);  // F.normalize eps (DSSM/model.py:69-71)
+  for (int c = lane; c < d; c += 32) y[r * yld + c] = __ldg(x + r * ld + c) / den;
+}
+
+static inline unsigned warps_grid(long long items, int wpb) { return (unsigned)((items + wpb - 1) / wpb); }
+
+}  // namespace nrx
+
+using namespace nrx;
+
+extern "C" int nrx_field_logit_fwd(const float* x, int64_t ld, int64_t B, const int32_t* h_cols, const int32_t* h_dims,
+                                   int n_fields, int mode, float* logit, int accumulate, nrx_stream_t stream) {
+  Fields F;
+  int rc = make_fields(h_cols, h_dims, n_fields, mode, ld, &F);
+  if (rc != NRX_OK) return rc;
+  NRX_REQUIRE(x && logit, NRX_EINVAL, "null pointer");
+  if (B == 0) return NRX_OK;
+  field_logit_fwd_kernel<<<warps_grid(B, 8), 256, 0, (cudaStream_t)stream>>>(x, ld, B, F, logit, accumulate);
+  return check_launch("field_logit_fwd");
+}
+
+extern "C" int nrx_field_logit_bwd(const float* x, int64_t ld, int64_t B, const int32_t* h_cols, const int32_t* h_dims,
+                                   int n_fields, int mode, const float* dlogit, float* grad_x, int64_t grad_ld,
+                                   int accumulate, nrx_stream_t stream) {
+  Fields F;
+  int rc = make_fields(h_cols, h_dims, n_fields, mode, ld, &F);
+  if (rc != NRX_OK) return rc;
+  NRX_REQUIRE(x && dlogit && grad_x, NRX_EINVAL, "null pointer");
+  if (B == 0) return NRX_OK;
+  field_logit_bwd_kernel<<<warps_grid(B, 8), 256, 0, (cudaStream_t)stream>>>(x, ld, B, F, dlogit, grad_x, grad_ld, accumulate);
+  return check_launch("field_logit_bwd");
+}
+
+extern "C" int nrx_fm_fused_fwd(const NrxFeat* h_feats, int n_feats, int64_t B, const float* bias, const float* label,
+                                int64_t label_stride, float* logit, float* prob, float* loss_per_sample, float* dlogit,
+                                int32_t* status, nrx_stream_t stream) {
+  DFeats d;
+  int rc = make_dfeats(h_feats, n_feats, B, nullptr, 0, &d);
+  if (rc != NRX_OK) return rc;
+  int LPF = 0;
+  rc = fm_fused_check(d, &LPF);
+  if (rc != NRX_OK) return rc;
+  if (B == 0) return NRX_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (B < (long long)sm_count() * 64)
+    fm_fused_kernel<2, false><<<warps_grid((B + 1) / 2, 8), 256, 0, st>>>(d, B, LPF, bias, label, label_stride, logit, prob,
+                                                                        loss_per_sample, dlogit, nullptr, nullptr, 0, status);
+  else
+    fm_fused_kernel<4, false><<<warps_grid((B + 3) / 4, 8), 256, 0, st>>>(d, B, LPF, bias, label, label_stride, logit, prob,
+                                                                        loss_per_sample, dlogit, nullptr, nullptr, 0, status);
+  return check_launch("fm_fused_fwd");
+}
+
+extern "C" int nrx_fm_fused_bwd(const NrxFeat* h_feats, int n_feats, int64_t B, const float* dlogit, float* grad_x,
+                                int64_t grad_ld, nrx_stream_t stream) {
+  DFeats d;
+  int rc = make_dfeats(h_feats, n_feats, B, grad_x, grad_ld, &d);
+  if (rc != NRX_OK) return rc;
+  int LPF = 0;
+  rc = fm_fused_check(d, &LPF);
+  if (rc != NRX_OK) return rc;
+  NRX_REQUIRE(dlogit && grad_x, NRX_EINVAL, "null pointer");
+  NRX_REQUIRE(d.vec == 4, NRX_EUNSUPPORTED, "fm_fused_bwd: grad_x must be 16B aligned with ld %% 4 == 0 and out_col %% 4 == 0");
+  for (int i = 0; i < d.n; ++i) NRX_REQUIRE(d.f[i].out_col + d.f[i].dim <= grad_ld, NRX_EINVAL, "feature %d overruns grad_ld", i);
+  if (B == 0) return NRX_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (B < (long long)sm_count() * 64)
+    fm_fused_kernel<2, true><<<warps_grid((B + 1) / 2, 8), 256, 0, st>>>(d, B, LPF, nullptr, nullptr, 0, nullptr, nullptr, nullptr,
+                                                                       nullptr, dlogit, grad_x, grad_ld, nullptr);
+  else
+    fm_fused_kernel<4, true><<<warps_grid((B + 3) / 4, 8), 256, 0, st>>>(d, B, LPF, nullptr, nullptr, 0, nullptr, nullptr, nullptr,
+                                                                       nullptr, dlogit, grad_x, grad_ld, nullptr);
+  return check_launch("fm_fused_bwd");
+}
+
+extern "C" int nrx_logit_loss_fwd(const float* const* h_terms, int n_terms, const float* bias, int64_t B, const float* label,
+                                  int64_t label_stride, float* prob, float* loss_per_sample, float* dlogit,
+                                  nrx_stream_t stream) {
+  NRX_REQUIRE(n_terms >= 0 && n_terms <= 8 && (n_terms == 0 || h_terms), NRX_EINVAL, "n_terms=%d outside [0,8]", n_terms);
+  Terms T;
+  T.n = n_terms;
+  for (int i = 0; i < n_terms; ++i) {
+    NRX_REQUIRE(h_terms[i], NRX_EINVAL, "null term %d", i);
+    T.t[i] = h_terms[i];
+  }
+  if (B == 0) return NRX_OK;
+  logit_loss_kernel<<<(unsigned)((B + 255) / 256), 256, 0, (cudaStream_t)stream>>>(T, bias, B, label, label_stride, prob,
+                                                                                  loss_per_sample, dlogit);
+  return check_launch("logit_loss_fwd");
+}
+
+extern "C" int nrx_bce_fwd(const float* prob, const float* label, int64_t label_stride, int64_t B, float* loss_per_sample,
+                           nrx_stream_t stream) {
+  NRX_REQUIRE(prob && label && loss_per_sample, NRX_EINVAL, "null pointer");
+  if (B == 0) return NRX_OK;
+  bce_fwd_kernel<<<(unsigned)((B + 255) / 256), 256, 0, (cudaStream_t)stream>>>(prob, label, label_stride, B, loss_per_sample);
+  return check_launch("bce_fwd");
+}
+
+extern "C" int nrx_bce_bwd(const float* prob, const float* label, int64_t label_stride, int64_t B, const float* upstream,
+                           float* grad_prob, nrx_stream_t stream) {
+  NRX_REQUIRE(prob && label && upstream && grad_prob, NRX_EINVAL, "null pointer");
+  if (B == 0) return NRX_OK;
+  bce_bwd_kernel<<<(unsigned)((B + 255) / 256), 256, 0, (cudaStream_t)stream>>>(prob, label, label_stride, B, upstream, grad_prob);
+  return check_launch("bce_bwd");
+}
+
+extern "C" int nrx_sigmoid_bwd(const float* prob, const float* grad_prob, int64_t B, float* grad_logit, nrx_stream_t stream) {
+  NRX_REQUIRE(prob && grad_prob && grad_logit, NRX_EINVAL, "null pointer");
+  if (B == 0) return NRX_OK;
+  sigmoid_bwd_kernel<<<(unsigned)((B + 255) / 256), 256, 0, (cudaStream_t)stream>>>(prob, grad_prob, B, grad_logit);
+  return check_launch("sigmoid_bwd");
+}
+
+extern "C" int nrx_reduce_f32(const float* x, int64_t n, float scale, float* out, nrx_stream_t stream) {
+  NRX_REQUIRE(out && (x || n == 0) && n >= 0, NRX_EINVAL, "null pointer");
+  reduce_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(x, n, scale, out);
+  return check_launch("reduce_f32");
+}
+
+extern "C" int nrx_adamw_dense(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                               float eps, float weight_decay, int32_t step, nrx_stream_t stream) {
+  NRX_REQUIRE(p && g && m && v && n >= 0 && step >= 1, NRX_EINVAL, "bad AdamW arguments");
+  if (n == 0) return NRX_OK;
+  const float bc1 = (float)(1.0 - pow((double)beta1, (double)step));
+  const float bc2s = (float)sqrt(1.0 - pow((double)beta2, (double)step));
+  long long blocks = (n + 255) / 256;
+  const long long cap = (long long)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  adamw_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2s);
+  return check_launch("adamw_dense");
+}
+
+extern "C" int nrx_l2_normalize(const float* x, int64_t ld, int64_t n, int d, float* y, int64_t y_ld, nrx_stream_t stream) {
+  NRX_REQUIRE(x && y && d > 0 && ld >= d && y_ld >= d, NRX_EINVAL, "bad l2_normalize arguments");
+  if (n == 0) return NRX_OK;
+  l2norm_kernel<<<warps_grid(n, 8), 256, 0, (cudaStream_t)stream>>>(x, ld, n, d, y, y_ld);
+  return check_launch("l2_normalize");
+}

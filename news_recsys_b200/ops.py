@@ -1,0 +1,411 @@
+"""Host-side operator layer: thin wrappers over the C ABI (include/nrx.h) plus the
+torch.autograd.Function glue that lets the reference-shaped modules train with
+`loss.backward()` exactly like the Lightning modules they replace.
+
+Nothing here computes on the CPU and nothing falls back to PyTorch ops: every
+function requires CUDA tensors and raises otherwise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib as L
+
+
+def _require_cuda(t: torch.Tensor, what: str):
+    if not t.is_cuda:
+        raise L.NrxError(f"{what}: expected a CUDA tensor (the hot path has no CPU fallback)")
+
+
+# --------------------------------------------------------------------------- #
+# Feature descriptors                                                          #
+# --------------------------------------------------------------------------- #
+
+@dataclass
+class FeatSpec:
+    """One feature of get_embeddings_from_batch (reference base_model.py:284-308)."""
+    name: str
+    table: str        # after share_emb_table_features aliasing (base_model.py:119-122)
+    table_id: int
+    dim: int
+    L: int            # 1 = sparse
+    is_array: bool
+    out_col: int
+
+
+class FeatBinding:
+    """NrxFeat[] for one batch; keeps every tensor it points at alive."""
+
+    def __init__(self, specs: Sequence[FeatSpec], tables: Dict[str, torch.Tensor], batch: Dict[str, torch.Tensor],
+                 want_inv_den: bool = True):
+        self.specs = list(specs)
+        n = len(self.specs)
+        if n == 0 or n > L.NRX_MAX_FEATS:
+            raise L.NrxError(f"{n} features outside [1,{L.NRX_MAX_FEATS}]")
+        self.arr = (L.NrxFeat * n)()
+        self.keep: List[torch.Tensor] = []
+        self.inv_den: Dict[str, torch.Tensor] = {}
+        self.B = None
+        dev = None
+        for i, s in enumerate(self.specs):
+            w = tables[s.table]
+            _require_cuda(w, f"table {s.table}")
+            dev = w.device
+            if w.dtype != torch.float32 or w.dim() != 2 or w.stride(1) != 1:
+                raise L.NrxError(f"table {s.table}: need fp32 [rows, dim] with unit column stride")
+            idx = batch[s.name]
+            _require_cuda(idx, f"batch[{s.name}]")
+            if idx.dtype not in (torch.int64, torch.int32):
+                idx = idx.long()  # the reference casts with .long() (base_model.py:271)
+            idx = idx.contiguous()
+            B = idx.shape[0]
+            if self.B is None:
+                self.B = B
+            elif self.B != B:
+                raise L.NrxError("features disagree on the batch size")
+            f = self.arr[i]
+            f.table = w.data_ptr()
+            f.rows = w.shape[0]
+            f.dim = w.shape[1]
+            f.row_stride = w.stride(0)
+            f.table_id = s.table_id
+            f.idx_dtype = L.IDX_I32 if idx.dtype == torch.int32 else L.IDX_I64
+            f.idx = idx.data_ptr()
+            self.keep += [w, idx]
+            if s.is_array:
+                if idx.dim() != 2:
+                    raise L.NrxError(f"array feature {s.name}: expected [B, L] ids")
+                f.L = idx.shape[1]
+                mask = batch.get(f"{s.name}_mask", None)
+                if mask is not None:
+                    _require_cuda(mask, f"batch[{s.name}_mask]")
+                    mask = mask.to(torch.float32).contiguous()
+                    f.pool = L.POOL_MASKED_MEAN
+                    f.mask = mask.data_ptr()
+                    self.keep.append(mask)
+                    if want_inv_den:
+                        inv = torch.empty(B, dtype=torch.float32, device=dev)
+                        f.inv_den = inv.data_ptr()
+                        self.inv_den[s.name] = inv
+                else:
+                    f.pool = L.POOL_MEAN  # base_model.py:275-276
+            else:
+                if idx.dim() != 1:
+                    raise L.NrxError(f"sparse feature {s.name}: expected [B] ids")
+                f.L = 1
+                f.pool = L.POOL_NONE
+            f.out_col = s.out_col
+        self.device = dev
+        self.n = n
+
+
+def embed_pool_fwd(fb: FeatBinding, out_dim: int, status: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """K1 — replaces base_model.py:262-308."""
+    out = torch.empty((fb.B, out_dim), dtype=torch.float32, device=fb.device)
+    lib = L.load()
+    L.check(lib.nrx_embed_pool_fwd(fb.arr, fb.n, fb.B, out.data_ptr(), out.stride(0) if fb.B else out_dim,
+                                   L.ptr(status), L.stream_ptr(fb.device)), "nrx_embed_pool_fwd")
+    return out
+
+
+class BwdPlan:
+    """Sorted-occurrence plan for one batch (nrx_embed_bwd_plan); reusable for any number of applies."""
+
+    def __init__(self, fb: FeatBinding):
+        lib = L.load()
+        self.fb = fb
+        self.bytes = int(lib.nrx_embed_bwd_workspace_bytes(fb.arr, fb.n, fb.B))
+        if self.bytes == 0 and fb.B > 0:
+            L.check(-2, "nrx_embed_bwd_workspace_bytes")
+        self.ws = torch.empty(max(self.bytes, 16), dtype=torch.uint8, device=fb.device)
+        L.check(lib.nrx_embed_bwd_plan(fb.arr, fb.n, fb.B, self.ws.data_ptr(), self.bytes, L.stream_ptr(fb.device)),
+                "nrx_embed_bwd_plan")
+
+
+def embed_bwd_dense(plan: BwdPlan, grad_out: torch.Tensor, table_by_id: Sequence[Optional[torch.Tensor]]):
+    """K3 dense mode: returns one dense gradient per table id (None where unused)."""
+    fb = plan.fb
+    grad_out = grad_out.contiguous()
+    grads = [None if w is None else torch.empty_like(w) for w in table_by_id]
+    lib = L.load()
+    garr = L.ptr_array(grads, L.NRX_MAX_TABLES)
+    L.check(lib.nrx_embed_bwd_apply(fb.arr, fb.n, fb.B, grad_out.data_ptr(), grad_out.stride(0), L.BWD_DENSE,
+                                    garr, None, None, plan.ws.data_ptr(), plan.bytes, L.stream_ptr(fb.device)),
+            "nrx_embed_bwd_apply(dense)")
+    return grads
+
+
+def embed_bwd_rowopt(plan: BwdPlan, grad_out: torch.Tensor, table_by_id, mode: int, lr: float, step: int = 1,
+                     betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0, m_by_id=None, v_by_id=None):
+    """K3 fused sparse row update (SGD / AdamW on touched rows only), in place."""
+    fb = plan.fb
+    grad_out = grad_out.contiguous()
+    opt = L.NrxRowOpt()
+    opt.lr, opt.beta1, opt.beta2, opt.eps, opt.weight_decay, opt.step = lr, betas[0], betas[1], eps, weight_decay, step
+    for t in range(len(table_by_id)):
+        if m_by_id is not None and m_by_id[t] is not None:
+            opt.m[t] = m_by_id[t].data_ptr()
+            opt.v[t] = v_by_id[t].data_ptr()
+    lib = L.load()
+    L.check(lib.nrx_embed_bwd_apply(fb.arr, fb.n, fb.B, grad_out.data_ptr(), grad_out.stride(0), mode, None,
+                                    L.ptr_array(table_by_id, L.NRX_MAX_TABLES), C.byref(opt), plan.ws.data_ptr(),
+                                    plan.bytes, L.stream_ptr(fb.device)), "nrx_embed_bwd_apply(rowopt)")
+
+
+class EmbedPoolFn(torch.autograd.Function):
+    """features = get_embeddings_from_batch(batch); dense table gradients like nn.Embedding(padding_idx=0)."""
+
+    @staticmethod
+    def forward(ctx, fb: FeatBinding, out_dim: int, table_names: List[str], *weights):
+        ctx.fb = fb
+        ctx.table_names = table_names
+        ctx.weights = weights
+        return embed_pool_fwd(fb, out_dim)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        fb = ctx.fb
+        plan = BwdPlan(fb)
+        by_id: List[Optional[torch.Tensor]] = [None] * L.NRX_MAX_TABLES
+        name_to_id = {s.table: s.table_id for s in fb.specs}
+        for nme, w in zip(ctx.table_names, ctx.weights):
+            if nme in name_to_id:
+                by_id[name_to_id[nme]] = w
+        grads = embed_bwd_dense(plan, grad_out, by_id)
+        out = []
+        for nme, w in zip(ctx.table_names, ctx.weights):
+            out.append(grads[name_to_id[nme]] if nme in name_to_id else None)
+        return (None, None, None, *out)
+
+
+# --------------------------------------------------------------------------- #
+# Field logits (FM / wide / LR)                                                #
+# --------------------------------------------------------------------------- #
+
+def field_logit_fwd(x: torch.Tensor, cols, dims, mode: int, logit: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _require_cuda(x, "x")
+    B = x.shape[0]
+    acc = 1 if logit is not None else 0
+    if logit is None:
+        logit = torch.empty(B, dtype=torch.float32, device=x.device)
+    lib = L.load()
+    L.check(lib.nrx_field_logit_fwd(x.data_ptr(), x.stride(0), B, L.i32_array(cols), L.i32_array(dims), len(cols), mode,
+                                    logit.data_ptr(), acc, L.stream_ptr(x.device)), "nrx_field_logit_fwd")
+    return logit
+
+
+def field_logit_bwd(x, cols, dims, mode, dlogit, grad_x, accumulate: bool):
+    lib = L.load()
+    L.check(lib.nrx_field_logit_bwd(x.data_ptr(), x.stride(0), x.shape[0], L.i32_array(cols), L.i32_array(dims), len(cols),
+                                    mode, dlogit.data_ptr(), grad_x.data_ptr(), grad_x.stride(0), 1 if accumulate else 0,
+                                    L.stream_ptr(x.device)), "nrx_field_logit_bwd")
+
+
+class FieldLogitFn(torch.autograd.Function):
+    """[B, ΣD] features -> [B] logit term (FM / wide / sum); backward w.r.t. the features."""
+
+    @staticmethod
+    def forward(ctx, x, cols, dims, mode):
+        x = x.contiguous()
+        ctx.save_for_backward(x)
+        ctx.meta = (list(cols), list(dims), mode)
+        return field_logit_fwd(x, cols, dims, mode)
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        cols, dims, mode = ctx.meta
+        gx = torch.zeros_like(x)
+        field_logit_bwd(x, cols, dims, mode, g.contiguous(), gx, accumulate=False)
+        return gx, None, None, None
+
+
+# --------------------------------------------------------------------------- #
+# sigmoid + BCE                                                                #
+# --------------------------------------------------------------------------- #
+
+def logit_loss_fwd(terms: Sequence[torch.Tensor], bias: Optional[torch.Tensor], label: Optional[torch.Tensor],
+                   want_dlogit: bool = True):
+    """prob (+ per-sample loss, dL/dlogit of the MEAN loss when `label` is given)."""
+    t0 = terms[0]
+    B = t0.shape[0]
+    dev = t0.device
+    prob = torch.empty(B, dtype=torch.float32, device=dev)
+    loss = dl = None
+    lptr, lstride = 0, 0
+    if label is not None:
+        _require_cuda(label, "label")
+        if label.dtype != torch.float32:
+            label = label.float()
+        lptr, lstride = label.data_ptr(), label.stride(0)
+        loss = torch.empty(B, dtype=torch.float32, device=dev)
+        dl = torch.empty(B, dtype=torch.float32, device=dev) if want_dlogit else None
+    ts = [t.contiguous().view(-1) for t in terms]
+    lib = L.load()
+    L.check(lib.nrx_logit_loss_fwd(L.ptr_array(ts), len(ts), L.ptr(bias), B, lptr, lstride, prob.data_ptr(),
+                                   L.ptr(loss), L.ptr(dl), L.stream_ptr(dev)), "nrx_logit_loss_fwd")
+    return prob, loss, dl
+
+
+def reduce_sum(x: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
+    """Deterministic (fixed-tree) sum * scale -> 0-dim tensor."""
+    x = x.contiguous()
+    out = torch.empty(1, dtype=torch.float32, device=x.device)
+    lib = L.load()
+    L.check(lib.nrx_reduce_f32(x.data_ptr(), x.numel(), scale, out.data_ptr(), L.stream_ptr(x.device)), "nrx_reduce_f32")
+    return out[0]
+
+
+def reduce_mean(x: torch.Tensor) -> torch.Tensor:
+    return reduce_sum(x, 1.0 / max(x.numel(), 1))
+
+
+class SigmoidFn(torch.autograd.Function):
+    """prob = sigmoid(sum(terms) + bias) (nrx_logit_loss_fwd); backward = nrx_sigmoid_bwd."""
+
+    @staticmethod
+    def forward(ctx, bias, *terms):
+        prob, _, _ = logit_loss_fwd(terms, bias, None)
+        ctx.save_for_backward(prob)
+        ctx.has_bias = bias is not None
+        ctx.shapes = [t.shape for t in terms]
+        return prob
+
+    @staticmethod
+    def backward(ctx, g):
+        (p,) = ctx.saved_tensors
+        g = g.contiguous().view(-1)
+        gz = torch.empty_like(p)
+        lib = L.load()
+        L.check(lib.nrx_sigmoid_bwd(p.data_ptr(), g.data_ptr(), p.numel(), gz.data_ptr(), L.stream_ptr(p.device)),
+                "nrx_sigmoid_bwd")
+        gb = reduce_sum(gz).view(1) if ctx.has_bias else None
+        return (gb, *[gz.view(s) for s in ctx.shapes])
+
+
+class BceFn(torch.autograd.Function):
+    """F.binary_cross_entropy(prob, label, 'mean') (bceLoss, deep/model.py:32-33)."""
+
+    @staticmethod
+    def forward(ctx, prob, label):
+        p = prob.contiguous().view(-1)
+        y = label.view(-1)
+        if y.dtype != torch.float32:
+            y = y.float()
+        _require_cuda(p, "prob")
+        _require_cuda(y, "label")
+        loss = torch.empty_like(p)
+        lib = L.load()
+        L.check(lib.nrx_bce_fwd(p.data_ptr(), y.data_ptr(), y.stride(0), p.numel(), loss.data_ptr(), L.stream_ptr(p.device)),
+                "nrx_bce_fwd")
+        ctx.save_for_backward(p, y)
+        ctx.shape = prob.shape
+        return reduce_mean(loss)
+
+    @staticmethod
+    def backward(ctx, g):
+        p, y = ctx.saved_tensors
+        gp = torch.empty_like(p)
+        g = g.contiguous().view(1)
+        lib = L.load()
+        L.check(lib.nrx_bce_bwd(p.data_ptr(), y.data_ptr(), y.stride(0), p.numel(), g.data_ptr(), gp.data_ptr(),
+                                L.stream_ptr(p.device)), "nrx_bce_bwd")
+        return gp.view(ctx.shape), None
+
+
+# --------------------------------------------------------------------------- #
+# Optimizer                                                                    #
+# --------------------------------------------------------------------------- #
+
+def adamw_dense_(p, g, m, v, step, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01):
+    """torch.optim.AdamW update on one flat fp32 tensor, in place (deep/model.py:55)."""
+    lib = L.load()
+    L.check(lib.nrx_adamw_dense(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, betas[0], betas[1],
+                                eps, weight_decay, step, L.stream_ptr(p.device)), "nrx_adamw_dense")
+
+
+def l2_normalize(x: torch.Tensor) -> torch.Tensor:
+    x = x.contiguous()
+    y = torch.empty_like(x)
+    lib = L.load()
+    L.check(lib.nrx_l2_normalize(x.data_ptr(), x.stride(0), x.shape[0], x.shape[1], y.data_ptr(), y.stride(0),
+                                 L.stream_ptr(x.device)), "nrx_l2_normalize")
+    return y
+
+
+# --------------------------------------------------------------------------- #
+# Gather-fused FM (sparse-only, equal widths): BASELINE config 2                #
+# --------------------------------------------------------------------------- #
+
+def fm_fused_fwd(fb: FeatBinding, bias: Optional[torch.Tensor], label: Optional[torch.Tensor] = None,
+                 want_logit: bool = False, status: Optional[torch.Tensor] = None):
+    """-> (prob[B], loss_per_sample[B] | None, dlogit[B] | None, logit[B] | None)."""
+    dev = fb.device
+    B = fb.B
+    prob = torch.empty(B, dtype=torch.float32, device=dev)
+    logit = torch.empty(B, dtype=torch.float32, device=dev) if want_logit else None
+    loss = dl = None
+    lptr, lstride = 0, 0
+    if label is not None:
+        _require_cuda(label, "label")
+        if label.dtype != torch.float32:
+            label = label.float()
+        lptr, lstride = label.data_ptr(), label.stride(0)
+        loss = torch.empty(B, dtype=torch.float32, device=dev)
+        dl = torch.empty(B, dtype=torch.float32, device=dev)
+    lib = L.load()
+    L.check(lib.nrx_fm_fused_fwd(fb.arr, fb.n, B, L.ptr(bias), lptr, lstride, L.ptr(logit), prob.data_ptr(), L.ptr(loss),
+                                 L.ptr(dl), L.ptr(status), L.stream_ptr(dev)), "nrx_fm_fused_fwd")
+    return prob, loss, dl, logit
+
+
+def fm_fused_bwd(fb: FeatBinding, dlogit: torch.Tensor, out_dim: int) -> torch.Tensor:
+    gx = torch.empty((fb.B, out_dim), dtype=torch.float32, device=fb.device)
+    lib = L.load()
+    L.check(lib.nrx_fm_fused_bwd(fb.arr, fb.n, fb.B, dlogit.data_ptr(), gx.data_ptr(), gx.stride(0) if fb.B else out_dim,
+                                 L.stream_ptr(fb.device)), "nrx_fm_fused_bwd")
+    return gx
+
+
+def fm_fused_eligible(specs: Sequence[FeatSpec], tables: Dict[str, torch.Tensor]) -> bool:
+    if not specs or any(s.is_array for s in specs):
+        return False
+    d = specs[0].dim
+    if any(s.dim != d for s in specs) or d % 4 or d > 128 or ((d // 4) & (d // 4 - 1)):
+        return False
+    return all(tables[s.table].data_ptr() % 16 == 0 and tables[s.table].stride(0) % 4 == 0 for s in specs)
+
+
+class FmFusedFn(torch.autograd.Function):
+    """prob[B,1] = sigmoid(bias + FM(gathered rows)); the concat is never materialised in forward."""
+
+    @staticmethod
+    def forward(ctx, fb: FeatBinding, out_dim: int, table_names: List[str], bias, *weights):
+        prob, _, _, _ = fm_fused_fwd(fb, bias)
+        ctx.fb, ctx.out_dim, ctx.table_names, ctx.weights = fb, out_dim, table_names, weights
+        ctx.save_for_backward(prob)
+        return prob.view(-1, 1)
+
+    @staticmethod
+    def backward(ctx, g):
+        (p,) = ctx.saved_tensors
+        fb = ctx.fb
+        g = g.contiguous().view(-1)
+        dl = torch.empty_like(p)
+        lib = L.load()
+        L.check(lib.nrx_sigmoid_bwd(p.data_ptr(), g.data_ptr(), p.numel(), dl.data_ptr(), L.stream_ptr(p.device)),
+                "nrx_sigmoid_bwd")
+        gx = fm_fused_bwd(fb, dl, ctx.out_dim)
+        plan = BwdPlan(fb)
+        by_id: List[Optional[torch.Tensor]] = [None] * L.NRX_MAX_TABLES
+        name_to_id = {s.table: s.table_id for s in fb.specs}
+        for nme, w in zip(ctx.table_names, ctx.weights):
+            if nme in name_to_id:
+                by_id[name_to_id[nme]] = w
+        grads = embed_bwd_dense(plan, gx, by_id)
+        gw = [grads[name_to_id[n]] if n in name_to_id else None for n in ctx.table_names]
+        return (None, None, None, reduce_sum(dl).view(1), *gw)
