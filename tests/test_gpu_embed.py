@@ -75,7 +75,7 @@ def test_k1_edge_cases():
                 spec = ops.FeatSpec("h", "t", 0, D, 5, True, 0)
                 fb = ops.FeatBinding([spec], {"t": W.to(DEV)}, batch)
                 out = ops.embed_pool_fwd(fb, D).cpu()
-                ref = R.array_feature_pooling(R.feature_embedding({"t": W}, {}, "h", ids), mask if use_mask else None)
+                ref = R.array_feature_pooling(R.feature_embedding({"t": W}, {"h": "t"}, "h", ids), mask if use_mask else None)
                 torch.testing.assert_close(out, ref, rtol=FP32_RTOL, atol=1e-7)
                 if use_mask:
                     assert torch.count_nonzero(out[2]) == 0 and torch.isfinite(out).all()
