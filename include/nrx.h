@@ -175,6 +175,12 @@ int nrx_tower_bwd(const NrxTower* h_tower, const float* x, int64_t x_ld, int64_t
                   float* const* h_grad_w, float* const* h_grad_b,
                   void* ws, size_t ws_bytes, nrx_stream_t stream);
 
+/* Layout of the bf16 tile images the training forward/backward keep in `ws` (tests, tooling):
+ * image of layer l's input (width act_width[l]) and of dL/dz_l (width dz_width[l]), each stored as
+ * [tile][width/8][128 rows][8] bf16 — the UMMA operand layout, see DESIGN.md. */
+int nrx_tower_image_layout(const NrxTower* h_tower, int64_t B, int64_t* act_off, int32_t* act_width,
+                           int64_t* dz_off, int32_t* dz_width);
+
 /* DCN-v1 cross stack: x_{l+1} = x0 * (x_l . w_l) + b_l + x_l  (dcn_arch.py:14-30),
  * writes out[B, 2d] = cat[x, x_L] (dcn/model.py:29).  dots[L, B] keeps x_l . w_l. */
 int nrx_dcn_cross_fwd(const float* x, int64_t ld, int64_t B, int d, int n_layers,

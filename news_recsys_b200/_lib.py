@@ -83,6 +83,7 @@ SIGNATURES = {
     "nrx_tower_fwd": (C.c_int, [C.POINTER(NrxTower), _P, _I64, _I64, _P, _I64, C.c_int, _P, _SZ, _P]),
     "nrx_tower_bwd": (C.c_int, [C.POINTER(NrxTower), _P, _I64, _I64, _P, _I64, _P, _I64, C.c_int,
                                 C.POINTER(_P), C.POINTER(_P), _P, _SZ, _P]),
+    "nrx_tower_image_layout": (C.c_int, [C.POINTER(NrxTower), _I64, C.POINTER(_I64), C.POINTER(_I32), C.POINTER(_I64), C.POINTER(_I32)]),
     "nrx_dcn_cross_fwd": (C.c_int, [_P, _I64, _I64, C.c_int, C.c_int, C.POINTER(_P), C.POINTER(_P), _P, _I64, _P, _P]),
     "nrx_dcn_cross_bwd": (C.c_int, [_P, _I64, _I64, C.c_int, C.c_int, C.POINTER(_P), C.POINTER(_P), _P, _I64, _P,
                                     _P, _I64, C.POINTER(_P), C.POINTER(_P), _P, _SZ, _P]),

@@ -409,3 +409,101 @@ class FmFusedFn(torch.autograd.Function):
         grads = embed_bwd_dense(plan, gx, by_id)
         gw = [grads[name_to_id[n]] if n in name_to_id else None for n in ctx.table_names]
         return (None, None, None, reduce_sum(dl).view(1), *gw)
+
+
+# --------------------------------------------------------------------------- #
+# K4: fused bf16 tower (tcgen05)                                               #
+# --------------------------------------------------------------------------- #
+
+def _tower_struct(weights: Sequence[torch.Tensor], biases: Sequence[torch.Tensor], negative_slope: Optional[float]):
+    n = len(weights)
+    if n < 1 or n > L.NRX_MAX_LAYERS:
+        raise L.NrxError(f"{n} layers outside [1,{L.NRX_MAX_LAYERS}]")
+    t = L.NrxTower()
+    t.n_layers = n
+    t.dims[0] = weights[0].shape[1]
+    keep = []
+    for i, (w, b) in enumerate(zip(weights, biases)):
+        _require_cuda(w, f"tower weight {i}")
+        wc, bc = w.detach().contiguous(), b.detach().contiguous()
+        if wc.dtype != torch.float32 or bc.dtype != torch.float32:
+            raise L.NrxError("tower parameters must be fp32 (they are packed to bf16 on the device)")
+        keep += [wc, bc]
+        t.dims[i + 1] = wc.shape[0]
+        t.w[i] = wc.data_ptr()
+        t.b[i] = bc.data_ptr()
+    t.act = L.ACT_RELU if negative_slope is None else L.ACT_LEAKY
+    t.negative_slope = 0.0 if negative_slope is None else float(negative_slope)
+    return t, keep
+
+
+def tower_fwd(x: torch.Tensor, weights, biases, negative_slope=None, training=False):
+    """y = MLP(x) on tensor cores; returns (y, ctx) where ctx carries the workspace for tower_bwd."""
+    _require_cuda(x, "tower input")
+    if x.dtype != torch.float32 or x.stride(-1) != 1:
+        x = x.float().contiguous()
+    B = x.shape[0]
+    t, keep = _tower_struct(weights, biases, negative_slope)
+    lib = L.load()
+    nbytes = int(lib.nrx_tower_workspace_bytes(C.byref(t), B, 1 if training else 0))
+    if nbytes == 0:
+        L.check(-2, "nrx_tower_workspace_bytes")
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+    y = torch.empty((B, weights[-1].shape[0]), dtype=torch.float32, device=x.device)
+    L.check(lib.nrx_tower_fwd(C.byref(t), x.data_ptr(), x.stride(0), B, y.data_ptr(), y.stride(0), 1 if training else 0,
+                              ws.data_ptr(), nbytes, L.stream_ptr(x.device)), "nrx_tower_fwd")
+    return y, (t, keep, ws, nbytes, x)
+
+
+def tower_bwd(ctx, grad_y: torch.Tensor, need_gx: bool = True):
+    t, keep, ws, nbytes, x = ctx
+    B = x.shape[0]
+    grad_y = grad_y.contiguous()
+    n = t.n_layers
+    gws = [torch.empty((t.dims[i + 1], t.dims[i]), dtype=torch.float32, device=x.device) for i in range(n)]
+    gbs = [torch.empty((t.dims[i + 1],), dtype=torch.float32, device=x.device) for i in range(n)]
+    gx = torch.empty_like(x) if need_gx else None
+    lib = L.load()
+    L.check(lib.nrx_tower_bwd(C.byref(t), x.data_ptr(), x.stride(0), B, grad_y.data_ptr(), grad_y.stride(0), L.ptr(gx),
+                              gx.stride(0) if gx is not None else 0, 0, L.ptr_array(gws, L.NRX_MAX_LAYERS),
+                              L.ptr_array(gbs, L.NRX_MAX_LAYERS), ws.data_ptr(), nbytes, L.stream_ptr(x.device)),
+            "nrx_tower_bwd")
+    return gx, gws, gbs
+
+
+class TowerFn(torch.autograd.Function):
+    """MLP / DSSM tower: forward(x, slope, n, *weights, *biases)."""
+
+    @staticmethod
+    def forward(ctx, x, negative_slope, n, *params):
+        ws, bs = params[:n], params[n:]
+        training = any(ctx.needs_input_grad)  # grad mode is off inside Function.forward
+        y, tctx = tower_fwd(x, ws, bs, negative_slope, training=training)
+        ctx.tctx = tctx if training else None
+        ctx.n = n
+        ctx.need_gx = x.requires_grad
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        if ctx.tctx is None:
+            raise L.NrxError("tower backward without a training forward")
+        gx, gws, gbs = tower_bwd(ctx.tctx, gy, need_gx=ctx.need_gx)
+        return (gx, None, None, *gws, *gbs)
+
+
+def tower_images(ctx, B: int):
+    """Decode the saved bf16 tile images of a training forward/backward -> (a[l], dz[l]) as fp32 [B, width]."""
+    t, keep, ws, nbytes, x = ctx
+    n = t.n_layers
+    ao, aw = (C.c_int64 * n)(), (C.c_int32 * n)()
+    do, dw = (C.c_int64 * n)(), (C.c_int32 * n)()
+    lib = L.load()
+    L.check(lib.nrx_tower_image_layout(C.byref(t), B, ao, aw, do, dw), "nrx_tower_image_layout")
+    nt = (B + 127) // 128
+
+    def img(off, width):
+        raw = ws[off: off + nt * width * 256].view(torch.bfloat16).view(nt, width // 8, 128, 8)
+        return raw.permute(0, 2, 1, 3).reshape(nt * 128, width)[:B].float()
+
+    return [img(ao[l], aw[l]) for l in range(n)], [img(do[l], dw[l]) for l in range(n)]

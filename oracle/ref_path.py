@@ -363,3 +363,27 @@ def topk_merge(scores: Sequence[Tensor], ids: Sequence[Tensor], k: int) -> Tuple
     s, i = torch.gather(s, 1, o), torch.gather(i, 1, o)
     o = torch.argsort(s, dim=1, descending=True, stable=True)
     return torch.gather(s, 1, o)[:, :k], torch.gather(i, 1, o)[:, :k]
+
+
+# --------------------------------------------------------------------------- #
+# bf16 restatement of the MLP (same reference lines + the rounding points of    #
+# the tensor-core path) — used to check each forward/backward step exactly      #
+# --------------------------------------------------------------------------- #
+
+def bf16(x: Tensor) -> Tensor:
+    return x.to(torch.bfloat16).to(torch.float64)
+
+
+def mlp_bf16_layer(a: Tensor, w: Tensor, b: Tensor, last: bool, negative_slope: Optional[float]) -> Tensor:
+    """One utils.py:11 Linear (+ activation) with bf16 operands, wide accumulation, bf16 output."""
+    z = bf16(a) @ bf16(w).T + b.double()
+    if last:
+        return z
+    s = 0.0 if negative_slope is None else negative_slope
+    return bf16(torch.where(z > 0, z, z * s).float())
+
+
+def mlp_bf16_dx_step(dz: Tensor, w: Tensor, a_in: Tensor, negative_slope: Optional[float]) -> Tensor:
+    """dz_{l-1} = bf16((dz_l W_l) * act'(a_l)) — autograd of Linear+ReLU/LeakyReLU with bf16 operands."""
+    s = 0.0 if negative_slope is None else negative_slope
+    return bf16(((bf16(dz) @ bf16(w)) * torch.where(a_in > 0, 1.0, s)).float())

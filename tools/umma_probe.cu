@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(128) probe_kernel(const __nv_bfloat16* A, cons
     *reinterpret_cast<uint4*>(sB + canon_off(N, r, kc)) = *reinterpret_cast<const uint4*>(B + r * K + kc * 8);
   }
   if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
-  if (warp == 0) tmem_alloc<64>(&tmem_base_s);
+  if (warp == 0) tmem_alloc(&tmem_base_s, 64);
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(128) probe_kernel(const __nv_bfloat16* A, cons
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc<64>(tmem);
+  if (warp == 0) tmem_dealloc(tmem, 64);
 }
 
 int main() {
