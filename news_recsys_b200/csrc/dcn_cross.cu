@@ -1,0 +1,239 @@
+// K5 — DCN-v1 cross stack, fused (reference src/model/sort/dcn/dcn_arch.py:14-30 layer, :53-70 net;
+// concat with the raw features for the head: sort/dcn/model.py:29).
+//
+// The reference materialises x0 * xl^T as a [B, d, d] tensor per layer (3.3 GB at B = 65536, d = 112).
+// Algebraically (x0 xl^T) w == x0 * (xl . w), so one warp per row keeps x0 / x_l in registers, does the
+// row-dot with a shuffle reduction and writes cat[x, x_L] once: 4 B * (d + 2 d) of HBM traffic per row.
+// Backward recomputes the x_l chain in registers; the parameter gradients (sums over the batch) are
+// accumulated per warp in a fixed row order, combined per block in shared memory in warp order and summed
+// over blocks by a second kernel in block order => bitwise reproducible, no float atomics.
+#include "common.cuh"
+
+namespace nrx {
+
+static constexpr int kMaxCrossLayers = 8;
+static constexpr int kCrossNC = 8;  // lane owns columns lane + 32*k, k < 8  => d <= 256
+
+struct CrossP {
+  const float* w[kMaxCrossLayers];
+  const float* b[kMaxCrossLayers];
+  int n_layers, d;
+};
+
+template <int NC>
+__global__ void __launch_bounds__(256)
+dcn_cross_fwd_kernel(const float* __restrict__ x, long long ld, long long B, const __grid_constant__ CrossP P,
+                     float* __restrict__ out, long long old, float* __restrict__ dots) {
+  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= B) return;
+  const int d = P.d;
+  float x0[NC], xl[NC];
+#pragma unroll
+  for (int k = 0; k < NC; ++k) {
+    const int c = lane + 32 * k;
+    x0[k] = c < d ? __ldg(x + row * ld + c) : 0.f;
+    xl[k] = x0[k];
+  }
+  for (int l = 0; l < P.n_layers; ++l) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+      const int c = lane + 32 * k;
+      if (c < d) s = fmaf(xl[k], __ldg(P.w[l] + c), s);
+    }
+    s = warp_sum(s);
+    if (dots != nullptr && lane == 0) dots[(long long)l * B + row] = s;
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+      const int c = lane + 32 * k;
+      if (c < d) xl[k] = fmaf(x0[k], s, __ldg(P.b[l] + c) + xl[k]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < NC; ++k) {
+    const int c = lane + 32 * k;
+    if (c < d) {
+      out[row * old + c] = x0[k];
+      out[row * old + d + c] = xl[k];
+    }
+  }
+}
+
+// partials layout: [block][layer][2 (w,b)][d]
+template <int NC>
+__global__ void __launch_bounds__(256)
+dcn_cross_bwd_kernel(const float* __restrict__ x, long long ld, long long B, const __grid_constant__ CrossP P,
+                     const float* __restrict__ go, long long gold, float* __restrict__ gx, long long gxld,
+                     float* __restrict__ partials) {
+  extern __shared__ float sm[];  // [8 warps][layers][2][d]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int d = P.d, Lc = P.n_layers;
+  float gw[kMaxCrossLayers][NC], gb[kMaxCrossLayers][NC];
+#pragma unroll
+  for (int l = 0; l < kMaxCrossLayers; ++l)
+#pragma unroll
+    for (int k = 0; k < NC; ++k) { gw[l][k] = 0.f; gb[l][k] = 0.f; }
+
+  const long long warps_total = (long long)gridDim.x * 8;
+  for (long long row = (long long)blockIdx.x * 8 + warp; row < B; row += warps_total) {
+    float x0[NC], xs[kMaxCrossLayers][NC], s[kMaxCrossLayers];
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+      const int c = lane + 32 * k;
+      x0[k] = c < d ? __ldg(x + row * ld + c) : 0.f;
+    }
+    // recompute the chain, keeping x_l (input of layer l)
+#pragma unroll
+    for (int l = 0; l < kMaxCrossLayers; ++l) {
+      if (l >= Lc) break;
+#pragma unroll
+      for (int k = 0; k < NC; ++k) xs[l][k] = (l == 0) ? x0[k] : fmaf(x0[k], s[l - 1], __ldg(P.b[l - 1] + min(lane + 32 * k, d - 1)) + xs[l - 1][k]);
+      float t = 0.f;
+#pragma unroll
+      for (int k = 0; k < NC; ++k) {
+        const int c = lane + 32 * k;
+        if (c < d) t = fmaf(xs[l][k], __ldg(P.w[l] + c), t);
+      }
+      s[l] = warp_sum(t);
+    }
+    float g[NC], g0[NC];
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+      const int c = lane + 32 * k;
+      g0[k] = c < d ? __ldg(go + row * gold + c) : 0.f;        // d/dx through the concat's first half
+      g[k] = c < d ? __ldg(go + row * gold + d + c) : 0.f;     // d/dx_L
+    }
+#pragma unroll
+    for (int l = kMaxCrossLayers - 1; l >= 0; --l) {
+      if (l >= Lc) continue;
+      float ds = 0.f;
+#pragma unroll
+      for (int k = 0; k < NC; ++k) ds = fmaf(g[k], x0[k], ds);
+      ds = warp_sum(ds);
+#pragma unroll
+      for (int k = 0; k < NC; ++k) {
+        const int c = lane + 32 * k;
+        gb[l][k] += g[k];
+        gw[l][k] = fmaf(ds, xs[l][k], gw[l][k]);
+        g0[k] = fmaf(g[k], s[l], g0[k]);
+        if (c < d) g[k] = fmaf(ds, __ldg(P.w[l] + c), g[k]);
+      }
+    }
+    if (gx != nullptr) {
+#pragma unroll
+      for (int k = 0; k < NC; ++k) {
+        const int c = lane + 32 * k;
+        if (c < d) gx[row * gxld + c] = g0[k] + g[k];
+      }
+    }
+  }
+  // block combine in warp order
+#pragma unroll
+  for (int l = 0; l < kMaxCrossLayers; ++l) {
+    if (l >= Lc) break;
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+      const int c = lane + 32 * k;
+      if (c < d) {
+        sm[((warp * Lc + l) * 2 + 0) * d + c] = gw[l][k];
+        sm[((warp * Lc + l) * 2 + 1) * d + c] = gb[l][k];
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < Lc * 2 * d; i += blockDim.x) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += sm[w * Lc * 2 * d + i];
+    partials[(long long)blockIdx.x * Lc * 2 * d + i] = t;
+  }
+}
+
+struct CrossG { float* gw[kMaxCrossLayers]; float* gb[kMaxCrossLayers]; };
+__global__ void __launch_bounds__(256)
+dcn_cross_reduce_kernel(const float* __restrict__ partials, int n_blocks, int Lc, int d, const __grid_constant__ CrossG G) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Lc * 2 * d) return;
+  float t = 0.f;
+  for (int b = 0; b < n_blocks; ++b) t += partials[(long long)b * Lc * 2 * d + i];
+  const int l = i / (2 * d), which = (i / d) % 2, c = i % d;
+  float* dst = which == 0 ? G.gw[l] : G.gb[l];
+  if (dst) dst[c] = t;
+}
+
+static int make_cross(int d, int n_layers, const float* const* w, const float* const* b, CrossP* P) {
+  NRX_REQUIRE(d >= 1 && d <= 32 * kCrossNC, NRX_EUNSUPPORTED, "cross width %d outside [1,%d]", d, 32 * kCrossNC);
+  NRX_REQUIRE(n_layers >= 1 && n_layers <= kMaxCrossLayers, NRX_EINVAL, "cross layers %d outside [1,%d]", n_layers, kMaxCrossLayers);
+  NRX_REQUIRE(w && b, NRX_EINVAL, "null parameter arrays");
+  memset(P, 0, sizeof(*P));
+  P->d = d;
+  P->n_layers = n_layers;
+  for (int l = 0; l < n_layers; ++l) {
+    NRX_REQUIRE(w[l] && b[l], NRX_EINVAL, "cross layer %d: null w/b", l);
+    P->w[l] = w[l];
+    P->b[l] = b[l];
+  }
+  return NRX_OK;
+}
+
+static int cross_bwd_blocks(long long B) {
+  long long blocks = (B + 63) / 64;  // >= 8 rows per warp
+  const long long cap = (long long)sm_count() * 2;
+  if (blocks > cap) blocks = cap;
+  return blocks < 1 ? 1 : (int)blocks;
+}
+
+}  // namespace nrx
+
+using namespace nrx;
+
+extern "C" int nrx_dcn_cross_fwd(const float* x, int64_t ld, int64_t B, int d, int n_layers, const float* const* h_w,
+                                 const float* const* h_b, float* out, int64_t out_ld, float* dots, nrx_stream_t stream) {
+  CrossP P;
+  int rc = make_cross(d, n_layers, h_w, h_b, &P);
+  if (rc != NRX_OK) return rc;
+  NRX_REQUIRE((x && out) || B == 0, NRX_EINVAL, "null x / out");
+  NRX_REQUIRE(ld >= d && out_ld >= 2 * d, NRX_EINVAL, "leading dimension too small");
+  if (B == 0) return NRX_OK;
+  const unsigned blocks = (unsigned)((B + 7) / 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (d <= 128) dcn_cross_fwd_kernel<4><<<blocks, 256, 0, st>>>(x, ld, B, P, out, out_ld, dots);
+  else dcn_cross_fwd_kernel<8><<<blocks, 256, 0, st>>>(x, ld, B, P, out, out_ld, dots);
+  return check_launch("dcn_cross_fwd");
+}
+
+extern "C" size_t nrx_dcn_cross_workspace_bytes(int64_t B, int d, int n_layers) {
+  return (size_t)cross_bwd_blocks(B) * n_layers * 2 * d * sizeof(float);
+}
+
+extern "C" int nrx_dcn_cross_bwd(const float* x, int64_t ld, int64_t B, int d, int n_layers, const float* const* h_w,
+                                 const float* const* h_b, const float* grad_out, int64_t go_ld, const float* dots,
+                                 float* grad_x, int64_t gx_ld, float* const* h_grad_w, float* const* h_grad_b, void* ws,
+                                 size_t ws_bytes, nrx_stream_t stream) {
+  (void)dots;  // the chain is recomputed in registers
+  CrossP P;
+  int rc = make_cross(d, n_layers, h_w, h_b, &P);
+  if (rc != NRX_OK) return rc;
+  NRX_REQUIRE((x && grad_out) || B == 0, NRX_EINVAL, "null x / grad_out");
+  NRX_REQUIRE(ld >= d && go_ld >= 2 * d && (!grad_x || gx_ld >= d), NRX_EINVAL, "leading dimension too small");
+  NRX_REQUIRE(h_grad_w && h_grad_b, NRX_EINVAL, "null gradient pointer arrays");
+  const int blocks = cross_bwd_blocks(B);
+  const size_t need = (size_t)blocks * n_layers * 2 * d * sizeof(float);
+  NRX_REQUIRE(ws && ws_bytes >= need, NRX_EWORKSPACE, "workspace %zu < %zu", ws_bytes, need);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t smem = (size_t)8 * n_layers * 2 * d * sizeof(float);
+  if (d <= 128) {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(dcn_cross_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    dcn_cross_bwd_kernel<4><<<blocks, 256, smem, st>>>(x, ld, B, P, grad_out, go_ld, grad_x, gx_ld, (float*)ws);
+  } else {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(dcn_cross_bwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    dcn_cross_bwd_kernel<8><<<blocks, 256, smem, st>>>(x, ld, B, P, grad_out, go_ld, grad_x, gx_ld, (float*)ws);
+  }
+  rc = check_launch("dcn_cross_bwd");
+  if (rc != NRX_OK) return rc;
+  CrossG G;
+  memset(&G, 0, sizeof(G));
+  for (int l = 0; l < n_layers; ++l) { G.gw[l] = h_grad_w[l]; G.gb[l] = h_grad_b[l]; }
+  dcn_cross_reduce_kernel<<<(n_layers * 2 * d + 255) / 256, 256, 0, st>>>((const float*)ws, blocks, n_layers, d, G);
+  return check_launch("dcn_cross_reduce");
+}

@@ -507,3 +507,59 @@ def tower_images(ctx, B: int):
         return raw.permute(0, 2, 1, 3).reshape(nt * 128, width)[:B].float()
 
     return [img(ao[l], aw[l]) for l in range(n)], [img(do[l], dw[l]) for l in range(n)]
+
+
+# --------------------------------------------------------------------------- #
+# K5: DCN-v1 cross stack                                                       #
+# --------------------------------------------------------------------------- #
+
+def dcn_cross_fwd(x: torch.Tensor, ws: Sequence[torch.Tensor], bs: Sequence[torch.Tensor]) -> torch.Tensor:
+    """cat[x, cross_L(x)] ([B, 2d]) — dcn_arch.py:14-30,53-70 + dcn/model.py:29."""
+    _require_cuda(x, "cross input")
+    x = x.contiguous()
+    B, d = x.shape
+    out = torch.empty((B, 2 * d), dtype=torch.float32, device=x.device)
+    wl = [w.detach().contiguous().view(-1) for w in ws]
+    bl = [b.detach().contiguous().view(-1) for b in bs]
+    lib = L.load()
+    L.check(lib.nrx_dcn_cross_fwd(x.data_ptr(), x.stride(0), B, d, len(wl), L.ptr_array(wl), L.ptr_array(bl), out.data_ptr(),
+                                  out.stride(0), None, L.stream_ptr(x.device)), "nrx_dcn_cross_fwd")
+    return out
+
+
+def dcn_cross_bwd(x, ws, bs, grad_out, need_gx=True):
+    x = x.contiguous()
+    grad_out = grad_out.contiguous()
+    B, d = x.shape
+    n = len(ws)
+    wl = [w.detach().contiguous().view(-1) for w in ws]
+    bl = [b.detach().contiguous().view(-1) for b in bs]
+    gws = [torch.empty(d, dtype=torch.float32, device=x.device) for _ in range(n)]
+    gbs = [torch.empty(d, dtype=torch.float32, device=x.device) for _ in range(n)]
+    gx = torch.empty_like(x) if need_gx else None
+    lib = L.load()
+    nbytes = int(lib.nrx_dcn_cross_workspace_bytes(B, d, n))
+    wsb = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=x.device)
+    L.check(lib.nrx_dcn_cross_bwd(x.data_ptr(), x.stride(0), B, d, n, L.ptr_array(wl), L.ptr_array(bl), grad_out.data_ptr(),
+                                  grad_out.stride(0), None, L.ptr(gx), gx.stride(0) if gx is not None else 0,
+                                  L.ptr_array(gws), L.ptr_array(gbs), wsb.data_ptr(), nbytes, L.stream_ptr(x.device)),
+            "nrx_dcn_cross_bwd")
+    return gx, gws, gbs
+
+
+class CrossFn(torch.autograd.Function):
+    """forward(x, n, *w[d,1], *b[d,1]) -> cat[x, x_L]."""
+
+    @staticmethod
+    def forward(ctx, x, n, *params):
+        ws, bs = params[:n], params[n:]
+        ctx.save_for_backward(x, *params)
+        ctx.n = n
+        return dcn_cross_fwd(x, ws, bs)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, *params = ctx.saved_tensors
+        n = ctx.n
+        gx, gws, gbs = dcn_cross_bwd(x, params[:n], params[n:], g, need_gx=ctx.needs_input_grad[0])
+        return (gx, None, *[a.view_as(p) for a, p in zip(gws, params[:n])], *[a.view_as(p) for a, p in zip(gbs, params[n:])])

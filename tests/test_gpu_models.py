@@ -1,0 +1,157 @@
+"""-m gpu parity of the remaining drop-in heads (WideDeep, DCN, DeepFM) and the DCN cross kernel (K5)."""
+import pytest
+import torch
+import yaml
+
+from oracle import ref_path as R
+from tests._golden import load
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _rel(a, b):
+    a, b = a.detach().cpu().double(), b.detach().cpu().double()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def _cos(a, b):
+    a, b = a.detach().cpu().double().flatten(), b.detach().cpu().double().flatten()
+    return float((a @ b) / (a.norm() * b.norm()).clamp_min(1e-30))
+
+
+@pytest.mark.parametrize("B,d,L", [(7, 20, 3), (1000, 112, 3), (333, 144, 2), (64, 200, 4)])
+def test_dcn_cross_matches_reference_layers(B, d, L):
+    """fp32 kernel: cat[x, x_L] and all gradients within 1e-5 of the reference's (x0 xl^T) w formulation."""
+    from news_recsys_b200 import ops
+    g = torch.Generator().manual_seed(B)
+    x = torch.randn(B, d, generator=g)
+    ws = [torch.randn(d, 1, generator=g) / d ** 0.5 for _ in range(L)]
+    bs = [torch.randn(d, 1, generator=g) * 0.1 for _ in range(L)]
+    go = torch.randn(B, 2 * d, generator=g)
+    xr = x.clone().requires_grad_(True)
+    wr = [w.clone().requires_grad_(True) for w in ws]
+    br = [b.clone().requires_grad_(True) for b in bs]
+    yr = torch.cat([xr, R.dcn_cross_v1(xr, wr, br, materialise=True)], dim=1)
+    yr.backward(go)
+    xd = x.to(DEV).requires_grad_(True)
+    wd = [w.to(DEV).requires_grad_(True) for w in ws]
+    bd = [b.to(DEV).requires_grad_(True) for b in bs]
+    y = ops.CrossFn.apply(xd, L, *wd, *bd)
+    assert _rel(y, yr) < 1e-5
+    y.backward(go.to(DEV))
+    assert _rel(xd.grad, xr.grad) < 1e-5
+    for i in range(L):
+        assert wd[i].grad.shape == wr[i].grad.shape
+        assert _rel(wd[i].grad, wr[i].grad) < 2e-5, f"gw[{i}] {_rel(wd[i].grad, wr[i].grad)}"
+        assert _rel(bd[i].grad, br[i].grad) < 2e-5, f"gb[{i}]"
+    y2 = ops.CrossFn.apply(xd.detach(), L, *[w.detach() for w in wd], *[b.detach() for b in bd])
+    assert torch.equal(y2, y.detach())
+
+
+def test_dcn_unit_golden():
+    """DCNNet / DCNv2Net vs vectors produced by the reference classes (tests/golden/units.npz)."""
+    import numpy as np
+    from tests._golden import GOLD
+    from news_recsys_b200.model.sort.dcn.dcn_arch import DCNNet, DCNv2Net
+    z = np.load(f"{GOLD}/units.npz")
+    t = lambda k: torch.from_numpy(z[k]).to(DEV)
+    net = DCNNet(20, 3).to(DEV)
+    with torch.no_grad():
+        for i, l in enumerate(net.cross_net):
+            l.w.copy_(t(f"dcn_w{i}"))
+            l.b.copy_(t(f"dcn_b{i}"))
+        y = net(t("dcn_x"))
+    torch.testing.assert_close(y.cpu(), torch.from_numpy(z["dcn_y"]), rtol=1e-5, atol=1e-6)
+    net2 = DCNv2Net(20, 3).to(DEV)
+    with torch.no_grad():
+        j = 0
+        for l in net2.cross_net:
+            if hasattr(l, "linear"):
+                l.linear.weight.copy_(t(f"dcn2_W{j}"))
+                l.linear.bias.copy_(t(f"dcn2_b{j}"))
+                j += 1
+        y2 = net2(t("dcn_x"))
+    assert _rel(y2, torch.from_numpy(z["dcn2_y"])) < 2e-2  # bf16 d x d Linear on tensor cores
+
+
+def _model(kind, cfg_path):
+    from news_recsys_b200.model.sort.dcn.model import DCN
+    from news_recsys_b200.model.sort.widedeep.model import WideDeep
+    return {"dcn": DCN, "widedeep": WideDeep}[kind](cfg_path)
+
+
+@pytest.mark.parametrize("name", ["widedeep", "widedeep_hist", "dcn"])
+def test_heads_match_reference(name):
+    g = load(name)
+    m = _model(g["kind"], g["cfg_path"])
+    m.load_state_dict(g["sd"], strict=True)
+    m = m.to(DEV)
+    batch = {k: v.to(DEV) for k, v in g["batch"].items()}
+    prob = m(batch)
+    ref = torch.from_numpy(g["z"]["prob"])
+    assert prob.shape == ref.shape
+    torch.testing.assert_close(prob.detach().cpu(), ref, rtol=1e-2, atol=2e-3)
+    loss = m.bceLoss(prob, batch["label"][:, 0])
+    torch.testing.assert_close(loss.detach().cpu(), torch.from_numpy(g["z"]["loss"]), rtol=1e-2, atol=1e-3)
+    loss.backward()
+    params = dict(m.named_parameters())
+    for k, gr in g["grads"].items():
+        assert params[k].grad is not None, k
+        assert params[k].grad.shape == gr.shape
+        if gr.abs().max() > 0:
+            assert _cos(params[k].grad, gr) > 0.97, f"{name}:{k}: cos {_cos(params[k].grad, gr):.4f}"
+    if g["kind"] == "widedeep":  # wide path + bias are pure fp32 kernels
+        assert _rel(params["score_fc.bias"].grad, g["grads"]["score_fc.bias"]) < 2e-2
+    with torch.no_grad():
+        w, d = m.get_inp_embedding(batch) if g["kind"] == "widedeep" else (None, None)
+    if w is not None:
+        ow, od = R.widedeep_split(torch.from_numpy(g["z"]["features"]), g["z"]["dims"].tolist(), g["z"]["names"].tolist(),
+                                  g["cfg"]["wide_and_deep_cfg"]["wide_feature_names"])
+        torch.testing.assert_close(w.cpu(), ow, rtol=1e-5, atol=1e-7)
+        torch.testing.assert_close(d.cpu(), od, rtol=1e-5, atol=1e-7)
+
+
+def test_deepfm_matches_oracle_composition(tmp_path):
+    """DeepFM = FM logit (fm/model.py:18-25) + MLP logit (utils.py:6-17), one sigmoid; parity unpinned
+    (no reference class) so the check is against the oracle composition on the fm_hist schema."""
+    from news_recsys_b200.model.sort.deepfm.model import DeepFM
+    g = load("fm_hist")
+    cfg = dict(g["cfg"])
+    cfg["deepfm_cfg"] = {"fm_feature_names": sorted(set(cfg["features"]["user_feature_names"]) | set(cfg["features"]["item_feature_names"])),
+                         "fm_dim": 15}
+    p = tmp_path / "train_cf_deepfm.yaml"
+    p.write_text(yaml.safe_dump(cfg))
+    torch.manual_seed(5)
+    m = DeepFM(str(p))
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    with torch.no_grad():
+        for k in sd:
+            if k.startswith("embedding_tables."):
+                sd[k] = sd[k] * 0.3  # keep the FM logit out of saturation
+                sd[k][0] = 0
+    m.load_state_dict(sd)
+    m = m.to(DEV)
+    batch = {k: v.to(DEV) for k, v in g["batch"].items()}
+    prob = m(batch)
+    loss = m.bceLoss(prob, batch["label"][:, 0])
+    loss.backward()
+    p_ref, l_ref, g_ref = R.loss_and_grads("deepfm", sd, cfg, g["batch"])
+    torch.testing.assert_close(prob.detach().cpu(), p_ref, rtol=1e-2, atol=2e-3)
+    torch.testing.assert_close(loss.detach().cpu(), l_ref, rtol=1e-2, atol=1e-3)
+    params = dict(m.named_parameters())
+    for k, gr in g_ref.items():
+        if gr.abs().max() > 0:
+            assert _cos(params[k].grad, gr) > 0.97, f"deepfm:{k}: cos {_cos(params[k].grad, gr):.4f}"
+
+
+def test_dcn_too_wide_fails_loudly():
+    """DCN + user_history gives a 2d = 288 wide first layer; the SMEM-resident tower supports <= 240 columns
+    (known gaps).  The product path must raise, never fall back."""
+    from news_recsys_b200._lib import NrxError
+    g = load("dcn_hist")
+    m = _model("dcn", g["cfg_path"])
+    m.load_state_dict(g["sd"], strict=True)
+    m = m.to(DEV)
+    with pytest.raises(NrxError, match="widths up to 240"):
+        m({k: v.to(DEV) for k, v in g["batch"].items()})
