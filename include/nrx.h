@@ -89,6 +89,8 @@ typedef struct NrxRowOpt {
   int32_t step;               /* 1-based, for Adam bias correction */
   float* m[NRX_MAX_TABLES];   /* AdamW first moment per table (same shape as the table) */
   float* v[NRX_MAX_TABLES];   /* AdamW second moment per table */
+  const float* d_hparams;     /* optional DEVICE float[3] = {lr, 1-beta1^step, sqrt(1-beta2^step)}: read at run time
+                                 instead of lr/step above, so a captured CUDA graph can be replayed across steps */
 } NrxRowOpt;
 
 size_t nrx_embed_bwd_workspace_bytes(const NrxFeat* h_feats, int n_feats, int64_t B);
@@ -150,6 +152,17 @@ int nrx_adamw_dense(float* p, const float* g, float* m, float* v, int64_t n,
                     float lr, float beta1, float beta2, float eps, float weight_decay,
                     int32_t step, nrx_stream_t stream);
 
+/* Same update with {lr, 1-beta1^step, sqrt(1-beta2^step)} read from DEVICE memory (CUDA-graph replay). */
+int nrx_adamw_dense_dev(float* p, const float* g, float* m, float* v, int64_t n,
+                        const float* d_hparams, float beta1, float beta2, float eps, float weight_decay,
+                        nrx_stream_t stream);
+
+/* Device-side optimizer clock: ++d_step[0]; d_hparams = {lr per CosinDecayLR (model_utils/lr_schedule.py:16-28)
+ * at scheduler step d_step-1, 1-beta1^d_step, sqrt(1-beta2^d_step)}.  Lets a whole training step replay as a
+ * CUDA graph with no host-written scalars. */
+int nrx_hparams_step(int32_t* d_step, float* d_hparams, float lr, float min_lr, int32_t milestone0,
+                     int32_t milestone1, float beta1, float beta2, nrx_stream_t stream);
+
 /* ---- K4/K5: fused bf16 tower on tcgen05 (MLP utils.py:6-17, DSSM towers
  * recall/DSSM/model.py:26-44, DCN cross dcn_arch.py:14-30,53-70) --------------- */
 enum { NRX_ACT_RELU = 0, NRX_ACT_LEAKY = 1 };
@@ -198,6 +211,18 @@ size_t nrx_dcn_cross_workspace_bytes(int64_t B, int d, int n_layers);
  * Replaces faiss.IndexFlatIP.add/search (recall/DSSM/model.py:209,249-251;
  * model_utils/TopKSearcher.py:34-47,73-77): out ordered by (score desc, id asc),
  * ids are corpus positions + id_base, padding (k > N) is id -1 / score -FLT_MAX. */
+/* Index = the corpus packed once to bf16 tile images for the tensor-core scan (IndexFlatIP.add). */
+size_t nrx_topk_index_bytes(int64_t N, int D);
+int nrx_topk_index_build(const float* corpus, int64_t c_ld, int64_t N, int D, void* index, size_t index_bytes,
+                         nrx_stream_t stream);
+/* IndexFlatIP.search.  `corpus` (the same fp32 rows the index was built from) is read for the exact fp64
+ * re-scoring of the candidates; status[q] (optional) = 1 when query q was served by the exact fallback scan. */
+size_t nrx_topk_search_workspace_bytes(int64_t Q, int64_t N, int D, int k);
+int nrx_topk_search(const void* index, const float* corpus, int64_t c_ld, int64_t N, int D,
+                    const float* queries, int64_t q_ld, int64_t Q, int k, int64_t id_base,
+                    float* out_scores, int64_t* out_ids, int32_t* status, void* ws, size_t ws_bytes,
+                    nrx_stream_t stream);
+/* One-shot build + search (index lives in `ws`). */
 size_t nrx_topk_ip_workspace_bytes(int64_t Q, int64_t N, int D, int k);
 int nrx_topk_ip(const float* queries, int64_t q_ld, const float* corpus, int64_t c_ld,
                 int64_t Q, int64_t N, int D, int k, int64_t id_base,

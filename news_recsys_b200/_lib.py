@@ -43,6 +43,7 @@ class NrxRowOpt(C.Structure):
         ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
         ("weight_decay", C.c_float), ("step", C.c_int32),
         ("m", C.c_void_p * NRX_MAX_TABLES), ("v", C.c_void_p * NRX_MAX_TABLES),
+        ("d_hparams", C.c_void_p),
     ]
 
 
@@ -79,6 +80,8 @@ SIGNATURES = {
     "nrx_sigmoid_bwd": (C.c_int, [_P, _P, _I64, _P, _P]),
     "nrx_reduce_f32": (C.c_int, [_P, _I64, _F, _P, _P]),
     "nrx_adamw_dense": (C.c_int, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _I32, _P]),
+    "nrx_adamw_dense_dev": (C.c_int, [_P, _P, _P, _P, _I64, _P, _F, _F, _F, _F, _P]),
+    "nrx_hparams_step": (C.c_int, [_P, _P, _F, _F, _I32, _I32, _F, _F, _P]),
     "nrx_tower_workspace_bytes": (_SZ, [C.POINTER(NrxTower), _I64, C.c_int]),
     "nrx_tower_fwd": (C.c_int, [C.POINTER(NrxTower), _P, _I64, _I64, _P, _I64, C.c_int, _P, _SZ, _P]),
     "nrx_tower_bwd": (C.c_int, [C.POINTER(NrxTower), _P, _I64, _I64, _P, _I64, _P, _I64, C.c_int,
@@ -88,6 +91,10 @@ SIGNATURES = {
     "nrx_dcn_cross_bwd": (C.c_int, [_P, _I64, _I64, C.c_int, C.c_int, C.POINTER(_P), C.POINTER(_P), _P, _I64, _P,
                                     _P, _I64, C.POINTER(_P), C.POINTER(_P), _P, _SZ, _P]),
     "nrx_dcn_cross_workspace_bytes": (_SZ, [_I64, C.c_int, C.c_int]),
+    "nrx_topk_index_bytes": (_SZ, [_I64, C.c_int]),
+    "nrx_topk_index_build": (C.c_int, [_P, _I64, _I64, C.c_int, _P, _SZ, _P]),
+    "nrx_topk_search_workspace_bytes": (_SZ, [_I64, _I64, C.c_int, C.c_int]),
+    "nrx_topk_search": (C.c_int, [_P, _P, _I64, _I64, C.c_int, _P, _I64, _I64, C.c_int, _I64, _P, _P, _P, _P, _SZ, _P]),
     "nrx_topk_ip_workspace_bytes": (_SZ, [_I64, _I64, C.c_int, C.c_int]),
     "nrx_topk_ip": (C.c_int, [_P, _I64, _P, _I64, _I64, _I64, C.c_int, C.c_int, _I64, _P, _P, _P, _SZ, _P]),
     "nrx_topk_merge": (C.c_int, [_P, _P, C.c_int, _I64, C.c_int, _P, _P, _P]),
@@ -124,7 +131,17 @@ def load() -> C.CDLL:
     return _lib
 
 
+# kernels of OURS launched per successful API call (library kernels such as the CUB radix sort are not counted)
+KERNELS_PER_CALL = {"nrx_tower_fwd": 2, "nrx_tower_bwd": 3, "nrx_embed_bwd_apply": 2, "nrx_dcn_cross_bwd": 2,
+                    "nrx_embed_bwd_apply(dense)": 2, "nrx_embed_bwd_apply(rowopt)": 2, "nrx_topk_ip": 2,
+                    "nrx_topk_search": 5, "nrx_topk_index_build": 1,
+                    "nrx_tower_workspace_bytes": 0, "nrx_embed_bwd_workspace_bytes": 0, "nrx_tower_image_layout": 0}
+launch_count = 0  # running total, read by bench.py
+
+
 def check(rc: int, what: str) -> None:
+    global launch_count
+    launch_count += KERNELS_PER_CALL.get(what, 1)
     if rc != 0:
         msg = load().nrx_last_error()
         raise NrxError(f"{what} failed (code {rc}): {msg.decode() if msg else ''}")

@@ -32,6 +32,7 @@ struct DTables {
   int mode;
   int row_bits;
   float lr, beta1, beta2, eps, wd, bc1, bc2_sqrt;
+  const float* d_hp;  // optional device [lr, bc1, bc2_sqrt]: overrides the host scalars (CUDA-graph replay)
 };
 
 struct PlanLayout {
@@ -99,6 +100,9 @@ __device__ __forceinline__ void finalize_row(const DTables& T, uint32_t key, con
   const long long row = (long long)(key & ((1u << T.row_bits) - 1u));
   const int dim = T.dim[t];
   const long long base = row * T.stride[t];
+  const float lr = T.d_hp ? __ldg(T.d_hp) : T.lr;
+  const float bc1 = T.d_hp ? __ldg(T.d_hp + 1) : T.bc1;
+  const float bc2s = T.d_hp ? __ldg(T.d_hp + 2) : T.bc2_sqrt;
 #pragma unroll
   for (int k = 0; k < NC; ++k) {
     const int c = lane + 32 * k;
@@ -108,15 +112,15 @@ __device__ __forceinline__ void finalize_row(const DTables& T, uint32_t key, con
       T.g[t][base + c] = g;
     } else if (T.mode == NRX_BWD_SGD) {
       float p = T.w[t][base + c];
-      T.w[t][base + c] = p - T.lr * (g + T.wd * p);
+      T.w[t][base + c] = p - lr * (g + T.wd * p);
     } else {  // AdamW on the touched row (torch.optim.AdamW update rule)
       float p = T.w[t][base + c];
       float m = T.m[t][base + c], v = T.v[t][base + c];
-      p *= (1.f - T.lr * T.wd);
+      p *= (1.f - lr * T.wd);
       m = T.beta1 * m + (1.f - T.beta1) * g;
       v = T.beta2 * v + (1.f - T.beta2) * g * g;
-      const float denom = sqrtf(v) / T.bc2_sqrt + T.eps;
-      p -= (T.lr / T.bc1) * (m / denom);
+      const float denom = sqrtf(v) / bc2s + T.eps;
+      p -= (lr / bc1) * (m / denom);
       T.w[t][base + c] = p;
       T.m[t][base + c] = m;
       T.v[t][base + c] = v;
@@ -358,8 +362,9 @@ extern "C" int nrx_embed_bwd_apply(const NrxFeat* h_feats, int n_feats, int64_t 
   if (mode != NRX_BWD_DENSE) {
     T.lr = h_opt->lr; T.beta1 = h_opt->beta1; T.beta2 = h_opt->beta2; T.eps = h_opt->eps; T.wd = h_opt->weight_decay;
     const int step = h_opt->step > 0 ? h_opt->step : 1;
-    T.bc1 = 1.f - powf(T.beta1, (float)step);
-    T.bc2_sqrt = sqrtf(1.f - powf(T.beta2, (float)step));
+    T.bc1 = (float)(1.0 - pow((double)T.beta1, (double)step));
+    T.bc2_sqrt = (float)sqrt(1.0 - pow((double)T.beta2, (double)step));
+    T.d_hp = h_opt->d_hparams;
   }
   if (d.n_occ == 0) return NRX_OK;
   char* w = (char*)ws;

@@ -278,7 +278,9 @@ reduce_kernel(const float* __restrict__ x, long long n, float scale, float* __re
 // ---- dense AdamW -------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-             long long n, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2s) {
+             long long n, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2s,
+             const float* __restrict__ d_hp) {
+  if (d_hp) { lr = __ldg(d_hp); bc1 = __ldg(d_hp + 1); bc2s = __ldg(d_hp + 2); }
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     float pi = p[i] * (1.f - lr * wd);
@@ -288,6 +290,25 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
     pi -= (lr / bc1) * (mi / (sqrtf(vi) / bc2s + eps));
     p[i] = pi; m[i] = mi; v[i] = vi;
   }
+}
+
+// One thread: ++step, then hp = {lr(step-1) per CosinDecayLR (lr_schedule.py:16-28), 1-b1^step, sqrt(1-b2^step)}.
+__global__ void hparams_step_kernel(int* __restrict__ step, float* __restrict__ hp, float lr0, float lr1, int m0, int m1,
+                                    float b1, float b2) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const int s = step[0] + 1;  // 1-based optimizer step
+  step[0] = s;
+  const int e = s - 1;        // scheduler epoch used for this step
+  double lr;
+  if (e < m0) lr = lr0;
+  else if (e >= m1) lr = lr1;
+  else {
+    const double t = (double)(e - m0) / (double)max(1, m1 - m0);
+    lr = (double)lr1 + ((double)lr0 - (double)lr1) * 0.5 * (1.0 + cos(3.14159265358979323846 * t));
+  }
+  hp[0] = (float)lr;
+  hp[1] = (float)(1.0 - pow((double)b1, (double)s));
+  hp[2] = (float)sqrt(1.0 - pow((double)b2, (double)s));
 }
 
 __global__ void __launch_bounds__(256)
@@ -427,8 +448,26 @@ extern "C" int nrx_adamw_dense(float* p, const float* g, float* m, float* v, int
   long long blocks = (n + 255) / 256;
   const long long cap = (long long)sm_count() * 16;
   if (blocks > cap) blocks = cap;
-  adamw_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2s);
+  adamw_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2s, nullptr);
   return check_launch("adamw_dense");
+}
+
+extern "C" int nrx_adamw_dense_dev(float* p, const float* g, float* m, float* v, int64_t n, const float* d_hparams, float beta1,
+                                   float beta2, float eps, float weight_decay, nrx_stream_t stream) {
+  NRX_REQUIRE(p && g && m && v && d_hparams && n >= 0, NRX_EINVAL, "bad AdamW arguments");
+  if (n == 0) return NRX_OK;
+  long long blocks = (n + 255) / 256;
+  const long long cap = (long long)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  adamw_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, 0.f, beta1, beta2, eps, weight_decay, 1.f, 1.f, d_hparams);
+  return check_launch("adamw_dense_dev");
+}
+
+extern "C" int nrx_hparams_step(int32_t* d_step, float* d_hparams, float lr, float min_lr, int32_t milestone0,
+                                int32_t milestone1, float beta1, float beta2, nrx_stream_t stream) {
+  NRX_REQUIRE(d_step && d_hparams, NRX_EINVAL, "null pointer");
+  hparams_step_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(d_step, d_hparams, lr, min_lr, milestone0, milestone1, beta1, beta2);
+  return check_launch("hparams_step");
 }
 
 extern "C" int nrx_l2_normalize(const float* x, int64_t ld, int64_t n, int d, float* y, int64_t y_ld, nrx_stream_t stream) {

@@ -586,11 +586,18 @@ tower_bwd_reduce_body(const TowerK& T, const float* __restrict__ partials, int n
       const int n = (int)(i / (K + 1)), k = (int)(i % (K + 1));
       const int col = (k < K) ? k : T.Kp[l];
       const float* p = partials + T.part_layer_off[l] + (long long)n * ncols + col;
+      // CTAs past the last tile wrote nothing; the sum order over the live ones is fixed (c ascending)
+      const int live = (int)min((long long)n_parts, (T.n_tiles + tiles_per_part - 1) / tiles_per_part);
       float s = 0.f;
-      for (int c = 0; c < n_parts; ++c) {
-        if ((long long)c * tiles_per_part >= T.n_tiles) break;  // CTA had no tiles
-        s += p[(long long)c * T.part_stride];
+      int c = 0;
+      for (; c + 8 <= live; c += 8) {  // 8 independent loads in flight, added in order
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __ldg(p + (long long)(c + u) * T.part_stride);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s += v[u];
       }
+      for (; c < live; ++c) s += __ldg(p + (long long)c * T.part_stride);
       if (k < K) { if (gw[l]) gw[l][(long long)n * K + k] = s; }
       else if (gb[l]) gb[l][n] = s;
     }
@@ -620,7 +627,7 @@ extern "C" size_t nrx_tower_workspace_bytes(const NrxTower* h_tower, int64_t B, 
 }
 
 static int tower_pack(const TowerK& k, uint8_t* ws, cudaStream_t st) {
-  tower_pack_kernel<<<64, 256, 0, st>>>(k, ws + k.wpack_off, ws + k.wtpack_off);
+  tower_pack_kernel<<<sm_count(), 256, 0, st>>>(k, ws + k.wpack_off, ws + k.wtpack_off);
   return check_launch("tower_pack");
 }
 
@@ -689,7 +696,7 @@ extern "C" int nrx_tower_bwd(const NrxTower* h_tower, const float* x, int64_t x_
       P.gw[l] = l < k.n_layers ? h_grad_w[l] : nullptr;
       P.gb[l] = l < k.n_layers ? h_grad_b[l] : nullptr;
     }
-    tower_bwd_reduce_entry<<<64, 256, 0, st>>>(k, partials, (int)parts, per, P);
+    tower_bwd_reduce_entry<<<sm_count() * 2, 256, 0, st>>>(k, partials, (int)parts, per, P);
     rc = check_launch("tower_bwd_reduce");
   }
   return rc;

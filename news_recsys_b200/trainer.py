@@ -1,0 +1,309 @@
+"""FusedTrainer — one whole training step (fwd + BCE + bwd + optimizer) of a sort model as a single
+captured CUDA graph over libnrx kernels.
+
+What it replaces: the per-step work of Lightning's fit loop around the reference modules
+(`training_step` e.g. sort/deep/model.py:45-52, `loss.backward()`, `AdamW.step`, `CosinDecayLR.step`
+:54-65) minus logging and the per-step sklearn AUC.
+
+Differences from the autograd route (model(batch); loss.backward(); torch.optim.AdamW):
+  * embedding tables are updated by the fused sparse row AdamW inside K3 (rows the batch touched only;
+    the reference's dense AdamW also decays / moves untouched rows — see DESIGN.md "optimizer semantics");
+  * all dense parameters live in one flat fp32 buffer and take one nrx_adamw_dense_dev launch;
+  * lr / bias-correction scalars are produced on the device (nrx_hparams_step), so the graph replays
+    with no host-written arguments; the sort plan (radix sort of row keys) runs on a forked stream
+    concurrently with the forward.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional
+
+import torch
+
+from . import _lib as L
+from . import ops
+
+
+def _align(x, a=256):
+    return (x + a - 1) // a * a
+
+
+class BatchLayout:
+    """Byte layout of one batch as a single blob (ids | masks | label) so a step needs ONE copy
+    (pinned host -> device, or device pool slot -> static slot)."""
+
+    def __init__(self, model, B: int, id_dtype=torch.int64):
+        self.B = B
+        names = sorted(model.user_feature_names | model.item_feature_names)
+        self.fields = []  # (key, dtype, shape, offset)
+        off = 0
+        isz = 8 if id_dtype == torch.int64 else 4
+        for n in names:
+            if n in model.array_feature_names:
+                Lh = int(model.array_max_length[n])
+                self.fields.append((n, id_dtype, (B, Lh), off)); off = _align(off + B * Lh * isz)
+                self.fields.append((n + "_mask", torch.float32, (B, Lh), off)); off = _align(off + B * Lh * 4)
+            else:
+                self.fields.append((n, id_dtype, (B,), off)); off = _align(off + B * isz)
+        self.fields.append(("label", torch.float32, (B, 2), off)); off = _align(off + B * 2 * 4)
+        self.nbytes = off
+
+    def views(self, blob: torch.Tensor) -> Dict[str, torch.Tensor]:
+        out = {}
+        for key, dt, shape, off in self.fields:
+            n = 1
+            for s in shape:
+                n *= s
+            esz = torch.empty((), dtype=dt).element_size()
+            out[key] = blob[off: off + n * esz].view(dt).view(*shape)
+        return out
+
+    def pack(self, batch: Dict[str, torch.Tensor], blob: torch.Tensor):
+        v = self.views(blob)
+        for key, dt, shape, off in self.fields:
+            v[key].copy_(batch[key].to(dt).view(*shape))
+        return blob
+
+
+class FusedTrainer:
+    KINDS = ("lr", "fm", "deep", "widedeep", "dcn", "deepfm")
+
+    def __init__(self, model, B: int, kind: Optional[str] = None, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01,
+                 use_graph: bool = True, id_dtype=torch.int64):
+        self.model = model
+        self.kind = kind or type(model).__name__.lower()
+        if self.kind not in self.KINDS:
+            raise L.NrxError(f"unsupported model kind {self.kind}")
+        self.B = B
+        self.dev = next(model.parameters()).device
+        if self.dev.type != "cuda":
+            raise L.NrxError("FusedTrainer needs the model on a CUDA device (no CPU fallback)")
+        hp = model.train_hparams
+        self.lr, self.min_lr = float(hp.lr), float(hp.min_lr)
+        self.milestones = [int(x) for x in hp.lr_milestones]
+        self.betas, self.eps, self.wd = betas, eps, weight_decay
+        self.lib = L.load()
+        self.layout = BatchLayout(model, B, id_dtype)
+        self.blob = torch.zeros(self.layout.nbytes, dtype=torch.uint8, device=self.dev)
+        self.batch = self.layout.views(self.blob)
+        self.d_step = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        self.d_hp = torch.zeros(4, dtype=torch.float32, device=self.dev)
+        self._flatten_dense()
+        self._table_state()
+        self.fb, self.dims, self.names, self.out_dim = model.bind_features(self.batch, model.user_feature_names | model.item_feature_names)
+        self.fm_fused = self.kind == "fm" and ops.fm_fused_eligible(self.fb.specs, model._weights())
+        self._wd_idx = None
+        if self.kind == "widedeep":  # built outside graph capture (host -> device copy)
+            _, deep_cols = model._split_cols(self.dims, self.names)
+            self._wd_idx = torch.as_tensor(deep_cols, device=self.dev)
+        self.side = torch.cuda.Stream(device=self.dev)
+        self.loss = torch.zeros(1, dtype=torch.float32, device=self.dev)
+        self.prob = None
+        self.graph = None
+        self.launches_per_step = None
+        self.use_graph = use_graph
+        if use_graph:
+            self._capture()
+
+    # ---- parameter plumbing ------------------------------------------------------------------
+    def _flatten_dense(self):
+        dense = [(n, p) for n, p in self.model.named_parameters() if not n.startswith("embedding_tables.")]
+        total = sum(_align(p.numel(), 4) for _, p in dense)
+        self.flat_p = torch.zeros(max(total, 4), dtype=torch.float32, device=self.dev)
+        self.flat_g = torch.zeros_like(self.flat_p)
+        self.flat_m = torch.zeros_like(self.flat_p)
+        self.flat_v = torch.zeros_like(self.flat_p)
+        self.dense_views, self.grad_views = {}, {}
+        off = 0
+        for n, p in dense:
+            k = p.numel()
+            self.flat_p[off: off + k].copy_(p.detach().reshape(-1))
+            p.data = self.flat_p[off: off + k].view(p.shape)  # parameters become views of the flat buffer
+            self.dense_views[n] = p.data
+            self.grad_views[n] = self.flat_g[off: off + k].view(p.shape)
+            off += _align(k, 4)
+        self.n_dense = off
+
+    def _table_state(self):
+        self.tables_by_id: List[Optional[torch.Tensor]] = [None] * L.NRX_MAX_TABLES
+        self.m_by_id: List[Optional[torch.Tensor]] = [None] * L.NRX_MAX_TABLES
+        self.v_by_id: List[Optional[torch.Tensor]] = [None] * L.NRX_MAX_TABLES
+        for name, tid in self.model._table_ids.items():
+            w = self.model.embedding_tables[name].weight.data
+            self.tables_by_id[tid] = w
+            self.m_by_id[tid] = torch.zeros_like(w)
+            self.v_by_id[tid] = torch.zeros_like(w)
+
+    # ---- raw op helpers writing into preallocated buffers ------------------------------------------
+    def _sp(self):
+        return L.stream_ptr(self.dev)
+
+    def _reduce(self, x, scale, out):
+        L.check(self.lib.nrx_reduce_f32(x.data_ptr(), x.numel(), scale, out.data_ptr(), self._sp()), "nrx_reduce_f32")
+
+    def _tower(self, x, lin_names, ws_override=None):
+        ws = ws_override or [self.dense_views[n + ".weight"] for n in lin_names]
+        bs = [self.dense_views[n + ".bias"] for n in lin_names]
+        y, tctx = ops.tower_fwd(x, ws, bs, None, training=True)
+        return y, tctx
+
+    def _tower_bwd(self, tctx, dl, lin_names, gw_override=None):
+        t, keep, ws, nbytes, x = tctx
+        gws = gw_override or [self.grad_views[n + ".weight"] for n in lin_names]
+        gbs = [self.grad_views[n + ".bias"] for n in lin_names]
+        gx = torch.empty_like(x)
+        L.check(self.lib.nrx_tower_bwd(C.byref(t), x.data_ptr(), x.stride(0), x.shape[0], dl.data_ptr(), 1, gx.data_ptr(),
+                                       gx.stride(0), 0, L.ptr_array(gws, L.NRX_MAX_LAYERS), L.ptr_array(gbs, L.NRX_MAX_LAYERS),
+                                       ws.data_ptr(), nbytes, self._sp()), "nrx_tower_bwd")
+        return gx
+
+    def _lin_names(self, prefix):
+        names, i = [], 0
+        while f"{prefix}.{i}.weight" in self.dense_views:
+            names.append(f"{prefix}.{i}")
+            i += 2
+        return names
+
+    # ---- the step -------------------------------------------------------------------------------------
+    def _step(self):
+        m, fb, lib = self.model, self.fb, self.lib
+        main = torch.cuda.current_stream(self.dev)
+        self.side.wait_stream(main)
+        with torch.cuda.stream(self.side):  # sort plan: depends on the ids only -> overlaps the forward
+            plan = ops.BwdPlan(fb)
+        L.check(lib.nrx_hparams_step(self.d_step.data_ptr(), self.d_hp.data_ptr(), self.lr, self.min_lr, self.milestones[0],
+                                     self.milestones[1], self.betas[0], self.betas[1], self._sp()), "nrx_hparams_step")
+        label = self.batch["label"][:, 0]
+        bias = self.dense_views.get("score_fc.bias")
+        kind = self.kind
+        if self.fm_fused:
+            prob, loss_ps, dl, _ = ops.fm_fused_fwd(fb, bias, label)
+            gx = ops.fm_fused_bwd(fb, dl, self.out_dim)
+        else:
+            x = ops.embed_pool_fwd(fb, self.out_dim)
+            cols, c = [], 0
+            for d in self.dims:
+                cols.append(c)
+                c += d
+            terms, tctx, lin, field = [], None, None, None
+            gw_override = None
+            if kind in ("fm", "deepfm"):
+                if kind == "deepfm":
+                    fcols, fdims = m.fm_fields(self.dims, self.names)
+                else:
+                    fcols, fdims = cols, list(self.dims)
+                field = (fcols, fdims, L.FIELD_FM)
+            elif kind == "widedeep":
+                wide_cols, deep_cols = m._split_cols(self.dims, self.names)
+                field = (wide_cols, [1] * len(wide_cols), L.FIELD_WIDE)
+            elif kind == "lr":
+                field = (cols, list(self.dims), L.FIELD_SUM)
+            if field is not None:
+                terms.append(ops.field_logit_fwd(x, field[0], field[1], field[2]))
+            if kind in ("deep", "deepfm", "widedeep", "dcn"):
+                prefix = {"deep": "score_fc.network.network", "deepfm": "score_fc.deep_network.network",
+                          "widedeep": "score_fc.deep_network.network", "dcn": "score_fc.score_fc.network"}[kind]
+                lin = self._lin_names(prefix)
+                tin, ws_override = x, None
+                if kind == "widedeep":  # column selection moved to the weight side (see widedeep/model.py)
+                    w0 = self.dense_views[lin[0] + ".weight"]
+                    idx = self._wd_idx
+                    w0_full = w0.new_zeros(w0.shape[0], self.out_dim).index_copy(1, idx, w0)
+                    ws_override = [w0_full] + [self.dense_views[n + ".weight"] for n in lin[1:]]
+                    gw0_full = torch.empty_like(w0_full)
+                    gw_override = [gw0_full] + [self.grad_views[n + ".weight"] for n in lin[1:]]
+                if kind == "dcn":
+                    cw = [self.dense_views[f"score_fc.cross_net.cross_net.{i}.w"] for i in range(len(m.score_fc.cross_net.cross_net))]
+                    cb = [self.dense_views[f"score_fc.cross_net.cross_net.{i}.b"] for i in range(len(cw))]
+                    tin = ops.dcn_cross_fwd(x, cw, cb)
+                y, tctx = self._tower(tin, lin, ws_override)
+                terms.append(y.view(-1))
+            prob, loss_ps, dl = ops.logit_loss_fwd(terms, bias, label)
+            # ---- backward ----
+            gx = None
+            if tctx is not None:
+                g_tin = self._tower_bwd(tctx, dl, lin, gw_override)
+                if kind == "widedeep":
+                    self.grad_views[lin[0] + ".weight"].copy_(gw_override[0].index_select(1, idx))
+                if kind == "dcn":
+                    gx, gcw, gcb = ops.dcn_cross_bwd(x, cw, cb, g_tin)
+                    for i in range(len(cw)):
+                        self.grad_views[f"score_fc.cross_net.cross_net.{i}.w"].copy_(gcw[i].view(-1, 1))
+                        self.grad_views[f"score_fc.cross_net.cross_net.{i}.b"].copy_(gcb[i].view(-1, 1))
+                else:
+                    gx = g_tin
+            if field is not None:
+                if gx is None:
+                    gx = torch.zeros_like(x)
+                ops.field_logit_bwd(x, field[0], field[1], field[2], dl, gx, accumulate=True)
+        self._reduce(loss_ps, 1.0 / self.B, self.loss)
+        if bias is not None:
+            self._reduce(dl, 1.0, self.grad_views["score_fc.bias"])
+        main.wait_stream(self.side)
+        opt = L.NrxRowOpt()
+        opt.lr, opt.beta1, opt.beta2, opt.eps, opt.weight_decay, opt.step = self.lr, self.betas[0], self.betas[1], self.eps, self.wd, 1
+        for t in range(L.NRX_MAX_TABLES):
+            if self.m_by_id[t] is not None:
+                opt.m[t] = self.m_by_id[t].data_ptr()
+                opt.v[t] = self.v_by_id[t].data_ptr()
+        opt.d_hparams = self.d_hp.data_ptr()
+        gx = gx.contiguous()
+        L.check(lib.nrx_embed_bwd_apply(fb.arr, fb.n, fb.B, gx.data_ptr(), gx.stride(0), L.BWD_ADAMW, None,
+                                        L.ptr_array(self.tables_by_id, L.NRX_MAX_TABLES), C.byref(opt), plan.ws.data_ptr(),
+                                        plan.bytes, self._sp()), "nrx_embed_bwd_apply")
+        if self.n_dense > 0:
+            L.check(lib.nrx_adamw_dense_dev(self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.flat_m.data_ptr(),
+                                            self.flat_v.data_ptr(), self.n_dense, self.d_hp.data_ptr(), self.betas[0],
+                                            self.betas[1], self.eps, self.wd, self._sp()), "nrx_adamw_dense_dev")
+        self.prob = prob
+        self._keep = (plan, gx)
+
+    def _capture(self):
+        # warm up on a side stream (lazy module/attribute initialisation must not happen inside capture)
+        s = torch.cuda.Stream(device=self.dev)
+        s.wait_stream(torch.cuda.current_stream(self.dev))
+        snap = self._snapshot()
+        with torch.cuda.stream(s):
+            self._step()
+        torch.cuda.current_stream(self.dev).wait_stream(s)
+        torch.cuda.synchronize(self.dev)
+        self._restore(snap)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._step()
+        torch.cuda.synchronize(self.dev)
+        self._restore(snap)  # capture does not execute, but keep state identical to "no step taken" regardless
+
+    def _snapshot(self):
+        return dict(p=self.flat_p.clone(), m=self.flat_m.clone(), v=self.flat_v.clone(), step=self.d_step.clone(),
+                    t=[None if w is None else w.clone() for w in self.tables_by_id],
+                    tm=[None if w is None else w.clone() for w in self.m_by_id],
+                    tv=[None if w is None else w.clone() for w in self.v_by_id])
+
+    def _restore(self, s):
+        self.flat_p.copy_(s["p"]); self.flat_m.copy_(s["m"]); self.flat_v.copy_(s["v"]); self.d_step.copy_(s["step"])
+        for dst, src in ((self.tables_by_id, s["t"]), (self.m_by_id, s["tm"]), (self.v_by_id, s["tv"])):
+            for a, b in zip(dst, src):
+                if a is not None:
+                    a.copy_(b)
+
+    # ---- public API -------------------------------------------------------------------------------------
+    def load_blob(self, src: torch.Tensor):
+        """One copy: pinned host blob or device pool slot -> the static batch the graph reads."""
+        self.blob.copy_(src, non_blocking=True)
+
+    def load_batch(self, batch: Dict[str, torch.Tensor]):
+        for key, dt, shape, off in self.layout.fields:
+            self.batch[key].copy_(batch[key].to(device=self.dev, dtype=dt).view(*shape), non_blocking=True)
+
+    def step(self) -> torch.Tensor:
+        """Run one training step on the currently loaded batch; returns the (device) mean BCE loss."""
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._step()
+        return self.loss
+
+    def train_step(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
+        self.load_batch(batch)
+        return self.step()

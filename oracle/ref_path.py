@@ -346,10 +346,17 @@ def topk_ip(queries: Tensor, corpus: Tensor, k: int, normalize: bool = False,
     kk = min(k, n)
     out_s = torch.full((q.shape[0], k), -3.4028234663852886e38, dtype=torch.float32)
     out_i = torch.full((q.shape[0], k), -1, dtype=torch.int64)
+    if kk == 0:
+        return out_s, out_i
+    # faiss scores with an fp32 BLAS whose summation order is unspecified, so rows whose scores differ by
+    # less than ~1e-6 come out in an implementation-defined order.  The contract here pins the order with
+    # the inner product of the fp32 inputs accumulated in fp64 (products of fp32 values are exact in fp64),
+    # ties -> lower id; the returned score is that value rounded to fp32 (within 1e-6 of faiss').
+    qd, cd = q.double(), c.double()
     for s in range(0, q.shape[0], chunk):
-        sc = q[s:s + chunk] @ c.T
+        sc = qd[s:s + chunk] @ cd.T
         vals, idx = torch.sort(sc, dim=1, descending=True, stable=True)
-        out_s[s:s + chunk, :kk] = vals[:, :kk]
+        out_s[s:s + chunk, :kk] = vals[:, :kk].float()
         out_i[s:s + chunk, :kk] = idx[:, :kk]
     return out_s, out_i
 
