@@ -1,0 +1,107 @@
+"""DSSM — restatement of reference src/model/recall/DSSM/model.py on the B200 kernels.
+
+The reference file is not importable as shipped (stale `BaseModel.*` imports :4,11,13, calls to the
+non-existent `get_features_embedding` :151,168), so this mirrors its INTENT line by line:
+  towers            :26-44   Linear(in,128)-LeakyReLU(0.2)-Linear(128,128)-LReLU-Linear(128,64)-LReLU-Linear(64,out)
+                             (out = 16 in the reference; BASELINE config 4 uses 128 -> `hparams['out_dim']`)
+  forward           :51-73   user/item towers, in-batch `randperm` negatives x negative_sample_rate, L2 normalise
+  infoNCE_loss      :92-110  cross-entropy over [pos, negs] / temperature, masked by label[:,1]
+  get_*_embedding   :148-180 per-feature gather (+ masked mean for array features), concatenated
+  on_train_epoch_end:230-254 item tower over the corpus -> IndexFlatIP -> search  => build_item_index / retrieve
+Embeddings run on K1/K3, both towers on the fused tcgen05 tower (K4, LeakyReLU), scoring + top-k on K6.
+The normalise / InfoNCE tail works on [B, out] tensors and stays in PyTorch (outside the four hot ops of
+north_star).  The reference concatenates features in Python-set order (:150,:167); this mirror uses sorted
+order, the order every other model of the reference uses (base_model.py:286)."""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .... import ops
+from ....retrieval import TopkIndex
+from ...BaseModel.base_model import BaseModel
+
+
+def _tower(in_dim, out_dim):
+    return nn.Sequential(nn.Linear(in_dim, 128), nn.LeakyReLU(0.2), nn.Linear(128, 128), nn.LeakyReLU(0.2),
+                         nn.Linear(128, 64), nn.LeakyReLU(0.2), nn.Linear(64, out_dim))
+
+
+def _run_tower(seq, x):
+    lin = [m for m in seq if isinstance(m, nn.Linear)]
+    return ops.TowerFn.apply(x, 0.2, len(lin), *[m.weight for m in lin], *[m.bias for m in lin])
+
+
+class DSSM(BaseModel):
+    def __init__(self, config_path, dataloaders=None, hparams=None):
+        super().__init__(config_path)
+        self.hparams_ = dict(hparams or {})
+        self.hparams_.setdefault("negative_sample_rate", 3)
+        out_dim = int(self.hparams_.get("out_dim", 16))
+        self.user_fc = _tower(self.user_input_dim, out_dim)
+        self.item_fc = _tower(self.item_input_dim, out_dim)
+        dataloaders = dataloaders or {}
+        self.movies_dataloader = dataloaders.get("movies_dataloader", None)
+        self.val_dataloader_ = dataloaders.get("val_dataloader", None)
+        self.index = None
+
+    def get_user_embedding(self, batch):
+        x, _, _ = self.get_embeddings_from_batch(batch, self.user_feature_names)
+        return x
+
+    def get_item_embedding(self, batch):
+        x, _, _ = self.get_embeddings_from_batch(batch, self.item_feature_names)
+        return x
+
+    def user_tower(self, batch):
+        return _run_tower(self.user_fc, self.get_user_embedding(batch))
+
+    def item_tower(self, batch):
+        return _run_tower(self.item_fc, self.get_item_embedding(batch))
+
+    def forward(self, x, neg_perms=None):
+        user_emb = self.user_tower(x)
+        item_emb = self.item_tower(x)
+        B = item_emb.size(0)
+        if neg_perms is None:  # the reference draws torch.randperm on the CPU generator (:63)
+            neg_perms = [torch.randperm(B) for _ in range(self.hparams_["negative_sample_rate"])]
+        neg = torch.stack([item_emb[p.to(item_emb.device)] for p in neg_perms], dim=1)
+        return F.normalize(user_emb, p=2, dim=1), F.normalize(item_emb, p=2, dim=1), F.normalize(neg, p=2, dim=-1)
+
+    def infoNCE_loss(self, user_emb, pos_item_emb, neg_item_emb, temperature=0.1, mask=None):
+        pos = torch.sum(user_emb * pos_item_emb, dim=1) / temperature
+        neg = torch.bmm(user_emb.unsqueeze(1), neg_item_emb.permute(0, 2, 1)).squeeze(1) / temperature
+        logits = torch.cat([pos.unsqueeze(1), neg], dim=1)
+        labels = torch.zeros(user_emb.size(0), dtype=torch.long, device=user_emb.device)
+        losses = F.cross_entropy(logits, labels, reduction="none")
+        if mask is not None:
+            losses = losses * mask
+        return losses.mean()
+
+    def triplet_loss(self, user_emb, pos_item_emb, neg_item_emb, margin=1.0, mask=None):
+        n = neg_item_emb.size(1)
+        pos = torch.sum(user_emb * pos_item_emb, dim=1) * n
+        neg = torch.bmm(user_emb.unsqueeze(1), neg_item_emb.permute(0, 2, 1)).squeeze(1).sum(dim=1)
+        losses = F.relu(margin - pos + neg)
+        if mask is not None:
+            losses = losses * mask
+        return losses.mean()
+
+    def training_step(self, batch, batch_idx=0, neg_perms=None):
+        u, it, neg = self.forward(batch, neg_perms)
+        return self.infoNCE_loss(u, it, neg, mask=batch["label"][:, 1])
+
+    # ---- retrieval (on_train_epoch_end :230-254, hit_rate :209) ---------------------------------------
+    @torch.no_grad()
+    def build_item_index(self, item_batches, id_base=0):
+        """Item tower over the corpus (list of batches with the item features) -> normalised vectors -> index."""
+        embs = [ops.l2_normalize(self.item_tower(b)) for b in item_batches]
+        self.all_item_embeddings = torch.cat(embs, dim=0)
+        self.index = TopkIndex(self.all_item_embeddings, id_base=id_base)
+        return self.index
+
+    @torch.no_grad()
+    def retrieve(self, batch, k):
+        """(scores [B,k], corpus positions [B,k]) ordered by (inner product desc, id asc)."""
+        if self.index is None:
+            raise ValueError("Index not initialized. Call build_item_index first.")
+        return self.index.search(ops.l2_normalize(self.user_tower(batch)), k)
