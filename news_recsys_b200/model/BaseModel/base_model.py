@@ -78,7 +78,9 @@ class BaseModel(_Base):
         """base_model.py:141-166: one nn.Embedding(size, dim, padding_idx=0) per distinct table
         (fp32, N(0,1), row 0 zero).  Only `.weight` is used; the gather runs in K1."""
         tables = nn.ModuleDict()
-        for fname in self.sparse_feature_names.union(self.array_feature_names):
+        # sorted: the reference iterates a Python set here, whose order (hence the RNG draw order of the
+        # N(0,1) init and the ModuleDict order) changes from process to process; ranks must agree
+        for fname in sorted(self.sparse_feature_names.union(self.array_feature_names)):
             t = self._get_emb_feature_name(fname)
             if t in tables:
                 continue

@@ -166,11 +166,19 @@ class FusedTrainer:
 
     # ---- the step -------------------------------------------------------------------------------------
     def _step(self):
+        self._fwd_bwd()
+        self._update(self._plan_fb(), self._plan, self._gx)
+
+    def _plan_fb(self):
+        """Features whose occurrences the backward plan covers (the data-parallel trainer returns the global batch)."""
+        return self.fb
+
+    def _fwd_bwd(self):
         m, fb, lib = self.model, self.fb, self.lib
         main = torch.cuda.current_stream(self.dev)
         self.side.wait_stream(main)
         with torch.cuda.stream(self.side):  # sort plan: depends on the ids only -> overlaps the forward
-            plan = ops.BwdPlan(fb)
+            plan = ops.BwdPlan(self._plan_fb())
         L.check(lib.nrx_hparams_step(self.d_step.data_ptr(), self.d_hp.data_ptr(), self.lr, self.min_lr, self.milestones[0],
                                      self.milestones[1], self.betas[0], self.betas[1], self._sp()), "nrx_hparams_step")
         label = self.batch["label"][:, 0]
@@ -240,6 +248,13 @@ class FusedTrainer:
         if bias is not None:
             self._reduce(dl, 1.0, self.grad_views["score_fc.bias"])
         main.wait_stream(self.side)
+        self.prob = prob
+        self._plan = plan
+        self._gx = gx.contiguous()
+
+    def _update(self, fb, plan, gx):
+        """Optimizer: fused sparse-row AdamW on the tables (K3 apply) + dense AdamW on the flat buffer."""
+        lib = self.lib
         opt = L.NrxRowOpt()
         opt.lr, opt.beta1, opt.beta2, opt.eps, opt.weight_decay, opt.step = self.lr, self.betas[0], self.betas[1], self.eps, self.wd, 1
         for t in range(L.NRX_MAX_TABLES):
@@ -247,7 +262,6 @@ class FusedTrainer:
                 opt.m[t] = self.m_by_id[t].data_ptr()
                 opt.v[t] = self.v_by_id[t].data_ptr()
         opt.d_hparams = self.d_hp.data_ptr()
-        gx = gx.contiguous()
         L.check(lib.nrx_embed_bwd_apply(fb.arr, fb.n, fb.B, gx.data_ptr(), gx.stride(0), L.BWD_ADAMW, None,
                                         L.ptr_array(self.tables_by_id, L.NRX_MAX_TABLES), C.byref(opt), plan.ws.data_ptr(),
                                         plan.bytes, self._sp()), "nrx_embed_bwd_apply")
@@ -255,8 +269,6 @@ class FusedTrainer:
             L.check(lib.nrx_adamw_dense_dev(self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.flat_m.data_ptr(),
                                             self.flat_v.data_ptr(), self.n_dense, self.d_hp.data_ptr(), self.betas[0],
                                             self.betas[1], self.eps, self.wd, self._sp()), "nrx_adamw_dense_dev")
-        self.prob = prob
-        self._keep = (plan, gx)
 
     def _capture(self):
         # warm up on a side stream (lazy module/attribute initialisation must not happen inside capture)

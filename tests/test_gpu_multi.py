@@ -1,0 +1,95 @@
+"""-m gpu, needs >= 2 GPUs (skipped on a 1-GPU box; run with `gpurun --gpus 2`): data-parallel trainer on 2
+ranks == the single-GPU trainer on the concatenated batch, and sharded retrieval == one index."""
+import os
+import socket
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _dp_worker(rank, world, port, kind, out_dir):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import importlib
+    import torch.distributed as dist
+    from news_recsys_b200.parallel import DataParallelTrainer, ShardedTopk, shard_range
+    from news_recsys_b200.synthetic import mind_config, synth_batch
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    rows = {"user_id": 300, "item_id": 200, "category": 18, "subcategory": 70, "user_click_category": 18}
+    cfg = mind_config(kind, rows, history_len=6 if kind == "deep" else 0)
+    name = {"fm": "FM", "deep": "Deep", "deepfm": "DeepFM"}[kind]
+    cls = getattr(importlib.import_module(f"news_recsys_b200.model.sort.{kind}.model"), name)
+    torch.manual_seed(1)
+    model = cls(cfg).to(f"cuda:{rank}")
+    B = 128
+    tr = DataParallelTrainer(model, B, kind=kind)
+    for s in range(3):
+        full = synth_batch(cfg, B * world, seed=20 + s, label_p=0.5)
+        local = {k: v[rank * B:(rank + 1) * B] for k, v in full.items()}
+        tr.train_step(local)
+    torch.cuda.synchronize()
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    torch.save(sd, os.path.join(out_dir, f"dp_{kind}_{rank}.pt"))
+    # sharded retrieval
+    g = torch.Generator().manual_seed(0)
+    c = torch.nn.functional.normalize(torch.randn(30001, 64, generator=g), dim=1)
+    q = torch.nn.functional.normalize(torch.randn(21, 64, generator=g), dim=1)
+    lo, hi = shard_range(30001, rank, world)
+    st = ShardedTopk(c[lo:hi].cuda(), 30001)
+    s_, i_ = st.search(q.cuda(), 50)
+    torch.save((s_.cpu(), i_.cpu()), os.path.join(out_dir, f"topk_{rank}.pt"))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("kind", ["fm", "deepfm", "deep"])
+def test_dp2_equals_single_gpu(kind, tmp_path):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import importlib
+    import torch.multiprocessing as mp
+    from oracle import ref_path as R
+    from news_recsys_b200.synthetic import mind_config, synth_batch
+    from news_recsys_b200.trainer import FusedTrainer
+    mp.spawn(_dp_worker, args=(2, _free_port(), kind, str(tmp_path)), nprocs=2, join=True)
+    sd0 = torch.load(tmp_path / f"dp_{kind}_0.pt")
+    sd1 = torch.load(tmp_path / f"dp_{kind}_1.pt")
+    for k in sd0:
+        assert torch.equal(sd0[k], sd1[k]), f"replicas diverged on {k}"
+    # single GPU on the concatenated batches
+    rows = {"user_id": 300, "item_id": 200, "category": 18, "subcategory": 70, "user_click_category": 18}
+    cfg = mind_config(kind, rows, history_len=6 if kind == "deep" else 0)
+    name = {"fm": "FM", "deep": "Deep", "deepfm": "DeepFM"}[kind]
+    cls = getattr(importlib.import_module(f"news_recsys_b200.model.sort.{kind}.model"), name)
+    torch.manual_seed(1)
+    model = cls(cfg).cuda()
+    tr = FusedTrainer(model, 256, kind=kind)
+    for s in range(3):
+        tr.train_step(synth_batch(cfg, 256, seed=20 + s, label_p=0.5))
+    ref = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    for k in ref:
+        if k.startswith("embedding_tables.") and kind == "fm":
+            torch.testing.assert_close(sd0[k], ref[k], rtol=1e-5, atol=1e-6, msg=lambda m: f"{k}: {m}")
+        else:
+            upd, ref_upd = sd0[k] - ref[k], ref[k]
+            assert float(upd.abs().max()) <= 2.5e-3, f"{k}: {float(upd.abs().max())}"  # <= ~2 Adam steps of lr=1e-3
+    s0, i0 = torch.load(tmp_path / "topk_0.pt")
+    s1, i1 = torch.load(tmp_path / "topk_1.pt")
+    assert torch.equal(i0, i1)
+    g = torch.Generator().manual_seed(0)
+    c = torch.nn.functional.normalize(torch.randn(30001, 64, generator=g), dim=1)
+    q = torch.nn.functional.normalize(torch.randn(21, 64, generator=g), dim=1)
+    rs, ri = R.topk_ip(q, c, 50)
+    assert torch.equal(i0, ri)
