@@ -180,7 +180,7 @@ def profile_apis(trainer, pool, n=10):
         for i in range(n):
             trainer.load_blob(pool[i % len(pool)])
             torch.cuda.synchronize()
-            torch.cuda._sleep(int(6e6))  # ~3 ms blocker: everything below is queued before the GPU gets to it
+            torch.cuda._sleep(int(4e7))  # ~20 ms blocker: everything below is queued before the GPU gets to it
             c0 = L.launch_count
             trainer.step()
             per_step_launches = L.launch_count - c0
@@ -237,6 +237,96 @@ def algorithmic(kind, cfg, B):
     }
 
 
+def retrieval_leg(dev, world, rank, dist, quick):
+    """BASELINE config 4: DSSM top-100 over a synthetic 1M x 128 corpus (row-sharded across ranks), Q = 1024
+    L2-normalised queries per search.  queries/s = Q / (device time of one search incl. the shard merge)."""
+    from news_recsys_b200.parallel import ShardedTopk, shard_range
+    from news_recsys_b200.retrieval import TopkIndex
+    N, D, K, Q = 1_000_000, 128, 100, 1024
+    g = torch.Generator(device=dev).manual_seed(1234)  # identical stream on every rank: same corpus, same queries
+    lo, hi = shard_range(N, rank, world)
+    corpus = torch.empty((hi - lo, D), dtype=torch.float32, device=dev)
+    chunk = 125_000
+    for s in range(0, N, chunk):  # generate the global corpus in order, keep this rank's rows
+        blk = torch.nn.functional.normalize(torch.randn((min(chunk, N - s), D), generator=g, device=dev), dim=1)
+        a, b = max(s, lo), min(s + blk.shape[0], hi)
+        if a < b:
+            corpus[a - lo:b - lo] = blk[a - s:b - s]
+    n_q = 4
+    queries = [torch.nn.functional.normalize(torch.randn((Q, D), generator=g, device=dev), dim=1) for _ in range(n_q)]
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    if world > 1:
+        index = ShardedTopk(corpus, N)
+        search = lambda q: index.search(q, K)
+    else:
+        index = TopkIndex(corpus)
+        search = lambda q: index.search(q, K)
+    torch.cuda.synchronize()
+    build_s = time.perf_counter() - t0
+    for i in range(3):
+        search(queries[i % n_q])
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    iters = 3 if quick else 20
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(iters):
+        s_, i_ = search(queries[i % n_q])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    # status: how many queries needed the exact fallback scan (single-GPU index only)
+    fb = None
+    if world == 1:
+        _, _, st = index.search(queries[0], K, want_status=True)
+        fb = int(st.sum().item())
+    # end to end: pinned host queries -> H2D -> search -> D2H of (scores, ids)
+    hq = [q.cpu().pin_memory() for q in queries]
+    hs = torch.empty((Q, K), dtype=torch.float32).pin_memory()
+    hi_ = torch.empty((Q, K), dtype=torch.int64).pin_memory()
+    dq = torch.empty((Q, D), dtype=torch.float32, device=dev)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(iters):
+        dq.copy_(hq[i % n_q], non_blocking=True)
+        s_, i_ = search(dq)
+        hs.copy_(s_, non_blocking=True)
+        hi_.copy_(i_, non_blocking=True)
+        torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / iters
+    t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = float(t[0]), float(t[1])
+    if rank != 0:
+        return None
+    hbm_peak, tf_peak, peak_src = peaks()
+    flops = 2.0 * Q * N * D  # algorithmic: one inner product per (query, corpus row); the implementation scans twice
+    achieved = flops / (ms * 1e-3) / 1e12
+    out = {"metric": "DSSM top-100 retrieval queries/s (1M x 128 corpus)", "value": Q / (ms * 1e-3), "unit": "queries/s",
+           "ms_per_search": ms, "scaling": "strong (corpus sharded N/G per GPU)",
+           "config": {"workload": "cfg4: N=1,000,000 x D=128 L2-normalised, k=100, Q=1024 per search", "shards": world,
+                      "ordering": "(fp64 inner product desc, id asc), bit-exact vs oracle"},
+           "e2e": {"value": Q / (e2e_ms * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": Q * D * 4, "d2h_bytes_per_step": Q * K * 12},
+           "index_build_s": build_s, "fallback_queries": fb,
+           "roofline": {"bound": "tensor", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
+                        "traffic": None, "kernel": "nrx_topk_search (2 x topk_scan + theta + final)", "peak_source": peak_src,
+                        "algorithmic_per_launch": flops}}
+    if world == 1 and not quick:
+        from oracle import ref_path as R
+        cq = queries[0][:32].cpu()
+        cc = corpus.cpu()
+        torch.set_num_threads(os.cpu_count() or 1)
+        t0 = time.perf_counter()
+        R.topk_ip(cq, cc, K, chunk=32)
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": 32 / dt, "unit": "queries/s", "cores": torch.get_num_threads(), "kind": "port",
+                               "sample": "32 queries against the full 1M x 128 corpus (oracle/ref_path.py topk_ip: fp64 scores + stable sort)"}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -245,6 +335,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="deepfm")
     ap.add_argument("--cpu-steps", type=int, default=0, help="override the CPU arm's step count")
+    ap.add_argument("--no-retrieval", action="store_true", help="skip the DSSM top-100 retrieval leg (BASELINE config 4)")
     ap.add_argument("--quick", action="store_true",
                     help="profiler mode: skip the clock-sampling load loop, shorten the per-API pass and the CPU arm")
     args = ap.parse_args()
@@ -279,7 +370,8 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     torch.manual_seed(42)  # same init on every rank (replicated parameters)
     model = model_class(kind)(cfg).to(dev)
     if world > 1:
@@ -289,7 +381,7 @@ def main():
         trainer = FusedTrainer(model, B, kind=kind)
     # batch pools: device pool > L2 (126 MB) so consecutive steps never find their inputs in L2
     blob_bytes = trainer.layout.nbytes
-    n_pool = max(8, int(160e6 // blob_bytes) + 1)
+    n_pool = 8 if args.quick else max(8, int(160e6 // blob_bytes) + 1)  # --quick (profiler runs): few setup kernels
     host_pool = []
     for i in range(8):
         hb = torch.empty(blob_bytes, dtype=torch.uint8).pin_memory()
@@ -331,23 +423,27 @@ def main():
     ms = e0.elapsed_time(e1)
     final_loss = float(trainer.loss.item())
     clk = {}
+    windows, src = [(w0, w1)], "timed region"
+    # If the timed region is shorter than the sampler period, keep the identical load running for ~1.5 s right
+    # after it and sample the clocks there (NOT timed, does not enter `value`).  Every rank runs the same number
+    # of extra steps (the steps contain collectives), decided from rank 0's measurement.
+    n_extra = torch.tensor([0 if (args.quick or ms >= 1000.0) else int(1500.0 / max(ms / args.steps, 1e-3))],
+                           dtype=torch.int64, device=dev)
+    if dist is not None:
+        dist.broadcast(n_extra, src=0)
+    n_extra = int(n_extra.item())
+    if n_extra > 0:
+        snap = trainer._snapshot()
+        for i in range(n_extra):
+            trainer.load_blob(pool[i % n_pool])
+            trainer.step()
+            if i % 64 == 63:
+                torch.cuda.synchronize()
+        torch.cuda.synchronize()
+        windows, src = [(w0, time.time())], "timed region + the same loop repeated for ~1.5 s right after it"
+        trainer._restore(snap)
+    barrier()
     if clocks:
-        windows, src = [(w0, w1)], "timed region"
-        if w1 - w0 < 1.0 and not args.quick:
-            # the timed region is shorter than the sampler period: keep the identical load running for ~1.5 s
-            # right after it and sample there (this loop is NOT timed and does not enter `value`)
-            snap = trainer._snapshot()
-            x0 = time.time()
-            i = 0
-            while time.time() - x0 < 1.5:
-                trainer.load_blob(pool[i % n_pool])
-                trainer.step()
-                i += 1
-                if i % 64 == 0:
-                    torch.cuda.synchronize()
-            torch.cuda.synchronize()
-            windows, src = [(w0, time.time())], "timed region + the same loop repeated for 1.5 s right after it"
-            trainer._restore(snap)
         clk = clocks.stop(windows)
         clk["source"] = src
     # ---- end to end from pinned host memory ----------------------------------------------------------------
@@ -367,6 +463,9 @@ def main():
     if dist is not None:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
     ms, e2e_ms = float(tms[0]), float(tms[1])
+    retrieval = None
+    if args.workload == "deepfm" and not args.no_retrieval:
+        retrieval = retrieval_leg(dev, world, rank, dist, args.quick)
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -374,7 +473,13 @@ def main():
 
     value = world * B * args.steps / (ms * 1e-3)
     e2e_v = world * B * e_steps / (e2e_ms * 1e-3)
-    per_api, launches_per_step = profile_apis(trainer, pool, n=2 if args.quick else 10)
+    prof_trainer = trainer
+    if world > 1:
+        # per-kernel timing must not issue collectives from rank 0 alone: time the same per-GPU kernels on a
+        # private single-GPU trainer (same model class / config / batch size)
+        torch.manual_seed(42)
+        prof_trainer = FusedTrainer(model_class(kind)(cfg).to(dev), B, kind=kind)
+    per_api, launches_per_step = profile_apis(prof_trainer, pool, n=2 if args.quick else 10)
     alg = algorithmic(kind, cfg, B)
     hbm_peak, tf_peak, peak_src = peaks()
     dom = max(per_api, key=lambda k: per_api[k])
@@ -398,7 +503,12 @@ def main():
         breakdown[k] = {"us_per_step": round(us, 2), "bound": b_, "achieved": round(a_, 1),
                         "frac": round(a_ / (hbm_peak if b_ == "hbm" else tf_peak), 4)}
     cpu_steps = args.cpu_steps or (1 if args.quick else 20)
-    cv, cms, cores = cpu_arm(kind, cfg, B, cpu_steps, 2)
+    cpu_base = None
+    if world == 1:  # the CPU arm is timed on rank 0 at N = 1 only
+        cv, cms, cores = cpu_arm(kind, cfg, B, cpu_steps, 2)
+        cpu_base = {"value": cv, "unit": UNIT, "cores": cores, "kind": "port",
+                    "sample": f"{cpu_steps} full steps of B={B} (oracle/ref_path.py, torch CPU, fwd+bce+bwd+AdamW)",
+                    "ms_per_step": cms}
     line = {
         "metric": metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
@@ -415,11 +525,11 @@ def main():
         "launches_per_step": launches_per_step,
         "roofline": roof,
         "kernels": breakdown,
-        "cpu_baseline": {"value": cv, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{cpu_steps} full steps of B={B} (oracle/ref_path.py, torch CPU, fwd+bce+bwd+AdamW)",
-                         "ms_per_step": cms},
+        "cpu_baseline": cpu_base,
         "final_loss": final_loss,
     }
+    if retrieval is not None:
+        line["retrieval"] = retrieval
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
