@@ -20,7 +20,7 @@
 
 namespace nrx {
 
-static constexpr int kTile = 64;  // sorted occurrences per warp in phase A
+static constexpr int kTile = 32;  // sorted occurrences per warp in phase A (lane = occurrence)
 
 struct DTables {
   float* g[NRX_MAX_TABLES];   // dense grads
@@ -39,7 +39,7 @@ struct PlanLayout {
   size_t keys_in, vals_in, keys_out, vals_out, head, tail, cub, total;
   size_t cub_bytes;
   long long n_tiles;
-  int row_bits, key_bits, nc;
+  int row_bits, key_bits, nc, dp;  // dp: floats per tile partial (max dim rounded up to 4)
 };
 
 static int plan_layout(const DFeats& d, PlanLayout* L) {
@@ -64,7 +64,8 @@ static int plan_layout(const DFeats& d, PlanLayout* L) {
   L->vals_in = off;  off += al(n * 4);
   L->keys_out = off; off += al(n * 4);
   L->vals_out = off; off += al(n * 4);
-  const size_t part = al((size_t)L->n_tiles * 32 * L->nc * 4);
+  L->dp = (d.max_dim + 3) & ~3;
+  const size_t part = al((size_t)L->n_tiles * L->dp * 4);
   L->head = off; off += part;
   L->tail = off; off += part;
   size_t cub_bytes = 0;
@@ -128,130 +129,174 @@ __device__ __forceinline__ void finalize_row(const DTables& T, uint32_t key, con
   }
 }
 
-// Phase A.
-template <int NC>
+// Lane-per-run finalisation of CW consecutive columns starting at c0 (values in registers).
+template <int CW>
+__device__ __forceinline__ void finalize_cols(const DTables& T, uint32_t key, const float (&g)[CW], int c0) {
+  const int t = (int)(key >> T.row_bits);
+  const long long row = (long long)(key & ((1u << T.row_bits) - 1u));
+  const int dim = T.dim[t];
+  if (c0 >= dim) return;
+  const long long base = row * T.stride[t] + c0;
+  const float lr = T.d_hp ? __ldg(T.d_hp) : T.lr;
+  const float bc1 = T.d_hp ? __ldg(T.d_hp + 1) : T.bc1;
+  const float bc2s = T.d_hp ? __ldg(T.d_hp + 2) : T.bc2_sqrt;
+  if (T.mode == NRX_BWD_DENSE) {
+    float* dst = T.g[t] + base;
+#pragma unroll
+    for (int j = 0; j < CW; ++j)
+      if (c0 + j < dim) dst[j] = g[j];
+    return;
+  }
+  float* pw = T.w[t] + base;
+  if (T.mode == NRX_BWD_SGD) {
+    float p[CW];
+#pragma unroll
+    for (int j = 0; j < CW; ++j) p[j] = (c0 + j < dim) ? pw[j] : 0.f;
+#pragma unroll
+    for (int j = 0; j < CW; ++j)
+      if (c0 + j < dim) pw[j] = p[j] - lr * (g[j] + T.wd * p[j]);
+    return;
+  }
+  float* pm = T.m[t] + base;
+  float* pv = T.v[t] + base;
+  float p[CW], m[CW], v[CW];
+#pragma unroll
+  for (int j = 0; j < CW; ++j) {  // all loads first: one round trip per run instead of one per column
+    const bool ok = c0 + j < dim;
+    p[j] = ok ? pw[j] : 0.f;
+    m[j] = ok ? pm[j] : 0.f;
+    v[j] = ok ? pv[j] : 0.f;
+  }
+#pragma unroll
+  for (int j = 0; j < CW; ++j) {
+    if (c0 + j < dim) {  // torch.optim.AdamW update rule on the touched row
+      float pj = p[j] * (1.f - lr * T.wd);
+      const float mj = T.beta1 * m[j] + (1.f - T.beta1) * g[j];
+      const float vj = T.beta2 * v[j] + (1.f - T.beta2) * g[j] * g[j];
+      pj -= (lr / bc1) * (mj / (sqrtf(vj) / bc2s + T.eps));
+      pw[j] = pj; pm[j] = mj; pv[j] = vj;
+    }
+  }
+}
+
+// Phase A: one warp per tile of 32 sorted occurrences, LANE = OCCURRENCE.  Each lane loads its occurrence's
+// gradient row (CW columns per pass) into registers, a segmented inclusive scan over the lanes (fixed
+// shuffle tree => reproducible) leaves each run's total in the run's last lane, and all run-ends of the
+// tile finalise their rows concurrently.  Runs touching a tile border leave a head / tail partial.
+template <int CW>
 __global__ void __launch_bounds__(128)
 segment_reduce_kernel(const __grid_constant__ DFeats P, const __grid_constant__ DTables T,
                       const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
                       const float* __restrict__ grad, long long gld, long long n_occ, uint32_t sentinel,
-                      float* __restrict__ head, float* __restrict__ tail) {
+                      float* __restrict__ head, float* __restrict__ tail, int DP, int max_dim) {
   const long long tile = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const long long ts = tile * kTile;
   if (ts >= n_occ) return;
   const long long te = min(ts + (long long)kTile, n_occ);
-  const uint32_t prev_key = ts > 0 ? keys[ts - 1] : 0xffffffffu;
-  const uint32_t next_key = te < n_occ ? keys[te] : 0xffffffffu;
+  const int n = (int)(te - ts);
+  const bool valid = lane < n;
+  const uint32_t my_key = valid ? __ldg(keys + ts + lane) : 0xffffffffu;
+  const uint32_t prev_key = ts > 0 ? __ldg(keys + ts - 1) : 0xffffffffu;
+  const uint32_t next_key = te < n_occ ? __ldg(keys + te) : 0xfffffffeu;
+  uint32_t k_up = __shfl_up_sync(NRX_FULL_MASK, my_key, 1);
+  uint32_t k_dn = __shfl_down_sync(NRX_FULL_MASK, my_key, 1);
+  const bool is_head = (lane == 0) || (my_key != k_up);
+  const bool is_end = valid && (lane == n - 1 || k_dn != my_key);
+  const unsigned heads = __ballot_sync(NRX_FULL_MASK, is_head);
+  const int start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));  // first lane of my run
+  const uint32_t k0 = __shfl_sync(NRX_FULL_MASK, my_key, 0);
+  const bool from_prev = (start == 0) && (k0 == prev_key);
+  const bool to_next = is_end && (lane == n - 1) && (my_key == next_key);
+  const bool live = valid && my_key != sentinel;
 
-  float acc[NC];
+  long long off = 0;
+  float scale = 0.f;
+  int dim = 0;
+  if (live) {
+    const long long p = __ldg(vals + ts + lane);
+    int f = 0;
+    for (int q = 1; q < P.n; ++q)
+      if (p >= P.f[q].occ_off) f = q;
+    const DFeat& F = P.f[f];
+    const long long r = p - F.occ_off;
+    const long long b = (F.L == 1) ? r : r / F.L;
+    off = b * gld + F.out_col;
+    dim = F.dim;
+    if (F.pool == NRX_POOL_NONE) scale = 1.f;
+    else if (F.pool == NRX_POOL_MEAN) scale = 1.f / (float)F.L;
+    else scale = __ldg(F.mask + r) * __ldg(F.inv_den + b);
+  }
+  for (int c0 = 0; c0 < max_dim; c0 += CW) {
+    float v[CW];
 #pragma unroll
-  for (int k = 0; k < NC; ++k) acc[k] = 0.f;
-  uint32_t run_key = 0xffffffffu;
-  bool run_from_prev = false;
-
-  for (long long i0 = ts; i0 < te; i0 += 32) {
-    // lane-private decode of occurrence i0+lane
-    const long long i = i0 + lane;
-    uint32_t my_key = sentinel;
-    long long my_off = 0;
-    float my_scale = 0.f;
-    int my_dim = 0;
-    if (i < te) {
-      my_key = keys[i];
-      if (my_key != sentinel) {
-        const long long p = vals[i];
-        int f = 0;
-        for (int q = 1; q < P.n; ++q)
-          if (p >= P.f[q].occ_off) f = q;
-        const DFeat& F = P.f[f];
-        const long long r = p - F.occ_off;
-        const long long b = (F.L == 1) ? r : r / F.L;
-        my_off = b * gld + F.out_col;
-        my_dim = F.dim;
-        if (F.pool == NRX_POOL_NONE) my_scale = 1.f;
-        else if (F.pool == NRX_POOL_MEAN) my_scale = 1.f / (float)F.L;
-        else my_scale = __ldg(F.mask + r) * __ldg(F.inv_den + b);
+    for (int j = 0; j < CW; ++j) v[j] = (live && c0 + j < dim) ? scale * __ldg(grad + off + c0 + j) : 0.f;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const bool take = lane - d >= start;
+#pragma unroll
+      for (int j = 0; j < CW; ++j) {
+        const float up = __shfl_up_sync(NRX_FULL_MASK, v[j], d);
+        if (take) v[j] += up;
       }
     }
-    const int n = (int)min(32ll, te - i0);
-    for (int j0 = 0; j0 < n; j0 += 8) {
-      float g[8][NC];
-      uint32_t kj[8];
+    if (is_end && live) {
+      if (!from_prev && !to_next) {
+        finalize_cols<CW>(T, my_key, v, c0);
+      } else {
+        float* dst = (from_prev ? head : tail) + tile * DP + c0;
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int j = j0 + u;  // j < 32 always
-        kj[u] = __shfl_sync(NRX_FULL_MASK, my_key, j);
-        const long long off = __shfl_sync(NRX_FULL_MASK, my_off, j);
-        const float sc = __shfl_sync(NRX_FULL_MASK, my_scale, j);
-        const int dm = __shfl_sync(NRX_FULL_MASK, my_dim, j);
-#pragma unroll
-        for (int k = 0; k < NC; ++k) {
-          const int c = lane + 32 * k;
-          g[u][k] = (j < n && kj[u] != sentinel && c < dm) ? sc * __ldg(grad + off + c) : 0.f;
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int j = j0 + u;
-        if (j >= n) break;
-        const uint32_t k_cur = kj[u];
-        const long long pos = i0 + j;
-        if (k_cur != run_key) {  // a new run starts at pos
-          run_key = k_cur;
-          run_from_prev = (pos == ts) && (k_cur == prev_key);
-#pragma unroll
-          for (int k = 0; k < NC; ++k) acc[k] = 0.f;
-        }
-#pragma unroll
-        for (int k = 0; k < NC; ++k) acc[k] += g[u][k];
-        // does the run end at pos?
-        uint32_t k_next;
-        if (pos + 1 < te) k_next = (j + 1 < 32) ? __shfl_sync(NRX_FULL_MASK, my_key, (j + 1) & 31) : keys[pos + 1];
-        else k_next = 0xfffffffeu;  // forces "ends here" handling below
-        const bool last_in_tile = (pos + 1 == te);
-        if (last_in_tile || k_next != k_cur) {
-          if (k_cur != sentinel) {
-            const bool to_next = last_in_tile && (k_cur == next_key);
-            if (!run_from_prev && !to_next) {
-              finalize_row<NC>(T, k_cur, acc, lane);
-            } else {
-              float* dst = (run_from_prev ? head : tail) + (tile * 32 + lane) * NC;
-#pragma unroll
-              for (int k = 0; k < NC; ++k) dst[k] = acc[k];
-            }
-          }
-          run_key = 0xffffffffu;  // next element opens a new run
-        }
+        for (int j = 0; j < CW; ++j)
+          if (c0 + j < DP) dst[j] = v[j];
       }
     }
   }
 }
 
-// Phase B: tile `t` owns a run iff its last run starts in t and continues into t+1.
+// Phase B: tile `t` owns a run iff its last run starts in t and continues into t+1.  The owner warp first
+// finds how many following tiles the run covers (lanes test 32 tile-leading keys per round trip), then
+// sums the partials in tile order with lanes on columns.
 template <int NC>
 __global__ void __launch_bounds__(128)
 segment_fixup_kernel(const __grid_constant__ DTables T, const uint32_t* __restrict__ keys, long long n_occ,
                      long long n_tiles, uint32_t sentinel, const float* __restrict__ head,
-                     const float* __restrict__ tail) {
+                     const float* __restrict__ tail, int DP) {
   const long long t = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (t + 1 >= n_tiles) return;
   const long long ts = t * kTile, te = ts + kTile;  // full tile (not the last one)
-  const uint32_t K = keys[te - 1];
-  if (K == sentinel || keys[te] != K) return;                       // does not continue
-  const bool started_here = (keys[ts] != K) || ts == 0 || keys[ts - 1] != K;
+  const uint32_t K = __ldg(keys + te - 1);
+  if (K == sentinel || __ldg(keys + te) != K) return;               // does not continue
+  const bool started_here = (__ldg(keys + ts) != K) || ts == 0 || __ldg(keys + ts - 1) != K;
   if (!started_here) return;                                        // an earlier tile owns it
-  float acc[NC];
-  const float* src = tail + (t * 32 + lane) * NC;
-#pragma unroll
-  for (int k = 0; k < NC; ++k) acc[k] = src[k];
-  for (long long u = t + 1; u < n_tiles && keys[u * kTile] == K; ++u) {
-    const float* h = head + (u * 32 + lane) * NC;
-#pragma unroll
-    for (int k = 0; k < NC; ++k) acc[k] += h[k];
-    const long long ue = min((u + 1) * (long long)kTile, n_occ);
-    if (keys[ue - 1] != K) break;  // run ended inside tile u
+  long long cont = 0;  // number of following tiles whose first key is K
+  for (long long u0 = t + 1; u0 < n_tiles; u0 += 32) {
+    const long long u = u0 + lane;
+    const bool match = (u < n_tiles) && (__ldg(keys + u * kTile) == K);
+    const unsigned mm = __ballot_sync(NRX_FULL_MASK, match);
+    if (mm == 0xffffffffu) { cont += 32; continue; }
+    cont += __ffs(~mm) - 1;
+    break;
   }
+  float acc[NC];
+#pragma unroll
+  for (int k = 0; k < NC; ++k) { const int c = lane + 32 * k; acc[k] = c < DP ? tail[t * DP + c] : 0.f; }
+  long long u = t + 1;
+  const long long uend = t + 1 + cont;
+  for (; u + 8 <= uend; u += 8) {
+    float h[8][NC];
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+#pragma unroll
+      for (int k = 0; k < NC; ++k) { const int c = lane + 32 * k; h[q][k] = c < DP ? __ldg(head + (u + q) * DP + c) : 0.f; }
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+#pragma unroll
+      for (int k = 0; k < NC; ++k) acc[k] += h[q][k];
+  }
+  for (; u < uend; ++u)
+#pragma unroll
+    for (int k = 0; k < NC; ++k) { const int c = lane + 32 * k; if (c < DP) acc[k] += __ldg(head + u * DP + c); }
   finalize_row<NC>(T, K, acc, lane);
 }
 
@@ -265,11 +310,14 @@ static int launch_apply(const DFeats& d, const DTables& T, const PlanLayout& L, 
   float* tail = (float*)(ws + L.tail);
   const int wpb = 4;
   const unsigned blocks = (unsigned)((L.n_tiles + wpb - 1) / wpb);
-  segment_reduce_kernel<NC><<<blocks, wpb * 32, 0, st>>>(d, T, keys, vals, grad, gld, d.n_occ, sentinel, head, tail);
+  if (d.max_dim <= 16)
+    segment_reduce_kernel<16><<<blocks, wpb * 32, 0, st>>>(d, T, keys, vals, grad, gld, d.n_occ, sentinel, head, tail, L.dp, d.max_dim);
+  else
+    segment_reduce_kernel<32><<<blocks, wpb * 32, 0, st>>>(d, T, keys, vals, grad, gld, d.n_occ, sentinel, head, tail, L.dp, d.max_dim);
   int rc = check_launch("segment_reduce");
   if (rc != NRX_OK) return rc;
   if (L.n_tiles > 1) {
-    segment_fixup_kernel<NC><<<blocks, wpb * 32, 0, st>>>(T, keys, d.n_occ, L.n_tiles, sentinel, head, tail);
+    segment_fixup_kernel<NC><<<blocks, wpb * 32, 0, st>>>(T, keys, d.n_occ, L.n_tiles, sentinel, head, tail, L.dp);
     rc = check_launch("segment_fixup");
   }
   return rc;

@@ -33,16 +33,22 @@ field_logit_fwd_kernel(const float* __restrict__ x, long long ld, long long B, c
   if (F.mode == NRX_FIELD_FM) {
     float S[4] = {0.f, 0.f, 0.f, 0.f};
     float sq = 0.f;
-    for (int f = 0; f < F.n; ++f) {
+    for (int f0 = 0; f0 < F.n; f0 += 8) {  // 8 fields per round: all loads issued before any use
+      float v[8][4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int d = lane + 32 * k;
-        if (d < F.dim[f]) {
-          const float v = __ldg(xr + F.col[f] + d);
-          if (d == 0) first += v;
-          else { S[k] += v; sq = fmaf(v, v, sq); }
+      for (int u = 0; u < 8; ++u)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int d = lane + 32 * k;
+          v[u][k] = (f0 + u < F.n && d < F.dim[f0 + u]) ? __ldg(xr + F.col[f0 + u] + d) : 0.f;
         }
-      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (lane + 32 * k == 0) first += v[u][k];
+          else { S[k] += v[u][k]; sq = fmaf(v[u][k], v[u][k], sq); }
+        }
     }
     second = 0.5f * (S[0] * S[0] + S[1] * S[1] + S[2] * S[2] + S[3] * S[3] - sq);
   } else if (F.mode == NRX_FIELD_WIDE) {
@@ -66,6 +72,31 @@ field_logit_bwd_kernel(const float* __restrict__ x, long long ld, long long B, c
   const float g = __ldg(dlogit + b);
   if (F.mode == NRX_FIELD_FM) {
     float S[4] = {0.f, 0.f, 0.f, 0.f};
+    if (F.n <= 8) {  // common case: keep every field's values in registers (one round of loads)
+      float v[8][4], o[8][4];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int d = lane + 32 * k;
+          const bool ok = u < F.n && d < F.dim[u];
+          v[u][k] = ok ? __ldg(xr + F.col[u] + d) : 0.f;
+          o[u][k] = (ok && accumulate) ? gr[F.col[u] + d] : 0.f;
+        }
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (lane + 32 * k > 0) S[k] += v[u][k];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int d = lane + 32 * k;
+          if (u < F.n && d < F.dim[u]) gr[F.col[u] + d] = o[u][k] + ((d == 0) ? g : g * (S[k] - v[u][k]));
+        }
+      return;
+    }
     for (int f = 0; f < F.n; ++f) {
 #pragma unroll
       for (int k = 0; k < 4; ++k) {

@@ -25,7 +25,9 @@ namespace nrx {
 using namespace umma;
 
 static constexpr int kRows = 128;        // rows per tile == UMMA M
-static constexpr int kFwdThreads = 256;  // 8 warps: TMEM lane quadrant = warp % 4, column half = warp / 4
+static constexpr int kFwdThreads = 512;  // 16 warps: TMEM lane quadrant = warp % 4, column slice = warp / 4
+static constexpr int kColSplit = kFwdThreads / 128;
+static constexpr int kBiasStride = 256;   // floats of shared memory per layer bias
 static constexpr int kMaxTiny = 4;
 
 struct TowerK {
@@ -110,11 +112,14 @@ static int make_tower(const NrxTower* t, long long B, int training, TowerK* k) {
 // ---- weight packing: fp32 [N,K] -> bf16 canonical images of W (B operand of fwd) and W^T (B operand of dX) ----
 __global__ void __launch_bounds__(256)
 tower_pack_kernel(const __grid_constant__ TowerK T, uint8_t* __restrict__ wpack, uint8_t* __restrict__ wtpack) {
-  for (int l = 0; l < T.n_mma; ++l) {
+  int grand = 0;
+  for (int l = 0; l < T.n_mma; ++l) grand += (T.Kp[l] / 8) * T.Np[l];
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < grand; e += gridDim.x * blockDim.x) {
+    int l = 0, i = e;  // flat chunk index over all layers -> (layer, chunk)
+    while (i >= (T.Kp[l] / 8) * T.Np[l]) { i -= (T.Kp[l] / 8) * T.Np[l]; ++l; }
     const int Kp = T.Kp[l], Np = T.Np[l], K = T.K[l], N = T.N[l];
     const float* W = T.w[l];
-    const int nchunk = (Kp / 8) * Np;  // == (Np / 8) * Kp
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nchunk; i += gridDim.x * blockDim.x) {
+    {
       {  // W image: chunk (kc, n) = W[n][kc*8 .. +7]
         const int n = i % Np, kc = i / Np;
         uint32_t p[4];
@@ -166,7 +171,8 @@ tower_fwd_kernel(const __grid_constant__ TowerK T, const float* __restrict__ x, 
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sW = smem;
   uint8_t* sA = smem + ((T.w_bytes + 1023) & ~1023u);
-  float* xch = reinterpret_cast<float*>(sA + (size_t)kRows * T.max_kp * 2);  // [2][128][kMaxTiny]
+  float* xch = reinterpret_cast<float*>(sA + (size_t)kRows * T.max_kp * 2);  // [kColSplit][128][kMaxTiny]
+  float* sB = xch + kColSplit * kRows * kMaxTiny;                             // [n_mma][kBiasStride] biases (zero padded)
   __shared__ uint64_t wbar, mbar;
   __shared__ uint32_t tmem_s;
 
@@ -180,6 +186,8 @@ tower_fwd_kernel(const __grid_constant__ TowerK T, const float* __restrict__ x, 
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(&tmem_s, (uint32_t)T.tmem_cols);
+  for (int l = 0; l < T.n_mma; ++l)
+    for (int i = tid; i < kBiasStride; i += kFwdThreads) sB[l * kBiasStride + i] = i < T.N[l] ? __ldg(T.bias[l] + i) : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -244,15 +252,15 @@ tower_fwd_kernel(const __grid_constant__ TowerK T, const float* __restrict__ x, 
       const bool feeds_tiny = T.tiny && (l == T.n_mma - 1);
       const long long row = row0 + r;
       uint8_t* img = (training && l + 1 < T.n_layers) ? ws + T.act_off[l + 1] + (size_t)tile * Np * kRows * 2 : nullptr;
-      for (int g = h; g < Np / 16; g += 2) {
+      for (int g = h; g < Np / 16; g += kColSplit) {
         float v[16];
         tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)g * 16u, v);
         tmem_ld_wait();
-        const float* bp = T.bias[l] + g * 16;
+        const float* bp = sB + l * kBiasStride + g * 16;
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const int col = g * 16 + j;
-          float z = v[j] + (col < N ? __ldg(bp + j) : 0.f);
+          float z = v[j] + bp[j];
           if (!is_final) z = bf16_round(act_fwd(z, T.slope));
           v[j] = z;
         }
@@ -300,7 +308,12 @@ tower_fwd_kernel(const __grid_constant__ TowerK T, const float* __restrict__ x, 
       const int Nt = T.N[T.n_layers - 1];
       if (row < B) {
         for (int o = 0; o < Nt; ++o)
-          y[row * ldy + o] = xch[r * kMaxTiny + o] + xch[(kRows + r) * kMaxTiny + o] + __ldg(T.bias[T.n_layers - 1] + o);
+        {
+          float t = 0.f;
+#pragma unroll
+          for (int hh = 0; hh < kColSplit; ++hh) t += xch[(hh * kRows + r) * kMaxTiny + o];
+          y[row * ldy + o] = t + __ldg(T.bias[T.n_layers - 1] + o);
+        }
       }
     }
     if (T.tiny) __syncthreads();  // xch is reused by the next tile
@@ -379,7 +392,7 @@ tower_bwd_dx_kernel(const __grid_constant__ TowerK T, long long B, const float* 
         }
       }
       const uint8_t* aimg = T.tiny ? ws + T.act_off[L - 1] + (size_t)tile * Np * kRows * 2 : nullptr;
-      for (int g16 = h; g16 < Np / 16; g16 += 2) {
+      for (int g16 = h; g16 < Np / 16; g16 += kColSplit) {
         float v[16];
         if (T.tiny) {  // da = g (x) w_tiny, dz = da * act'(a)
           const int Kt = T.K[L - 1], Nt = T.N[L - 1];
@@ -428,7 +441,7 @@ tower_bwd_dx_kernel(const __grid_constant__ TowerK T, long long B, const float* 
       tc_fence_after();
       const uint8_t* aimg = l > 0 ? ws + T.act_off[l] + (size_t)tile * Kp * kRows * 2 : nullptr;
       uint8_t* dzimg = l > 0 ? ws + T.dz_off[l - 1] + (size_t)tile * Kp * kRows * 2 : nullptr;
-      for (int g16 = h; g16 < Kp / 16; g16 += 2) {
+      for (int g16 = h; g16 < Kp / 16; g16 += kColSplit) {
         float v[16];
         tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)g16 * 16u, v);
         tmem_ld_wait();
@@ -507,7 +520,9 @@ tower_bwd_dw_kernel(const __grid_constant__ TowerK T, const uint8_t* __restrict_
   bool stage_used[kDwStages] = {false, false};
   float* mypart = partials + (long long)blockIdx.x * T.part_stride;
 
-  for (int l = 0; l < T.n_layers; ++l) {
+  // layers are a grid dimension: CTA (x, y) reduces tile range x of layer y (5x more CTAs in flight than
+  // walking the layers inside one CTA)
+  for (int l = blockIdx.y; l < T.n_layers; l += gridDim.y) {
     const int Np = T.Np[l], Kp = T.Kp[l], N = T.N[l];
     const int ncols = Kp + 16;
     // ---- per-layer stage setup: zero the unused M columns, place the ones chunk pair after the a image ----
@@ -579,28 +594,32 @@ tower_bwd_dw_kernel(const __grid_constant__ TowerK T, const uint8_t* __restrict_
 __device__ __forceinline__ void
 tower_bwd_reduce_body(const TowerK& T, const float* __restrict__ partials, int n_parts, long long tiles_per_part,
                       float* const* gw, float* const* gb) {
-  for (int l = 0; l < T.n_layers; ++l) {
-    const int ncols = T.Kp[l] + 16, K = T.K[l], N = T.N[l];
-    const long long total = (long long)N * (K + 1);
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-      const int n = (int)(i / (K + 1)), k = (int)(i % (K + 1));
-      const int col = (k < K) ? k : T.Kp[l];
-      const float* p = partials + T.part_layer_off[l] + (long long)n * ncols + col;
-      // CTAs past the last tile wrote nothing; the sum order over the live ones is fixed (c ascending)
-      const int live = (int)min((long long)n_parts, (T.n_tiles + tiles_per_part - 1) / tiles_per_part);
-      float s = 0.f;
-      int c = 0;
-      for (; c + 8 <= live; c += 8) {  // 8 independent loads in flight, added in order
-        float v[8];
+  // one flat index space over all layers: every thread owns one output element, so the (latency-bound)
+  // partial loads of all layers are in flight together instead of layer after layer
+  long long grand = 0;
+  for (int l = 0; l < T.n_layers; ++l) grand += (long long)T.N[l] * (T.K[l] + 1);
+  // CTAs past the last tile wrote nothing; the sum order over the live ones is fixed (c ascending)
+  const int live = (int)min((long long)n_parts, (T.n_tiles + tiles_per_part - 1) / tiles_per_part);
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < grand; e += (long long)gridDim.x * blockDim.x) {
+    int l = 0;
+    long long i = e;
+    while (i >= (long long)T.N[l] * (T.K[l] + 1)) { i -= (long long)T.N[l] * (T.K[l] + 1); ++l; }
+    const int ncols = T.Kp[l] + 16, K = T.K[l];
+    const int n = (int)(i / (K + 1)), k = (int)(i % (K + 1));
+    const int col = (k < K) ? k : T.Kp[l];
+    const float* p = partials + T.part_layer_off[l] + (long long)n * ncols + col;
+    float s = 0.f;
+    int c = 0;
+    for (; c + 16 <= live; c += 16) {  // 16 independent loads in flight, added in order
+      float v[16];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = __ldg(p + (long long)(c + u) * T.part_stride);
+      for (int u = 0; u < 16; ++u) v[u] = __ldg(p + (long long)(c + u) * T.part_stride);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) s += v[u];
-      }
-      for (; c < live; ++c) s += __ldg(p + (long long)c * T.part_stride);
-      if (k < K) { if (gw[l]) gw[l][(long long)n * K + k] = s; }
-      else if (gb[l]) gb[l][n] = s;
+      for (int u = 0; u < 16; ++u) s += v[u];
     }
+    for (; c < live; ++c) s += __ldg(p + (long long)c * T.part_stride);
+    if (k < K) { if (gw[l]) gw[l][(long long)n * K + k] = s; }
+    else if (gb[l]) gb[l][n] = s;
   }
 }
 
@@ -613,7 +632,8 @@ tower_bwd_reduce_entry(const __grid_constant__ TowerK T, const float* __restrict
 
 static size_t fwd_smem_bytes(const TowerK& k, bool bwd) {
   const unsigned wb = bwd ? k.wt_bytes : k.w_bytes;
-  return ((wb + 1023) & ~1023u) + (size_t)kRows * k.max_kp * 2 + (bwd ? 0 : 2 * kRows * kMaxTiny * sizeof(float));
+  return ((wb + 1023) & ~1023u) + (size_t)kRows * k.max_kp * 2 +
+         (bwd ? 0 : (kColSplit * kRows * kMaxTiny + NRX_MAX_LAYERS * kBiasStride) * sizeof(float));
 }
 
 }  // namespace nrx
@@ -683,12 +703,14 @@ extern "C" int nrx_tower_bwd(const NrxTower* h_tower, const float* x, int64_t x_
     cudaError_t e = cudaFuncSetAttribute(tower_bwd_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     NRX_REQUIRE(e == cudaSuccess, NRX_ELAUNCH, "smem opt-in: %s", cudaGetErrorString(e));
     // >= 4 tiles per CTA so the partial-sum traffic stays small next to the GEMM work
-    long long parts = (k.n_tiles + 3) / 4;
-    if (parts > sm_count()) parts = sm_count();
+    // one wave of (tile range x layer) CTAs: parts * n_layers ~= SM count keeps every SM busy with the longest
+    // possible accumulation chains and the fewest partial buffers
+    long long parts = sm_count() / k.n_layers;
+    if (parts > k.n_tiles) parts = k.n_tiles;
     if (parts < 1) parts = 1;
     const long long per = (k.n_tiles + parts - 1) / parts;
     float* partials = (float*)(w + k.part_off);
-    tower_bwd_dw_kernel<<<(unsigned)parts, kDwThreads, smem, st>>>(k, w, partials);
+    tower_bwd_dw_kernel<<<dim3((unsigned)parts, (unsigned)k.n_layers), kDwThreads, smem, st>>>(k, w, partials);
     rc = check_launch("tower_bwd_dw");
     if (rc != NRX_OK) return rc;
     PtrPack P;

@@ -177,10 +177,11 @@ class FusedTrainer:
         m, fb, lib = self.model, self.fb, self.lib
         main = torch.cuda.current_stream(self.dev)
         self.side.wait_stream(main)
-        with torch.cuda.stream(self.side):  # sort plan: depends on the ids only -> overlaps the forward
+        with torch.cuda.stream(self.side):  # off the critical path: only the optimizer consumes these
+            # optimizer clock (lr schedule + bias corrections) and the sort plan (depends on the ids only)
+            L.check(lib.nrx_hparams_step(self.d_step.data_ptr(), self.d_hp.data_ptr(), self.lr, self.min_lr, self.milestones[0],
+                                         self.milestones[1], self.betas[0], self.betas[1], self._sp()), "nrx_hparams_step")
             plan = ops.BwdPlan(self._plan_fb())
-        L.check(lib.nrx_hparams_step(self.d_step.data_ptr(), self.d_hp.data_ptr(), self.lr, self.min_lr, self.milestones[0],
-                                     self.milestones[1], self.betas[0], self.betas[1], self._sp()), "nrx_hparams_step")
         label = self.batch["label"][:, 0]
         bias = self.dense_views.get("score_fc.bias")
         kind = self.kind
