@@ -30,12 +30,14 @@ using namespace umma;
 
 static constexpr int kTR = 128;        // corpus rows per tile == UMMA N; queries per tile == UMMA M
 static constexpr int kCap = 2048;      // candidate list capacity per query
-static constexpr int kScanThreads = 192;
+static constexpr int kScanThreads = 320;  // TMA warp + MMA warp + 8 epilogue warps
 static constexpr int kHdrBytes = 256;
 
 struct TopkGeom {
   long long N, Q, n_tiles, n_qtiles, Qp;
   int D, Dp, k, kprime, stages;
+  long long slices;   // corpus slices per query tile (grid.x of the scan)
+  int cap_s;          // candidate capacity per (query, slice): private region, no atomics
   size_t tile_bytes, index_bytes;
   // workspace offsets
   size_t gmax, theta, eps, count, cand, flag, total;
@@ -55,14 +57,20 @@ static int make_geom(long long Q, long long N, int D, int k, TopkGeom* g) {
   g->tile_bytes = (size_t)kTR * g->Dp * 2;
   g->index_bytes = kHdrBytes + (size_t)g->n_tiles * g->tile_bytes;
   g->stages = g->Dp <= 128 ? 4 : 2;
+  g->slices = g->n_qtiles > 0 ? sm_count() / g->n_qtiles : 1;
+  if (g->slices < 1) g->slices = 1;
+  if (g->slices > g->n_tiles) g->slices = g->n_tiles > 0 ? g->n_tiles : 1;
+  g->cap_s = (int)(kCap / (2 * g->slices));  // regions are per (query, slice, 64-column half)
+  if (g->cap_s < 16) g->cap_s = 16;
+  if (g->cap_s > 512) g->cap_s = 512;
   auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
   size_t o = 0;
-  g->gmax = o;  o += al((size_t)g->n_tiles * g->Qp * 4);
+  g->gmax = o;  o += al((size_t)g->n_tiles * 2 * g->Qp * 4);
   g->theta = o; o += al((size_t)g->Qp * 4);
   g->eps = o;   o += al((size_t)g->Qp * 4);
-  g->count = o; o += al((size_t)g->Qp * 4);
+  g->count = o; o += al((size_t)g->Qp * g->slices * 2 * 4);
   g->flag = o;  o += al((size_t)g->Qp * 4);
-  g->cand = o;  o += al((size_t)g->Qp * kCap * 4);
+  g->cand = o;  o += al((size_t)g->Qp * g->slices * 2 * g->cap_s * 4);
   g->total = o;
   return NRX_OK;
 }
@@ -105,7 +113,7 @@ template <int MODE>
 __global__ void __launch_bounds__(kScanThreads, 1)
 topk_scan_kernel(const uint8_t* __restrict__ img, long long N, long long n_tiles, int Dp, const float* __restrict__ q,
                  long long qld, long long Q, int D, long long Qp, int stages, float* __restrict__ gmax,
-                 const float* __restrict__ theta, unsigned* __restrict__ count, unsigned* __restrict__ cand) {
+                 const float* __restrict__ theta, unsigned* __restrict__ count, unsigned* __restrict__ cand, int cap_s) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const size_t tile_bytes = (size_t)kTR * Dp * 2;
   uint8_t* sQ = smem;
@@ -121,7 +129,7 @@ topk_scan_kernel(const uint8_t* __restrict__ img, long long N, long long n_tiles
 
   if (tid == 0) {
     for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 128); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 256); }
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(&tmem_s, 256u);
@@ -181,47 +189,61 @@ topk_scan_kernel(const uint8_t* __restrict__ img, long long N, long long n_tiles
           a ^= 1;
         }
       }
-    } else {  // epilogue: 4 warps, thread == query row (TMEM lane)
+    } else {  // epilogue: 8 warps = 2 per TMEM lane quadrant; thread == (query row, 64-column half of the tile)
       const int qd = warp & 3;
+      const int half = (warp - 2) >> 2;
       const int r = qd * 32 + lane;
       const long long qrow = q0 + r;
       uint32_t tph[2] = {0, 0};
       float th = 0.f;
       if (MODE == 1) th = __ldg(theta + qrow);  // theta is allocated for Qp rows
+      // this thread is the only writer of its (query, slice, half) candidate region: plain stores, register counter
+      unsigned mycnt = 0;
+      const size_t region = ((size_t)qrow * gridDim.x + blockIdx.x) * 2 + half;
+      unsigned* mycand = (MODE == 1) ? cand + region * cap_s : nullptr;
       int a = 0;
       for (long long t = t0; t < t1; ++t) {
         mbar_wait(&tfull[a], tph[a]); tph[a] ^= 1;
         tc_fence_after();
-        const long long base = t * kTR;
-        const bool tail = base + kTR > N;
-        float m = -FLT_MAX;
-#pragma unroll
-        for (int c0 = 0; c0 < kTR; c0 += 32) {
-          float v[32];
-          tmem_ld32(tmem + ((uint32_t)(qd * 32) << 16) + (uint32_t)(a * kTR + c0), v);
+        const long long base = t * kTR + half * 64;
+        const bool tail = base + 64 > N;
+        float v[64];
+        {  // both TMEM loads in flight before the single wait
+          float (&v0)[32] = *reinterpret_cast<float(*)[32]>(&v[0]);
+          float (&v1)[32] = *reinterpret_cast<float(*)[32]>(&v[32]);
+          const uint32_t ta = tmem + ((uint32_t)(qd * 32) << 16) + (uint32_t)(a * kTR + half * 64);
+          tmem_ld32(ta, v0);
+          tmem_ld32(ta + 32u, v1);
           tmem_ld_wait();
-          if (MODE == 0) {
+        }
+        tc_fence_before();
+        mbar_arrive(&tempty[a]);  // values are in registers: hand the accumulator back before the scan
+        if (tail) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float s = (tail && base + c0 + j >= N) ? -FLT_MAX : v[j];
-              m = fmaxf(m, s);
-            }
-          } else {
+          for (int j = 0; j < 64; ++j)
+            if (base + j >= N) v[j] = __int_as_float(0xff800000);  // -inf: never admitted, even by theta = -FLT_MAX
+        }
+        float m4[4] = {v[0], v[1], v[2], v[3]};  // four independent max chains
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (v[j] >= th && base + c0 + j < N && qrow < Q) {
-                const unsigned slot = atomicAdd(count + qrow, 1u);
-                if (slot < (unsigned)kCap) cand[qrow * kCap + slot] = (unsigned)(base + c0 + j);
-              }
+        for (int j = 4; j < 64; ++j) m4[j & 3] = fmaxf(m4[j & 3], v[j]);
+        const float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+        if (MODE == 0) {
+          gmax[(qrow * n_tiles + t) * 2 + half] = m;   // groups of 64 corpus rows
+        } else if (m >= th) {  // rare: a few hundred rows out of N pass the threshold
+#pragma unroll
+          for (int j = 0; j < 64; ++j) {
+            if (v[j] >= th) {
+              if (mycnt < (unsigned)cap_s) mycand[mycnt] = (unsigned)(base + j);
+              ++mycnt;
             }
           }
         }
-        tc_fence_before();
-        mbar_arrive(&tempty[a]);
-        if (MODE == 0) gmax[t * Qp + qrow] = m;
         a ^= 1;
       }
+      if (MODE == 1) count[region] = mycnt;
     }
+  } else if (MODE == 1 && warp >= 2) {  // slice without tiles
+    count[((size_t)(q0 + (warp & 3) * 32 + lane) * gridDim.x + blockIdx.x) * 2 + ((warp - 2) >> 2)] = 0;
   }
   tc_fence_before();
   __syncthreads();
@@ -241,7 +263,7 @@ topk_theta_kernel(const float* __restrict__ gmax, long long n_tiles, long long Q
   __shared__ float s_norm[8];
   const long long qi = blockIdx.x;
   const int tid = threadIdx.x;
-  if (tid == 0) { count[qi] = 0; flag[qi] = 0; }
+  if (tid == 0) flag[qi] = 0;
   if (qi >= Q) { if (tid == 0) { theta[qi] = FLT_MAX; eps[qi] = 0.f; } return; }
   // |q|
   float ss = 0.f;
@@ -264,7 +286,7 @@ topk_theta_kernel(const float* __restrict__ gmax, long long n_tiles, long long Q
     hist[tid] = 0;
     __syncthreads();
     for (long long t = tid; t < n_tiles; t += 256) {
-      const unsigned key = f2key(__ldg(gmax + t * Qp + qi));
+      const unsigned key = f2key(__ldg(gmax + qi * n_tiles + t));
       if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
     }
     __syncthreads();
@@ -289,9 +311,18 @@ topk_theta_kernel(const float* __restrict__ gmax, long long n_tiles, long long Q
 
 // ---- exact scoring + ordering -------------------------------------------------------------------------------
 __device__ __forceinline__ double dot64(const float* __restrict__ qs, const float* __restrict__ row, int D) {
-  double s = 0.0;
-  for (int d = 0; d < D; ++d) s = fma((double)qs[d], (double)__ldg(row + d), s);
-  return s;
+  // four independent fp64 chains (shorter dependency chain), combined in a fixed order; every path that
+  // scores a row uses this one function, so equal rows always get bit-equal scores
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  int d = 0;
+  for (; d + 4 <= D; d += 4) {
+    s0 = fma((double)qs[d], (double)__ldg(row + d), s0);
+    s1 = fma((double)qs[d + 1], (double)__ldg(row + d + 1), s1);
+    s2 = fma((double)qs[d + 2], (double)__ldg(row + d + 2), s2);
+    s3 = fma((double)qs[d + 3], (double)__ldg(row + d + 3), s3);
+  }
+  for (; d < D; ++d) s0 = fma((double)qs[d], (double)__ldg(row + d), s0);
+  return (s0 + s1) + (s2 + s3);
 }
 
 // (score desc, id asc): returns true if a must come before b
@@ -319,33 +350,47 @@ __device__ void bitonic_sort(double* s, unsigned* id, int n, int tid, int nthrea
 __global__ void __launch_bounds__(256)
 topk_final_kernel(const float* __restrict__ c, long long cld, long long N, int D, const float* __restrict__ q, long long qld,
                   int k, long long id_base, const float* __restrict__ theta, const float* __restrict__ eps,
-                  const unsigned* __restrict__ count, const unsigned* __restrict__ cand, int* __restrict__ flag,
-                  float* __restrict__ out_s, long long* __restrict__ out_i) {
+                  const unsigned* __restrict__ count, const unsigned* __restrict__ cand, int n_slices, int cap_s,
+                  int* __restrict__ flag, float* __restrict__ out_s, long long* __restrict__ out_i) {
   extern __shared__ __align__(16) uint8_t sm_raw[];
   double* s = reinterpret_cast<double*>(sm_raw);              // [kCap]
   unsigned* id = reinterpret_cast<unsigned*>(s + kCap);       // [kCap]
   float* qs = reinterpret_cast<float*>(id + kCap);            // [D]
   const long long qi = blockIdx.x;
   const int tid = threadIdx.x;
-  const unsigned cnt = count[qi];
+  __shared__ unsigned s_off[320];
+  __shared__ unsigned s_total, s_over;
   const long long kk = k < N ? k : N;
-  if (cnt > (unsigned)kCap || (long long)cnt < kk) {
-    if (tid == 0) flag[qi] = 1;
-    return;
+  if (tid == 0) {  // exclusive scan of the per-slice counts (n_slices <= SM count)
+    unsigned tot = 0, over = 0;
+    for (int sl = 0; sl < n_slices; ++sl) {
+      const unsigned cs = count[qi * n_slices + sl];
+      if (cs > (unsigned)cap_s) over = 1;
+      s_off[sl] = tot;
+      tot += cs < (unsigned)cap_s ? cs : (unsigned)cap_s;
+    }
+    s_total = tot;
+    s_over = over;
   }
   for (int d = tid; d < D; d += 256) qs[d] = __ldg(q + qi * qld + d);
   __syncthreads();
+  const unsigned cnt = s_total;
+  if (s_over || cnt > (unsigned)kCap || (long long)cnt < kk) {
+    if (tid == 0) flag[qi] = 1;
+    return;
+  }
   int n2 = 1;
   while (n2 < (int)cnt) n2 <<= 1;
-  for (int i = tid; i < n2; i += 256) {
-    if (i < (int)cnt) {
-      const unsigned row = cand[qi * kCap + i];
-      id[i] = row;
-      s[i] = dot64(qs, c + (long long)row * cld, D);
-    } else {
-      id[i] = 0xffffffffu;
-      s[i] = -DBL_MAX;
+  for (int i = (int)cnt + tid; i < n2; i += 256) { id[i] = 0xffffffffu; s[i] = -DBL_MAX; }
+  for (unsigned i = tid; i < cnt; i += 256) {  // all candidates in flight together: slice by binary search
+    int lo = 0, hi = n_slices - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (s_off[mid] <= i) lo = mid; else hi = mid - 1;
     }
+    const unsigned row = cand[((size_t)qi * n_slices + lo) * cap_s + (i - s_off[lo])];
+    id[i] = row;
+    s[i] = dot64(qs, c + (long long)row * cld, D);
   }
   __syncthreads();
   bitonic_sort(s, id, n2, tid, 256);
@@ -514,25 +559,24 @@ extern "C" int nrx_topk_search(const void* index, const float* corpus, int64_t c
     const size_t smem = (size_t)(1 + g.stages) * g.tile_bytes;
     cudaFuncSetAttribute(topk_scan_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(topk_scan_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    long long slices = sm_count() / g.n_qtiles;
-    if (slices < 1) slices = 1;
-    if (slices > g.n_tiles) slices = g.n_tiles;
-    dim3 grid((unsigned)slices, (unsigned)g.n_qtiles);
+    NRX_REQUIRE(g.slices <= 160, NRX_EUNSUPPORTED, "more than 160 corpus slices");
+    dim3 grid((unsigned)g.slices, (unsigned)g.n_qtiles);
     topk_scan_kernel<0><<<grid, kScanThreads, smem, st>>>(img, N, g.n_tiles, g.Dp, queries, q_ld, Q, D, g.Qp, g.stages, gmax,
-                                                          nullptr, nullptr, nullptr);
+                                                          nullptr, nullptr, nullptr, g.cap_s);
     rc = check_launch("topk_scan<A>");
     if (rc != NRX_OK) return rc;
-    topk_theta_kernel<<<(unsigned)g.Qp, 256, 0, st>>>(gmax, g.n_tiles, g.Qp, Q, g.kprime, queries, q_ld, D, (const unsigned*)index,
+    topk_theta_kernel<<<(unsigned)g.Qp, 256, 0, st>>>(gmax, 2 * g.n_tiles /* groups of 64 rows */, g.Qp, Q, g.kprime, queries, q_ld, D, (const unsigned*)index,
                                                      theta, eps, count, flag);
     rc = check_launch("topk_theta");
     if (rc != NRX_OK) return rc;
     topk_scan_kernel<1><<<grid, kScanThreads, smem, st>>>(img, N, g.n_tiles, g.Dp, queries, q_ld, Q, D, g.Qp, g.stages, nullptr,
-                                                          theta, count, cand);
+                                                          theta, count, cand, g.cap_s);
     rc = check_launch("topk_scan<B>");
     if (rc != NRX_OK) return rc;
     const size_t fsm = (size_t)kCap * 12 + (size_t)D * 4;
     cudaFuncSetAttribute(topk_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm);
-    topk_final_kernel<<<(unsigned)Q, 256, fsm, st>>>(corpus, c_ld, N, D, queries, q_ld, k, id_base, theta, eps, count, cand, flag,
+    topk_final_kernel<<<(unsigned)Q, 256, fsm, st>>>(corpus, c_ld, N, D, queries, q_ld, k, id_base, theta, eps, count, cand,
+                                                    (int)(2 * g.slices), g.cap_s, flag,
                                                     out_scores, (long long*)out_ids);
     rc = check_launch("topk_final");
     if (rc != NRX_OK) return rc;

@@ -207,27 +207,47 @@ tower_fwd_kernel(const __grid_constant__ TowerK T, const float* __restrict__ x, 
     {
       const int Kp0 = T.Kp[0], K0 = T.K[0];
       uint8_t* img = training ? ws + T.act_off[0] + (size_t)tile * Kp0 * kRows * 2 : nullptr;
-      for (int i = tid; i < (Kp0 / 8) * kRows; i += kFwdThreads) {
-        const int rr = i % kRows, kc = i / kRows;
-        const long long row = row0 + rr;
-        float f[8];
-        if (row < B) {
-          const float* src = x + row * ldx + kc * 8;
-          if (vec_ok && kc * 8 + 8 <= K0) {
-            const float4 a = __ldg(reinterpret_cast<const float4*>(src));
-            const float4 b = __ldg(reinterpret_cast<const float4*>(src) + 1);
-            f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
-          } else {
+      constexpr int kBatch = 4;  // chunks per thread whose loads are all issued before the first use
+      const int nchunk = (Kp0 / 8) * kRows;
+      for (int i0 = tid; i0 < nchunk; i0 += kFwdThreads * kBatch) {
+        float4 la[kBatch], lb[kBatch];
+        const bool fast = vec_ok && (K0 % 8 == 0);
+        if (fast) {
+#pragma unroll
+          for (int u = 0; u < kBatch; ++u) {
+            const int i = i0 + u * kFwdThreads;
+            const int rr = i % kRows, kc = i / kRows;
+            const long long row = row0 + rr;
+            la[u] = lb[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < nchunk && row < B && kc * 8 < K0) {
+              const float4* src = reinterpret_cast<const float4*>(x + row * ldx + kc * 8);
+              la[u] = __ldg(src);
+              lb[u] = __ldg(src + 1);
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {
+          const int i = i0 + u * kFwdThreads;
+          if (i >= nchunk) break;
+          const int rr = i % kRows, kc = i / kRows;
+          const long long row = row0 + rr;
+          float f[8];
+          if (fast) {
+            f[0] = la[u].x; f[1] = la[u].y; f[2] = la[u].z; f[3] = la[u].w;
+            f[4] = lb[u].x; f[5] = lb[u].y; f[6] = lb[u].z; f[7] = lb[u].w;
+          } else if (row < B) {
+            const float* src = x + row * ldx + kc * 8;
 #pragma unroll
             for (int j = 0; j < 8; ++j) f[j] = (kc * 8 + j < K0) ? __ldg(src + j) : 0.f;
-          }
-        } else {
+          } else {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) f[j] = 0.f;
+            for (int j = 0; j < 8; ++j) f[j] = 0.f;
+          }
+          const uint4 pk = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+          *reinterpret_cast<uint4*>(sA + canon_off(kRows, rr, kc)) = pk;
+          if (img) *reinterpret_cast<uint4*>(img + canon_off(kRows, rr, kc)) = pk;
         }
-        const uint4 pk = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
-        *reinterpret_cast<uint4*>(sA + canon_off(kRows, rr, kc)) = pk;
-        if (img) *reinterpret_cast<uint4*>(img + canon_off(kRows, rr, kc)) = pk;
       }
     }
     fence_async_smem();
