@@ -128,6 +128,137 @@ class DataParallelTrainer(FusedTrainer):
 
 
 # --------------------------------------------------------------------------- #
+# row-sharded embedding tables (BASELINE config 5)                             #
+# --------------------------------------------------------------------------- #
+
+class ShardedEmbeddingTrainer(FusedTrainer):
+    """Data-parallel step with the BIG embedding tables row-sharded across ranks.
+
+    Rank r keeps rows [lo_r, hi_r) of every table with >= `shard_min_rows` rows, stored behind one extra
+    all-zero row (local row 0); small tables stay replicated.  Per step, with fixed shapes throughout:
+      1. ids / masks of all ranks are all-gathered (as in DataParallelTrainer);
+      2. ids are remapped to LOCAL rows: owned -> id - lo + 1, not owned -> 0 (the zero row).  For replicated
+         tables a rank keeps only the ids of its own sample block, so every (sample, feature) is produced once;
+      3. K1 runs over the GLOBAL batch on the local shard: each rank emits the partial pooled features of the
+         rows it owns (masked-mean denominators come from the full mask, so partials simply add up);
+      4. one reduce-scatter(sum) hands every rank the complete features of its own B samples — single-id
+         fields get exactly one non-zero contribution (bit-exact vs one GPU), pooled fields differ only in
+         summation order;
+      5. heads forward/backward locally; dense grads all-reduced (AVG), per-sample embedding grads all-gathered;
+      6. K3 over the global batch with the local ids updates exactly the rows this rank owns (not-owned
+         occurrences map to the padding sentinel and are skipped); replicated tables see all ids on every
+         rank and stay bitwise identical.
+    The exchange moves G*B*ΣD*4 bytes per direction (a reduce-scatter instead of the ids/vectors all-to-all
+    of an owner-compute design): simple and shape-static first, traffic-optimal later."""
+
+    def __init__(self, model, B: int, kind=None, group=None, shard_min_rows: int = 100_000, **kw):
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        G = self.world
+        dev = next(model.parameters()).device
+        # ---- shard the big tables in place: [zero row | rows lo..hi) ----
+        self.shards: Dict[str, Tuple[int, int, int]] = {}
+        for name, emb in model.embedding_tables.items():
+            rows = emb.weight.shape[0]
+            if rows >= shard_min_rows and G > 1:
+                lo, hi = shard_range(rows, self.rank, G)
+                w = torch.zeros((hi - lo + 1, emb.weight.shape[1]), dtype=torch.float32, device=dev)
+                w[1:].copy_(emb.weight.data[lo:hi])
+                if lo == 0:
+                    w[1].zero_()  # global padding row
+                emb.weight = torch.nn.Parameter(w)
+                self.shards[name] = (lo, hi, rows)
+        # Replicated tables get the LOWEST table ids: the sort key is (table id, row), so their occurrences then
+        # occupy the same sorted positions on every rank regardless of how many sharded rows a rank owns, which
+        # keeps K3's summation tree — and therefore the replicas — bitwise identical across ranks.
+        rep = [n for n in model.embedding_tables.keys() if n not in self.shards]
+        sh = [n for n in model.embedding_tables.keys() if n in self.shards]
+        model._table_ids = {n: i for i, n in enumerate(rep + sh)}
+        kw.pop("use_graph", None)
+        super().__init__(model, B, kind=kind, use_graph=False, **kw)
+        self.fm_fused = False  # the gather is distributed: K1 + field logits instead of the gather-fused FM
+        self.id_keys = [key for key, dt, shape, off in self.layout.fields if key != "label"]
+        mk = lambda: {key: torch.zeros((G * shape[0],) + tuple(shape[1:]), dtype=dt, device=dev)
+                      for key, dt, shape, off in self.layout.fields if key != "label"}
+        self.gbatch = mk()       # true global ids
+        self.fbatch = mk()       # ids K1 sees: sharded -> local rows, replicated -> own sample block only
+        self.bbatch = mk()       # ids the backward plan sees: sharded -> local rows, replicated -> global ids
+        for k in self.id_keys:   # masks are shared
+            if k.endswith("_mask"):
+                self.fbatch[k] = self.gbatch[k]
+                self.bbatch[k] = self.gbatch[k]
+        self.gfb_fwd = ops.FeatBinding(self.fb.specs, model._weights(), self.fbatch, want_inv_den=True)
+        self.gfb_bwd = ops.FeatBinding(self.fb.specs, model._weights(), self.bbatch, want_inv_den=True)
+        for name, inv in self.gfb_fwd.inv_den.items():  # one set of denominators (written by K1, read by K3)
+            self.gfb_bwd.inv_den[name] = inv
+        for i, s in enumerate(self.gfb_bwd.specs):
+            if s.name in self.gfb_fwd.inv_den:
+                self.gfb_bwd.arr[i].inv_den = self.gfb_fwd.inv_den[s.name].data_ptr()
+        self.partial = torch.zeros((G * B, self.out_dim), dtype=torch.float32, device=dev)
+        self.x_local = torch.zeros((B, self.out_dim), dtype=torch.float32, device=dev)
+        self.gx_global = torch.zeros((G * B, self.out_dim), dtype=torch.float32, device=dev)
+        own = torch.zeros(G * B, dtype=torch.bool, device=dev)
+        own[self.rank * B:(self.rank + 1) * B] = True
+        self._own_rows = own
+        self._sharded_ready = True
+
+    def _plan_fb(self):
+        return self.gfb_bwd if getattr(self, "_sharded_ready", False) else self.fb
+
+    def _exchange_ids(self):
+        with dist._coalescing_manager(group=self.group, device=self.dev, async_ops=False):
+            for k in self.id_keys:
+                dist.all_gather_into_tensor(self.gbatch[k], self.batch[k], group=self.group)
+        for s in self.fb.specs:
+            g = self.gbatch[s.name]
+            if s.table in self.shards:
+                lo, hi, _ = self.shards[s.table]
+                local = torch.where((g >= lo) & (g < hi), g - (lo - 1), torch.zeros_like(g))
+                if lo == 0:
+                    local = torch.where(g == 0, torch.zeros_like(g), local)  # global pad id stays the pad row
+                self.fbatch[s.name].copy_(local)
+                self.bbatch[s.name].copy_(local)
+            else:
+                own = self._own_rows if g.dim() == 1 else self._own_rows[:, None]
+                self.fbatch[s.name].copy_(torch.where(own, g, torch.zeros_like(g)))
+                self.bbatch[s.name].copy_(g)
+
+    def _embed_fwd(self):
+        ops_out = ops.embed_pool_fwd(self.gfb_fwd, self.out_dim)  # partial features of the rows this rank owns
+        dist.reduce_scatter_tensor(self.x_local, ops_out, op=dist.ReduceOp.SUM, group=self.group)
+        return self.x_local
+
+    def step(self) -> torch.Tensor:
+        self._exchange_ids()
+        self._fwd_bwd()
+        self._gx.mul_(1.0 / self.world)
+        if self.n_dense > 0:
+            dist.all_reduce(self.flat_g, op=dist.ReduceOp.AVG, group=self.group)
+        dist.all_gather_into_tensor(self.gx_global, self._gx, group=self.group)
+        self._update(self.gfb_bwd, self._plan, self.gx_global)
+        return self.loss
+
+    def gather_table(self, name: str) -> torch.Tensor:
+        """Full [rows, D] table on every rank (tests / checkpointing)."""
+        w = self.model.embedding_tables[name].weight.data
+        if name not in self.shards:
+            return w.clone()
+        lo, hi, rows = self.shards[name]
+        base, rem = divmod(rows, self.world)
+        mx = base + (1 if rem else 0)
+        pad = torch.zeros((mx, w.shape[1]), dtype=w.dtype, device=w.device)
+        pad[: hi - lo].copy_(w[1:])
+        allp = torch.empty((self.world * mx, w.shape[1]), dtype=w.dtype, device=w.device)
+        dist.all_gather_into_tensor(allp, pad, group=self.group)
+        parts = []
+        for r in range(self.world):
+            a, b = shard_range(rows, r, self.world)
+            parts.append(allp[r * mx: r * mx + (b - a)])
+        return torch.cat(parts, dim=0)
+
+
+# --------------------------------------------------------------------------- #
 # sharded retrieval                                                            #
 # --------------------------------------------------------------------------- #
 

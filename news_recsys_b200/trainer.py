@@ -173,6 +173,10 @@ class FusedTrainer:
         """Features whose occurrences the backward plan covers (the data-parallel trainer returns the global batch)."""
         return self.fb
 
+    def _embed_fwd(self):
+        """K1: features [B, ΣD] of the local batch (the row-sharded trainer overrides this with the exchange)."""
+        return ops.embed_pool_fwd(self.fb, self.out_dim)
+
     def _fwd_bwd(self):
         m, fb, lib = self.model, self.fb, self.lib
         main = torch.cuda.current_stream(self.dev)
@@ -189,7 +193,7 @@ class FusedTrainer:
             prob, loss_ps, dl, _ = ops.fm_fused_fwd(fb, bias, label)
             gx = ops.fm_fused_bwd(fb, dl, self.out_dim)
         else:
-            x = ops.embed_pool_fwd(fb, self.out_dim)
+            x = self._embed_fwd()
             cols, c = [], 0
             for d in self.dims:
                 cols.append(c)
