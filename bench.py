@@ -484,7 +484,7 @@ def main():
     hbm_peak, tf_peak, peak_src = peaks()
     # dominant call ON THE CRITICAL PATH: the sort plan and the optimizer clock run on the forked stream,
     # concurrently with forward + backward, and are listed in `kernels` with "stream": "forked"
-    forked = {"nrx_embed_bwd_plan", "nrx_hparams_step"}
+    forked = {"nrx_embed_bwd_plan", "nrx_hparams_step", "nrx_tower_pack"}
     dom = max((k for k in per_api if k not in forked), key=lambda k: per_api[k])
     bound, qty = alg.get(dom, ("hbm", 0))
     dur_s = per_api[dom] * 1e-6

@@ -144,6 +144,9 @@ int nrx_bce_bwd(const float* prob, const float* label, int64_t label_stride, int
                 const float* upstream, float* grad_prob, nrx_stream_t stream);
 int nrx_sigmoid_bwd(const float* prob, const float* grad_prob, int64_t B, float* grad_logit,
                     nrx_stream_t stream);
+/* Two independent reductions in one launch: out1[0] = scale1 * sum(x1[0..n1)), out2[0] = scale2 * sum(x2[0..n2)). */
+int nrx_reduce2_f32(const float* x1, int64_t n1, float scale1, float* out1,
+                    const float* x2, int64_t n2, float scale2, float* out2, nrx_stream_t stream);
 /* Deterministic mean/sum of n floats into out[0] (fixed reduction tree). */
 int nrx_reduce_f32(const float* x, int64_t n, float scale, float* out, nrx_stream_t stream);
 
@@ -176,6 +179,11 @@ typedef struct NrxTower {
 } NrxTower;
 
 size_t nrx_tower_workspace_bytes(const NrxTower* h_tower, int64_t B, int training);
+/* Packs the fp32 weights into the bf16 operand images kept in `ws` (same B / training as the forward that
+ * follows).  nrx_tower_fwd does this itself unless `training` carries NRX_TOWER_PREPACKED — a trainer can
+ * issue the pack on another stream as soon as the optimizer has written the weights. */
+enum { NRX_TOWER_TRAINING = 1, NRX_TOWER_PREPACKED = 2 };
+int nrx_tower_pack(const NrxTower* h_tower, int64_t B, int training, void* ws, size_t ws_bytes, nrx_stream_t stream);
 /* y[B, dims[n]] = tower(x[B, dims[0]]); with training != 0 the bf16 activations of
  * every layer are kept in `ws` for nrx_tower_bwd. */
 int nrx_tower_fwd(const NrxTower* h_tower, const float* x, int64_t x_ld, int64_t B,

@@ -78,11 +78,13 @@ SIGNATURES = {
     "nrx_bce_fwd": (C.c_int, [_P, _P, _I64, _I64, _P, _P]),
     "nrx_bce_bwd": (C.c_int, [_P, _P, _I64, _I64, _P, _P, _P]),
     "nrx_sigmoid_bwd": (C.c_int, [_P, _P, _I64, _P, _P]),
+    "nrx_reduce2_f32": (C.c_int, [_P, _I64, _F, _P, _P, _I64, _F, _P, _P]),
     "nrx_reduce_f32": (C.c_int, [_P, _I64, _F, _P, _P]),
     "nrx_adamw_dense": (C.c_int, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _I32, _P]),
     "nrx_adamw_dense_dev": (C.c_int, [_P, _P, _P, _P, _I64, _P, _F, _F, _F, _F, _P]),
     "nrx_hparams_step": (C.c_int, [_P, _P, _F, _F, _I32, _I32, _F, _F, _P]),
     "nrx_tower_workspace_bytes": (_SZ, [C.POINTER(NrxTower), _I64, C.c_int]),
+    "nrx_tower_pack": (C.c_int, [C.POINTER(NrxTower), _I64, C.c_int, _P, _SZ, _P]),
     "nrx_tower_fwd": (C.c_int, [C.POINTER(NrxTower), _P, _I64, _I64, _P, _I64, C.c_int, _P, _SZ, _P]),
     "nrx_tower_bwd": (C.c_int, [C.POINTER(NrxTower), _P, _I64, _I64, _P, _I64, _P, _I64, C.c_int,
                                 C.POINTER(_P), C.POINTER(_P), _P, _SZ, _P]),
@@ -132,7 +134,7 @@ def load() -> C.CDLL:
 
 
 # kernels of OURS launched per successful API call (library kernels such as the CUB radix sort are not counted)
-KERNELS_PER_CALL = {"nrx_tower_fwd": 2, "nrx_tower_bwd": 3, "nrx_embed_bwd_apply": 2, "nrx_dcn_cross_bwd": 2,
+KERNELS_PER_CALL = {"nrx_tower_fwd": 2, "nrx_tower_fwd(prepacked)": 1, "nrx_tower_bwd": 3, "nrx_embed_bwd_apply": 2, "nrx_dcn_cross_bwd": 2,
                     "nrx_embed_bwd_apply(dense)": 2, "nrx_embed_bwd_apply(rowopt)": 2, "nrx_topk_ip": 2,
                     "nrx_topk_search": 5, "nrx_topk_index_build": 1,
                     "nrx_tower_workspace_bytes": 0, "nrx_embed_bwd_workspace_bytes": 0, "nrx_tower_image_layout": 0}

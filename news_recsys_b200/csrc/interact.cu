@@ -464,6 +464,30 @@ extern "C" int nrx_sigmoid_bwd(const float* prob, const float* grad_prob, int64_
   return check_launch("sigmoid_bwd");
 }
 
+__global__ void __launch_bounds__(1024)
+reduce2_kernel(const float* __restrict__ x1, long long n1, float s1, float* __restrict__ o1, const float* __restrict__ x2,
+               long long n2, float s2, float* __restrict__ o2) {
+  __shared__ float sm[32];
+  const float* x = blockIdx.x == 0 ? x1 : x2;
+  const long long n = blockIdx.x == 0 ? n1 : n2;
+  float a = 0.f;
+  for (long long i = threadIdx.x; i < n; i += 1024) a += __ldg(x + i);
+  a = warp_sum(a);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = a;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    a = warp_sum(sm[threadIdx.x]);
+    if (threadIdx.x == 0) { if (blockIdx.x == 0) o1[0] = a * s1; else o2[0] = a * s2; }
+  }
+}
+
+extern "C" int nrx_reduce2_f32(const float* x1, int64_t n1, float scale1, float* out1, const float* x2, int64_t n2,
+                               float scale2, float* out2, nrx_stream_t stream) {
+  NRX_REQUIRE(out1 && out2 && x1 && x2 && n1 >= 0 && n2 >= 0, NRX_EINVAL, "null pointer");
+  reduce2_kernel<<<2, 1024, 0, (cudaStream_t)stream>>>(x1, n1, scale1, out1, x2, n2, scale2, out2);
+  return check_launch("reduce2_f32");
+}
+
 extern "C" int nrx_reduce_f32(const float* x, int64_t n, float scale, float* out, nrx_stream_t stream) {
   NRX_REQUIRE(out && (x || n == 0) && n >= 0, NRX_EINVAL, "null pointer");
   reduce_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(x, n, scale, out);

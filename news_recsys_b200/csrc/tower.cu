@@ -456,19 +456,35 @@ tower_bwd_dx_kernel(const __grid_constant__ TowerK T, long long B, const float* 
         issue_layer_mma(tmem, smem_u32(sA), smem_u32(sW + T.wt_off[l]), T.Np[l], Kp);
         mma_commit(&mbar);
       }
+      const uint8_t* aimg = l > 0 ? ws + T.act_off[l] + (size_t)tile * Kp * kRows * 2 : nullptr;
+      uint8_t* dzimg = l > 0 ? ws + T.dz_off[l - 1] + (size_t)tile * Kp * kRows * 2 : nullptr;
+      // the saved activations (for act') do not depend on the MMA: fetch them while it runs
+      constexpr int kMaxG = 4;  // 16-column groups per thread: Kp <= 240 -> 15 groups over kColSplit = 4 slices
+      uint4 pa[kMaxG][2];
+      if (l > 0) {
+#pragma unroll
+        for (int u = 0; u < kMaxG; ++u) {
+          const int g16 = h + u * kColSplit;
+          if (g16 < Kp / 16) {
+            pa[u][0] = *reinterpret_cast<const uint4*>(aimg + canon_off(kRows, r, 2 * g16));
+            pa[u][1] = *reinterpret_cast<const uint4*>(aimg + canon_off(kRows, r, 2 * g16 + 1));
+          }
+        }
+      }
       mbar_wait(&mbar, phase);
       phase ^= 1;
       tc_fence_after();
-      const uint8_t* aimg = l > 0 ? ws + T.act_off[l] + (size_t)tile * Kp * kRows * 2 : nullptr;
-      uint8_t* dzimg = l > 0 ? ws + T.dz_off[l - 1] + (size_t)tile * Kp * kRows * 2 : nullptr;
-      for (int g16 = h; g16 < Kp / 16; g16 += kColSplit) {
+#pragma unroll
+      for (int u = 0; u < kMaxG; ++u) {
+        const int g16 = h + u * kColSplit;
+        if (g16 >= Kp / 16) break;
         float v[16];
         tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)g16 * 16u, v);
         tmem_ld_wait();
         if (l > 0) {
           float a[16];
-          unpack8(*reinterpret_cast<const uint4*>(aimg + canon_off(kRows, r, 2 * g16)), *reinterpret_cast<float(*)[8]>(&a[0]));
-          unpack8(*reinterpret_cast<const uint4*>(aimg + canon_off(kRows, r, 2 * g16 + 1)), *reinterpret_cast<float(*)[8]>(&a[8]));
+          unpack8(pa[u][0], *reinterpret_cast<float(*)[8]>(&a[0]));
+          unpack8(pa[u][1], *reinterpret_cast<float(*)[8]>(&a[8]));
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] *= (a[j] > 0.f ? 1.f : T.slope);
           const uint4 c0 = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
@@ -478,13 +494,14 @@ tower_bwd_dx_kernel(const __grid_constant__ TowerK T, long long B, const float* 
           *reinterpret_cast<uint4*>(dzimg + canon_off(kRows, r, 2 * g16)) = c0;
           *reinterpret_cast<uint4*>(dzimg + canon_off(kRows, r, 2 * g16 + 1)) = c1;
         } else if (row < B) {
+          float* p = gx + row * ldgx + g16 * 16;
+          if (!accumulate_gx && g16 * 16 + 16 <= K && (ldgx % 4 == 0) && ((reinterpret_cast<uintptr_t>(gx) & 15) == 0)) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int col = g16 * 16 + j;
-            if (col < K) {
-              float* p = gx + row * ldgx + col;
-              *p = accumulate_gx ? *p + v[j] : v[j];
-            }
+            for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(p + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (g16 * 16 + j < K) p[j] = accumulate_gx ? p[j] + v[j] : v[j];
           }
         }
       }
@@ -671,8 +688,18 @@ static int tower_pack(const TowerK& k, uint8_t* ws, cudaStream_t st) {
   return check_launch("tower_pack");
 }
 
+extern "C" int nrx_tower_pack(const NrxTower* h_tower, int64_t B, int training, void* ws, size_t ws_bytes, nrx_stream_t stream) {
+  TowerK k;
+  int rc = make_tower(h_tower, B, training & 1, &k);
+  if (rc != NRX_OK) return rc;
+  NRX_REQUIRE(ws && ws_bytes >= k.total_bytes, NRX_EWORKSPACE, "workspace %zu < %zu", ws_bytes, k.total_bytes);
+  return tower_pack(k, (uint8_t*)ws, (cudaStream_t)stream);
+}
+
 extern "C" int nrx_tower_fwd(const NrxTower* h_tower, const float* x, int64_t x_ld, int64_t B, float* y, int64_t y_ld,
                              int training, void* ws, size_t ws_bytes, nrx_stream_t stream) {
+  const int prepacked = training & NRX_TOWER_PREPACKED;
+  training &= 1;
   TowerK k;
   int rc = make_tower(h_tower, B, training, &k);
   if (rc != NRX_OK) return rc;
@@ -683,8 +710,10 @@ extern "C" int nrx_tower_fwd(const NrxTower* h_tower, const float* x, int64_t x_
   const size_t smem = fwd_smem_bytes(k, false);
   NRX_REQUIRE(smem <= 227 * 1024, NRX_EUNSUPPORTED, "tower needs %zu B of shared memory (> 227 KB)", smem);
   cudaStream_t st = (cudaStream_t)stream;
-  rc = tower_pack(k, (uint8_t*)ws, st);
-  if (rc != NRX_OK) return rc;
+  if (!prepacked) {
+    rc = tower_pack(k, (uint8_t*)ws, st);
+    if (rc != NRX_OK) return rc;
+  }
   cudaError_t e = cudaFuncSetAttribute(tower_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   NRX_REQUIRE(e == cudaSuccess, NRX_ELAUNCH, "smem opt-in: %s", cudaGetErrorString(e));
   const long long grid = k.n_tiles < sm_count() ? k.n_tiles : sm_count();

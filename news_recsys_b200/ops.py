@@ -437,21 +437,41 @@ def _tower_struct(weights: Sequence[torch.Tensor], biases: Sequence[torch.Tensor
     return t, keep
 
 
-def tower_fwd(x: torch.Tensor, weights, biases, negative_slope=None, training=False):
+def tower_prepack(B: int, weights, biases, negative_slope=None, training=False):
+    """Allocate the tower workspace and pack the weights into it on the CURRENT stream (nrx_tower_pack).
+    Returns a handle for tower_fwd(..., packed=handle): lets a trainer pack on a forked stream."""
+    t, keep = _tower_struct(weights, biases, negative_slope)
+    dev = weights[0].device
+    lib = L.load()
+    nbytes = int(lib.nrx_tower_workspace_bytes(C.byref(t), B, 1 if training else 0))
+    if nbytes == 0:
+        L.check(-2, "nrx_tower_workspace_bytes")
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    L.check(lib.nrx_tower_pack(C.byref(t), B, 1 if training else 0, ws.data_ptr(), nbytes, L.stream_ptr(dev)), "nrx_tower_pack")
+    return t, keep, ws, nbytes
+
+
+def tower_fwd(x: torch.Tensor, weights, biases, negative_slope=None, training=False, packed=None):
     """y = MLP(x) on tensor cores; returns (y, ctx) where ctx carries the workspace for tower_bwd."""
     _require_cuda(x, "tower input")
     if x.dtype != torch.float32 or x.stride(-1) != 1:
         x = x.float().contiguous()
     B = x.shape[0]
-    t, keep = _tower_struct(weights, biases, negative_slope)
     lib = L.load()
-    nbytes = int(lib.nrx_tower_workspace_bytes(C.byref(t), B, 1 if training else 0))
-    if nbytes == 0:
-        L.check(-2, "nrx_tower_workspace_bytes")
-    ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
-    y = torch.empty((B, weights[-1].shape[0]), dtype=torch.float32, device=x.device)
-    L.check(lib.nrx_tower_fwd(C.byref(t), x.data_ptr(), x.stride(0), B, y.data_ptr(), y.stride(0), 1 if training else 0,
-                              ws.data_ptr(), nbytes, L.stream_ptr(x.device)), "nrx_tower_fwd")
+    flags = 1 if training else 0
+    if packed is not None:
+        t, keep, ws, nbytes = packed
+        flags |= 2  # NRX_TOWER_PREPACKED
+    else:
+        t, keep = _tower_struct(weights, biases, negative_slope)
+        nbytes = int(lib.nrx_tower_workspace_bytes(C.byref(t), B, flags))
+        if nbytes == 0:
+            L.check(-2, "nrx_tower_workspace_bytes")
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+    y = torch.empty((B, t.dims[t.n_layers]), dtype=torch.float32, device=x.device)
+    L.check(lib.nrx_tower_fwd(C.byref(t), x.data_ptr(), x.stride(0), B, y.data_ptr(), y.stride(0), flags,
+                              ws.data_ptr(), nbytes, L.stream_ptr(x.device)),
+            "nrx_tower_fwd(prepacked)" if packed is not None else "nrx_tower_fwd")
     return y, (t, keep, ws, nbytes, x)
 
 

@@ -67,6 +67,8 @@ class BatchLayout:
 
 class FusedTrainer:
     KINDS = ("lr", "fm", "deep", "widedeep", "dcn", "deepfm")
+    _TOWER_PREFIX = {"deep": "score_fc.network.network", "deepfm": "score_fc.deep_network.network",
+                     "widedeep": "score_fc.deep_network.network", "dcn": "score_fc.score_fc.network"}
 
     def __init__(self, model, B: int, kind: Optional[str] = None, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01,
                  use_graph: bool = True, id_dtype=torch.int64):
@@ -97,6 +99,7 @@ class FusedTrainer:
             _, deep_cols = model._split_cols(self.dims, self.names)
             self._wd_idx = torch.as_tensor(deep_cols, device=self.dev)
         self.side = torch.cuda.Stream(device=self.dev)
+        self.side2 = torch.cuda.Stream(device=self.dev)
         self.loss = torch.zeros(1, dtype=torch.float32, device=self.dev)
         self.prob = None
         self.graph = None
@@ -141,11 +144,20 @@ class FusedTrainer:
     def _reduce(self, x, scale, out):
         L.check(self.lib.nrx_reduce_f32(x.data_ptr(), x.numel(), scale, out.data_ptr(), self._sp()), "nrx_reduce_f32")
 
-    def _tower(self, x, lin_names, ws_override=None):
+    def _tower(self, x, lin_names, ws_override=None, packed=None):
         ws = ws_override or [self.dense_views[n + ".weight"] for n in lin_names]
         bs = [self.dense_views[n + ".bias"] for n in lin_names]
-        y, tctx = ops.tower_fwd(x, ws, bs, None, training=True)
+        y, tctx = ops.tower_fwd(x, ws, bs, None, training=True, packed=packed)
         return y, tctx
+
+    def _prepack(self, lin_names, main):
+        """Pack the tower weights on a second forked stream while K1 / the field logits run (the weights were
+        final when the previous step's optimizer finished)."""
+        ws = [self.dense_views[n + ".weight"] for n in lin_names]
+        bs = [self.dense_views[n + ".bias"] for n in lin_names]
+        self.side2.wait_stream(main)
+        with torch.cuda.stream(self.side2):
+            return ops.tower_prepack(self.B, ws, bs, None, training=True)
 
     def _tower_bwd(self, tctx, dl, lin_names, gw_override=None):
         t, keep, ws, nbytes, x = tctx
@@ -186,6 +198,9 @@ class FusedTrainer:
             L.check(lib.nrx_hparams_step(self.d_step.data_ptr(), self.d_hp.data_ptr(), self.lr, self.min_lr, self.milestones[0],
                                          self.milestones[1], self.betas[0], self.betas[1], self._sp()), "nrx_hparams_step")
             plan = ops.BwdPlan(self._plan_fb())
+        packed = None
+        if self.kind in ("deep", "deepfm", "dcn"):
+            packed = self._prepack(self._lin_names(self._TOWER_PREFIX[self.kind]), main)
         label = self.batch["label"][:, 0]
         bias = self.dense_views.get("score_fc.bias")
         kind = self.kind
@@ -214,9 +229,7 @@ class FusedTrainer:
             if field is not None:
                 terms.append(ops.field_logit_fwd(x, field[0], field[1], field[2]))
             if kind in ("deep", "deepfm", "widedeep", "dcn"):
-                prefix = {"deep": "score_fc.network.network", "deepfm": "score_fc.deep_network.network",
-                          "widedeep": "score_fc.deep_network.network", "dcn": "score_fc.score_fc.network"}[kind]
-                lin = self._lin_names(prefix)
+                lin = self._lin_names(self._TOWER_PREFIX[kind])
                 tin, ws_override = x, None
                 if kind == "widedeep":  # column selection moved to the weight side (see widedeep/model.py)
                     w0 = self.dense_views[lin[0] + ".weight"]
@@ -229,7 +242,9 @@ class FusedTrainer:
                     cw = [self.dense_views[f"score_fc.cross_net.cross_net.{i}.w"] for i in range(len(m.score_fc.cross_net.cross_net))]
                     cb = [self.dense_views[f"score_fc.cross_net.cross_net.{i}.b"] for i in range(len(cw))]
                     tin = ops.dcn_cross_fwd(x, cw, cb)
-                y, tctx = self._tower(tin, lin, ws_override)
+                if packed is not None:
+                    main.wait_stream(self.side2)
+                y, tctx = self._tower(tin, lin, ws_override, packed=packed)
                 terms.append(y.view(-1))
             prob, loss_ps, dl = ops.logit_loss_fwd(terms, bias, label)
             # ---- backward ----
@@ -249,9 +264,11 @@ class FusedTrainer:
                 if gx is None:
                     gx = torch.zeros_like(x)
                 ops.field_logit_bwd(x, field[0], field[1], field[2], dl, gx, accumulate=True)
-        self._reduce(loss_ps, 1.0 / self.B, self.loss)
-        if bias is not None:
-            self._reduce(dl, 1.0, self.grad_views["score_fc.bias"])
+        if bias is not None:  # mean loss and d/dbias = sum(dlogit) in one launch
+            L.check(lib.nrx_reduce2_f32(loss_ps.data_ptr(), loss_ps.numel(), 1.0 / self.B, self.loss.data_ptr(), dl.data_ptr(),
+                                        dl.numel(), 1.0, self.grad_views["score_fc.bias"].data_ptr(), self._sp()), "nrx_reduce2_f32")
+        else:
+            self._reduce(loss_ps, 1.0 / self.B, self.loss)
         main.wait_stream(self.side)
         self.prob = prob
         self._plan = plan
