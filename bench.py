@@ -229,6 +229,8 @@ def algorithmic(kind, cfg, B):
         "nrx_logit_loss_fwd": ("hbm", B * 24),
         "nrx_tower_fwd": ("tensor", B * tower_flops),
         "nrx_tower_bwd": ("tensor", 2 * B * tower_flops),
+        "nrx_tower_bwd_dx": ("tensor", B * tower_flops),
+        "nrx_tower_bwd_dw": ("tensor", B * tower_flops),
         "nrx_dcn_cross_fwd": ("hbm", B * 4 * (sd + 2 * sd)),
         "nrx_dcn_cross_bwd": ("hbm", B * 4 * (sd + 2 * sd + sd)),
         "nrx_embed_bwd_plan": ("hbm", B * n_occ * (8 + 8 + 3 * 16)),
@@ -485,6 +487,8 @@ def main():
     # dominant call ON THE CRITICAL PATH: the sort plan and the optimizer clock run on the forked stream,
     # concurrently with forward + backward, and are listed in `kernels` with "stream": "forked"
     forked = {"nrx_embed_bwd_plan", "nrx_hparams_step", "nrx_tower_pack"}
+    if kind in ("deep", "deepfm", "widedeep", "dcn"):  # these run beside the tower kernels on the third stream
+        forked |= {"nrx_field_logit_fwd", "nrx_field_logit_bwd", "nrx_reduce2_f32", "nrx_reduce_f32", "nrx_adamw_dense_dev"}
     dom = max((k for k in per_api if k not in forked), key=lambda k: per_api[k])
     bound, qty = alg.get(dom, ("hbm", 0))
     dur_s = per_api[dom] * 1e-6

@@ -196,6 +196,14 @@ int nrx_tower_bwd(const NrxTower* h_tower, const float* x, int64_t x_ld, int64_t
                   float* const* h_grad_w, float* const* h_grad_b,
                   void* ws, size_t ws_bytes, nrx_stream_t stream);
 
+/* The two halves of nrx_tower_bwd as separate calls: dX chain (writes grad_x and the dz images into `ws`) and
+ * dW / db (consumes the images).  A trainer can overlap other work that only needs grad_x with the dW half. */
+int nrx_tower_bwd_dx(const NrxTower* h_tower, int64_t B, const float* grad_y, int64_t gy_ld,
+                     float* grad_x, int64_t gx_ld, int accumulate_gx, void* ws, size_t ws_bytes,
+                     nrx_stream_t stream);
+int nrx_tower_bwd_dw(const NrxTower* h_tower, int64_t B, float* const* h_grad_w, float* const* h_grad_b,
+                     void* ws, size_t ws_bytes, nrx_stream_t stream);
+
 /* Layout of the bf16 tile images the training forward/backward keep in `ws` (tests, tooling):
  * image of layer l's input (width act_width[l]) and of dL/dz_l (width dz_width[l]), each stored as
  * [tile][width/8][128 rows][8] bf16 — the UMMA operand layout, see DESIGN.md. */

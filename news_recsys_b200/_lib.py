@@ -88,6 +88,8 @@ SIGNATURES = {
     "nrx_tower_fwd": (C.c_int, [C.POINTER(NrxTower), _P, _I64, _I64, _P, _I64, C.c_int, _P, _SZ, _P]),
     "nrx_tower_bwd": (C.c_int, [C.POINTER(NrxTower), _P, _I64, _I64, _P, _I64, _P, _I64, C.c_int,
                                 C.POINTER(_P), C.POINTER(_P), _P, _SZ, _P]),
+    "nrx_tower_bwd_dx": (C.c_int, [C.POINTER(NrxTower), _I64, _P, _I64, _P, _I64, C.c_int, _P, _SZ, _P]),
+    "nrx_tower_bwd_dw": (C.c_int, [C.POINTER(NrxTower), _I64, C.POINTER(_P), C.POINTER(_P), _P, _SZ, _P]),
     "nrx_tower_image_layout": (C.c_int, [C.POINTER(NrxTower), _I64, C.POINTER(_I64), C.POINTER(_I32), C.POINTER(_I64), C.POINTER(_I32)]),
     "nrx_dcn_cross_fwd": (C.c_int, [_P, _I64, _I64, C.c_int, C.c_int, C.POINTER(_P), C.POINTER(_P), _P, _I64, _P, _P]),
     "nrx_dcn_cross_bwd": (C.c_int, [_P, _I64, _I64, C.c_int, C.c_int, C.POINTER(_P), C.POINTER(_P), _P, _I64, _P,
@@ -134,7 +136,7 @@ def load() -> C.CDLL:
 
 
 # kernels of OURS launched per successful API call (library kernels such as the CUB radix sort are not counted)
-KERNELS_PER_CALL = {"nrx_tower_fwd": 2, "nrx_tower_fwd(prepacked)": 1, "nrx_tower_bwd": 3, "nrx_embed_bwd_apply": 2, "nrx_dcn_cross_bwd": 2,
+KERNELS_PER_CALL = {"nrx_tower_fwd": 2, "nrx_tower_fwd(prepacked)": 1, "nrx_tower_bwd": 3, "nrx_tower_bwd_dw": 2, "nrx_embed_bwd_apply": 2, "nrx_dcn_cross_bwd": 2,
                     "nrx_embed_bwd_apply(dense)": 2, "nrx_embed_bwd_apply(rowopt)": 2, "nrx_topk_ip": 2,
                     "nrx_topk_search": 5, "nrx_topk_index_build": 1,
                     "nrx_tower_workspace_bytes": 0, "nrx_embed_bwd_workspace_bytes": 0, "nrx_tower_image_layout": 0}

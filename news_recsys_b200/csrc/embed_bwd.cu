@@ -94,6 +94,82 @@ build_keys_kernel(const __grid_constant__ DFeats P, int row_bits, uint32_t senti
   vals[p] = (uint32_t)p;
 }
 
+// ---- small-batch plan: one CTA per table, keys built and sorted in shared memory ---------------------------
+// Segment s holds every occurrence of table s (features in descriptor order); it occupies positions
+// [seg_off[s], seg_off[s+1]) of the sorted arrays.  Inside a segment valid keys come first (ascending row,
+// stable), then the segment's sentinels; equal keys stay contiguous, which is all the apply kernels need.
+static constexpr int kSmallThreads = 1024;
+static constexpr int kSmallItems = 16;  // 16384 occurrences per table at most
+using SmallSort = cub::BlockRadixSort<uint32_t, kSmallThreads, kSmallItems, uint32_t>;
+
+struct SmallPlan {
+  int n_seg;
+  int seg_table[NRX_MAX_TABLES];
+  int seg_off[NRX_MAX_TABLES + 1];
+};
+
+static bool make_small_plan(const DFeats& d, SmallPlan* sp) {
+  memset(sp, 0, sizeof(*sp));
+  long long off = 0;
+  for (int t = 0; t < d.n_tables; ++t) {
+    long long cnt = 0;
+    for (int i = 0; i < d.n; ++i)
+      if (d.f[i].table_id == t) cnt += (i + 1 < d.n ? d.f[i + 1].occ_off : d.n_occ) - d.f[i].occ_off;
+    if (cnt == 0) continue;
+    if (cnt > kSmallThreads * kSmallItems) return false;
+    sp->seg_table[sp->n_seg] = t;
+    sp->seg_off[sp->n_seg] = (int)off;
+    off += cnt;
+    ++sp->n_seg;
+  }
+  sp->seg_off[sp->n_seg] = (int)off;
+  return sp->n_seg > 0 && off == d.n_occ;
+}
+
+__global__ void __launch_bounds__(kSmallThreads, 1)
+plan_small_kernel(const __grid_constant__ DFeats P, const __grid_constant__ SmallPlan S, int row_bits, uint32_t sentinel,
+                  uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out) {
+  extern __shared__ __align__(16) unsigned char sm_raw[];
+  SmallSort::TempStorage& temp = *reinterpret_cast<SmallSort::TempStorage*>(sm_raw);
+  const int seg = blockIdx.x;
+  const int t = S.seg_table[seg];
+  const int n = S.seg_off[seg + 1] - S.seg_off[seg];
+  uint32_t k[kSmallItems], v[kSmallItems];
+#pragma unroll
+  for (int j = 0; j < kSmallItems; ++j) {
+    const int e = threadIdx.x * kSmallItems + j;  // blocked arrangement: position inside the segment
+    k[j] = 0xffffffffu;                           // padding beyond the segment sorts last and is never written
+    v[j] = 0;
+    if (e < n) {
+      // e-th occurrence of table t: walk the features of this table in descriptor order
+      int rem = e;
+      for (int i = 0; i < P.n; ++i) {
+        if (P.f[i].table_id != t) continue;
+        const long long cnt = (i + 1 < P.n ? P.f[i + 1].occ_off : P.n_occ) - P.f[i].occ_off;
+        if (rem < cnt) {
+          const DFeat& F = P.f[i];
+          const long long id = load_idx(F.idx, rem, F.idx32);
+          bool valid = id > 0 && id < F.rows;
+          if (valid && F.pool == NRX_POOL_MASKED_MEAN) valid = __ldg(F.mask + rem) != 0.f;
+          k[j] = valid ? (((uint32_t)t << row_bits) | (uint32_t)id) : sentinel;
+          v[j] = (uint32_t)(F.occ_off + rem);
+          break;
+        }
+        rem -= (int)cnt;
+      }
+    }
+  }
+  // sort on the key bits + the sentinel bit only (the 0xffffffff padding still sorts last: all ones below the cut)
+  SmallSort(temp).Sort(k, v, 0, 32 - __clz(sentinel));
+  uint32_t* ko = keys_out + S.seg_off[seg];
+  uint32_t* vo = vals_out + S.seg_off[seg];
+#pragma unroll
+  for (int j = 0; j < kSmallItems; ++j) {
+    const int e = threadIdx.x * kSmallItems + j;
+    if (e < n) { ko[e] = k[j]; vo[e] = v[j]; }
+  }
+}
+
 // ---- finalise one unique row (lanes own columns c = lane + 32*k) -------------------------
 template <int NC>
 __device__ __forceinline__ void finalize_row(const DTables& T, uint32_t key, const float (&acc)[NC], int lane) {
@@ -348,6 +424,19 @@ extern "C" int nrx_embed_bwd_plan(const NrxFeat* h_feats, int n_feats, int64_t B
   cudaStream_t st = (cudaStream_t)stream;
   char* w = (char*)ws;
   const uint32_t sentinel = 1u << L.key_bits;
+  {
+    // Small-batch fast path: when every table's occurrences fit one CTA (<= 16384), a single launch builds
+    // the keys and sorts each table's segment in shared memory (one CTA per table).
+    SmallPlan sp;
+    if (make_small_plan(d, &sp)) {
+      const size_t smem = sizeof(SmallSort::TempStorage);
+      cudaError_t e = cudaFuncSetAttribute(plan_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      NRX_REQUIRE(e == cudaSuccess, NRX_ELAUNCH, "smem opt-in: %s", cudaGetErrorString(e));
+      plan_small_kernel<<<sp.n_seg, kSmallThreads, smem, st>>>(d, sp, L.row_bits, sentinel, (uint32_t*)(w + L.keys_out),
+                                                              (uint32_t*)(w + L.vals_out));
+      return check_launch("plan_small");
+    }
+  }
   const unsigned blocks = (unsigned)((d.n_occ + 255) / 256);
   build_keys_kernel<<<blocks, 256, 0, st>>>(d, L.row_bits, sentinel, (uint32_t*)(w + L.keys_in), (uint32_t*)(w + L.vals_in));
   rc = check_launch("build_keys");

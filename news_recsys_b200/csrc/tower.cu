@@ -722,17 +722,14 @@ extern "C" int nrx_tower_fwd(const NrxTower* h_tower, const float* x, int64_t x_
   return check_launch("tower_fwd");
 }
 
-extern "C" int nrx_tower_bwd(const NrxTower* h_tower, const float* x, int64_t x_ld, int64_t B, const float* grad_y,
-                             int64_t gy_ld, float* grad_x, int64_t gx_ld, int accumulate_gx, float* const* h_grad_w,
-                             float* const* h_grad_b, void* ws, size_t ws_bytes, nrx_stream_t stream) {
-  (void)x; (void)x_ld;  // the forward saved the bf16 image of x in ws
+extern "C" int nrx_tower_bwd_dx(const NrxTower* h_tower, int64_t B, const float* grad_y, int64_t gy_ld, float* grad_x,
+                                int64_t gx_ld, int accumulate_gx, void* ws, size_t ws_bytes, nrx_stream_t stream) {
   TowerK k;
   int rc = make_tower(h_tower, B, 1, &k);
   if (rc != NRX_OK) return rc;
   NRX_REQUIRE(ws && ws_bytes >= k.total_bytes, NRX_EWORKSPACE, "workspace %zu < %zu", ws_bytes, k.total_bytes);
   NRX_REQUIRE(grad_y || B == 0, NRX_EINVAL, "null grad_y");
   NRX_REQUIRE(gy_ld >= k.N[k.n_layers - 1] && (!grad_x || gx_ld >= k.K[0]), NRX_EINVAL, "leading dimension too small");
-  NRX_REQUIRE(h_grad_w && h_grad_b, NRX_EINVAL, "null gradient pointer arrays");
   if (B == 0) return NRX_OK;
   cudaStream_t st = (cudaStream_t)stream;
   uint8_t* w = (uint8_t*)ws;
@@ -745,8 +742,20 @@ extern "C" int nrx_tower_bwd(const NrxTower* h_tower, const float* x, int64_t x_
     tower_bwd_dx_kernel<<<(unsigned)grid, kFwdThreads, smem, st>>>(k, B, grad_y, gy_ld, grad_x, gx_ld, accumulate_gx,
                                                                   w + k.wtpack_off, w);
     rc = check_launch("tower_bwd_dx");
-    if (rc != NRX_OK) return rc;
   }
+  return rc;
+}
+
+extern "C" int nrx_tower_bwd_dw(const NrxTower* h_tower, int64_t B, float* const* h_grad_w, float* const* h_grad_b, void* ws,
+                                size_t ws_bytes, nrx_stream_t stream) {
+  TowerK k;
+  int rc = make_tower(h_tower, B, 1, &k);
+  if (rc != NRX_OK) return rc;
+  NRX_REQUIRE(ws && ws_bytes >= k.total_bytes, NRX_EWORKSPACE, "workspace %zu < %zu", ws_bytes, k.total_bytes);
+  NRX_REQUIRE(h_grad_w && h_grad_b, NRX_EINVAL, "null gradient pointer arrays");
+  if (B == 0) return NRX_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  uint8_t* w = (uint8_t*)ws;
   {
     const size_t smem = (size_t)kDwStages * (kStageM + kStageN);
     cudaError_t e = cudaFuncSetAttribute(tower_bwd_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -771,6 +780,15 @@ extern "C" int nrx_tower_bwd(const NrxTower* h_tower, const float* x, int64_t x_
     rc = check_launch("tower_bwd_reduce");
   }
   return rc;
+}
+
+extern "C" int nrx_tower_bwd(const NrxTower* h_tower, const float* x, int64_t x_ld, int64_t B, const float* grad_y,
+                             int64_t gy_ld, float* grad_x, int64_t gx_ld, int accumulate_gx, float* const* h_grad_w,
+                             float* const* h_grad_b, void* ws, size_t ws_bytes, nrx_stream_t stream) {
+  (void)x; (void)x_ld;  // the forward saved the bf16 image of x in ws
+  int rc = nrx_tower_bwd_dx(h_tower, B, grad_y, gy_ld, grad_x, gx_ld, accumulate_gx, ws, ws_bytes, stream);
+  if (rc != NRX_OK) return rc;
+  return nrx_tower_bwd_dw(h_tower, B, h_grad_w, h_grad_b, ws, ws_bytes, stream);
 }
 
 // Byte offsets (inside the training workspace) and widths of the saved tile images, for tests and tooling:

@@ -53,6 +53,8 @@ def gather_batch(local: Dict[str, torch.Tensor], keys: List[str], group=None) ->
 # --------------------------------------------------------------------------- #
 
 class DataParallelTrainer(FusedTrainer):
+    _inline_update = False  # the row update needs the all-gathered gradients of every rank
+
     def __init__(self, model, B: int, kind=None, group=None, use_graph: bool = True, **kw):
         self.group = group
         self.world = dist.get_world_size(group)
@@ -150,6 +152,8 @@ class ShardedEmbeddingTrainer(FusedTrainer):
          rank and stay bitwise identical.
     The exchange moves G*B*ΣD*4 bytes per direction (a reduce-scatter instead of the ids/vectors all-to-all
     of an owner-compute design): simple and shape-static first, traffic-optimal later."""
+
+    _inline_update = False
 
     def __init__(self, model, B: int, kind=None, group=None, shard_min_rows: int = 100_000, **kw):
         self.group = group

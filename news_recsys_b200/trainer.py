@@ -16,6 +16,7 @@ Differences from the autograd route (model(batch); loss.backward(); torch.optim.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -100,6 +101,7 @@ class FusedTrainer:
             self._wd_idx = torch.as_tensor(deep_cols, device=self.dev)
         self.side = torch.cuda.Stream(device=self.dev)
         self.side2 = torch.cuda.Stream(device=self.dev)
+        self.side3 = torch.cuda.Stream(device=self.dev)
         self.loss = torch.zeros(1, dtype=torch.float32, device=self.dev)
         self.prob = None
         self.graph = None
@@ -159,15 +161,28 @@ class FusedTrainer:
         with torch.cuda.stream(self.side2):
             return ops.tower_prepack(self.B, ws, bs, None, training=True)
 
-    def _tower_bwd(self, tctx, dl, lin_names, gw_override=None):
+    def _tower_bwd_dx(self, tctx, dl):
+        t, keep, ws, nbytes, x = tctx
+        gx = torch.empty_like(x)
+        L.check(self.lib.nrx_tower_bwd_dx(C.byref(t), x.shape[0], dl.data_ptr(), 1, gx.data_ptr(), gx.stride(0), 0,
+                                          ws.data_ptr(), nbytes, self._sp()), "nrx_tower_bwd_dx")
+        return gx
+
+    def _tower_bwd_dw(self, tctx, lin_names, gw_override=None):
         t, keep, ws, nbytes, x = tctx
         gws = gw_override or [self.grad_views[n + ".weight"] for n in lin_names]
         gbs = [self.grad_views[n + ".bias"] for n in lin_names]
-        gx = torch.empty_like(x)
-        L.check(self.lib.nrx_tower_bwd(C.byref(t), x.data_ptr(), x.stride(0), x.shape[0], dl.data_ptr(), 1, gx.data_ptr(),
-                                       gx.stride(0), 0, L.ptr_array(gws, L.NRX_MAX_LAYERS), L.ptr_array(gbs, L.NRX_MAX_LAYERS),
-                                       ws.data_ptr(), nbytes, self._sp()), "nrx_tower_bwd")
-        return gx
+        L.check(self.lib.nrx_tower_bwd_dw(C.byref(t), x.shape[0], L.ptr_array(gws, L.NRX_MAX_LAYERS),
+                                          L.ptr_array(gbs, L.NRX_MAX_LAYERS), ws.data_ptr(), nbytes, self._sp()),
+                "nrx_tower_bwd_dw")
+
+    def _loss_and_bias_grad(self, loss_ps, dl, bias):
+        if bias is not None:  # mean loss and d/dbias = sum(dlogit) in one launch
+            L.check(self.lib.nrx_reduce2_f32(loss_ps.data_ptr(), loss_ps.numel(), 1.0 / self.B, self.loss.data_ptr(),
+                                             dl.data_ptr(), dl.numel(), 1.0, self.grad_views["score_fc.bias"].data_ptr(),
+                                             self._sp()), "nrx_reduce2_f32")
+        else:
+            self._reduce(loss_ps, 1.0 / self.B, self.loss)
 
     def _lin_names(self, prefix):
         names, i = [], 0
@@ -189,8 +204,13 @@ class FusedTrainer:
         """K1: features [B, ΣD] of the local batch (the row-sharded trainer overrides this with the exchange)."""
         return ops.embed_pool_fwd(self.fb, self.out_dim)
 
+    # single-GPU trainers apply the sparse-row update inside _fwd_bwd (overlapped with dW); the distributed
+    # trainers need the gradient exchange first and keep it in _update
+    _inline_update = os.environ.get("NRX_INLINE_APPLY", "0") == "1"
+
     def _fwd_bwd(self):
         m, fb, lib = self.model, self.fb, self.lib
+        self._rows_applied = False
         main = torch.cuda.current_stream(self.dev)
         self.side.wait_stream(main)
         with torch.cuda.stream(self.side):  # off the critical path: only the optimizer consumes these
@@ -226,9 +246,16 @@ class FusedTrainer:
                 field = (wide_cols, [1] * len(wide_cols), L.FIELD_WIDE)
             elif kind == "lr":
                 field = (cols, list(self.dims), L.FIELD_SUM)
+            has_tower = kind in ("deep", "deepfm", "widedeep", "dcn")
+            s3 = self.side3
             if field is not None:
-                terms.append(ops.field_logit_fwd(x, field[0], field[1], field[2]))
-            if kind in ("deep", "deepfm", "widedeep", "dcn"):
+                if has_tower:  # field logit || tower forward (both only read x)
+                    s3.wait_stream(main)
+                    with torch.cuda.stream(s3):
+                        terms.append(ops.field_logit_fwd(x, field[0], field[1], field[2]))
+                else:
+                    terms.append(ops.field_logit_fwd(x, field[0], field[1], field[2]))
+            if has_tower:
                 lin = self._lin_names(self._TOWER_PREFIX[kind])
                 tin, ws_override = x, None
                 if kind == "widedeep":  # column selection moved to the weight side (see widedeep/model.py)
@@ -246,11 +273,26 @@ class FusedTrainer:
                     main.wait_stream(self.side2)
                 y, tctx = self._tower(tin, lin, ws_override, packed=packed)
                 terms.append(y.view(-1))
+                if field is not None:
+                    main.wait_stream(s3)
             prob, loss_ps, dl = ops.logit_loss_fwd(terms, bias, label)
             # ---- backward ----
             gx = None
             if tctx is not None:
-                g_tin = self._tower_bwd(tctx, dl, lin, gw_override)
+                g_tin = self._tower_bwd_dx(tctx, dl)
+                # the scalar reductions and the field-logit backward only need dl / grad_x: run them on the third
+                # stream while the dW GEMMs (and, for DCN, the cross backward) proceed on the main one
+                s3.wait_stream(main)
+                inline = self._inline_update and kind != "dcn"
+                with torch.cuda.stream(s3):
+                    self._loss_and_bias_grad(loss_ps, dl, bias)
+                    if field is not None:
+                        ops.field_logit_bwd(x, field[0], field[1], field[2], dl, g_tin, accumulate=True)
+                    if inline:  # grad_x is final here: update the embedding rows while dW is still being computed
+                        s3.wait_stream(self.side)
+                        self._apply_rows(self._plan_fb(), plan, g_tin)
+                        self._rows_applied = True
+                self._tower_bwd_dw(tctx, lin, gw_override)
                 if kind == "widedeep":
                     self.grad_views[lin[0] + ".weight"].copy_(gw_override[0].index_select(1, idx))
                 if kind == "dcn":
@@ -260,22 +302,20 @@ class FusedTrainer:
                         self.grad_views[f"score_fc.cross_net.cross_net.{i}.b"].copy_(gcb[i].view(-1, 1))
                 else:
                     gx = g_tin
-            if field is not None:
-                if gx is None:
-                    gx = torch.zeros_like(x)
+                main.wait_stream(s3)
+            else:
+                gx = torch.zeros_like(x)
                 ops.field_logit_bwd(x, field[0], field[1], field[2], dl, gx, accumulate=True)
-        if bias is not None:  # mean loss and d/dbias = sum(dlogit) in one launch
-            L.check(lib.nrx_reduce2_f32(loss_ps.data_ptr(), loss_ps.numel(), 1.0 / self.B, self.loss.data_ptr(), dl.data_ptr(),
-                                        dl.numel(), 1.0, self.grad_views["score_fc.bias"].data_ptr(), self._sp()), "nrx_reduce2_f32")
-        else:
-            self._reduce(loss_ps, 1.0 / self.B, self.loss)
+                self._loss_and_bias_grad(loss_ps, dl, bias)
+        if self.fm_fused:
+            self._loss_and_bias_grad(loss_ps, dl, bias)
         main.wait_stream(self.side)
         self.prob = prob
         self._plan = plan
         self._gx = gx.contiguous()
 
-    def _update(self, fb, plan, gx):
-        """Optimizer: fused sparse-row AdamW on the tables (K3 apply) + dense AdamW on the flat buffer."""
+    def _apply_rows(self, fb, plan, gx):
+        """K3 apply: fused sparse-row AdamW on the embedding tables, on the current stream."""
         lib = self.lib
         opt = L.NrxRowOpt()
         opt.lr, opt.beta1, opt.beta2, opt.eps, opt.weight_decay, opt.step = self.lr, self.betas[0], self.betas[1], self.eps, self.wd, 1
@@ -287,10 +327,35 @@ class FusedTrainer:
         L.check(lib.nrx_embed_bwd_apply(fb.arr, fb.n, fb.B, gx.data_ptr(), gx.stride(0), L.BWD_ADAMW, None,
                                         L.ptr_array(self.tables_by_id, L.NRX_MAX_TABLES), C.byref(opt), plan.ws.data_ptr(),
                                         plan.bytes, self._sp()), "nrx_embed_bwd_apply")
+
+    def _update(self, fb, plan, gx):
+        """Optimizer: fused sparse-row AdamW on the tables (K3 apply) + dense AdamW on the flat buffer."""
+        lib = self.lib
+        if self._rows_applied:  # the rows were updated inside _fwd_bwd; only the dense parameters are left
+            if self.n_dense > 0:
+                L.check(lib.nrx_adamw_dense_dev(self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.flat_m.data_ptr(),
+                                                self.flat_v.data_ptr(), self.n_dense, self.d_hp.data_ptr(), self.betas[0],
+                                                self.betas[1], self.eps, self.wd, self._sp()), "nrx_adamw_dense_dev")
+            return
+        opt = L.NrxRowOpt()
+        opt.lr, opt.beta1, opt.beta2, opt.eps, opt.weight_decay, opt.step = self.lr, self.betas[0], self.betas[1], self.eps, self.wd, 1
+        for t in range(L.NRX_MAX_TABLES):
+            if self.m_by_id[t] is not None:
+                opt.m[t] = self.m_by_id[t].data_ptr()
+                opt.v[t] = self.v_by_id[t].data_ptr()
+        opt.d_hparams = self.d_hp.data_ptr()
+        main = torch.cuda.current_stream(self.dev)
+        if self.n_dense > 0:  # dense AdamW || sparse-row apply: disjoint parameters
+            self.side3.wait_stream(main)
+            with torch.cuda.stream(self.side3):
+                L.check(lib.nrx_adamw_dense_dev(self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.flat_m.data_ptr(),
+                                                self.flat_v.data_ptr(), self.n_dense, self.d_hp.data_ptr(), self.betas[0],
+                                                self.betas[1], self.eps, self.wd, self._sp()), "nrx_adamw_dense_dev")
+        L.check(lib.nrx_embed_bwd_apply(fb.arr, fb.n, fb.B, gx.data_ptr(), gx.stride(0), L.BWD_ADAMW, None,
+                                        L.ptr_array(self.tables_by_id, L.NRX_MAX_TABLES), C.byref(opt), plan.ws.data_ptr(),
+                                        plan.bytes, self._sp()), "nrx_embed_bwd_apply")
         if self.n_dense > 0:
-            L.check(lib.nrx_adamw_dense_dev(self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.flat_m.data_ptr(),
-                                            self.flat_v.data_ptr(), self.n_dense, self.d_hp.data_ptr(), self.betas[0],
-                                            self.betas[1], self.eps, self.wd, self._sp()), "nrx_adamw_dense_dev")
+            main.wait_stream(self.side3)
 
     def _capture(self):
         # warm up on a side stream (lazy module/attribute initialisation must not happen inside capture)
