@@ -46,7 +46,7 @@ int make_dfeats(const NrxFeat* feats, int n, long long B, const void* out, long 
   int max_table = -1;
   for (int i = 0; i < n; ++i) {
     const NrxFeat& s = feats[i];
-    NRX_REQUIRE(s.table && s.idx, NRX_EINVAL, "feature %d: null table/idx", i);
+    NRX_REQUIRE(s.table && (s.idx || B == 0), NRX_EINVAL, "feature %d: null table/idx", i);  // empty batch: null idx ok
     NRX_REQUIRE(s.rows > 0 && s.dim > 0 && s.row_stride >= s.dim, NRX_EINVAL, "feature %d: bad rows/dim/stride", i);
     NRX_REQUIRE(s.L >= 1, NRX_EINVAL, "feature %d: L must be >= 1", i);
     NRX_REQUIRE(s.pool == NRX_POOL_NONE || s.pool == NRX_POOL_MASKED_MEAN || s.pool == NRX_POOL_MEAN, NRX_EINVAL,
