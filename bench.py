@@ -336,6 +336,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="deepfm")
+    ap.add_argument("--table-update", default="dense", choices=["dense", "sparse"],
+                    help="dense: the reference's optimizer (dense AdamW over every table row, every step); "
+                         "sparse: fused lazy sparse-row AdamW inside K3 (touched rows only)")
     ap.add_argument("--cpu-steps", type=int, default=0, help="override the CPU arm's step count")
     ap.add_argument("--no-retrieval", action="store_true", help="skip the DSSM top-100 retrieval leg (BASELINE config 4)")
     ap.add_argument("--quick", action="store_true",
@@ -378,9 +381,9 @@ def main():
     model = model_class(kind)(cfg).to(dev)
     if world > 1:
         from news_recsys_b200.parallel import DataParallelTrainer
-        trainer = DataParallelTrainer(model, B, kind=kind)
+        trainer = DataParallelTrainer(model, B, kind=kind, table_update=args.table_update)
     else:
-        trainer = FusedTrainer(model, B, kind=kind)
+        trainer = FusedTrainer(model, B, kind=kind, table_update=args.table_update)
     # batch pools: device pool > L2 (126 MB) so consecutive steps never find their inputs in L2
     blob_bytes = trainer.layout.nbytes
     n_pool = 8 if args.quick else max(8, int(160e6 // blob_bytes) + 1)  # --quick (profiler runs): few setup kernels
@@ -480,7 +483,7 @@ def main():
         # per-kernel timing must not issue collectives from rank 0 alone: time the same per-GPU kernels on a
         # private single-GPU trainer (same model class / config / batch size)
         torch.manual_seed(42)
-        prof_trainer = FusedTrainer(model_class(kind)(cfg).to(dev), B, kind=kind)
+        prof_trainer = FusedTrainer(model_class(kind)(cfg).to(dev), B, kind=kind, table_update=args.table_update)
     per_api, launches_per_step = profile_apis(prof_trainer, pool, n=2 if args.quick else 10)
     alg = algorithmic(kind, cfg, B)
     hbm_peak, tf_peak, peak_src = peaks()
@@ -522,7 +525,10 @@ def main():
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
         "config": {"workload": wl_desc, "batch_per_gpu": B,
-                   "step": "fwd + BCE + bwd + optimizer (fused sparse-row AdamW on tables, dense AdamW on the tower), one CUDA graph",
+                   "step": ("fwd + BCE + bwd + dense AdamW over tables and tower (the reference's optimizer semantics), one CUDA graph"
+                            if args.table_update == "dense" else
+                            "fwd + BCE + bwd + optimizer (fused lazy sparse-row AdamW on tables, dense AdamW on the tower), one CUDA graph"),
+                   "table_update": args.table_update,
                    "tables": "fp32", "tower": "bf16 tcgen05, fp32 accumulate",
                    "l2": f"inputs rotate over a {n_pool}-slot device pool ({n_pool * blob_bytes / 1e6:.0f} MB > 126 MB L2); "
                          "the MIND-small tables (10 MB) are L2-resident by nature of the workload",

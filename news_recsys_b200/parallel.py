@@ -2,7 +2,13 @@
 
 The reference is single-GPU only (`devices=1`, sort/deep/train.py:41-42); everything here is new.
 
-* DataParallelTrainer — synchronous data parallelism for the sort models with REPLICATED parameters:
+* DataParallelTrainer — synchronous data parallelism for the sort models with REPLICATED parameters.
+    table_update="dense" (default; the reference's optimizer semantics, dense AdamW over every row):
+    each rank runs forward/backward and K3 on its OWN B samples, K3 writing dense table gradients into
+    the same flat buffer as the tower gradients; ONE all-reduce (AVG) of that buffer; one dense AdamW.
+    Per-rank work does not grow with the world size; the all-reduce moves the table bytes, so this is the
+    scheme for tables that fit the NVLink budget of a step (MIND-small: ~8 MB) — larger tables shard.
+    table_update="sparse" (lazy rows, touched rows only):
     ids (and masks) of every rank are all-gathered at step start (they are known before the forward),
     so the sort plan of the GLOBAL batch runs on the forked stream while each rank does forward/backward
     on its own B samples;  then one all-reduce (AVG) of the flat dense-gradient buffer and one all-gather
@@ -15,6 +21,7 @@ The reference is single-GPU only (`devices=1`, sort/deep/train.py:41-42); everyt
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Tuple
 
 import torch
@@ -55,14 +62,18 @@ def gather_batch(local: Dict[str, torch.Tensor], keys: List[str], group=None) ->
 class DataParallelTrainer(FusedTrainer):
     _inline_update = False  # the row update needs the all-gathered gradients of every rank
 
-    def __init__(self, model, B: int, kind=None, group=None, use_graph: bool = True, **kw):
+    def __init__(self, model, B: int, kind=None, group=None, use_graph: bool = True, table_update: str = "dense", **kw):
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self._dp_ready = False
-        super().__init__(model, B, kind=kind, use_graph=False, **kw)
+        super().__init__(model, B, kind=kind, use_graph=False, table_update=table_update, **kw)
         dev = self.dev
         G = self.world
+        self.graph_a = self.graph_b = None
+        if self.table_update == "dense":
+            self._init_dense(use_graph)
+            return
         # global batch (ids / masks of every rank, rank-major) and the global feature binding for the plan
         self.id_keys = [key for key, dt, shape, off in self.layout.fields if key != "label"]
         self.gbatch = {}
@@ -73,7 +84,6 @@ class DataParallelTrainer(FusedTrainer):
         self.gfb = ops.FeatBinding(self.fb.specs, model._weights(), self.gbatch, want_inv_den=True)
         self.gx_global = torch.zeros((G * B, self.out_dim), dtype=torch.float32, device=dev)
         self._dp_ready = True
-        self.graph_a = self.graph_b = None
         # eager warm-up (also initialises NCCL communicators), then capture the two halves
         snap = self._snapshot()
         self._dp_step_eager()
@@ -92,6 +102,38 @@ class DataParallelTrainer(FusedTrainer):
 
     def _plan_fb(self):
         return self.gfb if self._dp_ready else self.fb
+
+    # ---- dense mode: local K3 into the flat gradient buffer, ONE all-reduce, one AdamW ----------
+    def _init_dense(self, use_graph):
+        snap = self._snapshot()
+        self._dense_step_eager()       # warm-up; also initialises the NCCL communicator
+        torch.cuda.synchronize(self.dev)
+        self._restore(snap)
+        self.graph_one = None
+        if use_graph and os.environ.get("NRX_DP_ONE_GRAPH", "0") == "1":
+            # whole step, all-reduce included, as ONE graph (NCCL kernels are capturable)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._dense_step_eager()
+            torch.cuda.synchronize(self.dev)
+            self._restore(snap)
+            self.graph_one = g
+        elif use_graph:
+            self.graph_a = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_a):
+                self._fwd_bwd()
+                self._dense_table_grads(self.fb, self._plan, self._gx)
+            self.graph_b = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_b, pool=self.graph_a.pool()):
+                self._adamw_flat()
+            torch.cuda.synchronize(self.dev)
+            self._restore(snap)
+
+    def _dense_step_eager(self):
+        self._fwd_bwd()
+        self._dense_table_grads(self.fb, self._plan, self._gx)
+        dist.all_reduce(self.flat_g[: self.n_dense], op=dist.ReduceOp.AVG, group=self.group)
+        self._adamw_flat()
 
     # ---- exchange steps ------------------------------------------------------------------------
     def _gather_ids(self):
@@ -114,6 +156,17 @@ class DataParallelTrainer(FusedTrainer):
         self._update(self.gfb, self._plan, self.gx_global)
 
     def step(self) -> torch.Tensor:
+        if self.table_update == "dense":
+            if self.graph_one is not None:
+                self.graph_one.replay()
+                return self.loss
+            if self.graph_a is None:
+                self._dense_step_eager()
+                return self.loss
+            self.graph_a.replay()
+            dist.all_reduce(self.flat_g[: self.n_dense], op=dist.ReduceOp.AVG, group=self.group)
+            self.graph_b.replay()
+            return self.loss
         if self.graph_a is None:
             self._dp_step_eager()
             return self.loss

@@ -72,7 +72,15 @@ class FusedTrainer:
                      "widedeep": "score_fc.deep_network.network", "dcn": "score_fc.score_fc.network"}
 
     def __init__(self, model, B: int, kind: Optional[str] = None, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01,
-                 use_graph: bool = True, id_dtype=torch.int64):
+                 use_graph: bool = True, id_dtype=torch.int64, table_update: str = "sparse"):
+        """table_update:
+             "sparse" — fused sparse-row AdamW inside K3: only the rows the batch touched move (lazy rows);
+             "dense"  — the reference's semantics: K3 writes dense table gradients into the same flat buffer as
+                        the tower gradients and ONE dense AdamW (weight decay 0.01) updates every parameter,
+                        touched or not (sort/deep/model.py:55).  Costs a pass over the tables per step."""
+        if table_update not in ("sparse", "dense"):
+            raise L.NrxError(f"table_update must be 'sparse' or 'dense', got {table_update!r}")
+        self.table_update = table_update
         self.model = model
         self.kind = kind or type(model).__name__.lower()
         if self.kind not in self.KINDS:
@@ -112,7 +120,8 @@ class FusedTrainer:
 
     # ---- parameter plumbing ------------------------------------------------------------------
     def _flatten_dense(self):
-        dense = [(n, p) for n, p in self.model.named_parameters() if not n.startswith("embedding_tables.")]
+        dense = [(n, p) for n, p in self.model.named_parameters()
+                 if self.table_update == "dense" or not n.startswith("embedding_tables.")]
         total = sum(_align(p.numel(), 4) for _, p in dense)
         self.flat_p = torch.zeros(max(total, 4), dtype=torch.float32, device=self.dev)
         self.flat_g = torch.zeros_like(self.flat_p)
@@ -133,11 +142,15 @@ class FusedTrainer:
         self.tables_by_id: List[Optional[torch.Tensor]] = [None] * L.NRX_MAX_TABLES
         self.m_by_id: List[Optional[torch.Tensor]] = [None] * L.NRX_MAX_TABLES
         self.v_by_id: List[Optional[torch.Tensor]] = [None] * L.NRX_MAX_TABLES
+        self.table_grads_by_id: List[Optional[torch.Tensor]] = [None] * L.NRX_MAX_TABLES
         for name, tid in self.model._table_ids.items():
             w = self.model.embedding_tables[name].weight.data
             self.tables_by_id[tid] = w
-            self.m_by_id[tid] = torch.zeros_like(w)
-            self.v_by_id[tid] = torch.zeros_like(w)
+            if self.table_update == "dense":   # moments live in the flat buffers
+                self.table_grads_by_id[tid] = self.grad_views[f"embedding_tables.{name}.weight"]
+            else:
+                self.m_by_id[tid] = torch.zeros_like(w)
+                self.v_by_id[tid] = torch.zeros_like(w)
 
     # ---- raw op helpers writing into preallocated buffers ------------------------------------------
     def _sp(self):
@@ -283,7 +296,7 @@ class FusedTrainer:
                 # the scalar reductions and the field-logit backward only need dl / grad_x: run them on the third
                 # stream while the dW GEMMs (and, for DCN, the cross backward) proceed on the main one
                 s3.wait_stream(main)
-                inline = self._inline_update and kind != "dcn"
+                inline = self._inline_update and kind != "dcn" and self.table_update == "sparse"
                 with torch.cuda.stream(s3):
                     self._loss_and_bias_grad(loss_ps, dl, bias)
                     if field is not None:
@@ -328,9 +341,24 @@ class FusedTrainer:
                                         L.ptr_array(self.tables_by_id, L.NRX_MAX_TABLES), C.byref(opt), plan.ws.data_ptr(),
                                         plan.bytes, self._sp()), "nrx_embed_bwd_apply")
 
+    def _dense_table_grads(self, fb, plan, gx):
+        """K3 dense mode: per-table [rows, D] gradients (zero-filled by the call) written into the flat grad buffer."""
+        L.check(self.lib.nrx_embed_bwd_apply(fb.arr, fb.n, fb.B, gx.data_ptr(), gx.stride(0), L.BWD_DENSE,
+                                             L.ptr_array(self.table_grads_by_id, L.NRX_MAX_TABLES), None, None,
+                                             plan.ws.data_ptr(), plan.bytes, self._sp()), "nrx_embed_bwd_apply(dense)")
+
+    def _adamw_flat(self):
+        L.check(self.lib.nrx_adamw_dense_dev(self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.flat_m.data_ptr(),
+                                             self.flat_v.data_ptr(), self.n_dense, self.d_hp.data_ptr(), self.betas[0],
+                                             self.betas[1], self.eps, self.wd, self._sp()), "nrx_adamw_dense_dev")
+
     def _update(self, fb, plan, gx):
         """Optimizer: fused sparse-row AdamW on the tables (K3 apply) + dense AdamW on the flat buffer."""
         lib = self.lib
+        if self.table_update == "dense":
+            self._dense_table_grads(fb, plan, gx)
+            self._adamw_flat()
+            return
         if self._rows_applied:  # the rows were updated inside _fwd_bwd; only the dense parameters are left
             if self.n_dense > 0:
                 L.check(lib.nrx_adamw_dense_dev(self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.flat_m.data_ptr(),

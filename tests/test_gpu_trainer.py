@@ -86,3 +86,60 @@ def test_graph_replay_is_deterministic():
         outs.append({k: v.detach().clone() for k, v in model.state_dict().items()})
     for k in outs[0]:
         assert torch.equal(outs[0][k], outs[1][k]), k
+
+
+@pytest.mark.parametrize("name", ["fm", "deep"])
+def test_dense_mode_matches_reference_adamw_golden(name):
+    """table_update="dense" is the reference's optimizer (dense AdamW, wd 0.01, every row every step): three
+    fused steps on the fixture batches land on the parameters the REFERENCE itself produced with its own
+    torch.optim.AdamW + CosinDecayLR (tests/golden/{fm,deep}.npz `sdopt__*`, oracle/make_golden.py)."""
+    from tests._golden import load, opt_batches
+    from news_recsys_b200.trainer import FusedTrainer
+    g = load(name)
+    z = g["z"]
+    batches = opt_batches(z)
+    B = batches[0]["label"].shape[0]
+    model = _cls(g["kind"])(g["cfg_path"])
+    model.load_state_dict(g["sd"], strict=True)
+    model = model.to(DEV)
+    tr = FusedTrainer(model, B, kind=g["kind"], table_update="dense")
+    bf16 = g["kind"] != "fm"
+    for s, b in enumerate(batches):
+        loss = float(tr.train_step(b).item())
+        ref = float(z[f"opt{s}_loss"])
+        assert abs(loss - ref) <= (2e-2 if bf16 else 1e-5) * max(1.0, abs(ref)), (s, loss, ref)
+    new_sd = model.state_dict()
+    for k, v0 in g["sd"].items():
+        got, ref = new_sd[k].detach().cpu(), torch.from_numpy(z["sdopt__" + k])
+        if not bf16:
+            torch.testing.assert_close(got, ref, rtol=1e-4, atol=2e-5, msg=lambda m: f"{name}:{k}: {m}")
+        else:
+            upd, ref_upd = got - v0, ref - v0
+            denom = ref_upd.abs().max().clamp_min(1e-12)
+            frac_bad = float(((upd - ref_upd).abs() > 0.5 * denom).float().mean())
+            assert frac_bad < 0.05, f"{name}:{k}: {frac_bad:.4f} of the updates differ"
+
+
+def test_dense_and_sparse_agree_on_touched_rows_first_step():
+    """After ONE step both modes moved the touched rows identically; dense additionally decays untouched rows."""
+    from news_recsys_b200.synthetic import mind_config, synth_batch
+    from news_recsys_b200.trainer import FusedTrainer
+    rows = {"user_id": 3000, "item_id": 200, "category": 18, "subcategory": 70, "user_click_category": 18}
+    cfg = mind_config("fm", rows)
+    b = synth_batch(cfg, 256, seed=5, label_p=0.5)
+    out = {}
+    for mode in ("sparse", "dense"):
+        torch.manual_seed(2)
+        model = _cls("fm")(cfg).to(DEV)
+        w0 = model.embedding_tables["user_id"].weight.detach().clone()
+        FusedTrainer(model, 256, kind="fm", table_update=mode).train_step(b)
+        out[mode] = model.embedding_tables["user_id"].weight.detach().clone()
+    touched = torch.zeros(3000, dtype=torch.bool, device=DEV)
+    touched[b["user_id"].view(-1).to(DEV)] = True
+    touched[0] = False
+    torch.testing.assert_close(out["dense"][touched], out["sparse"][touched], rtol=1e-6, atol=1e-7)
+    lr = cfg["train_hparams"]["lr"]
+    un = ~touched
+    un[0] = False
+    assert torch.equal(out["sparse"][un], w0[un])
+    torch.testing.assert_close(out["dense"][un], w0[un] * (1 - lr * 0.01), rtol=1e-6, atol=1e-9)
