@@ -339,6 +339,9 @@ def main():
     ap.add_argument("--table-update", default="dense", choices=["dense", "sparse"],
                     help="dense: the reference's optimizer (dense AdamW over every table row, every step); "
                          "sparse: fused lazy sparse-row AdamW inside K3 (touched rows only)")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N>1, dense mode: peer = gradient all-reduce fused with AdamW over NVLink peer memory (one graph); "
+                         "nccl = NCCL all-reduce between two graphs")
     ap.add_argument("--cpu-steps", type=int, default=0, help="override the CPU arm's step count")
     ap.add_argument("--no-retrieval", action="store_true", help="skip the DSSM top-100 retrieval leg (BASELINE config 4)")
     ap.add_argument("--quick", action="store_true",
@@ -381,7 +384,7 @@ def main():
     model = model_class(kind)(cfg).to(dev)
     if world > 1:
         from news_recsys_b200.parallel import DataParallelTrainer
-        trainer = DataParallelTrainer(model, B, kind=kind, table_update=args.table_update)
+        trainer = DataParallelTrainer(model, B, kind=kind, table_update=args.table_update, exchange=args.exchange)
     else:
         trainer = FusedTrainer(model, B, kind=kind, table_update=args.table_update)
     # batch pools: device pool > L2 (126 MB) so consecutive steps never find their inputs in L2
@@ -529,6 +532,7 @@ def main():
                             if args.table_update == "dense" else
                             "fwd + BCE + bwd + optimizer (fused lazy sparse-row AdamW on tables, dense AdamW on the tower), one CUDA graph"),
                    "table_update": args.table_update,
+                   "exchange": (None if world == 1 else (args.exchange if args.table_update == "dense" else "nccl")),
                    "tables": "fp32", "tower": "bf16 tcgen05, fp32 accumulate",
                    "l2": f"inputs rotate over a {n_pool}-slot device pool ({n_pool * blob_bytes / 1e6:.0f} MB > 126 MB L2); "
                          "the MIND-small tables (10 MB) are L2-resident by nature of the workload",

@@ -166,6 +166,42 @@ int nrx_adamw_dense_dev(float* p, const float* g, float* m, float* v, int64_t n,
 int nrx_hparams_step(int32_t* d_step, float* d_hparams, float lr, float min_lr, int32_t milestone0,
                      int32_t milestone1, float beta1, float beta2, nrx_stream_t stream);
 
+/* ---- K7: gradient all-reduce FUSED with the dense AdamW over NVLink peer memory (multi-GPU).
+ * The reference trains on one GPU (`devices=1`, sort/deep/train.py:41-42); this replaces what
+ * DistributedDataParallel's NCCL all-reduce + torch.optim.AdamW.step() would be for its models.
+ * Every rank owns one contiguous slice of the flat parameter buffer.  ONE kernel per rank per step:
+ *   barrier (all ranks finished writing their gradients)  ->  load the owned slice of g from EVERY rank's
+ *   buffer (peer loads, summed in rank order, x 1/world)  ->  AdamW on the slice with the local moments  ->
+ *   store the new parameters into EVERY rank's parameter buffer (peer stores)  ->  barrier.
+ * Replicas stay bitwise identical (each element is computed once, by its owner) and the optimizer state of a
+ * slice is live on its owner only.  Buffers come from nrx_peer_alloc (cudaMalloc'd, IPC-exportable); the 64-byte
+ * handles travel through the host's own control plane (e.g. torch.distributed all_gather_object). */
+enum { NRX_MAX_PEERS = 16, NRX_PEER_SIG_WORDS = 256 };
+
+int nrx_peer_alloc(size_t bytes, void** ptr);                        /* zero-filled device memory */
+int nrx_peer_free(void* ptr);
+int nrx_peer_export(void* ptr, unsigned char handle[64]);            /* cudaIpcGetMemHandle */
+int nrx_peer_open(const unsigned char handle[64], void** ptr);       /* map a peer's buffer (same node) */
+int nrx_peer_close(void* ptr);
+
+typedef struct NrxPeerStep {
+  int32_t rank, world;
+  float* p[NRX_MAX_PEERS];        /* flat parameter buffer of every rank; p[rank] is the local one */
+  const float* g[NRX_MAX_PEERS];  /* flat gradient buffer of every rank */
+  uint32_t* sig[NRX_MAX_PEERS];   /* signal pad of every rank: NRX_PEER_SIG_WORDS u32, zero at start */
+  float* m;                       /* local AdamW moments, n floats (only the owned slice is touched) */
+  float* v;
+  int64_t n;                      /* floats in the flat buffers; multiple of 4, buffers 16-byte aligned */
+  const float* d_hparams;         /* {lr, 1-beta1^t, sqrt(1-beta2^t)} on the device (nrx_hparams_step) */
+  float beta1, beta2, eps, weight_decay;
+} NrxPeerStep;
+
+/* Returns NRX_OK after the launch; a peer that never arrives makes the kernel give up after ~2 s and set
+ * sig[rank][NRX_PEER_SIG_ERR] (read it with nrx_peer_status) instead of hanging the GPU. */
+enum { NRX_PEER_SIG_ERR = 130 };
+int nrx_adamw_allreduce_peer(const NrxPeerStep* step, nrx_stream_t stream);
+int nrx_peer_status(const uint32_t* sig, int32_t* timed_out, nrx_stream_t stream);  /* synchronises the stream */
+
 /* ---- K4/K5: fused bf16 tower on tcgen05 (MLP utils.py:6-17, DSSM towers
  * recall/DSSM/model.py:26-44, DCN cross dcn_arch.py:14-30,53-70) --------------- */
 enum { NRX_ACT_RELU = 0, NRX_ACT_LEAKY = 1 };

@@ -17,6 +17,8 @@ LIB_PATH = os.path.join(_HERE, "libnrx.so")
 NRX_MAX_FEATS = 16
 NRX_MAX_TABLES = 16
 NRX_MAX_LAYERS = 8
+NRX_MAX_PEERS = 16
+NRX_PEER_SIG_WORDS = 256
 
 POOL_NONE, POOL_MASKED_MEAN, POOL_MEAN = 0, 1, 2
 IDX_I64, IDX_I32 = 0, 1
@@ -44,6 +46,15 @@ class NrxRowOpt(C.Structure):
         ("weight_decay", C.c_float), ("step", C.c_int32),
         ("m", C.c_void_p * NRX_MAX_TABLES), ("v", C.c_void_p * NRX_MAX_TABLES),
         ("d_hparams", C.c_void_p),
+    ]
+
+
+class NrxPeerStep(C.Structure):
+    _fields_ = [
+        ("rank", C.c_int32), ("world", C.c_int32),
+        ("p", C.c_void_p * NRX_MAX_PEERS), ("g", C.c_void_p * NRX_MAX_PEERS), ("sig", C.c_void_p * NRX_MAX_PEERS),
+        ("m", C.c_void_p), ("v", C.c_void_p), ("n", C.c_int64), ("d_hparams", C.c_void_p),
+        ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("weight_decay", C.c_float),
     ]
 
 
@@ -83,6 +94,13 @@ SIGNATURES = {
     "nrx_adamw_dense": (C.c_int, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _I32, _P]),
     "nrx_adamw_dense_dev": (C.c_int, [_P, _P, _P, _P, _I64, _P, _F, _F, _F, _F, _P]),
     "nrx_hparams_step": (C.c_int, [_P, _P, _F, _F, _I32, _I32, _F, _F, _P]),
+    "nrx_peer_alloc": (C.c_int, [_SZ, C.POINTER(_P)]),
+    "nrx_peer_free": (C.c_int, [_P]),
+    "nrx_peer_export": (C.c_int, [_P, C.c_char_p]),
+    "nrx_peer_open": (C.c_int, [C.c_char_p, C.POINTER(_P)]),
+    "nrx_peer_close": (C.c_int, [_P]),
+    "nrx_adamw_allreduce_peer": (C.c_int, [C.POINTER(NrxPeerStep), _P]),
+    "nrx_peer_status": (C.c_int, [_P, C.POINTER(C.c_int32), _P]),
     "nrx_tower_workspace_bytes": (_SZ, [C.POINTER(NrxTower), _I64, C.c_int]),
     "nrx_tower_pack": (C.c_int, [C.POINTER(NrxTower), _I64, C.c_int, _P, _SZ, _P]),
     "nrx_tower_fwd": (C.c_int, [C.POINTER(NrxTower), _P, _I64, _I64, _P, _I64, C.c_int, _P, _SZ, _P]),
@@ -139,6 +157,8 @@ def load() -> C.CDLL:
 KERNELS_PER_CALL = {"nrx_tower_fwd": 2, "nrx_tower_fwd(prepacked)": 1, "nrx_tower_bwd": 3, "nrx_tower_bwd_dw": 2, "nrx_embed_bwd_apply": 2, "nrx_dcn_cross_bwd": 2,
                     "nrx_embed_bwd_apply(dense)": 2, "nrx_embed_bwd_apply(rowopt)": 2, "nrx_topk_ip": 2,
                     "nrx_topk_search": 5, "nrx_topk_index_build": 1,
+                    "nrx_peer_alloc": 0, "nrx_peer_free": 0, "nrx_peer_export": 0, "nrx_peer_open": 0, "nrx_peer_close": 0,
+                    "nrx_peer_status": 0,
                     "nrx_tower_workspace_bytes": 0, "nrx_embed_bwd_workspace_bytes": 0, "nrx_tower_image_layout": 0}
 launch_count = 0  # running total, read by bench.py
 

@@ -57,6 +57,17 @@ __device__ __forceinline__ long long load_idx(const void* p, long long i, int id
                : __ldg(reinterpret_cast<const long long*>(p) + i);
 }
 
+// torch.optim.AdamW update of one element (deep/model.py:55); shared by the dense kernels and K7 so that the
+// single-GPU and the peer-memory step round identically.
+__device__ __forceinline__ void adamw_update(float& p, float g, float& m, float& v, float lr, float bc1, float bc2s,
+                                             float b1, float b2, float eps, float wd) {
+  float pi = p * (1.f - lr * wd);
+  m = b1 * m + (1.f - b1) * g;
+  v = b2 * v + (1.f - b2) * g * g;
+  pi -= (lr / bc1) * (m / (sqrtf(v) / bc2s + eps));
+  p = pi;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(NRX_FULL_MASK, v, o);

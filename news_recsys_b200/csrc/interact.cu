@@ -314,13 +314,42 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
   if (d_hp) { lr = __ldg(d_hp); bc1 = __ldg(d_hp + 1); bc2s = __ldg(d_hp + 2); }
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    float pi = p[i] * (1.f - lr * wd);
-    const float gi = g[i];
-    const float mi = b1 * m[i] + (1.f - b1) * gi;
-    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
-    pi -= (lr / bc1) * (mi / (sqrtf(vi) / bc2s + eps));
+    float pi = p[i], mi = m[i], vi = v[i];
+    adamw_update(pi, g[i], mi, vi, lr, bc1, bc2s, b1, b2, eps, wd);
     p[i] = pi; m[i] = mi; v[i] = vi;
   }
+}
+
+// float4 flavour: n4 = n / 4, all four buffers 16-byte aligned (the trainers' flat buffers always are)
+__global__ void __launch_bounds__(256)
+adamw_kernel_v4(float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ m, float4* __restrict__ v,
+                long long n4, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2s,
+                const float* __restrict__ d_hp) {
+  if (d_hp) { lr = __ldg(d_hp); bc1 = __ldg(d_hp + 1); bc2s = __ldg(d_hp + 2); }
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 pi = p[i], mi = m[i], vi = v[i];
+    const float4 gi = g[i];
+    adamw_update(pi.x, gi.x, mi.x, vi.x, lr, bc1, bc2s, b1, b2, eps, wd);
+    adamw_update(pi.y, gi.y, mi.y, vi.y, lr, bc1, bc2s, b1, b2, eps, wd);
+    adamw_update(pi.z, gi.z, mi.z, vi.z, lr, bc1, bc2s, b1, b2, eps, wd);
+    adamw_update(pi.w, gi.w, mi.w, vi.w, lr, bc1, bc2s, b1, b2, eps, wd);
+    p[i] = pi; m[i] = mi; v[i] = vi;
+  }
+}
+
+static void launch_adamw(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
+                         float wd, float bc1, float bc2s, const float* d_hp, cudaStream_t st) {
+  const bool v4 = n % 4 == 0 && ((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) % 16 == 0;
+  const long long items = v4 ? n / 4 : n;
+  long long blocks = (items + 255) / 256;
+  const long long cap = 8LL * sm_count();
+  if (blocks > cap) blocks = cap;
+  if (v4)
+    adamw_kernel_v4<<<(unsigned)blocks, 256, 0, st>>>((float4*)p, (const float4*)g, (float4*)m, (float4*)v, items, lr, b1, b2,
+                                                      eps, wd, bc1, bc2s, d_hp);
+  else
+    adamw_kernel<<<(unsigned)blocks, 256, 0, st>>>(p, g, m, v, items, lr, b1, b2, eps, wd, bc1, bc2s, d_hp);
 }
 
 // One thread: ++step, then hp = {lr(step-1) per CosinDecayLR (lr_schedule.py:16-28), 1-b1^step, sqrt(1-b2^step)}.
@@ -500,10 +529,7 @@ extern "C" int nrx_adamw_dense(float* p, const float* g, float* m, float* v, int
   if (n == 0) return NRX_OK;
   const float bc1 = (float)(1.0 - pow((double)beta1, (double)step));
   const float bc2s = (float)sqrt(1.0 - pow((double)beta2, (double)step));
-  long long blocks = (n + 255) / 256;
-  const long long cap = (long long)sm_count() * 16;
-  if (blocks > cap) blocks = cap;
-  adamw_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2s, nullptr);
+  launch_adamw(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2s, nullptr, (cudaStream_t)stream);
   return check_launch("adamw_dense");
 }
 
@@ -511,10 +537,7 @@ extern "C" int nrx_adamw_dense_dev(float* p, const float* g, float* m, float* v,
                                    float beta2, float eps, float weight_decay, nrx_stream_t stream) {
   NRX_REQUIRE(p && g && m && v && d_hparams && n >= 0, NRX_EINVAL, "bad AdamW arguments");
   if (n == 0) return NRX_OK;
-  long long blocks = (n + 255) / 256;
-  const long long cap = (long long)sm_count() * 16;
-  if (blocks > cap) blocks = cap;
-  adamw_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, 0.f, beta1, beta2, eps, weight_decay, 1.f, 1.f, d_hparams);
+  launch_adamw(p, g, m, v, n, 0.f, beta1, beta2, eps, weight_decay, 1.f, 1.f, d_hparams, (cudaStream_t)stream);
   return check_launch("adamw_dense_dev");
 }
 

@@ -1,0 +1,237 @@
+// K7 — gradient all-reduce fused with the dense AdamW over NVLink peer memory (include/nrx.h, "K7").
+//
+// One kernel per rank per step.  Slice r of the flat buffers (float4 granularity) belongs to rank r:
+//   A  every rank tells every peer "my gradients are written" (release store into the peer's signal pad) and
+//      waits until all peers said the same (acquire loads of its own pad);
+//   1  the owner loads its slice of g from every rank (peer loads over NVLink, all `world` loads in flight,
+//      summed in rank order, x 1/world), updates p/m/v with the torch.optim.AdamW rule and stores the new
+//      parameters into every rank's parameter buffer (peer stores);
+//   B  the last block of a rank to finish signals "my stores are out" to every peer and waits for theirs, so
+//      the kernel retires only when this rank's parameters are complete and nobody still reads its gradients.
+// Signal values are a launch counter kept in the pad itself (monotone; never reset by optimizer-state restores).
+// Pad layout (u32 words): [0,16) A flags by source rank, [64,80) B flags, 128 launch counter, 129 block counter,
+// 130 timed-out flag.
+#include <cuda_runtime.h>
+
+#include "common.cuh"
+
+namespace nrx {
+
+constexpr int kPeerThreads = 256;
+constexpr int kSigA = 0, kSigB = 64, kSigEpoch = 128, kSigBlocks = 129;
+constexpr unsigned long long kSpinLimitNs = 2000000000ull;  // 2 s: a peer that never arrives must not hang the GPU
+
+struct PeerArgs {
+  int rank, world;
+  float4* p[NRX_MAX_PEERS];
+  const float4* g[NRX_MAX_PEERS];
+  uint32_t* sig[NRX_MAX_PEERS];
+  float4* m;
+  float4* v;
+  long long lo4, hi4;  // owned slice in float4 units
+  const float* d_hp;
+  float b1, b2, eps, wd;
+};
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 ld_peer(const float4* p) {  // written by another GPU before barrier A
+  float4 v;
+  asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long now_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// Spin until *flag >= want (wrap-safe signed distance); false on time-out.
+__device__ __forceinline__ bool wait_flag(const uint32_t* flag, uint32_t want) {
+  const unsigned long long t0 = now_ns();
+  while ((int32_t)(ld_acquire_sys(flag) - want) < 0) {
+    if (now_ns() - t0 > kSpinLimitNs) return false;
+    __nanosleep(64);
+  }
+  return true;
+}
+
+// W = compile-time bound on the world size (loads of all ranks in flight), U = float4 per thread per trip.
+template <int W, int U>
+__global__ void __launch_bounds__(kPeerThreads)
+adamw_allreduce_peer_kernel(const __grid_constant__ PeerArgs a) {
+  __shared__ int s_flag;
+  uint32_t* sig = a.sig[a.rank];
+  const int tid = threadIdx.x;
+  const uint32_t epoch = *(volatile uint32_t*)(sig + kSigEpoch) + 1u;  // bumped by the last block, after all read it
+  if (tid == 0) s_flag = 0;
+  __syncthreads();
+  // ---- barrier A ------------------------------------------------------------------------------------
+  if (blockIdx.x == 0 && tid < a.world) {
+    __threadfence_system();
+    st_release_sys(a.sig[tid] + kSigA + a.rank, epoch);
+  }
+  if (tid < a.world && !wait_flag(sig + kSigA + tid, epoch)) s_flag = 1;
+  __syncthreads();
+  if (s_flag) {  // a peer never arrived: flag it and leave the parameters untouched
+    if (tid == 0) sig[NRX_PEER_SIG_ERR] = 1u;
+    return;
+  }
+  // ---- reduce + AdamW + broadcast over the owned slice ---------------------------------------------
+  const float lr = __ldg(a.d_hp), bc1 = __ldg(a.d_hp + 1), bc2s = __ldg(a.d_hp + 2);
+  const float inv_world = 1.f / (float)a.world;
+  const long long stride = (long long)gridDim.x * kPeerThreads;
+  float4* __restrict__ p_loc = a.p[a.rank];
+  for (long long i0 = a.lo4 + (long long)blockIdx.x * kPeerThreads + tid; i0 < a.hi4; i0 += stride * U) {
+    float4 gs[U][W], p[U], m[U], v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < a.hi4) {
+#pragma unroll
+        for (int j = 0; j < W; ++j)
+          if (j < a.world) gs[u][j] = ld_peer(a.g[j] + i);
+        p[u] = p_loc[i]; m[u] = a.m[i]; v[u] = a.v[i];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      if (i >= a.hi4) continue;
+      float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < W; ++j)
+        if (j < a.world) { g.x += gs[u][j].x; g.y += gs[u][j].y; g.z += gs[u][j].z; g.w += gs[u][j].w; }
+      g.x *= inv_world; g.y *= inv_world; g.z *= inv_world; g.w *= inv_world;
+      adamw_update(p[u].x, g.x, m[u].x, v[u].x, lr, bc1, bc2s, a.b1, a.b2, a.eps, a.wd);
+      adamw_update(p[u].y, g.y, m[u].y, v[u].y, lr, bc1, bc2s, a.b1, a.b2, a.eps, a.wd);
+      adamw_update(p[u].z, g.z, m[u].z, v[u].z, lr, bc1, bc2s, a.b1, a.b2, a.eps, a.wd);
+      adamw_update(p[u].w, g.w, m[u].w, v[u].w, lr, bc1, bc2s, a.b1, a.b2, a.eps, a.wd);
+      a.m[i] = m[u];
+      a.v[i] = v[u];
+#pragma unroll
+      for (int j = 0; j < W; ++j)
+        if (j < a.world) a.p[j][i] = p[u];
+    }
+  }
+  // ---- barrier B: last block of this rank signals, then waits for every peer's stores ----------------
+  __threadfence_system();
+  __syncthreads();
+  if (tid == 0) s_flag = (atomicAdd(sig + kSigBlocks, 1u) == gridDim.x - 1) ? 2 : 0;
+  __syncthreads();
+  if (s_flag != 2) return;
+  __threadfence_system();
+  if (tid < a.world) {
+    st_release_sys(a.sig[tid] + kSigB + a.rank, epoch);
+    if (!wait_flag(sig + kSigB + tid, epoch)) sig[NRX_PEER_SIG_ERR] = 1u;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    sig[kSigBlocks] = 0u;
+    *(volatile uint32_t*)(sig + kSigEpoch) = epoch;
+  }
+}
+
+}  // namespace nrx
+
+extern "C" int nrx_peer_alloc(size_t bytes, void** ptr) {
+  using namespace nrx;
+  NRX_REQUIRE(ptr != nullptr && bytes > 0, NRX_EINVAL, "bad peer_alloc arguments");
+  cudaError_t e = cudaMalloc(ptr, bytes);
+  NRX_REQUIRE(e == cudaSuccess, NRX_ELAUNCH, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
+  e = cudaMemset(*ptr, 0, bytes);
+  NRX_REQUIRE(e == cudaSuccess, NRX_ELAUNCH, "cudaMemset: %s", cudaGetErrorString(e));
+  return NRX_OK;
+}
+
+extern "C" int nrx_peer_free(void* ptr) {
+  using namespace nrx;
+  cudaError_t e = cudaFree(ptr);
+  NRX_REQUIRE(e == cudaSuccess, NRX_ELAUNCH, "cudaFree: %s", cudaGetErrorString(e));
+  return NRX_OK;
+}
+
+extern "C" int nrx_peer_export(void* ptr, unsigned char handle[64]) {
+  using namespace nrx;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  NRX_REQUIRE(ptr != nullptr && handle != nullptr, NRX_EINVAL, "null pointer");
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, ptr);
+  NRX_REQUIRE(e == cudaSuccess, NRX_ELAUNCH, "cudaIpcGetMemHandle: %s", cudaGetErrorString(e));
+  memcpy(handle, &h, 64);
+  return NRX_OK;
+}
+
+extern "C" int nrx_peer_open(const unsigned char handle[64], void** ptr) {
+  using namespace nrx;
+  NRX_REQUIRE(ptr != nullptr && handle != nullptr, NRX_EINVAL, "null pointer");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  cudaError_t e = cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess);
+  NRX_REQUIRE(e == cudaSuccess, NRX_ELAUNCH, "cudaIpcOpenMemHandle: %s", cudaGetErrorString(e));
+  return NRX_OK;
+}
+
+extern "C" int nrx_peer_close(void* ptr) {
+  using namespace nrx;
+  cudaError_t e = cudaIpcCloseMemHandle(ptr);
+  NRX_REQUIRE(e == cudaSuccess, NRX_ELAUNCH, "cudaIpcCloseMemHandle: %s", cudaGetErrorString(e));
+  return NRX_OK;
+}
+
+extern "C" int nrx_adamw_allreduce_peer(const NrxPeerStep* s, nrx_stream_t stream) {
+  using namespace nrx;
+  NRX_REQUIRE(s != nullptr, NRX_EINVAL, "null step");
+  NRX_REQUIRE(s->world >= 1 && s->world <= NRX_MAX_PEERS && s->rank >= 0 && s->rank < s->world, NRX_EINVAL,
+              "rank %d / world %d outside [1,%d]", s->rank, s->world, (int)NRX_MAX_PEERS);
+  NRX_REQUIRE(s->n >= 0 && s->n % 4 == 0, NRX_EINVAL, "n=%lld must be a non-negative multiple of 4", (long long)s->n);
+  NRX_REQUIRE(s->m && s->v && s->d_hparams, NRX_EINVAL, "null moments / hparams");
+  PeerArgs a;
+  memset(&a, 0, sizeof(a));
+  a.rank = s->rank;
+  a.world = s->world;
+  for (int j = 0; j < s->world; ++j) {
+    NRX_REQUIRE(s->p[j] && s->g[j] && s->sig[j], NRX_EINVAL, "rank %d: null peer buffer", j);
+    NRX_REQUIRE((uintptr_t)s->p[j] % 16 == 0 && (uintptr_t)s->g[j] % 16 == 0, NRX_EINVAL, "rank %d: buffers must be 16-byte aligned", j);
+    a.p[j] = (float4*)s->p[j];
+    a.g[j] = (const float4*)s->g[j];
+    a.sig[j] = s->sig[j];
+  }
+  NRX_REQUIRE((uintptr_t)s->m % 16 == 0 && (uintptr_t)s->v % 16 == 0, NRX_EINVAL, "moments must be 16-byte aligned");
+  a.m = (float4*)s->m;
+  a.v = (float4*)s->v;
+  const long long n4 = s->n / 4, base = n4 / s->world, rem = n4 % s->world;  // same split as parallel.shard_range
+  a.lo4 = s->rank * base + (s->rank < rem ? s->rank : rem);
+  a.hi4 = a.lo4 + base + (s->rank < rem ? 1 : 0);
+  a.d_hp = s->d_hparams;
+  a.b1 = s->beta1; a.b2 = s->beta2; a.eps = s->eps; a.wd = s->weight_decay;
+  // Blocks that are not resident yet simply find barrier A already satisfied when they start: the grid needs
+  // no co-residency on ITS device, only that every rank's kernel eventually starts on its own device.
+  const int U = s->world <= 2 ? 4 : (s->world <= 4 ? 2 : 1);
+  long long blocks = (a.hi4 - a.lo4 + (long long)kPeerThreads * U - 1) / ((long long)kPeerThreads * U);
+  const long long cap = 4LL * sm_count();
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (s->world <= 2) adamw_allreduce_peer_kernel<2, 4><<<(unsigned)blocks, kPeerThreads, 0, st>>>(a);
+  else if (s->world <= 4) adamw_allreduce_peer_kernel<4, 2><<<(unsigned)blocks, kPeerThreads, 0, st>>>(a);
+  else if (s->world <= 8) adamw_allreduce_peer_kernel<8, 1><<<(unsigned)blocks, kPeerThreads, 0, st>>>(a);
+  else adamw_allreduce_peer_kernel<16, 1><<<(unsigned)blocks, kPeerThreads, 0, st>>>(a);
+  return check_launch("adamw_allreduce_peer");
+}
+
+extern "C" int nrx_peer_status(const uint32_t* sig, int32_t* timed_out, nrx_stream_t stream) {
+  using namespace nrx;
+  NRX_REQUIRE(sig && timed_out, NRX_EINVAL, "null pointer");
+  uint32_t v = 0;
+  cudaError_t e = cudaMemcpyAsync(&v, sig + NRX_PEER_SIG_ERR, sizeof(v), cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
+  NRX_REQUIRE(e == cudaSuccess, NRX_ELAUNCH, "peer_status: %s", cudaGetErrorString(e));
+  *timed_out = (int32_t)v;
+  return NRX_OK;
+}

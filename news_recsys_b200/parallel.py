@@ -21,7 +21,7 @@ The reference is single-GPU only (`devices=1`, sort/deep/train.py:41-42); everyt
 """
 from __future__ import annotations
 
-import os
+import ctypes as C
 from typing import Dict, List, Tuple
 
 import torch
@@ -56,21 +56,82 @@ def gather_batch(local: Dict[str, torch.Tensor], keys: List[str], group=None) ->
 
 
 # --------------------------------------------------------------------------- #
+# NVLink peer memory (K7 plumbing)                                             #
+# --------------------------------------------------------------------------- #
+
+class PeerBuffer:
+    """Device memory from `nrx_peer_alloc` (cudaMalloc'd, zero-filled, IPC-exportable), viewed as a torch tensor
+    through `__cuda_array_interface__` (zero copy; the tensor keeps this object alive)."""
+
+    def __init__(self, nbytes: int, device, typestr: str = "<f4"):
+        self.lib = L.load()
+        ptr = C.c_void_p()
+        with torch.cuda.device(device):
+            L.check(self.lib.nrx_peer_alloc(nbytes, C.byref(ptr)), "nrx_peer_alloc")
+        self.ptr, self.nbytes, self.device = int(ptr.value), int(nbytes), torch.device(device)
+        self.__cuda_array_interface__ = {"shape": (nbytes // 4,), "typestr": typestr, "data": (self.ptr, False),
+                                         "version": 2, "strides": None}
+
+    def tensor(self) -> torch.Tensor:
+        return torch.as_tensor(self, device=self.device)
+
+    def export(self) -> bytes:
+        h = C.create_string_buffer(64)
+        L.check(self.lib.nrx_peer_export(self.ptr, h), "nrx_peer_export")
+        return h.raw
+
+
+def open_peers(bufs: List["PeerBuffer"], group=None) -> List[List[int]]:
+    """Exchange the IPC handles of `bufs` (same list on every rank) and map every peer's copy.
+    Returns ptrs[k][j] = device address, valid on THIS rank, of rank j's k-th buffer (own buffers as they are)."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    mine = [b.export() for b in bufs]
+    allh = [None] * world
+    dist.all_gather_object(allh, mine, group=group)
+    lib = L.load()
+    out = []
+    for k, b in enumerate(bufs):
+        row = []
+        for j in range(world):
+            if j == rank:
+                row.append(b.ptr)
+                continue
+            p = C.c_void_p()
+            with torch.cuda.device(b.device):
+                L.check(lib.nrx_peer_open(allh[j][k], C.byref(p)), "nrx_peer_open")
+            row.append(int(p.value))
+        out.append(row)
+    return out
+
+
+# --------------------------------------------------------------------------- #
 # data-parallel training                                                       #
 # --------------------------------------------------------------------------- #
 
 class DataParallelTrainer(FusedTrainer):
     _inline_update = False  # the row update needs the all-gathered gradients of every rank
 
-    def __init__(self, model, B: int, kind=None, group=None, use_graph: bool = True, table_update: str = "dense", **kw):
+    def __init__(self, model, B: int, kind=None, group=None, use_graph: bool = True, table_update: str = "dense",
+                 exchange: str = "peer", **kw):
+        """exchange (dense mode only): "peer" — K7, gradient all-reduce fused with AdamW over NVLink peer memory,
+        the whole step one CUDA graph, no NCCL on the data path (single node); "nccl" — all-reduce between two graphs."""
+        if exchange not in ("peer", "nccl"):
+            raise L.NrxError(f"exchange must be 'peer' or 'nccl', got {exchange!r}")
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self._dp_ready = False
+        self._use_peer = table_update == "dense" and exchange == "peer"
+        if self._use_peer and self.world > L.NRX_MAX_PEERS:
+            raise L.NrxError(f"exchange='peer' supports up to {L.NRX_MAX_PEERS} ranks of one node")
+        self._peer_bufs: List[PeerBuffer] = []
         super().__init__(model, B, kind=kind, use_graph=False, table_update=table_update, **kw)
         dev = self.dev
         G = self.world
         self.graph_a = self.graph_b = None
+        if self._use_peer:
+            self._init_peer(use_graph)
+            return
         if self.table_update == "dense":
             self._init_dense(use_graph)
             return
@@ -103,22 +164,49 @@ class DataParallelTrainer(FusedTrainer):
     def _plan_fb(self):
         return self.gfb if self._dp_ready else self.fb
 
+    # ---- dense mode over peer memory (K7): the step is the single-GPU graph with a different optimizer kernel ----
+    def _alloc_flat(self, n: int) -> torch.Tensor:
+        if not self._use_peer:
+            return super()._alloc_flat(n)
+        buf = PeerBuffer(4 * n, self.dev)
+        self._peer_bufs.append(buf)   # order: flat_p, flat_g
+        return buf.tensor()
+
+    def _init_peer(self, use_graph):
+        sig = PeerBuffer(4 * L.NRX_PEER_SIG_WORDS, self.dev, typestr="<i4")
+        self._peer_bufs.append(sig)
+        self.sig = sig.tensor()
+        ptrs = open_peers(self._peer_bufs, self.group)   # [p, g, sig][rank]
+        st = L.NrxPeerStep()
+        st.rank, st.world = self.rank, self.world
+        for j in range(self.world):
+            st.p[j], st.g[j], st.sig[j] = ptrs[0][j], ptrs[1][j], ptrs[2][j]
+        st.m, st.v, st.n = self.flat_m.data_ptr(), self.flat_v.data_ptr(), self.n_dense
+        st.d_hparams = self.d_hp.data_ptr()
+        st.beta1, st.beta2, st.eps, st.weight_decay = self.betas[0], self.betas[1], self.eps, self.wd
+        self._peer_step = st
+        dist.barrier(group=self.group)    # every rank has mapped every buffer before the first kernel touches them
+        if use_graph:
+            self._capture()               # warm-up step (all ranks in lockstep) + capture of the whole step
+
+    def _adamw_flat(self):
+        if not self._use_peer:
+            return super()._adamw_flat()
+        L.check(self.lib.nrx_adamw_allreduce_peer(C.byref(self._peer_step), self._sp()), "nrx_adamw_allreduce_peer")
+
+    def peer_timed_out(self) -> bool:
+        """True if a K7 launch gave up waiting for a peer (the parameters are then stale, not corrupted)."""
+        flag = C.c_int32(0)
+        L.check(self.lib.nrx_peer_status(self.sig.data_ptr(), C.byref(flag), self._sp()), "nrx_peer_status")
+        return bool(flag.value)
+
     # ---- dense mode: local K3 into the flat gradient buffer, ONE all-reduce, one AdamW ----------
     def _init_dense(self, use_graph):
         snap = self._snapshot()
         self._dense_step_eager()       # warm-up; also initialises the NCCL communicator
         torch.cuda.synchronize(self.dev)
         self._restore(snap)
-        self.graph_one = None
-        if use_graph and os.environ.get("NRX_DP_ONE_GRAPH", "0") == "1":
-            # whole step, all-reduce included, as ONE graph (NCCL kernels are capturable)
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                self._dense_step_eager()
-            torch.cuda.synchronize(self.dev)
-            self._restore(snap)
-            self.graph_one = g
-        elif use_graph:
+        if use_graph:
             self.graph_a = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph_a):
                 self._fwd_bwd()
@@ -156,10 +244,9 @@ class DataParallelTrainer(FusedTrainer):
         self._update(self.gfb, self._plan, self.gx_global)
 
     def step(self) -> torch.Tensor:
+        if self._use_peer:
+            return FusedTrainer.step(self)   # one graph; the exchange happens inside K7
         if self.table_update == "dense":
-            if self.graph_one is not None:
-                self.graph_one.replay()
-                return self.loss
             if self.graph_a is None:
                 self._dense_step_eager()
                 return self.loss

@@ -119,12 +119,15 @@ class FusedTrainer:
             self._capture()
 
     # ---- parameter plumbing ------------------------------------------------------------------
+    def _alloc_flat(self, n: int) -> torch.Tensor:
+        return torch.zeros(n, dtype=torch.float32, device=self.dev)
+
     def _flatten_dense(self):
         dense = [(n, p) for n, p in self.model.named_parameters()
                  if self.table_update == "dense" or not n.startswith("embedding_tables.")]
         total = sum(_align(p.numel(), 4) for _, p in dense)
-        self.flat_p = torch.zeros(max(total, 4), dtype=torch.float32, device=self.dev)
-        self.flat_g = torch.zeros_like(self.flat_p)
+        self.flat_p = self._alloc_flat(max(total, 4))   # hook: the multi-GPU trainer puts these in peer-mapped memory
+        self.flat_g = self._alloc_flat(max(total, 4))
         self.flat_m = torch.zeros_like(self.flat_p)
         self.flat_v = torch.zeros_like(self.flat_p)
         self.dense_views, self.grad_views = {}, {}

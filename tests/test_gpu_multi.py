@@ -17,7 +17,7 @@ def _free_port():
     return p
 
 
-def _dp_worker(rank, world, port, kind, out_dir, mode):
+def _dp_worker(rank, world, port, kind, out_dir, mode, exchange):
     import sys
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     import importlib
@@ -35,12 +35,14 @@ def _dp_worker(rank, world, port, kind, out_dir, mode):
     torch.manual_seed(1)
     model = cls(cfg).to(f"cuda:{rank}")
     B = 128
-    tr = DataParallelTrainer(model, B, kind=kind, table_update=mode)
+    tr = DataParallelTrainer(model, B, kind=kind, table_update=mode, exchange=exchange)
     for s in range(3):
         full = synth_batch(cfg, B * world, seed=20 + s, label_p=0.5)
         local = {k: v[rank * B:(rank + 1) * B] for k, v in full.items()}
         tr.train_step(local)
     torch.cuda.synchronize()
+    if mode == "dense" and exchange == "peer":
+        assert not tr.peer_timed_out()
     sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
     torch.save(sd, os.path.join(out_dir, f"dp_{kind}_{rank}.pt"))
     # sharded retrieval
@@ -54,11 +56,12 @@ def _dp_worker(rank, world, port, kind, out_dir, mode):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("kind,mode", [("fm", "dense"), ("deepfm", "dense"), ("deep", "dense"),
-                                       ("fm", "sparse"), ("deepfm", "sparse")])
-def test_dp2_equals_single_gpu(kind, mode, tmp_path):
-    """2 ranks x B=128 == one GPU x B=256 with the same table_update semantics (dense: one all-reduce of the
-    flat gradient buffer; sparse: global-batch row apply on every replica)."""
+@pytest.mark.parametrize("kind,mode,exchange", [("fm", "dense", "peer"), ("deepfm", "dense", "peer"), ("deep", "dense", "peer"),
+                                                ("fm", "dense", "nccl"), ("fm", "sparse", "nccl"), ("deepfm", "sparse", "nccl")])
+def test_dp2_equals_single_gpu(kind, mode, exchange, tmp_path):
+    """2 ranks x B=128 == one GPU x B=256 with the same table_update semantics (dense + peer: K7, all-reduce fused
+    with AdamW over NVLink peer memory; dense + nccl: one NCCL all-reduce of the flat gradient buffer; sparse:
+    global-batch row apply on every replica)."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import importlib
@@ -66,7 +69,7 @@ def test_dp2_equals_single_gpu(kind, mode, tmp_path):
     from oracle import ref_path as R
     from news_recsys_b200.synthetic import mind_config, synth_batch
     from news_recsys_b200.trainer import FusedTrainer
-    mp.spawn(_dp_worker, args=(2, _free_port(), kind, str(tmp_path), mode), nprocs=2, join=True)
+    mp.spawn(_dp_worker, args=(2, _free_port(), kind, str(tmp_path), mode, exchange), nprocs=2, join=True)
     sd0 = torch.load(tmp_path / f"dp_{kind}_0.pt")
     sd1 = torch.load(tmp_path / f"dp_{kind}_1.pt")
     for k in sd0:
