@@ -196,7 +196,7 @@ def profile_apis(trainer, pool, n=10):
     return {k: sum(v) / len(v) * (len(v) / n) for k, v in agg.items()}, per_step_launches  # us per step per API
 
 
-def algorithmic(kind, cfg, B):
+def algorithmic(kind, cfg, B, table_update="sparse"):
     """Algorithmic bytes / flops per launch of each API (formulas in DESIGN.md §Kernels)."""
     emb = cfg["embeddings"]
     feats = cfg["features"]
@@ -220,6 +220,13 @@ def algorithmic(kind, cfg, B):
     layers = [mlp_in, 128, 128, 128, 64, 1]
     tower_flops = 2 * sum(layers[i] * layers[i + 1] for i in range(5)) if mlp_in else 0
     uniq_row_bytes = sum(dims[n] * 4 * 7 for n in names if n not in arr) + sum((feats["array_max_length"][n] / 2) * dims[n] * 4 * 7 for n in arr)
+    n_table = sum(emb["embedding_table_size"][t] * emb["embedding_size"][t] for t in emb["embedding_size"])
+    n_tower = sum(layers[i] * layers[i + 1] + layers[i + 1] for i in range(5)) if mlp_in else 0
+    apply_bytes = B * (4 * sd + 8 * n_occ) + B * uniq_row_bytes
+    adamw_bytes = 28 * n_tower          # p, g, m, v read + p, m, v written
+    if table_update == "dense":         # K3 zero-fills and scatters dense table gradients; AdamW sweeps the tables too
+        apply_bytes = B * (4 * sd + 8 * n_occ) + 4 * n_table + B * uniq_row_bytes / 7
+        adamw_bytes = 28 * (n_tower + n_table)
     return {
         "nrx_embed_pool_fwd": ("hbm", B * k1),
         "nrx_fm_fused_fwd": ("hbm", B * (sum(8 + 4 * d for d in dims.values()) + 4 + 12)),
@@ -234,8 +241,8 @@ def algorithmic(kind, cfg, B):
         "nrx_dcn_cross_fwd": ("hbm", B * 4 * (sd + 2 * sd)),
         "nrx_dcn_cross_bwd": ("hbm", B * 4 * (sd + 2 * sd + sd)),
         "nrx_embed_bwd_plan": ("hbm", B * n_occ * (8 + 8 + 3 * 16)),
-        "nrx_embed_bwd_apply": ("hbm", B * (4 * sd + 8 * n_occ) + B * uniq_row_bytes),
-        "nrx_adamw_dense_dev": ("hbm", 0),
+        "nrx_embed_bwd_apply": ("hbm", apply_bytes),
+        "nrx_adamw_dense_dev": ("hbm", adamw_bytes),
     }
 
 
@@ -329,7 +336,26 @@ def retrieval_leg(dev, world, rank, dist, quick):
     return out
 
 
+_OUT = None
+
+
+def claim_stdout():
+    """Keep stdout for the ONE JSON line: everything libraries print to fd 1 (e.g. NCCL's version banner) goes to stderr."""
+    global _OUT
+    if _OUT is None:
+        sys.stdout.flush()
+        _OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
@@ -365,7 +391,7 @@ def main():
                 "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                  "sample": f"{steps} full steps of B={B} after {warm} warm-up"},
                 "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        emit(line)
         return
 
     if not torch.cuda.is_available():
@@ -487,14 +513,36 @@ def main():
         # private single-GPU trainer (same model class / config / batch size)
         torch.manual_seed(42)
         prof_trainer = FusedTrainer(model_class(kind)(cfg).to(dev), B, kind=kind, table_update=args.table_update)
+    variants = None
+    if world == 1 and not args.quick:
+        # the other optimizer semantics on the same pool, same timing rules (reported beside the headline, not as it)
+        other = "sparse" if args.table_update == "dense" else "dense"
+        torch.manual_seed(42)
+        tr2 = FusedTrainer(model_class(kind)(cfg).to(dev), B, kind=kind, table_update=other)
+        for i in range(max(args.warmup, 3)):
+            tr2.load_blob(pool[i % n_pool]); tr2.step()
+        torch.cuda.synchronize()
+        v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        v0.record()
+        for i in range(args.steps):
+            tr2.load_blob(pool[(i + 7) % n_pool]); tr2.step()
+        v1.record()
+        torch.cuda.synchronize()
+        vms = v0.elapsed_time(v1)
+        variants = {f"table_update={other}": {"value": B * args.steps / (vms * 1e-3), "unit": UNIT, "ms_per_step": vms / args.steps,
+                                              "note": ("lazy rows: fused sparse-row AdamW inside K3, untouched rows do not decay"
+                                                       if other == "sparse" else "the reference's dense AdamW over every row")}}
+        del tr2
     per_api, launches_per_step = profile_apis(prof_trainer, pool, n=2 if args.quick else 10)
-    alg = algorithmic(kind, cfg, B)
+    alg = algorithmic(kind, cfg, B, args.table_update)
     hbm_peak, tf_peak, peak_src = peaks()
     # dominant call ON THE CRITICAL PATH: the sort plan and the optimizer clock run on the forked stream,
     # concurrently with forward + backward, and are listed in `kernels` with "stream": "forked"
     forked = {"nrx_embed_bwd_plan", "nrx_hparams_step", "nrx_tower_pack"}
     if kind in ("deep", "deepfm", "widedeep", "dcn"):  # these run beside the tower kernels on the third stream
-        forked |= {"nrx_field_logit_fwd", "nrx_field_logit_bwd", "nrx_reduce2_f32", "nrx_reduce_f32", "nrx_adamw_dense_dev"}
+        forked |= {"nrx_field_logit_fwd", "nrx_field_logit_bwd", "nrx_reduce2_f32", "nrx_reduce_f32"}
+        if args.table_update == "sparse":
+            forked.add("nrx_adamw_dense_dev")
     dom = max((k for k in per_api if k not in forked), key=lambda k: per_api[k])
     bound, qty = alg.get(dom, ("hbm", 0))
     dur_s = per_api[dom] * 1e-6
@@ -546,9 +594,11 @@ def main():
         "cpu_baseline": cpu_base,
         "final_loss": final_loss,
     }
+    if variants is not None:
+        line["variants"] = variants
     if retrieval is not None:
         line["retrieval"] = retrieval
-    print(json.dumps(line))
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
