@@ -437,3 +437,52 @@ class FusedTrainer:
     def train_step(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
         self.load_batch(batch)
         return self.step()
+
+    # ---- pipelined feeding from pinned host memory ---------------------------------------------------
+    def feed(self, host_blob: torch.Tensor) -> Optional[float]:
+        """One host-fed training step, software-pipelined one deep.
+
+        Enqueues (i) the H2D copy of this step's pinned blob on a copy stream — it overlaps the kernels of the
+        step launched by the previous call —, (ii) the step, (iii) the D2H read of its loss into pinned memory;
+        then returns the loss of the PREVIOUS fed step (None on the first call), which is already on the host, so
+        the CPU never stalls on the step it just launched.  `drain()` returns the last loss."""
+        f = self._feed_state()
+        k = f["i"] & 1
+        f["i"] += 1
+        main = torch.cuda.current_stream(self.dev)
+        with torch.cuda.stream(f["copy"]):
+            f["copy"].wait_event(f["free"][k])           # the step that read stage[k] two calls ago has consumed it
+            f["stage"][k].copy_(host_blob, non_blocking=True)
+            f["ready"][k].record(f["copy"])
+        main.wait_event(f["ready"][k])
+        self.blob.copy_(f["stage"][k], non_blocking=True)
+        f["free"][k].record(main)
+        self.step()
+        f["loss_host"][k].copy_(self.loss, non_blocking=True)
+        f["done"][k].record(main)
+        prev, f["pending"] = f["pending"], k
+        if prev is None:
+            return None
+        f["done"][prev].synchronize()
+        return float(f["loss_host"][prev])
+
+    def drain(self) -> Optional[float]:
+        """Loss of the last fed step (waits for it)."""
+        f = self._feed_state()
+        prev, f["pending"] = f["pending"], None
+        if prev is None:
+            return None
+        f["done"][prev].synchronize()
+        return float(f["loss_host"][prev])
+
+    def _feed_state(self):
+        f = getattr(self, "_feed", None)
+        if f is None:
+            ev = lambda: [torch.cuda.Event(), torch.cuda.Event()]
+            f = dict(copy=torch.cuda.Stream(device=self.dev), stage=[torch.empty_like(self.blob) for _ in range(2)],
+                     loss_host=[torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)],
+                     ready=ev(), free=ev(), done=ev(), i=0, pending=None)
+            for e in f["free"]:
+                e.record(torch.cuda.current_stream(self.dev))
+            self._feed = f
+        return f

@@ -143,3 +143,29 @@ def test_dense_and_sparse_agree_on_touched_rows_first_step():
     un[0] = False
     assert torch.equal(out["sparse"][un], w0[un])
     torch.testing.assert_close(out["dense"][un], w0[un] * (1 - lr * 0.01), rtol=1e-6, atol=1e-9)
+
+
+def test_pipelined_feed_equals_step_by_step():
+    """feed(pinned blob) (H2D on the copy stream, loss read one step late) == load_batch + step."""
+    from news_recsys_b200.synthetic import mind_config, synth_batch
+    from news_recsys_b200.trainer import FusedTrainer
+    rows = {"user_id": 300, "item_id": 200, "category": 18, "subcategory": 70, "user_click_category": 18}
+    cfg = mind_config("deepfm", rows)
+    batches = [synth_batch(cfg, 256, seed=70 + i, label_p=0.5) for i in range(5)]
+    torch.manual_seed(4)
+    tr = FusedTrainer(_cls("deepfm")(cfg).to(DEV), 256, kind="deepfm")
+    want = [float(tr.train_step(b).item()) for b in batches]
+    torch.manual_seed(4)
+    tr2 = FusedTrainer(_cls("deepfm")(cfg).to(DEV), 256, kind="deepfm")
+    blobs = []
+    for b in batches:
+        hb = torch.empty(tr2.layout.nbytes, dtype=torch.uint8).pin_memory()
+        tr2.layout.pack(b, hb)
+        blobs.append(hb)
+    got = [tr2.feed(hb) for hb in blobs]
+    assert got[0] is None
+    got = got[1:] + [tr2.drain()]
+    assert got == want
+    assert tr2.drain() is None
+    for k, v in tr.model.state_dict().items():
+        assert torch.equal(v, tr2.model.state_dict()[k]), k
