@@ -14,6 +14,7 @@
 //          phase B, one warp per run that crosses a tile border: adds the partials in tile order.
 //          Every unique row is finalised by exactly one warp in a fixed order => bitwise
 //          reproducible, no float atomics.
+#include <cub/block/block_radix_sort.cuh>
 #include <cub/device/device_radix_sort.cuh>
 
 #include "common.cuh"
@@ -94,51 +95,85 @@ build_keys_kernel(const __grid_constant__ DFeats P, int row_bits, uint32_t senti
   vals[p] = (uint32_t)p;
 }
 
-// ---- small-batch plan: one CTA per table, keys built and sorted in shared memory ---------------------------
+// ---- small-batch plan: chunk sort + rank merge, two launches spread over the whole GPU ------------------------
 // Segment s holds every occurrence of table s (features in descriptor order); it occupies positions
 // [seg_off[s], seg_off[s+1]) of the sorted arrays.  Inside a segment valid keys come first (ascending row,
 // stable), then the segment's sentinels; equal keys stay contiguous, which is all the apply kernels need.
-static constexpr int kSmallThreads = 1024;
-static constexpr int kSmallItems = 16;  // 16384 occurrences per table at most
-using SmallSort = cub::BlockRadixSort<uint32_t, kSmallThreads, kSmallItems, uint32_t>;
+//   1. plan_chunk_sort_kernel: the segment is cut into chunks of 1024 occurrences; one 256-thread CTA builds the
+//      keys of a chunk (row id, or 1 << bits for an invalid occurrence) and sorts them stably on exactly the bits
+//      this table needs (cub::BlockRadixSort in shared memory).
+//   2. plan_merge_kernel: one CTA per chunk again; the chunk-sorted keys of the WHOLE segment are staged in shared
+//      memory and every element's final position is its rank: position inside its own chunk + #(keys <= it) in
+//      earlier chunks + #(keys < it) in later chunks (two binary searches' worth per chunk) — a stable multiway
+//      merge without any inter-CTA dependency.
+// (A single-CTA-per-table block sort measured 67.6 us at B = 16384: one SM busy, 147 idle, on the step's
+//  critical path — profiles/r1_ncu_launches_deepfm_final.csv.)
+static constexpr int kChunkThreads = 256;
+static constexpr int kChunkItems = 4;
+static constexpr int kChunk = kChunkThreads * kChunkItems;  // 1024 occurrences
+static constexpr int kMaxChunks = 40;                        // per table: 40960 occurrences, 160 KB of keys in SMEM
+using ChunkSort = cub::BlockRadixSort<uint32_t, kChunkThreads, kChunkItems, uint32_t>;
 
 struct SmallPlan {
   int n_seg;
+  int total_chunks;
   int seg_table[NRX_MAX_TABLES];
-  int seg_off[NRX_MAX_TABLES + 1];
+  int seg_bits[NRX_MAX_TABLES];       // bits of (rows - 1): valid ids are < 1 << bits, the invalid marker is 1 << bits
+  int seg_off[NRX_MAX_TABLES + 1];    // occurrence offsets
+  int chunk_off[NRX_MAX_TABLES + 1];  // chunk offsets (blockIdx.x space)
 };
 
 static bool make_small_plan(const DFeats& d, SmallPlan* sp) {
   memset(sp, 0, sizeof(*sp));
   long long off = 0;
+  int chunks = 0;
   for (int t = 0; t < d.n_tables; ++t) {
-    long long cnt = 0;
+    long long cnt = 0, rows = 1;
     for (int i = 0; i < d.n; ++i)
-      if (d.f[i].table_id == t) cnt += (i + 1 < d.n ? d.f[i + 1].occ_off : d.n_occ) - d.f[i].occ_off;
+      if (d.f[i].table_id == t) {
+        cnt += (i + 1 < d.n ? d.f[i + 1].occ_off : d.n_occ) - d.f[i].occ_off;
+        rows = d.f[i].rows;
+      }
     if (cnt == 0) continue;
-    if (cnt > kSmallThreads * kSmallItems) return false;
+    if (cnt > (long long)kChunk * kMaxChunks) return false;
+    int bits = 1;
+    while ((1ll << bits) < rows) ++bits;
+    if (bits > 30) return false;
     sp->seg_table[sp->n_seg] = t;
+    sp->seg_bits[sp->n_seg] = bits;
     sp->seg_off[sp->n_seg] = (int)off;
+    sp->chunk_off[sp->n_seg] = chunks;
     off += cnt;
+    chunks += (int)((cnt + kChunk - 1) / kChunk);
     ++sp->n_seg;
   }
   sp->seg_off[sp->n_seg] = (int)off;
+  sp->chunk_off[sp->n_seg] = chunks;
+  sp->total_chunks = chunks;
   return sp->n_seg > 0 && off == d.n_occ;
 }
 
-__global__ void __launch_bounds__(kSmallThreads, 1)
-plan_small_kernel(const __grid_constant__ DFeats P, const __grid_constant__ SmallPlan S, int row_bits, uint32_t sentinel,
-                  uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out) {
-  extern __shared__ __align__(16) unsigned char sm_raw[];
-  SmallSort::TempStorage& temp = *reinterpret_cast<SmallSort::TempStorage*>(sm_raw);
-  const int seg = blockIdx.x;
+__device__ __forceinline__ int chunk_segment(const SmallPlan& S, int b) {
+  int s = 0;
+  for (int i = 1; i < S.n_seg; ++i)
+    if (b >= S.chunk_off[i]) s = i;
+  return s;
+}
+
+__global__ void __launch_bounds__(kChunkThreads)
+plan_chunk_sort_kernel(const __grid_constant__ DFeats P, const __grid_constant__ SmallPlan S,
+                       uint32_t* __restrict__ keys_mid, uint32_t* __restrict__ vals_mid) {
+  __shared__ typename ChunkSort::TempStorage temp;
+  const int seg = chunk_segment(S, blockIdx.x);
   const int t = S.seg_table[seg];
   const int n = S.seg_off[seg + 1] - S.seg_off[seg];
-  uint32_t k[kSmallItems], v[kSmallItems];
+  const int base = (blockIdx.x - S.chunk_off[seg]) * kChunk;
+  const int bits = S.seg_bits[seg];
+  uint32_t k[kChunkItems], v[kChunkItems];
 #pragma unroll
-  for (int j = 0; j < kSmallItems; ++j) {
-    const int e = threadIdx.x * kSmallItems + j;  // blocked arrangement: position inside the segment
-    k[j] = 0xffffffffu;                           // padding beyond the segment sorts last and is never written
+  for (int j = 0; j < kChunkItems; ++j) {
+    const int e = base + threadIdx.x * kChunkItems + j;  // blocked arrangement: position inside the segment
+    k[j] = 0xffffffffu;                                  // beyond the segment: sorts last, never written
     v[j] = 0;
     if (e < n) {
       // e-th occurrence of table t: walk the features of this table in descriptor order
@@ -151,7 +186,7 @@ plan_small_kernel(const __grid_constant__ DFeats P, const __grid_constant__ Smal
           const long long id = load_idx(F.idx, rem, F.idx32);
           bool valid = id > 0 && id < F.rows;
           if (valid && F.pool == NRX_POOL_MASKED_MEAN) valid = __ldg(F.mask + rem) != 0.f;
-          k[j] = valid ? (((uint32_t)t << row_bits) | (uint32_t)id) : sentinel;
+          k[j] = valid ? (uint32_t)id : (1u << bits);
           v[j] = (uint32_t)(F.occ_off + rem);
           break;
         }
@@ -159,15 +194,80 @@ plan_small_kernel(const __grid_constant__ DFeats P, const __grid_constant__ Smal
       }
     }
   }
-  // sort on the key bits + the sentinel bit only (the 0xffffffff padding still sorts last: all ones below the cut)
-  SmallSort(temp).Sort(k, v, 0, 32 - __clz(sentinel));
-  uint32_t* ko = keys_out + S.seg_off[seg];
-  uint32_t* vo = vals_out + S.seg_off[seg];
-#pragma unroll
-  for (int j = 0; j < kSmallItems; ++j) {
-    const int e = threadIdx.x * kSmallItems + j;
-    if (e < n) { ko[e] = k[j]; vo[e] = v[j]; }
+  ChunkSort(temp).Sort(k, v, 0, bits + 1);
+  uint32_t* ko = keys_mid + S.seg_off[seg] + base;
+  uint32_t* vo = vals_mid + S.seg_off[seg] + base;
+  const int len = min(kChunk, n - base);
+  if (threadIdx.x * kChunkItems + kChunkItems <= len) {  // whole 16-byte group inside the chunk
+    if ((((uintptr_t)ko) & 15) == 0) {
+      reinterpret_cast<uint4*>(ko)[threadIdx.x] = make_uint4(k[0], k[1], k[2], k[3]);
+      reinterpret_cast<uint4*>(vo)[threadIdx.x] = make_uint4(v[0], v[1], v[2], v[3]);
+      return;
+    }
   }
+#pragma unroll
+  for (int j = 0; j < kChunkItems; ++j) {
+    const int e = threadIdx.x * kChunkItems + j;
+    if (e < len) { ko[e] = k[j]; vo[e] = v[j]; }
+  }
+}
+
+// #(x in a[0, len) with x < key) and #(x <= key), branch-free binary searches over a sorted SMEM run (len <= 1024)
+__device__ __forceinline__ int count_less(const uint32_t* a, int len, uint32_t key) {
+  int lo = 0;
+#pragma unroll
+  for (int step = kChunk; step >= 1; step >>= 1) {
+    const int mid = lo + step;
+    if (mid <= len && a[mid - 1] < key) lo = mid;
+  }
+  return lo;
+}
+__device__ __forceinline__ int count_less_equal(const uint32_t* a, int len, uint32_t key) {
+  int lo = 0;
+#pragma unroll
+  for (int step = kChunk; step >= 1; step >>= 1) {
+    const int mid = lo + step;
+    if (mid <= len && a[mid - 1] <= key) lo = mid;
+  }
+  return lo;
+}
+
+// grid = chunks x kChunkItems: CTA (chunk c, quarter q) ranks 256 elements of chunk c (one per thread), so a CTA lives
+// for one SMEM fill + (n_chunks - 1) binary searches and the whole merge is a single wave.
+__global__ void __launch_bounds__(kChunkThreads)
+plan_merge_kernel(const __grid_constant__ SmallPlan S, int row_bits, uint32_t sentinel,
+                  const uint32_t* __restrict__ keys_mid, const uint32_t* __restrict__ vals_mid,
+                  uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out) {
+  extern __shared__ __align__(16) uint32_t sk[];  // the segment's chunk-sorted keys
+  const int chunk = blockIdx.x / kChunkItems, q = blockIdx.x % kChunkItems;
+  const int seg = chunk_segment(S, chunk);
+  const int t = S.seg_table[seg];
+  const int n = S.seg_off[seg + 1] - S.seg_off[seg];
+  const int c = chunk - S.chunk_off[seg];
+  const int n_chunks = S.chunk_off[seg + 1] - S.chunk_off[seg];
+  const int bits = S.seg_bits[seg];
+  const int base = c * kChunk;
+  const int len = min(kChunk, n - base);
+  if (q * kChunkThreads >= len) return;          // ragged last chunk: nothing in this quarter
+  const uint32_t* km = keys_mid + S.seg_off[seg];
+  if ((((uintptr_t)km) & 15) == 0) {
+    const int n4 = n >> 2;
+    for (int i = threadIdx.x; i < n4; i += kChunkThreads)
+      reinterpret_cast<uint4*>(sk)[i] = __ldg(reinterpret_cast<const uint4*>(km) + i);
+    for (int i = (n4 << 2) + threadIdx.x; i < n; i += kChunkThreads) sk[i] = __ldg(km + i);
+  } else {
+    for (int i = threadIdx.x; i < n; i += kChunkThreads) sk[i] = __ldg(km + i);
+  }
+  __syncthreads();
+  const int j = q * kChunkThreads + threadIdx.x;
+  if (j >= len) return;
+  const uint32_t key = sk[base + j];
+  const uint32_t val = __ldg(vals_mid + S.seg_off[seg] + base + j);
+  int pos = j;
+  for (int c2 = 0; c2 < c; ++c2) pos += count_less_equal(sk + c2 * kChunk, kChunk, key);   // earlier chunks are full
+  for (int c2 = c + 1; c2 < n_chunks; ++c2) pos += count_less(sk + c2 * kChunk, min(kChunk, n - c2 * kChunk), key);
+  keys_out[S.seg_off[seg] + pos] = (key >> bits) ? sentinel : (((uint32_t)t << row_bits) | key);
+  vals_out[S.seg_off[seg] + pos] = val;
 }
 
 // ---- finalise one unique row (lanes own columns c = lane + 32*k) -------------------------
@@ -425,16 +525,22 @@ extern "C" int nrx_embed_bwd_plan(const NrxFeat* h_feats, int n_feats, int64_t B
   char* w = (char*)ws;
   const uint32_t sentinel = 1u << L.key_bits;
   {
-    // Small-batch fast path: when every table's occurrences fit one CTA (<= 16384), a single launch builds
-    // the keys and sorts each table's segment in shared memory (one CTA per table).
+    // Small-batch fast path (every table <= 40960 occurrences): chunk sort + rank merge, see above.
     SmallPlan sp;
     if (make_small_plan(d, &sp)) {
-      const size_t smem = sizeof(SmallSort::TempStorage);
-      cudaError_t e = cudaFuncSetAttribute(plan_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      int max_n = 0;
+      for (int s = 0; s < sp.n_seg; ++s) max_n = max(max_n, sp.seg_off[s + 1] - sp.seg_off[s]);
+      const size_t smem = (size_t)max_n * sizeof(uint32_t);
+      cudaError_t e = cudaFuncSetAttribute(plan_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       NRX_REQUIRE(e == cudaSuccess, NRX_ELAUNCH, "smem opt-in: %s", cudaGetErrorString(e));
-      plan_small_kernel<<<sp.n_seg, kSmallThreads, smem, st>>>(d, sp, L.row_bits, sentinel, (uint32_t*)(w + L.keys_out),
-                                                              (uint32_t*)(w + L.vals_out));
-      return check_launch("plan_small");
+      uint32_t* km = (uint32_t*)(w + L.keys_in);
+      uint32_t* vm = (uint32_t*)(w + L.vals_in);
+      plan_chunk_sort_kernel<<<sp.total_chunks, kChunkThreads, 0, st>>>(d, sp, km, vm);
+      rc = check_launch("plan_chunk_sort");
+      if (rc != NRX_OK) return rc;
+      plan_merge_kernel<<<sp.total_chunks * kChunkItems, kChunkThreads, smem, st>>>(sp, L.row_bits, sentinel, km, vm,
+                                                                     (uint32_t*)(w + L.keys_out), (uint32_t*)(w + L.vals_out));
+      return check_launch("plan_merge");
     }
   }
   const unsigned blocks = (unsigned)((d.n_occ + 255) / 256);

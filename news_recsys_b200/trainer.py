@@ -399,7 +399,10 @@ class FusedTrainer:
         torch.cuda.synchronize(self.dev)
         self._restore(snap)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        # the forward/backward chain is captured on a high-priority stream: when its CTAs and those of the forked
+        # streams (sort plan, weight packing, field logits) are pending together, the chain's are placed first
+        cap = torch.cuda.Stream(device=self.dev, priority=-1) if os.environ.get("NRX_MAIN_PRIO", "1") == "1" else None
+        with torch.cuda.graph(self.graph, stream=cap):
             self._step()
         torch.cuda.synchronize(self.dev)
         self._restore(snap)  # capture does not execute, but keep state identical to "no step taken" regardless

@@ -128,7 +128,10 @@ def _oracle_grads(tables, batch, gout):
     (1000, (500, 300, 18), (32, 16, 17), 50, False),      # scalar path (D=17), long runs on an 18-row table
     (4096, (5000, 3000, 18), (32, 32, 16), 50, True),     # zipf: runs spanning many tiles
     (3, (5, 4, 3), (1, 1, 1), 1, False),
-    (777, (100, 60, 20), (64, 48, 8), 7, False),          # dims > 32 (NC = 2)
+    (777, (100, 60, 20), (64, 48, 8), 7, False),          # dims > 32 (NC = 2); 7-chunk merge plan
+    (1024, (90000, 60000, 18), (16, 16, 16), 15, False),  # table i: 1024 + 15360 = 16 full chunks exactly
+    (2048, (5000, 3000, 2), (16, 32, 16), 12, True),      # zipf + 26 chunks with one ragged; a 2-row table (1 key bit)
+    (16384, (94058, 65239, 270), (16, 16, 16), 1, False), # the bench shape: 32 chunks on the shared table
 ])
 def test_k3_dense_backward_matches_autograd(B, rows, D, L, zipf):
     from news_recsys_b200 import ops
