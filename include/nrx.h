@@ -166,6 +166,20 @@ int nrx_adamw_dense_dev(float* p, const float* g, float* m, float* v, int64_t n,
 int nrx_hparams_step(int32_t* d_step, float* d_hparams, float lr, float min_lr, int32_t milestone0,
                      int32_t milestone1, float beta1, float beta2, nrx_stream_t stream);
 
+/* ---- dense-AdamW semantics at sparse cost ---------------------------------------------------------------
+ * The reference's torch.optim.AdamW (deep/model.py:55) sweeps whole tables every step.  For a row no occurrence of
+ * the batch touches the gradient is exactly zero, so its update does not depend on the backward pass:
+ *   nrx_adamw_untouched_rows   — as soon as the ids are on the device: marks the rows the batch touches (same
+ *                                validity rule as the plan: id 0, masked and out-of-range ids touch nothing) and
+ *                                applies the g = 0 AdamW step to every OTHER row — off the critical path, beside
+ *                                forward/backward, on a few SMs; it writes rows the batch never reads;
+ *   nrx_embed_bwd_apply(ADAMW) — the fused row update of the touched rows.
+ * Together they equal one dense AdamW step over tables + moments.  `scratch`: row map, sized by *_scratch_bytes.
+ * `opt->d_hparams` (device {lr, 1-beta1^t, sqrt(1-beta2^t)}) is required. */
+size_t nrx_adamw_untouched_rows_scratch_bytes(const NrxFeat* h_feats, int n_feats);
+int nrx_adamw_untouched_rows(const NrxFeat* h_feats, int n_feats, int64_t B, float* const* h_tables,
+                             const NrxRowOpt* opt, void* scratch, size_t scratch_bytes, nrx_stream_t stream);
+
 /* ---- K7: gradient all-reduce FUSED with the dense AdamW over NVLink peer memory (multi-GPU).
  * The reference trains on one GPU (`devices=1`, sort/deep/train.py:41-42); this replaces what
  * DistributedDataParallel's NCCL all-reduce + torch.optim.AdamW.step() would be for its models.

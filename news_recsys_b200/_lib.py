@@ -81,6 +81,8 @@ SIGNATURES = {
     "nrx_embed_bwd_plan": (C.c_int, [C.POINTER(NrxFeat), C.c_int, _I64, _P, _SZ, _P]),
     "nrx_embed_bwd_apply": (C.c_int, [C.POINTER(NrxFeat), C.c_int, _I64, _P, _I64, C.c_int,
                                       C.POINTER(_P), C.POINTER(_P), C.POINTER(NrxRowOpt), _P, _SZ, _P]),
+    "nrx_adamw_untouched_rows_scratch_bytes": (_SZ, [C.POINTER(NrxFeat), C.c_int]),
+    "nrx_adamw_untouched_rows": (C.c_int, [C.POINTER(NrxFeat), C.c_int, _I64, C.POINTER(_P), C.POINTER(NrxRowOpt), _P, _SZ, _P]),
     "nrx_field_logit_fwd": (C.c_int, [_P, _I64, _I64, C.POINTER(_I32), C.POINTER(_I32), C.c_int, C.c_int, _P, C.c_int, _P]),
     "nrx_field_logit_bwd": (C.c_int, [_P, _I64, _I64, C.POINTER(_I32), C.POINTER(_I32), C.c_int, C.c_int, _P, _P, _I64, C.c_int, _P]),
     "nrx_fm_fused_fwd": (C.c_int, [C.POINTER(NrxFeat), C.c_int, _I64, _P, _P, _I64, _P, _P, _P, _P, _P, _P]),
@@ -154,7 +156,7 @@ def load() -> C.CDLL:
 
 
 # kernels of OURS launched per successful API call (library kernels such as the CUB radix sort are not counted)
-KERNELS_PER_CALL = {"nrx_tower_fwd": 2, "nrx_tower_fwd(prepacked)": 1, "nrx_tower_bwd": 3, "nrx_tower_bwd_dw": 2, "nrx_embed_bwd_apply": 2, "nrx_embed_bwd_plan": 2, "nrx_dcn_cross_bwd": 2,
+KERNELS_PER_CALL = {"nrx_tower_fwd": 2, "nrx_tower_fwd(prepacked)": 1, "nrx_tower_bwd": 3, "nrx_tower_bwd_dw": 2, "nrx_embed_bwd_apply": 2, "nrx_embed_bwd_plan": 2, "nrx_adamw_untouched_rows": 2, "nrx_adamw_untouched_rows_scratch_bytes": 0, "nrx_dcn_cross_bwd": 2,
                     "nrx_embed_bwd_apply(dense)": 2, "nrx_embed_bwd_apply(rowopt)": 2, "nrx_topk_ip": 2,
                     "nrx_topk_search": 5, "nrx_topk_index_build": 1,
                     "nrx_peer_alloc": 0, "nrx_peer_free": 0, "nrx_peer_export": 0, "nrx_peer_open": 0, "nrx_peer_close": 0,

@@ -17,6 +17,8 @@
 #include <cub/block/block_radix_sort.cuh>
 #include <cub/device/device_radix_sort.cuh>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace nrx {
@@ -293,11 +295,7 @@ __device__ __forceinline__ void finalize_row(const DTables& T, uint32_t key, con
     } else {  // AdamW on the touched row (torch.optim.AdamW update rule)
       float p = T.w[t][base + c];
       float m = T.m[t][base + c], v = T.v[t][base + c];
-      p *= (1.f - lr * T.wd);
-      m = T.beta1 * m + (1.f - T.beta1) * g;
-      v = T.beta2 * v + (1.f - T.beta2) * g * g;
-      const float denom = sqrtf(v) / bc2s + T.eps;
-      p -= (lr / bc1) * (m / denom);
+      adamw_update(p, g, m, v, lr, bc1, bc2s, T.beta1, T.beta2, T.eps, T.wd);
       T.w[t][base + c] = p;
       T.m[t][base + c] = m;
       T.v[t][base + c] = v;
@@ -499,6 +497,101 @@ static int launch_apply(const DFeats& d, const DTables& T, const PlanLayout& L, 
   return rc;
 }
 
+// ---- dense-AdamW semantics at sparse cost: the zero-gradient step on every row the batch does NOT touch ----------
+struct SweepArgs {
+  float* w[NRX_MAX_TABLES];
+  float* m[NRX_MAX_TABLES];
+  float* v[NRX_MAX_TABLES];
+  long long unit_off[NRX_MAX_TABLES + 1];   // prefix of rows * units_per_row
+  long long touched_off[NRX_MAX_TABLES];    // byte offset of the table's row map
+  int upr[NRX_MAX_TABLES];                  // units (float4 or float) per row
+  int stride[NRX_MAX_TABLES];
+  int n_tables, vec;
+  float beta1, beta2, eps, wd;
+  const float* d_hp;
+};
+
+// one thread per occurrence, straight from the raw ids (no dependence on the sort plan): idempotent byte stores
+__global__ void __launch_bounds__(256)
+mark_rows_kernel(const __grid_constant__ DFeats P, const __grid_constant__ SweepArgs A, unsigned char* __restrict__ touched) {
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P.n_occ) return;
+  int f = 0;
+  for (int i = 1; i < P.n; ++i)
+    if (p >= P.f[i].occ_off) f = i;
+  const DFeat& F = P.f[f];
+  const long long r = p - F.occ_off;
+  const long long id = load_idx(F.idx, r, F.idx32);
+  bool valid = id > 0 && id < F.rows;   // same validity rule as the plan's keys
+  if (valid && F.pool == NRX_POOL_MASKED_MEAN) valid = __ldg(F.mask + r) != 0.f;
+  if (valid) touched[A.touched_off[F.table_id] + id] = 1;
+}
+
+// A deliberately SMALL grid of FULL-SM CTAs (1024 threads): it runs beside the forward/backward chain for most of
+// the step, and a CTA that needs a whole SM can only land on one the persistent tower kernels leave free (128 tiles
+// on 148 SMs at B = 16384) instead of squatting on theirs.  Two independent rows' worth of loads in flight per thread.
+constexpr int kSweepThreads = 1024;
+template <int V>
+__global__ void __launch_bounds__(kSweepThreads, 1)
+sweep_untouched_kernel(const __grid_constant__ SweepArgs A, const unsigned char* __restrict__ touched) {
+  constexpr int U = 2;
+  const float lr = __ldg(A.d_hp), bc1 = __ldg(A.d_hp + 1), bc2s = __ldg(A.d_hp + 2);
+  const long long total = A.unit_off[A.n_tables];
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long u0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; u0 < total; u0 += stride * U) {
+    long long e[U];
+    int tb[U];
+    bool live[U];
+    unsigned char hit[U];
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      const long long u = u0 + k * stride;
+      live[k] = u < total;
+      int t = 0;
+      for (int i = 1; i < A.n_tables; ++i)
+        if (u >= A.unit_off[i]) t = i;
+      const long long local = live[k] ? u - A.unit_off[t] : 0;
+      const long long row = (long long)((unsigned long long)local / (unsigned)A.upr[t]);
+      tb[k] = t;
+      e[k] = row * A.stride[t] + (local - row * A.upr[t]) * V;
+      hit[k] = live[k] ? __ldg(touched + A.touched_off[t] + row) : (unsigned char)1;
+    }
+    // the row map and the row data are fetched in ONE round trip (loads for the few touched rows are wasted)
+    if (V == 4) {
+      float4 p[U], m[U], v[U];
+#pragma unroll
+      for (int k = 0; k < U; ++k)
+        if (live[k]) {
+          p[k] = *reinterpret_cast<const float4*>(A.w[tb[k]] + e[k]);
+          m[k] = *reinterpret_cast<const float4*>(A.m[tb[k]] + e[k]);
+          v[k] = *reinterpret_cast<const float4*>(A.v[tb[k]] + e[k]);
+        }
+#pragma unroll
+      for (int k = 0; k < U; ++k)
+        if (!hit[k]) {   // touched rows belong to K3's fused update
+          adamw_update(p[k].x, 0.f, m[k].x, v[k].x, lr, bc1, bc2s, A.beta1, A.beta2, A.eps, A.wd);
+          adamw_update(p[k].y, 0.f, m[k].y, v[k].y, lr, bc1, bc2s, A.beta1, A.beta2, A.eps, A.wd);
+          adamw_update(p[k].z, 0.f, m[k].z, v[k].z, lr, bc1, bc2s, A.beta1, A.beta2, A.eps, A.wd);
+          adamw_update(p[k].w, 0.f, m[k].w, v[k].w, lr, bc1, bc2s, A.beta1, A.beta2, A.eps, A.wd);
+          *reinterpret_cast<float4*>(A.w[tb[k]] + e[k]) = p[k];
+          *reinterpret_cast<float4*>(A.m[tb[k]] + e[k]) = m[k];
+          *reinterpret_cast<float4*>(A.v[tb[k]] + e[k]) = v[k];
+        }
+    } else {
+      float p[U], m[U], v[U];
+#pragma unroll
+      for (int k = 0; k < U; ++k)
+        if (live[k]) { p[k] = A.w[tb[k]][e[k]]; m[k] = A.m[tb[k]][e[k]]; v[k] = A.v[tb[k]][e[k]]; }
+#pragma unroll
+      for (int k = 0; k < U; ++k)
+        if (!hit[k]) {
+          adamw_update(p[k], 0.f, m[k], v[k], lr, bc1, bc2s, A.beta1, A.beta2, A.eps, A.wd);
+          A.w[tb[k]][e[k]] = p[k]; A.m[tb[k]][e[k]] = m[k]; A.v[tb[k]][e[k]] = v[k];
+        }
+    }
+  }
+}
+
 }  // namespace nrx
 
 extern "C" size_t nrx_embed_bwd_workspace_bytes(const NrxFeat* h_feats, int n_feats, int64_t B) {
@@ -616,4 +709,68 @@ extern "C" int nrx_embed_bwd_apply(const NrxFeat* h_feats, int n_feats, int64_t 
     case 2: return launch_apply<2>(d, T, L, w, grad_out, grad_ld, st);
     default: return launch_apply<4>(d, T, L, w, grad_out, grad_ld, st);
   }
+}
+
+extern "C" size_t nrx_adamw_untouched_rows_scratch_bytes(const NrxFeat* h_feats, int n_feats) {
+  using namespace nrx;
+  DFeats d;
+  if (make_dfeats(h_feats, n_feats, 0, nullptr, 0, &d) != NRX_OK) return 0;
+  long long rows[NRX_MAX_TABLES] = {0};
+  for (int i = 0; i < d.n; ++i) rows[d.f[i].table_id] = d.f[i].rows;
+  size_t total = 0;
+  for (int t = 0; t < d.n_tables; ++t) total += ((size_t)rows[t] + 15) & ~(size_t)15;
+  return total ? total : 16;
+}
+
+extern "C" int nrx_adamw_untouched_rows(const NrxFeat* h_feats, int n_feats, int64_t B, float* const* h_tables,
+                                        const NrxRowOpt* h_opt, void* scratch, size_t scratch_bytes, nrx_stream_t stream) {
+  using namespace nrx;
+  DFeats d;
+  int rc = make_dfeats(h_feats, n_feats, B, nullptr, 0, &d);
+  if (rc != NRX_OK) return rc;
+  NRX_REQUIRE(h_tables && h_opt && h_opt->d_hparams && scratch, NRX_EINVAL, "null tables / options / device hparams / scratch");
+  SweepArgs A;
+  memset(&A, 0, sizeof(A));
+  long long rows[NRX_MAX_TABLES] = {0};
+  int dim[NRX_MAX_TABLES] = {0};
+  bool vec4 = true;
+  for (int i = 0; i < d.n; ++i) {
+    const DFeat& F = d.f[i];
+    rows[F.table_id] = F.rows; dim[F.table_id] = F.dim; A.stride[F.table_id] = F.stride;
+  }
+  for (int t = 0; t < d.n_tables; ++t) {
+    if (dim[t] == 0) continue;
+    NRX_REQUIRE(h_tables[t] && h_opt->m[t] && h_opt->v[t], NRX_EINVAL, "missing table / moments for table %d", t);
+    A.w[t] = h_tables[t]; A.m[t] = h_opt->m[t]; A.v[t] = h_opt->v[t];
+    if (dim[t] % 4 || A.stride[t] % 4 || ((uintptr_t)A.w[t] | (uintptr_t)A.m[t] | (uintptr_t)A.v[t]) % 16) vec4 = false;
+  }
+  A.vec = vec4 ? 4 : 1;
+  A.n_tables = d.n_tables;
+  size_t toff = 0;
+  for (int t = 0; t < d.n_tables; ++t) {
+    A.upr[t] = dim[t] ? dim[t] / A.vec : 1;
+    A.unit_off[t + 1] = A.unit_off[t] + (dim[t] ? rows[t] * A.upr[t] : 0);
+    A.touched_off[t] = (long long)toff;
+    toff += ((size_t)rows[t] + 15) & ~(size_t)15;
+  }
+  NRX_REQUIRE(scratch_bytes >= toff, NRX_EWORKSPACE, "row-map scratch %zu < %zu", scratch_bytes, toff);
+  A.beta1 = h_opt->beta1; A.beta2 = h_opt->beta2; A.eps = h_opt->eps; A.wd = h_opt->weight_decay;
+  A.d_hp = h_opt->d_hparams;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(scratch, 0, toff, st);
+  NRX_REQUIRE(e == cudaSuccess, NRX_ELAUNCH, "memset: %s", cudaGetErrorString(e));
+  if (d.n_occ > 0) {
+    mark_rows_kernel<<<(unsigned)((d.n_occ + 255) / 256), 256, 0, st>>>(d, A, (unsigned char*)scratch);
+    rc = check_launch("mark_rows");
+    if (rc != NRX_OK) return rc;
+  }
+  const long long total = A.unit_off[d.n_tables];
+  if (total == 0) return NRX_OK;
+  long long blocks = (total + 2 * kSweepThreads - 1) / (2 * kSweepThreads);
+  long long cap = sm_count() / 8 > 16 ? sm_count() / 8 : 16;   // ~1/8 of the SMs
+  if (const char* e = getenv("NRX_SWEEP_CTAS")) { const long long v = atoll(e); if (v > 0) cap = v; }   // tuning knob
+  if (blocks > cap) blocks = cap;
+  if (vec4) sweep_untouched_kernel<4><<<(unsigned)blocks, kSweepThreads, 0, st>>>(A, (const unsigned char*)scratch);
+  else sweep_untouched_kernel<1><<<(unsigned)blocks, kSweepThreads, 0, st>>>(A, (const unsigned char*)scratch);
+  return check_launch("sweep_untouched");
 }

@@ -125,7 +125,7 @@ class DataParallelTrainer(FusedTrainer):
         if self._use_peer and self.world > L.NRX_MAX_PEERS:
             raise L.NrxError(f"exchange='peer' supports up to {L.NRX_MAX_PEERS} ranks of one node")
         self._peer_bufs: List[PeerBuffer] = []
-        super().__init__(model, B, kind=kind, use_graph=False, table_update=table_update, **kw)
+        super().__init__(model, B, kind=kind, use_graph=False, table_update=table_update, dense_impl="flat", **kw)
         dev = self.dev
         G = self.world
         self.graph_a = self.graph_b = None

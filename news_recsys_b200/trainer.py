@@ -72,15 +72,30 @@ class FusedTrainer:
                      "widedeep": "score_fc.deep_network.network", "dcn": "score_fc.score_fc.network"}
 
     def __init__(self, model, B: int, kind: Optional[str] = None, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01,
-                 use_graph: bool = True, id_dtype=torch.int64, table_update: str = "sparse"):
+                 use_graph: bool = True, id_dtype=torch.int64, table_update: str = "sparse", dense_impl: str = "flat"):
         """table_update:
              "sparse" — fused sparse-row AdamW inside K3: only the rows the batch touched move (lazy rows);
-             "dense"  — the reference's semantics: K3 writes dense table gradients into the same flat buffer as
-                        the tower gradients and ONE dense AdamW (weight decay 0.01) updates every parameter,
-                        touched or not (sort/deep/model.py:55).  Costs a pass over the tables per step."""
+             "dense"  — the reference's semantics (sort/deep/model.py:55): AdamW with weight decay 0.01 moves every
+                        row of every table every step, touched or not.
+           dense_impl (dense only; bitwise-identical results, tests/test_gpu_trainer.py):
+             "flat"   — K3 writes dense table gradients into the same flat buffer as the tower gradients and ONE dense
+                        AdamW sweeps every parameter (also what the data-parallel trainer exchanges);
+             "split"  — touched rows: fused row AdamW inside K3; untouched rows: the g = 0 AdamW step swept on a few
+                        SMs beside forward/backward (nrx_adamw_untouched_rows).  Measured equal to "flat" at
+                        MIND-small (122-124 us vs 124 us per step): the sweep's full-SM CTAs collide with the
+                        persistent tower CTAs; kept as an option."""
         if table_update not in ("sparse", "dense"):
             raise L.NrxError(f"table_update must be 'sparse' or 'dense', got {table_update!r}")
+        if dense_impl not in ("split", "flat"):
+            raise L.NrxError(f"dense_impl must be 'split' or 'flat', got {dense_impl!r}")
         self.table_update = table_update
+        # dense semantics, two implementations with identical results:
+        #   "split" — touched rows: fused row AdamW inside K3; untouched rows: the g = 0 AdamW step, swept on the forked
+        #             stream right after the sort plan, concurrently with forward/backward (nrx_adamw_untouched_rows);
+        #   "flat"  — K3 writes dense table gradients into the flat gradient buffer, one AdamW sweeps everything
+        #             (what the data-parallel trainer all-reduces).
+        self._flat_tables = table_update == "dense" and dense_impl == "flat"
+        self._split_dense = table_update == "dense" and dense_impl == "split"
         self.model = model
         self.kind = kind or type(model).__name__.lower()
         if self.kind not in self.KINDS:
@@ -110,6 +125,7 @@ class FusedTrainer:
         self.side = torch.cuda.Stream(device=self.dev)
         self.side2 = torch.cuda.Stream(device=self.dev)
         self.side3 = torch.cuda.Stream(device=self.dev)
+        self.side4 = torch.cuda.Stream(device=self.dev)   # untouched-row sweep: from the end of the plan to the end of the step
         self.loss = torch.zeros(1, dtype=torch.float32, device=self.dev)
         self.prob = None
         self.graph = None
@@ -124,7 +140,7 @@ class FusedTrainer:
 
     def _flatten_dense(self):
         dense = [(n, p) for n, p in self.model.named_parameters()
-                 if self.table_update == "dense" or not n.startswith("embedding_tables.")]
+                 if self._flat_tables or not n.startswith("embedding_tables.")]
         total = sum(_align(p.numel(), 4) for _, p in dense)
         self.flat_p = self._alloc_flat(max(total, 4))   # hook: the multi-GPU trainer puts these in peer-mapped memory
         self.flat_g = self._alloc_flat(max(total, 4))
@@ -149,7 +165,7 @@ class FusedTrainer:
         for name, tid in self.model._table_ids.items():
             w = self.model.embedding_tables[name].weight.data
             self.tables_by_id[tid] = w
-            if self.table_update == "dense":   # moments live in the flat buffers
+            if self._flat_tables:   # moments live in the flat buffers
                 self.table_grads_by_id[tid] = self.grad_views[f"embedding_tables.{name}.weight"]
             else:
                 self.m_by_id[tid] = torch.zeros_like(w)
@@ -233,6 +249,10 @@ class FusedTrainer:
             # optimizer clock (lr schedule + bias corrections) and the sort plan (depends on the ids only)
             L.check(lib.nrx_hparams_step(self.d_step.data_ptr(), self.d_hp.data_ptr(), self.lr, self.min_lr, self.milestones[0],
                                          self.milestones[1], self.betas[0], self.betas[1], self._sp()), "nrx_hparams_step")
+            if self._split_dense:   # needs the ids and the optimizer clock only; nothing in this step reads the rows it writes
+                self.side4.wait_stream(self.side)
+                with torch.cuda.stream(self.side4):
+                    self._sweep_untouched(self._plan_fb())
             plan = ops.BwdPlan(self._plan_fb())
         packed = None
         if self.kind in ("deep", "deepfm", "dcn"):
@@ -299,7 +319,7 @@ class FusedTrainer:
                 # the scalar reductions and the field-logit backward only need dl / grad_x: run them on the third
                 # stream while the dW GEMMs (and, for DCN, the cross backward) proceed on the main one
                 s3.wait_stream(main)
-                inline = self._inline_update and kind != "dcn" and self.table_update == "sparse"
+                inline = self._inline_update and kind != "dcn" and not self._flat_tables
                 with torch.cuda.stream(s3):
                     self._loss_and_bias_grad(loss_ps, dl, bias)
                     if field is not None:
@@ -344,6 +364,26 @@ class FusedTrainer:
                                         L.ptr_array(self.tables_by_id, L.NRX_MAX_TABLES), C.byref(opt), plan.ws.data_ptr(),
                                         plan.bytes, self._sp()), "nrx_embed_bwd_apply")
 
+    def _row_opt(self):
+        opt = L.NrxRowOpt()
+        opt.lr, opt.beta1, opt.beta2, opt.eps, opt.weight_decay, opt.step = self.lr, self.betas[0], self.betas[1], self.eps, self.wd, 1
+        for t in range(L.NRX_MAX_TABLES):
+            if self.m_by_id[t] is not None:
+                opt.m[t] = self.m_by_id[t].data_ptr()
+                opt.v[t] = self.v_by_id[t].data_ptr()
+        opt.d_hparams = self.d_hp.data_ptr()
+        return opt
+
+    def _sweep_untouched(self, fb):
+        """Dense semantics, split implementation: g = 0 AdamW step on every row the plan does not touch."""
+        if getattr(self, "_row_map", None) is None:
+            n = self.lib.nrx_adamw_untouched_rows_scratch_bytes(fb.arr, fb.n)
+            self._row_map = torch.zeros(n, dtype=torch.uint8, device=self.dev)
+        opt = self._row_opt()
+        L.check(self.lib.nrx_adamw_untouched_rows(fb.arr, fb.n, fb.B, L.ptr_array(self.tables_by_id, L.NRX_MAX_TABLES),
+                                                  C.byref(opt), self._row_map.data_ptr(), self._row_map.numel(), self._sp()),
+                "nrx_adamw_untouched_rows")
+
     def _dense_table_grads(self, fb, plan, gx):
         """K3 dense mode: per-table [rows, D] gradients (zero-filled by the call) written into the flat grad buffer."""
         L.check(self.lib.nrx_embed_bwd_apply(fb.arr, fb.n, fb.B, gx.data_ptr(), gx.stride(0), L.BWD_DENSE,
@@ -356,9 +396,14 @@ class FusedTrainer:
                                              self.betas[1], self.eps, self.wd, self._sp()), "nrx_adamw_dense_dev")
 
     def _update(self, fb, plan, gx):
+        self._update_impl(fb, plan, gx)
+        if self._split_dense:
+            torch.cuda.current_stream(self.dev).wait_stream(self.side4)
+
+    def _update_impl(self, fb, plan, gx):
         """Optimizer: fused sparse-row AdamW on the tables (K3 apply) + dense AdamW on the flat buffer."""
         lib = self.lib
-        if self.table_update == "dense":
+        if self._flat_tables:
             self._dense_table_grads(fb, plan, gx)
             self._adamw_flat()
             return

@@ -88,8 +88,9 @@ def test_graph_replay_is_deterministic():
         assert torch.equal(outs[0][k], outs[1][k]), k
 
 
+@pytest.mark.parametrize("impl", ["split", "flat"])
 @pytest.mark.parametrize("name", ["fm", "deep"])
-def test_dense_mode_matches_reference_adamw_golden(name):
+def test_dense_mode_matches_reference_adamw_golden(name, impl):
     """table_update="dense" is the reference's optimizer (dense AdamW, wd 0.01, every row every step): three
     fused steps on the fixture batches land on the parameters the REFERENCE itself produced with its own
     torch.optim.AdamW + CosinDecayLR (tests/golden/{fm,deep}.npz `sdopt__*`, oracle/make_golden.py)."""
@@ -102,7 +103,7 @@ def test_dense_mode_matches_reference_adamw_golden(name):
     model = _cls(g["kind"])(g["cfg_path"])
     model.load_state_dict(g["sd"], strict=True)
     model = model.to(DEV)
-    tr = FusedTrainer(model, B, kind=g["kind"], table_update="dense")
+    tr = FusedTrainer(model, B, kind=g["kind"], table_update="dense", dense_impl=impl)
     bf16 = g["kind"] != "fm"
     for s, b in enumerate(batches):
         loss = float(tr.train_step(b).item())
@@ -169,3 +170,24 @@ def test_pipelined_feed_equals_step_by_step():
     assert tr2.drain() is None
     for k, v in tr.model.state_dict().items():
         assert torch.equal(v, tr2.model.state_dict()[k]), k
+
+
+@pytest.mark.parametrize("kind,hist", [("fm", 0), ("deepfm", 0), ("deep", 6)])
+def test_dense_split_equals_dense_flat_bitwise(kind, hist):
+    """The two implementations of the dense semantics — (fused row AdamW on touched rows + g = 0 sweep of the rest) and
+    (dense table gradients + one AdamW over everything) — produce the same bits, tables and tower, after 4 steps."""
+    from news_recsys_b200.synthetic import mind_config, synth_batch
+    from news_recsys_b200.trainer import FusedTrainer
+    rows = {"user_id": 3000, "item_id": 2000, "category": 18, "subcategory": 70, "user_click_category": 18}
+    cfg = mind_config(kind, rows, history_len=hist)
+    batches = [synth_batch(cfg, 256, seed=90 + i, label_p=0.5) for i in range(4)]
+    out = {}
+    for impl in ("split", "flat"):
+        torch.manual_seed(6)
+        model = _cls(kind)(cfg).to(DEV)
+        tr = FusedTrainer(model, 256, kind=kind, table_update="dense", dense_impl=impl)
+        losses = [float(tr.train_step(b).item()) for b in batches]
+        out[impl] = (losses, {k: v.detach().clone() for k, v in model.state_dict().items()})
+    assert out["split"][0] == out["flat"][0]
+    for k, v in out["flat"][1].items():
+        assert torch.equal(out["split"][1][k], v), k
