@@ -12,6 +12,7 @@
 // Pad layout (u32 words): [0,16) A flags by source rank, [64,80) B flags, 128 launch counter, 129 block counter,
 // 130 timed-out flag.
 #include <cuda_runtime.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -36,6 +37,9 @@ struct PeerArgs {
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ void st_relaxed_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
   uint32_t v;
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -53,12 +57,13 @@ __device__ __forceinline__ unsigned long long now_ns() {
 }
 // Spin until *flag >= want (wrap-safe signed distance); false on time-out.
 __device__ __forceinline__ bool wait_flag(const uint32_t* flag, uint32_t want) {
+  if ((int32_t)(ld_acquire_sys(flag) - want) >= 0) return true;
   const unsigned long long t0 = now_ns();
-  while ((int32_t)(ld_acquire_sys(flag) - want) < 0) {
-    if (now_ns() - t0 > kSpinLimitNs) return false;
-    __nanosleep(64);
+  for (unsigned it = 0;; ++it) {
+    if ((int32_t)(ld_acquire_sys(flag) - want) >= 0) return true;
+    if ((it & 63u) == 63u && now_ns() - t0 > kSpinLimitNs) return false;
+    __nanosleep(32);
   }
-  return true;
 }
 
 // W = compile-time bound on the world size (loads of all ranks in flight), U = float4 per thread per trip.
@@ -72,10 +77,10 @@ adamw_allreduce_peer_kernel(const __grid_constant__ PeerArgs a) {
   if (tid == 0) s_flag = 0;
   __syncthreads();
   // ---- barrier A ------------------------------------------------------------------------------------
-  if (blockIdx.x == 0 && tid < a.world) {
-    __threadfence_system();
-    st_release_sys(a.sig[tid] + kSigA + a.rank, epoch);
-  }
+  // This rank's gradients were written by EARLIER kernels of the stream: the kernel boundary already made them
+  // visible at the L2 the peers read through, so the "ready" flag is a plain system-scope store (no fence: a
+  // MEMBAR.SYS costs microseconds and sits on the critical path of every rank waiting for this flag).
+  if (blockIdx.x == 0 && tid < a.world) st_relaxed_sys(a.sig[tid] + kSigA + a.rank, epoch);
   if (tid < a.world && !wait_flag(sig + kSigA + tid, epoch)) s_flag = 1;
   __syncthreads();
   if (s_flag) {  // a peer never arrived: flag it and leave the parameters untouched
@@ -120,12 +125,15 @@ adamw_allreduce_peer_kernel(const __grid_constant__ PeerArgs a) {
     }
   }
   // ---- barrier B: last block of this rank signals, then waits for every peer's stores ----------------
-  __threadfence_system();
+  // one system-scope fence per CTA: bar.sync orders every thread's stores before thread 0's fence (fences are cumulative)
   __syncthreads();
-  if (tid == 0) s_flag = (atomicAdd(sig + kSigBlocks, 1u) == gridDim.x - 1) ? 2 : 0;
+  if (tid == 0) {
+    __threadfence_system();                                   // release this CTA's peer stores (the one sys fence per CTA)
+    s_flag = (atomicAdd(sig + kSigBlocks, 1u) == gridDim.x - 1) ? 2 : 0;
+    if (s_flag == 2) __threadfence();                         // last CTA: acquire the other CTAs' counter increments
+  }
   __syncthreads();
   if (s_flag != 2) return;
-  __threadfence_system();
   if (tid < a.world) {
     st_release_sys(a.sig[tid] + kSigB + a.rank, epoch);
     if (!wait_flag(sig + kSigB + tid, epoch)) sig[NRX_PEER_SIG_ERR] = 1u;
@@ -214,7 +222,8 @@ extern "C" int nrx_adamw_allreduce_peer(const NrxPeerStep* s, nrx_stream_t strea
   // no co-residency on ITS device, only that every rank's kernel eventually starts on its own device.
   const int U = s->world <= 2 ? 4 : (s->world <= 4 ? 2 : 1);
   long long blocks = (a.hi4 - a.lo4 + (long long)kPeerThreads * U - 1) / ((long long)kPeerThreads * U);
-  const long long cap = 4LL * sm_count();
+  long long cap = 2LL * sm_count();   // one wave at 2 CTAs/SM (76-118 registers/thread); the loop strides
+  if (const char* e = getenv("NRX_K7_CAP")) { const long long v = atoll(e); if (v > 0) cap = v; }   // tuning knob
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   cudaStream_t st = (cudaStream_t)stream;

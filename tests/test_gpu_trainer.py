@@ -191,3 +191,23 @@ def test_dense_split_equals_dense_flat_bitwise(kind, hist):
     assert out["split"][0] == out["flat"][0]
     for k, v in out["flat"][1].items():
         assert torch.equal(out["split"][1][k], v), k
+
+
+def test_int32_ids_equal_int64_ids():
+    """SURVEY §8 f1 (compact batch ingestion): the same step fed int32 ids (half the id bytes per batch) == int64 ids."""
+    from news_recsys_b200.synthetic import mind_config, synth_batch
+    from news_recsys_b200.trainer import FusedTrainer
+    rows = {"user_id": 3000, "item_id": 2000, "category": 18, "subcategory": 70, "user_click_category": 18}
+    cfg = mind_config("deep", rows, history_len=6)
+    batches = [synth_batch(cfg, 256, seed=30 + i, label_p=0.5) for i in range(3)]
+    out = {}
+    for idt in (torch.int64, torch.int32):
+        torch.manual_seed(8)
+        model = _cls("deep")(cfg).to(DEV)
+        tr = FusedTrainer(model, 256, kind="deep", id_dtype=idt)
+        losses = [float(tr.train_step(b).item()) for b in batches]
+        out[idt] = (losses, {k: v.detach().clone() for k, v in model.state_dict().items()}, tr.layout.nbytes)
+    assert out[torch.int32][2] < out[torch.int64][2]
+    assert out[torch.int32][0] == out[torch.int64][0]
+    for k, v in out[torch.int64][1].items():
+        assert torch.equal(out[torch.int32][1][k], v), k
