@@ -18,6 +18,8 @@
 // Tensor-bound when fused (AI >> ridge); flops per sample in DESIGN.md.
 #include <math.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -342,6 +344,202 @@ tower_fwd_kernel(const __grid_constant__ TowerK T, const float* __restrict__ x, 
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, (uint32_t)T.tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Forward, two tile slots per CTA (large batches).  Two groups of 8 warps each run the same per-tile pipeline on
+// their own tile, A-operand buffer and TMEM accumulator, sharing one SMEM weight image: while one group is in its
+// epilogue (TMEM -> bias/act -> bf16 -> SMEM/HBM, CUDA cores) the other group's MMAs run on the tensor pipe, and
+// one group's input-tile loads hide behind the other's compute.  Groups synchronise on named barriers only.
+// ------------------------------------------------------------------------------------------------------------
+static constexpr int kGrpThreads = 256;
+static constexpr int kGrpSplit = kGrpThreads / 128;  // column slices per group
+
+__device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(kGrpThreads) : "memory"); }
+
+__global__ void __launch_bounds__(2 * kGrpThreads, 1)
+tower_fwd2_kernel(const __grid_constant__ TowerK T, const float* __restrict__ x, long long ldx, long long B,
+                  float* __restrict__ y, long long ldy, const uint8_t* __restrict__ wpack, uint8_t* __restrict__ ws,
+                  int training) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int grp = threadIdx.x / kGrpThreads, tid = threadIdx.x % kGrpThreads;
+  const int warp = tid >> 5, lane = tid & 31;   // warp inside the group; CTA warp id = grp * 8 + warp, same value mod 4
+  const int q = warp & 3, h = warp >> 2;
+  const int r = q * 32 + lane;
+  const size_t a_bytes = (size_t)kRows * T.max_kp * 2;
+  uint8_t* sW = smem;
+  uint8_t* sA = smem + ((T.w_bytes + 1023) & ~1023u) + grp * a_bytes;
+  float* xch = reinterpret_cast<float*>(smem + ((T.w_bytes + 1023) & ~1023u) + 2 * a_bytes) + grp * (kGrpSplit * kRows * kMaxTiny);
+  float* sB = reinterpret_cast<float*>(smem + ((T.w_bytes + 1023) & ~1023u) + 2 * a_bytes) + 2 * (kGrpSplit * kRows * kMaxTiny);
+  __shared__ uint64_t wbar, mbar2[2];
+  __shared__ uint32_t tmem_s;
+  uint64_t* mbar = &mbar2[grp];
+
+  if (threadIdx.x == 0) {
+    mbar_init(&wbar, 1);
+    mbar_init(&mbar2[0], 1);
+    mbar_init(&mbar2[1], 1);
+    fence_mbar_init();
+  }
+  if (threadIdx.x < 32) tmem_alloc(&tmem_s, (uint32_t)(2 * T.tmem_cols));
+  for (int l = 0; l < T.n_mma; ++l)
+    for (int i = threadIdx.x; i < kBiasStride; i += 2 * kGrpThreads) sB[l * kBiasStride + i] = i < T.N[l] ? __ldg(T.bias[l] + i) : 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_s + (uint32_t)(grp * T.tmem_cols);
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(&wbar, T.w_bytes);
+    for (int l = 0; l < T.n_mma; ++l)
+      bulk_g2s(sW + T.w_off[l], wpack + T.w_off[l], (uint32_t)T.Kp[l] * T.Np[l] * 2u, &wbar);
+  }
+  bool w_ready = false;
+  uint32_t phase = 0;
+  const bool vec_ok = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && (ldx % 4 == 0);
+
+  for (long long tile = (long long)blockIdx.x * 2 + grp; tile < T.n_tiles; tile += 2LL * gridDim.x) {
+    const long long row0 = tile * kRows;
+    {
+      const int Kp0 = T.Kp[0], K0 = T.K[0];
+      uint8_t* img = training ? ws + T.act_off[0] + (size_t)tile * Kp0 * kRows * 2 : nullptr;
+      constexpr int kBatch = 4;
+      const int nchunk = (Kp0 / 8) * kRows;
+      const bool fast = vec_ok && (K0 % 8 == 0);
+      for (int i0 = tid; i0 < nchunk; i0 += kGrpThreads * kBatch) {
+        float4 la[kBatch], lb[kBatch];
+        if (fast) {
+#pragma unroll
+          for (int u = 0; u < kBatch; ++u) {
+            const int i = i0 + u * kGrpThreads;
+            const int rr = i % kRows, kc = i / kRows;
+            const long long row = row0 + rr;
+            la[u] = lb[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < nchunk && row < B && kc * 8 < K0) {
+              const float4* src = reinterpret_cast<const float4*>(x + row * ldx + kc * 8);
+              la[u] = __ldg(src);
+              lb[u] = __ldg(src + 1);
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {
+          const int i = i0 + u * kGrpThreads;
+          if (i >= nchunk) break;
+          const int rr = i % kRows, kc = i / kRows;
+          const long long row = row0 + rr;
+          float f[8];
+          if (fast) {
+            f[0] = la[u].x; f[1] = la[u].y; f[2] = la[u].z; f[3] = la[u].w;
+            f[4] = lb[u].x; f[5] = lb[u].y; f[6] = lb[u].z; f[7] = lb[u].w;
+          } else if (row < B) {
+            const float* src = x + row * ldx + kc * 8;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = (kc * 8 + j < K0) ? __ldg(src + j) : 0.f;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = 0.f;
+          }
+          const uint4 pk = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+          *reinterpret_cast<uint4*>(sA + canon_off(kRows, rr, kc)) = pk;
+          if (img) *reinterpret_cast<uint4*>(img + canon_off(kRows, rr, kc)) = pk;
+        }
+      }
+    }
+    fence_async_smem();
+    group_sync(grp);
+    if (!w_ready) { mbar_wait(&wbar, 0); w_ready = true; }
+
+    float dot[kMaxTiny];
+#pragma unroll
+    for (int o = 0; o < kMaxTiny; ++o) dot[o] = 0.f;
+
+    for (int l = 0; l < T.n_mma; ++l) {
+      const int Np = T.Np[l], N = T.N[l];
+      if (tid == 0) {
+        tc_fence_after();
+        issue_layer_mma(tmem, smem_u32(sA), smem_u32(sW + T.w_off[l]), T.Kp[l], Np);
+        mma_commit(mbar);
+      }
+      mbar_wait(mbar, phase);
+      phase ^= 1;
+      tc_fence_after();
+      const bool is_final = (l == T.n_layers - 1);
+      const bool feeds_tiny = T.tiny && (l == T.n_mma - 1);
+      const long long row = row0 + r;
+      uint8_t* img = (training && l + 1 < T.n_layers) ? ws + T.act_off[l + 1] + (size_t)tile * Np * kRows * 2 : nullptr;
+      for (int g = h; g < Np / 16; g += kGrpSplit) {
+        float v[16];
+        tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)g * 16u, v);
+        tmem_ld_wait();
+        const float* bp = sB + l * kBiasStride + g * 16;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float z = v[j] + bp[j];
+          if (!is_final) z = bf16_round(act_fwd(z, T.slope));
+          v[j] = z;
+        }
+        if (is_final) {
+          if (row < B) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (g * 16 + j < N) y[row * ldy + g * 16 + j] = v[j];
+          }
+        } else {
+          const uint4 c0 = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+          const uint4 c1 = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
+          *reinterpret_cast<uint4*>(sA + canon_off(kRows, r, 2 * g)) = c0;
+          *reinterpret_cast<uint4*>(sA + canon_off(kRows, r, 2 * g + 1)) = c1;
+          if (img) {
+            *reinterpret_cast<uint4*>(img + canon_off(kRows, r, 2 * g)) = c0;
+            *reinterpret_cast<uint4*>(img + canon_off(kRows, r, 2 * g + 1)) = c1;
+          }
+          if (feeds_tiny) {
+            const int Kt = T.K[T.n_layers - 1], Nt = T.N[T.n_layers - 1];
+            const float* wt = T.w[T.n_layers - 1];
+#pragma unroll
+            for (int o = 0; o < kMaxTiny; ++o) {
+              if (o < Nt) {
+                float sacc = dot[o];
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                  if (g * 16 + j < Kt) sacc = fmaf(v[j], __ldg(wt + o * Kt + g * 16 + j), sacc);
+                dot[o] = sacc;
+              }
+            }
+          }
+        }
+      }
+      if (feeds_tiny) {
+#pragma unroll
+        for (int o = 0; o < kMaxTiny; ++o) xch[(h * kRows + r) * kMaxTiny + o] = dot[o];
+      }
+      fence_async_smem();
+      tc_fence_before();
+      group_sync(grp);
+    }
+    if (T.tiny && h == 0) {
+      const long long row = row0 + r;
+      const int Nt = T.N[T.n_layers - 1];
+      if (row < B) {
+        for (int o = 0; o < Nt; ++o) {
+          float t = 0.f;
+#pragma unroll
+          for (int hh = 0; hh < kGrpSplit; ++hh) t += xch[(hh * kRows + r) * kMaxTiny + o];
+          y[row * ldy + o] = t + __ldg(T.bias[T.n_layers - 1] + o);
+        }
+      }
+    }
+    if (T.tiny) group_sync(grp);  // xch is reused by the group's next tile
+  }
+  if (!w_ready) mbar_wait(&wbar, 0);
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) tmem_dealloc(tmem_s, (uint32_t)(2 * T.tmem_cols));
+}
+
+static size_t fwd2_smem_bytes(const TowerK& k) {
+  return ((k.w_bytes + 1023) & ~1023u) + 2 * (size_t)kRows * k.max_kp * 2 +
+         (2 * kGrpSplit * kRows * kMaxTiny + NRX_MAX_LAYERS * kBiasStride) * sizeof(float);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -713,6 +911,19 @@ extern "C" int nrx_tower_fwd(const NrxTower* h_tower, const float* x, int64_t x_
   if (!prepacked) {
     rc = tower_pack(k, (uint8_t*)ws, st);
     if (rc != NRX_OK) return rc;
+  }
+  {
+    // large batches: two tile slots per CTA (needs >= 3 tiles per SM to pay, 2 A buffers + 2 accumulators to fit)
+    const size_t smem2 = fwd2_smem_bytes(k);
+    const char* env = getenv("NRX_TOWER_V2");
+    const bool want = env ? atoi(env) != 0 : true;
+    if (want && k.n_tiles >= 3LL * sm_count() && smem2 <= 227 * 1024 && 2 * k.tmem_cols <= 512) {
+      cudaError_t e2 = cudaFuncSetAttribute(tower_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+      NRX_REQUIRE(e2 == cudaSuccess, NRX_ELAUNCH, "smem opt-in: %s", cudaGetErrorString(e2));
+      tower_fwd2_kernel<<<(unsigned)sm_count(), 2 * kGrpThreads, smem2, st>>>(k, x, x_ld, B, y, y_ld, (const uint8_t*)ws + k.wpack_off,
+                                                                            (uint8_t*)ws, training);
+      return check_launch("tower_fwd2");
+    }
   }
   cudaError_t e = cudaFuncSetAttribute(tower_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   NRX_REQUIRE(e == cudaSuccess, NRX_ELAUNCH, "smem opt-in: %s", cudaGetErrorString(e));

@@ -160,3 +160,33 @@ def test_deep_model_matches_reference(name):
     for k, gr in g["grads"].items():
         assert params[k].grad is not None, k
         assert _cos(params[k].grad, gr) > 0.98, f"{name}:{k}: cos {_cos(params[k].grad, gr):.4f}"
+
+
+@pytest.mark.parametrize("dims,slope", [([112, 128, 128, 128, 64, 1], None), ([80, 128, 64, 16], 0.2), ([64, 128, 128], None)])
+def test_two_slot_forward_equals_one_slot(dims, slope, monkeypatch):
+    """Large batches run tower_fwd2_kernel (two tile slots per CTA).  Same per-element arithmetic as the one-slot
+    kernel: saved activation images bitwise equal, outputs equal up to the summation order of the <= 4-wide last
+    layer; a ragged last tile and a batch that leaves one group of some CTAs without a tile are included."""
+    from news_recsys_b200 import ops
+    ws, bs = _mk(dims, seed=5)
+    wd, bd = [w.to(DEV) for w in ws], [b.to(DEV) for b in bs]
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    B = 3 * sms * 128 + 77          # just above the switch point, ragged
+    x = torch.randn(B, dims[0], device=DEV)
+    out = {}
+    for v2 in ("0", "1"):
+        monkeypatch.setenv("NRX_TOWER_V2", v2)
+        y_inf, _ = ops.tower_fwd(x, wd, bd, slope, training=False)
+        y_tr, tctx = ops.tower_fwd(x, wd, bd, slope, training=True)
+        A, _ = ops.tower_images(tctx, B)
+        out[v2] = (y_inf.clone(), y_tr.clone(), [a.clone() for a in A])
+    tiny = dims[-1] <= 4
+    for a, b in zip(out["0"][2], out["1"][2]):
+        assert torch.equal(a, b)
+    for k in (0, 1):
+        if tiny:
+            torch.testing.assert_close(out["1"][k], out["0"][k], rtol=1e-5, atol=1e-6)
+        else:
+            assert torch.equal(out["1"][k], out["0"][k])
+    idx = torch.randint(0, B, (256,), device=DEV)
+    assert _rel(out["1"][0][idx], R.mlp(x[idx].cpu(), ws, bs, negative_slope=slope)) < BF16_RTOL
