@@ -278,13 +278,22 @@ tower_fwd_kernel(const __grid_constant__ TowerK T, const float* __restrict__ x, 
         float v[16];
         tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)g * 16u, v);
         tmem_ld_wait();
-        const float* bp = sB + l * kBiasStride + g * 16;
+        // bias as four 16-byte SMEM loads; the bf16 rounding happens once, in pack_bf16 below — only the layer that
+        // feeds the register dot product of the tiny last layer needs the rounded VALUES as floats
+        const float4* bp4 = reinterpret_cast<const float4*>(sB + l * kBiasStride + g * 16);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int col = g * 16 + j;
-          float z = v[j] + bp[j];
-          if (!is_final) z = bf16_round(act_fwd(z, T.slope));
-          v[j] = z;
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const float4 b4 = bp4[j4];
+          const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            float z = v[j4 * 4 + jj] + bb[jj];
+            if (!is_final) {
+              z = act_fwd(z, T.slope);
+              if (feeds_tiny) z = bf16_round(z);
+            }
+            v[j4 * 4 + jj] = z;
+          }
         }
         if (is_final) {
           if (row < B) {
@@ -471,12 +480,22 @@ tower_fwd2_kernel(const __grid_constant__ TowerK T, const float* __restrict__ x,
         float v[16];
         tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)g * 16u, v);
         tmem_ld_wait();
-        const float* bp = sB + l * kBiasStride + g * 16;
+        // bias as four 16-byte SMEM loads; the bf16 rounding happens once, in pack_bf16 below — only the layer that
+        // feeds the register dot product of the tiny last layer needs the rounded VALUES as floats
+        const float4* bp4 = reinterpret_cast<const float4*>(sB + l * kBiasStride + g * 16);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float z = v[j] + bp[j];
-          if (!is_final) z = bf16_round(act_fwd(z, T.slope));
-          v[j] = z;
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const float4 b4 = bp4[j4];
+          const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            float z = v[j4 * 4 + jj] + bb[jj];
+            if (!is_final) {
+              z = act_fwd(z, T.slope);
+              if (feeds_tiny) z = bf16_round(z);
+            }
+            v[j4 * 4 + jj] = z;
+          }
         }
         if (is_final) {
           if (row < B) {
