@@ -1,5 +1,7 @@
 """CPU-only: host-side mirror of the reference interface (config schema, column layout, state_dict keys,
 LR schedule, batch blob layout) — no GPU work."""
+import os
+
 import pytest
 import torch
 
@@ -104,3 +106,22 @@ def test_synthetic_batch_layout_matches_data_reader_contract():
     for r in range(64):
         assert torch.all(b["user_history_mask"][r, :lens[r]] == 1) and torch.all(b["user_history_mask"][r, lens[r]:] == 0)
     assert b["label"].shape == (64, 2)
+
+
+def test_bench_reference_arm_prints_exactly_one_json_line():
+    """bench.py keeps stdout for the single JSON line (library banners go to stderr); the CPU arm carries the
+    keys the driver reads."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "3", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, out.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "samples/s" and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert d["value"] > 0
