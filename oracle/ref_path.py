@@ -13,10 +13,18 @@ Parity status
   holds no arithmetic) in the build container and writes inputs, parameters,
   outputs and gradients to `tests/golden/*.npz`; `tests/test_oracle_golden.py`
   checks every function below against those vectors.
-* DSSM towers / InfoNCE, DeepFM and inner-product top-k: "parity unpinned".
-  `recall/DSSM/model.py` is not importable as shipped, the reference has no
-  DeepFM class and `faiss` is not vendored, so these are restatements of the
-  cited lines with no reference-produced vector behind them.
+* DSSM (towers, per-feature gather / masked pooling, forward with in-batch negatives and
+  L2 normalisation, InfoNCE): PINNED.  `recall/DSSM/model.py` is not importable as
+  shipped, but `oracle/make_golden_dssm.py` runs the UNMODIFIED class with import aliases
+  only (top-level `BaseModel` / `model_utils` / `DataReader` names bound to the same
+  reference modules, an empty `faiss` stub, the stale `get_features_embedding` name
+  aliased to `get_feature_embedding`) and writes `tests/golden/dssm.npz`;
+  `tests/test_oracle_golden.py::test_dssm_matches_reference` checks tower inputs
+  (bit-equal), towers, outputs, loss and every gradient.
+* DeepFM and inner-product top-k: "parity unpinned".  The reference has no DeepFM
+  class (composed from the pinned FM logit + pinned MLP) and `faiss` is not vendored,
+  so these are restatements of the cited lines with no reference-produced vector
+  behind them.
 
 Each function cites the reference file:line it follows (paths relative to
 /root/reference).
@@ -296,7 +304,7 @@ def cosine_decay_lr(step: int, lrs: Sequence[float], milestones: Sequence[int]) 
 
 
 # --------------------------------------------------------------------------- #
-# DSSM (restatement — parity unpinned)                                         #
+# DSSM (pinned: tests/golden/dssm.npz)                                         #
 # --------------------------------------------------------------------------- #
 
 def dssm_tower(x: Tensor, weights: Sequence[Tensor], biases: Sequence[Tensor]) -> Tensor:

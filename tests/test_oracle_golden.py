@@ -114,3 +114,64 @@ def test_topk_ties_lower_id_first():
     b = R.topk_ip(torch.ones(1, 1), c[3:], 2)
     ms, mi = R.topk_merge([a[0], b[0]], [a[1], b[1] + 3], 3)
     assert mi.tolist() == [[1, 2, 4]]
+
+
+def _dssm_fixture():
+    z = np.load(f"{GOLD}/dssm.npz", allow_pickle=False)
+    import os
+    import yaml
+    cfg = yaml.safe_load(open(os.path.join(GOLD, "configs", f"train_cf_{str(z['cfg'])}.yaml")))
+    sd = {k[4:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd__")}
+    batch = {k[4:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("in__")}
+    return z, cfg, sd, batch
+
+
+def _dssm_side(sd, cfg, batch, order, leaf=None):
+    """Tower input in the recorded set-iteration order of the reference process (DSSM/model.py:150,:167)."""
+    feats = cfg["features"]
+    share = cfg["embeddings"].get("share_emb_table_features", {}) or {}
+    arrays = set(feats.get("array_feature_names", []) or [])
+    tables = leaf if leaf is not None else R._tables(sd)
+    cols = []
+    for f in order:
+        e = R.feature_embedding(tables, share, f, batch[f])
+        if f in arrays:
+            e = R.array_feature_pooling(e, batch.get(f + "_mask"))
+        cols.append(e)
+    return torch.cat(cols, dim=1)
+
+
+def _dssm_params(sd, side):
+    idx = (0, 2, 4, 6)
+    return [sd[f"{side}_fc.{i}.weight"] for i in idx], [sd[f"{side}_fc.{i}.bias"] for i in idx]
+
+
+def test_dssm_matches_reference():
+    """tests/golden/dssm.npz was produced by the reference's own DSSM class (oracle/make_golden_dssm.py): tower inputs,
+    towers, normalised outputs with in-batch negatives, InfoNCE with the label mask, and every gradient."""
+    z, cfg, sd, batch = _dssm_fixture()
+    t = lambda k: torch.from_numpy(z[k])
+    uo, io = z["user_order"].tolist(), z["item_order"].tolist()
+    ux, ix = _dssm_side(sd, cfg, batch, uo), _dssm_side(sd, cfg, batch, io)
+    assert torch.equal(ux, t("user_vector")) and torch.equal(ix, t("item_vector"))
+    up, ip = _dssm_params(sd, "user"), _dssm_params(sd, "item")
+    torch.testing.assert_close(R.dssm_tower(ux, *up), t("user_tower"), rtol=1e-6, atol=1e-7)
+    torch.testing.assert_close(R.dssm_tower(ix, *ip), t("item_tower"), rtol=1e-6, atol=1e-7)
+    perms = [p for p in t("neg_perms")]
+    u, it, neg = R.dssm_forward(ux, ix, up, ip, perms)
+    torch.testing.assert_close(u, t("user_emb"), rtol=1e-6, atol=1e-7)
+    torch.testing.assert_close(it, t("item_emb"), rtol=1e-6, atol=1e-7)
+    torch.testing.assert_close(neg, t("neg_emb"), rtol=1e-6, atol=1e-7)
+    mask = batch["label"][:, 1]
+    torch.testing.assert_close(R.infonce_loss(u, it, neg, mask=mask), t("infonce"), rtol=1e-6, atol=1e-7)
+    torch.testing.assert_close(R.infonce_loss(u, it, neg), t("infonce_nomask"), rtol=1e-6, atol=1e-7)
+    # gradients through the restated path
+    leaf = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    tabs = {k[len("embedding_tables."):-len(".weight")]: v for k, v in leaf.items() if k.startswith("embedding_tables.")}
+    ux, ix = _dssm_side(sd, cfg, batch, uo, tabs), _dssm_side(sd, cfg, batch, io, tabs)
+    u, it, neg = R.dssm_forward(ux, ix, _dssm_params(leaf, "user"), _dssm_params(leaf, "item"), perms)
+    R.infonce_loss(u, it, neg, mask=mask).backward()
+    for k in sd:
+        ref = t("grad__" + k)
+        got = leaf[k].grad if leaf[k].grad is not None else torch.zeros_like(ref)
+        torch.testing.assert_close(got, ref, rtol=1e-5, atol=1e-8, msg=lambda m: f"{k}: {m}")
