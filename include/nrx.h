@@ -166,6 +166,35 @@ int nrx_adamw_dense_dev(float* p, const float* g, float* m, float* v, int64_t n,
 int nrx_hparams_step(int32_t* d_step, float* d_hparams, float lr, float min_lr, int32_t milestone0,
                      int32_t milestone1, float beta1, float beta2, nrx_stream_t stream);
 
+/* ---- batch ingestion, HOST side ---------------------------------------------------------------
+ * Replaces DataReader.__getitem__ + default collate (src/dataset/DataReader/data_reader.py:54-114): the per-sample
+ * split(':') / list padding / torch.tensor of the reference becomes three copies per batch out of a columnar feature
+ * file (int32 id columns; array features as CSR offsets + values, already truncated to max_len; float labels),
+ * written STRAIGHT into the pinned batch blob.  All pointers here are HOST pointers; no CUDA call is made.
+ * `rows`: B row numbers (shuffled batches) or NULL for the contiguous rows [row0, row0 + B).
+ * Output = what the reference collates: ids right-padded with 0, mask 1/0, first L ids kept. */
+int nrx_ingest_gather_ids(const int32_t* column, int64_t n_rows, const int64_t* rows, int64_t row0, int64_t B,
+                          void* out, int idx_dtype);
+int nrx_ingest_csr_expand(const int64_t* offsets, const int32_t* values, int64_t n_rows, const int64_t* rows,
+                          int64_t row0, int64_t B, int32_t L, void* out_ids, int idx_dtype, float* out_mask /* nullable */);
+int nrx_ingest_gather_labels(const float* labels, int64_t n_rows, int32_t n_labels, const int64_t* rows, int64_t row0,
+                             int64_t B, float* out, int32_t out_ld);
+
+/* Device-resident feature file: the same batch assembled ON THE GPU from device copies of the columns (the whole
+ * columnar click log fits HBM), one warp per sample; `d_rows` (device int64[B], nullable) selects shuffled rows, a row
+ * outside the file yields an all-padding sample.  All pointers are DEVICE pointers except `h_cols`. */
+typedef struct NrxIngestCol {
+  const int32_t* data;      /* sparse: ids [n_rows]; array: CSR values */
+  const int64_t* offsets;   /* array: CSR offsets [n_rows + 1]; NULL for a sparse column */
+  int32_t L;                /* array: padded length of the output */
+  int32_t idx_dtype;        /* dtype of out_ids: NRX_IDX_I64 / NRX_IDX_I32 */
+  void* out_ids;            /* [B] or [B, L] */
+  float* out_mask;          /* [B, L] or NULL */
+} NrxIngestCol;
+int nrx_ingest_assemble_device(const NrxIngestCol* h_cols, int n_cols, const float* labels, int32_t n_labels,
+                               float* out_labels, int32_t out_ld, int64_t n_rows, const int64_t* d_rows, int64_t row0,
+                               int64_t B, nrx_stream_t stream);
+
 /* ---- dense-AdamW semantics at sparse cost ---------------------------------------------------------------
  * The reference's torch.optim.AdamW (deep/model.py:55) sweeps whole tables every step.  For a row no occurrence of
  * the batch touches the gradient is exactly zero, so its update does not depend on the backward pass:

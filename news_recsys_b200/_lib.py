@@ -58,6 +58,11 @@ class NrxPeerStep(C.Structure):
     ]
 
 
+class NrxIngestCol(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("offsets", C.c_void_p), ("L", C.c_int32), ("idx_dtype", C.c_int32),
+                ("out_ids", C.c_void_p), ("out_mask", C.c_void_p)]
+
+
 class NrxTower(C.Structure):
     _fields_ = [
         ("n_layers", C.c_int32), ("dims", C.c_int32 * (NRX_MAX_LAYERS + 1)),
@@ -81,6 +86,10 @@ SIGNATURES = {
     "nrx_embed_bwd_plan": (C.c_int, [C.POINTER(NrxFeat), C.c_int, _I64, _P, _SZ, _P]),
     "nrx_embed_bwd_apply": (C.c_int, [C.POINTER(NrxFeat), C.c_int, _I64, _P, _I64, C.c_int,
                                       C.POINTER(_P), C.POINTER(_P), C.POINTER(NrxRowOpt), _P, _SZ, _P]),
+    "nrx_ingest_gather_ids": (C.c_int, [_P, _I64, _P, _I64, _I64, _P, C.c_int]),
+    "nrx_ingest_csr_expand": (C.c_int, [_P, _P, _I64, _P, _I64, _I64, _I32, _P, C.c_int, _P]),
+    "nrx_ingest_gather_labels": (C.c_int, [_P, _I64, _I32, _P, _I64, _I64, _P, _I32]),
+    "nrx_ingest_assemble_device": (C.c_int, [C.POINTER(NrxIngestCol), C.c_int, _P, _I32, _P, _I32, _I64, _P, _I64, _I64, _P]),
     "nrx_adamw_untouched_rows_scratch_bytes": (_SZ, [C.POINTER(NrxFeat), C.c_int]),
     "nrx_adamw_untouched_rows": (C.c_int, [C.POINTER(NrxFeat), C.c_int, _I64, C.POINTER(_P), C.POINTER(NrxRowOpt), _P, _SZ, _P]),
     "nrx_field_logit_fwd": (C.c_int, [_P, _I64, _I64, C.POINTER(_I32), C.POINTER(_I32), C.c_int, C.c_int, _P, C.c_int, _P]),
@@ -160,7 +169,7 @@ KERNELS_PER_CALL = {"nrx_tower_fwd": 2, "nrx_tower_fwd(prepacked)": 1, "nrx_towe
                     "nrx_embed_bwd_apply(dense)": 2, "nrx_embed_bwd_apply(rowopt)": 2, "nrx_topk_ip": 2,
                     "nrx_topk_search": 5, "nrx_topk_index_build": 1,
                     "nrx_peer_alloc": 0, "nrx_peer_free": 0, "nrx_peer_export": 0, "nrx_peer_open": 0, "nrx_peer_close": 0,
-                    "nrx_peer_status": 0,
+                    "nrx_peer_status": 0, "nrx_ingest_gather_ids": 0, "nrx_ingest_csr_expand": 0, "nrx_ingest_gather_labels": 0,
                     "nrx_tower_workspace_bytes": 0, "nrx_embed_bwd_workspace_bytes": 0, "nrx_tower_image_layout": 0}
 launch_count = 0  # running total, read by bench.py
 

@@ -474,6 +474,11 @@ class FusedTrainer:
         for key, dt, shape, off in self.layout.fields:
             self.batch[key].copy_(batch[key].to(device=self.dev, dtype=dt).view(*shape), non_blocking=True)
 
+    def load_rows(self, device_file, rows: Optional[torch.Tensor] = None, start: int = 0):
+        """Assemble the batch on the GPU from a device-resident feature file (ingest.DeviceFeatureFile): rows `rows`
+        (device int64[B], e.g. a slice of a device-side permutation) or the contiguous rows [start, start + B)."""
+        device_file.assemble(self.layout, self.blob, rows=rows, start=start)
+
     def step(self) -> torch.Tensor:
         """Run one training step on the currently loaded batch; returns the (device) mean BCE loss."""
         if self.graph is not None:

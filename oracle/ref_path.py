@@ -21,6 +21,10 @@ Parity status
   aliased to `get_feature_embedding`) and writes `tests/golden/dssm.npz`;
   `tests/test_oracle_golden.py::test_dssm_matches_reference` checks tower inputs
   (bit-equal), towers, outputs, loss and every gradient.
+* Batch ingestion (`DataReader.__getitem__` + default collate): PINNED.
+  `oracle/make_golden_ingest.py` writes a text file in the reference's wire format and
+  the batches the reference's own DataReader + default collate produce from it
+  (`tests/golden/ingest_features.txt`, `ingest.npz`).
 * DeepFM and inner-product top-k: "parity unpinned".  The reference has no DeepFM
   class (composed from the pinned FM logit + pinned MLP) and `faiss` is not vendored,
   so these are restatements of the cited lines with no reference-produced vector
@@ -301,6 +305,66 @@ def cosine_decay_lr(step: int, lrs: Sequence[float], milestones: Sequence[int]) 
         return lrs[-1]
     prog = (step - milestones[0]) / max(1, milestones[1] - milestones[0])
     return lrs[1] + (lrs[0] - lrs[1]) * 0.5 * (1.0 + math.cos(math.pi * prog))
+
+
+# --------------------------------------------------------------------------- #
+# Batch ingestion (pinned: tests/golden/ingest.npz)                            #
+# --------------------------------------------------------------------------- #
+
+def datareader_getitem(raw_line: str, cfg: dict, idx: int = 0) -> Dict[str, object]:
+    """src/dataset/DataReader/data_reader.py:54-114 (`DataReader.__getitem__`) for one stripped line:
+    "name:value ... \t labels"; sparse -> int, dense -> float, array -> int64[L] right-padded with 0 / truncated to the
+    first L + float32 mask `<name>_mask`; names not in the config are ignored; label -> float32[n_labels]."""
+    feats = cfg["features"]
+    sparse = set(feats.get("sparse_feature_names") or [])
+    dense = set(feats.get("dense_feature_names") or [])
+    arrays = set(feats.get("array_feature_names") or [])
+    amax = feats.get("array_max_length") or {}
+    try:
+        feature_part, label_part = raw_line.split("\t")
+    except ValueError:
+        raise ValueError(f"Line {idx} format error: missing tab separator between features and labels.")
+    out: Dict[str, object] = {}
+    for item in feature_part.split(" "):
+        if ":" not in item:
+            raise ValueError(f"Feature item format error: '{item}' does not contain ':' separator.")
+        name, val = item.split(":", 1)
+        if name in sparse:
+            out[name] = int(val)
+        elif name in dense:
+            out[name] = float(val)
+        elif name in arrays:
+            max_len = amax.get(name)
+            if max_len is None:
+                raise ValueError(f"Max length for array feature '{name}' missing in config.")
+            ids = [int(x) for x in val.split(",")] if val else []
+            n = len(ids)
+            if n < max_len:
+                ids = ids + [0] * (max_len - n)
+                mask = [1.0] * n + [0.0] * (max_len - n)
+            else:
+                ids = ids[:max_len]
+                mask = [1.0] * max_len
+            out[name] = torch.tensor(ids, dtype=torch.long)
+            out[f"{name}_mask"] = torch.tensor(mask, dtype=torch.float32)
+    out["label"] = torch.tensor([float(l) for l in label_part.strip().split(" ")], dtype=torch.float32)
+    return out
+
+
+def datareader_batch(lines: Sequence[str], cfg: dict, rows: Sequence[int]) -> Dict[str, Tensor]:
+    """DataReader rows -> torch default collate (pl_dataloader.py:77-95): ints -> int64[B], floats -> float64[B],
+    tensors stacked."""
+    samples = [datareader_getitem(lines[i], cfg, i) for i in rows]
+    out: Dict[str, Tensor] = {}
+    for k in samples[0]:
+        v0 = samples[0][k]
+        if isinstance(v0, torch.Tensor):
+            out[k] = torch.stack([s[k] for s in samples])
+        elif isinstance(v0, int):
+            out[k] = torch.tensor([s[k] for s in samples], dtype=torch.int64)
+        else:
+            out[k] = torch.tensor([s[k] for s in samples], dtype=torch.float64)
+    return out
 
 
 # --------------------------------------------------------------------------- #
