@@ -310,9 +310,9 @@ class DeviceFeatureFile:
     optional row permutation.  Same output as FeatureFile.pack()."""
 
     def __init__(self, ff: FeatureFile, device):
-        self.ff, self.dev = ff, torch.device(device)
-        if self.dev.type != "cuda":
+        if torch.device(device).type != "cuda":
             raise L.NrxError("DeviceFeatureFile needs a CUDA device (the host path is FeatureFile.pack)")
+        self.ff, self.dev = ff, torch.empty(0, device=device).device   # normalised: "cuda" -> cuda:<current>
         up = lambda a: torch.from_numpy(np.array(a)).to(self.dev)
         self.n_rows, self.n_labels = ff.n_rows, ff.n_labels
         self.cols = {}
