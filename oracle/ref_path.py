@@ -25,6 +25,9 @@ Parity status
   `oracle/make_golden_ingest.py` writes a text file in the reference's wire format and
   the batches the reference's own DataReader + default collate produce from it
   (`tests/golden/ingest_features.txt`, `ingest.npz`).
+* Validation scoring / metrics (`validation_step` + `on_validation_epoch_end`): PINNED.
+  `oracle/make_golden_valmetrics.py` runs the reference's own methods on a reference Deep
+  model and captures the `results` dict they build (`tests/golden/valmetrics.npz`).
 * DeepFM and inner-product top-k: "parity unpinned".  The reference has no DeepFM
   class (composed from the pinned FM logit + pinned MLP) and `faiss` is not vendored,
   so these are restatements of the cited lines with no reference-produced vector
@@ -364,6 +367,106 @@ def datareader_batch(lines: Sequence[str], cfg: dict, rows: Sequence[int]) -> Di
             out[k] = torch.tensor([s[k] for s in samples], dtype=torch.int64)
         else:
             out[k] = torch.tensor([s[k] for s in samples], dtype=torch.float64)
+    return out
+
+
+# --------------------------------------------------------------------------- #
+# Validation scoring / metrics (pinned: tests/golden/valmetrics.npz)           #
+# --------------------------------------------------------------------------- #
+
+def validation_pairs(user_ids: Tensor, scores: Tensor, label: Tensor):
+    """base_model.py:320-330 (`validation_step`): `zip(user_id.view(-1), scores.view(-1), label.view(-1))`.
+    NOTE the reference flattens the WHOLE [B, n_labels] label tensor, so zip pairs sample i with
+    `label.view(-1)[i]` (= label[i // n, i % n]), not with label[i, 0]; restated as is."""
+    u = user_ids.view(-1).cpu().numpy()
+    s = scores.view(-1).cpu().numpy()
+    l = label.view(-1).cpu().numpy()
+    n = min(len(u), len(s), len(l))
+    return u[:n], s[:n], l[:n]
+
+
+def roc_auc(labels, preds) -> float:
+    """sklearn.metrics.roc_auc_score for binary labels (the call at base_model.py:379,445): area under the ROC
+    curve == Mann-Whitney statistic with ties counted one half."""
+    import numpy as np
+    y = np.asarray(labels, dtype=np.float64)
+    p = np.asarray(preds, dtype=np.float64)
+    n_pos, n_neg = float((y == 1).sum()), float((y != 1).sum())
+    order = np.argsort(p, kind="mergesort")
+    ps, ys = p[order], y[order]
+    ranks = np.empty(len(p), dtype=np.float64)
+    i = 0
+    while i < len(ps):          # average ranks inside tie groups
+        j = i
+        while j + 1 < len(ps) and ps[j + 1] == ps[i]:
+            j += 1
+        ranks[i:j + 1] = 0.5 * (i + j) + 1.0
+        i = j + 1
+    return float((ranks[ys == 1].sum() - n_pos * (n_pos + 1) / 2.0) / (n_pos * n_neg))
+
+
+def validation_metrics(user_ids, preds, labels, k: int = 10, user_in_train_set=None) -> Dict[str, Dict[str, float]]:
+    """base_model.py:333-478 (`on_validation_epoch_end`): users in first-appearance order (dict insertion, :327-330);
+    per user AUC when both classes occur (:376-383), top-k by score descending with a STABLE sort (:387), HR / NDCG /
+    MRR @k (0 for users without positives, :393-401); warm / cold split by membership of uid or str(uid) in
+    `user_in_train_set` (:362-366); overall AUC + log-loss per group (:443-461, float32 arithmetic as numpy does it)."""
+    import numpy as np
+    per_user: Dict[object, list] = {}
+    for uid, sc, lb in zip(user_ids, preds, labels):
+        per_user.setdefault(uid, []).append((sc, lb))
+    groups = {g: {"preds": [], "labels": [], "auc": [], "ndcg": [], "hr": [], "mrr": []} for g in ("all", "warm", "cold")}
+    for uid, items in per_user.items():
+        ps = [x[0] for x in items]
+        ls = [x[1] for x in items]
+        cold = bool(user_in_train_set) and uid not in user_in_train_set and str(uid) not in user_in_train_set
+        tgt = groups["cold" if cold else "warm"]
+        for g in (groups["all"], tgt):
+            g["preds"].extend(ps)
+            g["labels"].extend(ls)
+        if len(set(ls)) > 1:
+            a = roc_auc(ls, ps)
+            groups["all"]["auc"].append(a)
+            tgt["auc"].append(a)
+        top = sorted(items, key=lambda x: x[0], reverse=True)[:k]
+        n_pos = sum(1 for x in items if x[1] == 1)
+        if n_pos == 0:
+            for g in (groups["all"], tgt):
+                g["hr"].append(0.0); g["ndcg"].append(0.0); g["mrr"].append(0.0)
+            continue
+        hr = 1.0 if any(x[1] == 1 for x in top) else 0.0
+        dcg = sum(1.0 / np.log2(r + 1) for r, (_, lb) in enumerate(top, start=1) if lb == 1)
+        idcg = sum(1.0 / np.log2(r + 1) for r in range(1, min(n_pos, k) + 1))
+        ndcg = dcg / idcg if idcg > 0 else 0.0
+        mrr = 0.0
+        for r, (_, lb) in enumerate(top, start=1):
+            if lb == 1:
+                mrr = 1.0 / r
+                break
+        for g in (groups["all"], tgt):
+            g["hr"].append(hr); g["ndcg"].append(ndcg); g["mrr"].append(mrr)
+
+    def mean(l):
+        return float(np.mean(l)) if l else 0.0
+
+    def auc_logloss(ps, ls):
+        auc, ll = 0.0, 0.0
+        if len(ps) > 0:
+            if len(set(ls)) > 1:
+                auc = roc_auc(ls, ps)
+            eps = 1e-15
+            pa = np.clip(ps, eps, 1 - eps)
+            la = np.array(ls)
+            ll = float(-np.mean(la * np.log(pa) + (1 - la) * np.log(1 - pa)))
+        return auc, ll
+
+    out = {}
+    for name, g in (("Overall", "all"), ("Warm_Start", "warm"), ("Cold_Start", "cold")):
+        G = groups[g]
+        auc, ll = auc_logloss(G["preds"], G["labels"])
+        out[name] = {"AUC": auc, "LogLoss": ll, "GAUC": mean(G["auc"]), f"NDCG@{k}": mean(G["ndcg"]), f"HR@{k}": mean(G["hr"]),
+                     f"MRR@{k}": mean(G["mrr"])}
+        if name != "Overall":
+            out[name]["User_Count"] = len(G["hr"])
     return out
 
 
