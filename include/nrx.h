@@ -195,6 +195,14 @@ int nrx_ingest_assemble_device(const NrxIngestCol* h_cols, int n_cols, const flo
                                float* out_labels, int32_t out_ld, int64_t n_rows, const int64_t* d_rows, int64_t row0,
                                int64_t B, nrx_stream_t stream);
 
+/* ---- validation metrics ------------------------------------------------------------------------
+ * Per-user AUC / NDCG@k / HR@k / MRR@k, replacing the Python loop of BaseModel.on_validation_epoch_end
+ * (src/model/BaseModel/base_model.py:352-437).  Samples sorted by (user, score descending, arrival order);
+ * d_seg_off [n_users + 1] delimits the users.  d_out [n_users, 4] = {auc, ndcg, hr, mrr} in fp64,
+ * d_flags [n_users]: bit 0 = both classes present (AUC counts towards GAUC), bit 1 = has a positive. */
+int nrx_grouped_rank_metrics(const float* d_scores, const float* d_labels, const int64_t* d_seg_off, int64_t n_users,
+                             int32_t k, double* d_out, int32_t* d_flags, nrx_stream_t stream);
+
 /* ---- dense-AdamW semantics at sparse cost ---------------------------------------------------------------
  * The reference's torch.optim.AdamW (deep/model.py:55) sweeps whole tables every step.  For a row no occurrence of
  * the batch touches the gradient is exactly zero, so its update does not depend on the backward pass:

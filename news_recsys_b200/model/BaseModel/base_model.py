@@ -187,6 +187,21 @@ class BaseModel(_Base):
     def forward(self, x):
         raise NotImplementedError("Subclasses must implement forward()")
 
+    # ---- validation scoring / metrics on the device (reference :320-478) ---------------------------
+    def validation_step(self, batch, batch_idx=0):
+        from ...metrics import ValidationMetrics
+        if getattr(self, "_val_metrics", None) is None:
+            self._val_metrics = ValidationMetrics(k=10, user_in_train_set=getattr(self, "user_in_train_set", None))
+        self._val_metrics.update(batch["user_id"], self.inference(batch), batch["label"])
+
+    def on_validation_epoch_end(self):
+        """Returns the dict the reference builds and prints (Overall / Warm_Start / Cold_Start)."""
+        from ...metrics import ValidationMetrics
+        m = getattr(self, "_val_metrics", None) or ValidationMetrics(k=10)
+        results = m.compute()
+        self._val_metrics = None
+        return results
+
     def load_model(self, path: str):
         """base_model.py:531-536."""
         sd = torch.load(path, map_location="cpu")
