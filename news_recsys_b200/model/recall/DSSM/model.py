@@ -99,6 +99,40 @@ class DSSM(BaseModel):
         self.index = TopkIndex(self.all_item_embeddings, id_base=id_base)
         return self.index
 
+    @staticmethod
+    def filter_history_hits(ranked_ids, history, targets, k):
+        """The filtering tail of the reference's `hit_rate` (:207-223) for a whole batch of users at once.
+        ranked_ids [Q, >= k + H] corpus ids best first, history [Q, H] item ids already interacted with (padded with
+        -1), targets [Q].  Per user only the first k + |history| candidates count (:207-209), history items are
+        dropped, the first k survivors kept, hit = target among them.  Returns a bool [Q].  Tensor ops on
+        [Q, k + H] only (device-agnostic)."""
+        Q, W = ranked_ids.shape
+        hist_len = (history >= 0).sum(dim=1, keepdim=True)
+        pos = torch.arange(W, device=ranked_ids.device).unsqueeze(0)
+        in_window = pos < (k + hist_len)
+        seen = (ranked_ids.unsqueeze(2) == history.unsqueeze(1)).any(dim=2) & (ranked_ids >= 0)
+        alive = in_window & ~seen
+        rank = torch.cumsum(alive.to(torch.int64), dim=1)          # 1-based rank among the survivors
+        kept = alive & (rank <= k)
+        return (kept & (ranked_ids == targets.view(-1, 1))).any(dim=1)
+
+    @torch.no_grad()
+    def hit_rate(self, batches, k=10, history_key="user_history", target_key="item_id"):
+        """Batched `hit_rate` (:183-229): for every user of every batch search k + H candidates (H = padded history
+        length), drop the history, keep k, count targets hit.  The reference does this one user per call on the CPU."""
+        if self.index is None:
+            raise ValueError("Index not initialized. Call build_item_index first.")
+        hits, n = 0, 0
+        for b in batches:
+            hist = b[history_key].clone()
+            if history_key + "_mask" in b:
+                hist[b[history_key + "_mask"] == 0] = -1
+            hist[hist == 0] = -1                                    # id 0 is padding
+            _, ids = self.retrieve(b, k + hist.shape[1])
+            hits += int(self.filter_history_hits(ids, hist, b[target_key], k).sum())
+            n += ids.shape[0]
+        return hits / n if n > 0 else 0
+
     @torch.no_grad()
     def retrieve(self, batch, k):
         """(scores [B,k], corpus positions [B,k]) ordered by (inner product desc, id asc)."""

@@ -501,6 +501,26 @@ def infonce_loss(user_emb: Tensor, pos: Tensor, neg: Tensor, temperature: float 
     return losses.mean()
 
 
+def hit_rate_filtered(ranked_ids: Sequence[Sequence[int]], histories: Sequence[Iterable[int]], targets: Sequence[int],
+                      k: int = 10) -> float:
+    """recall/DSSM/model.py:183-229 (`hit_rate`), one query per user: the searcher returned `k + len(history)`
+    candidates (:207-209); candidates the user already interacted with are dropped, the first k survivors kept
+    (:213-220), a hit is the target among them (:221-223); hit rate = hits / users (:226).
+    (The id re-mapping dictionaries of the MovieLens-era code, :204-205,:212,:216, are identity here.)"""
+    hits, n = 0, 0
+    for I, hist, tgt in zip(ranked_ids, histories, targets):
+        hist = set(hist)
+        kept = []
+        for item in list(I)[: k + len(hist)]:
+            if item not in hist:
+                kept.append(item)
+            if len(kept) >= k:
+                break
+        hits += int(tgt in kept)
+        n += 1
+    return hits / n if n > 0 else 0
+
+
 # --------------------------------------------------------------------------- #
 # Exact inner-product top-k (faiss.IndexFlatIP restated — parity unpinned)     #
 # --------------------------------------------------------------------------- #

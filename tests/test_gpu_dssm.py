@@ -121,3 +121,31 @@ def test_dssm_matches_reference_golden():
             continue
         cos = float((g @ r) / (g.norm() * r.norm()).clamp_min(1e-30))
         assert cos > 0.97, f"{name}: cosine {cos:.4f}"
+
+
+def test_batched_hit_rate_equals_reference_loop():
+    """DSSM.hit_rate (one batched search of k + H candidates + history filter on the device) == the reference's
+    per-user loop (oracle.hit_rate_filtered) applied to the ids the index returned."""
+    from news_recsys_b200.model.recall.DSSM.model import DSSM
+    from news_recsys_b200.synthetic import synth_batch
+    cfg = _cfg()
+    torch.manual_seed(1)
+    m = DSSM(cfg, hparams={"out_dim": 16}).to(DEV)
+    items = {k: v.to(DEV) for k, v in synth_batch(cfg, 300, seed=2).items()}
+    items["item_id"] = torch.arange(1, 301, device=DEV) % 300     # corpus position p holds item ids 1..299, 0
+    m.build_item_index([items])
+    k = 10
+    batches = [{kk: v.to(DEV) for kk, v in synth_batch(cfg, 64, seed=10 + i).items()} for i in range(3)]
+    for b in batches:
+        b["item_id"] = torch.randint(0, 300, (64,), device=DEV)    # target = a corpus POSITION (identity id map)
+        b["user_history"] = torch.randint(0, 300, b["user_history"].shape, device=DEV) * (b["user_history_mask"] > 0)
+    got = m.hit_rate(batches, k=k)
+    ranked, hists, targets = [], [], []
+    for b in batches:
+        H = b["user_history"].shape[1]
+        _, ids = m.retrieve(b, k + H)
+        for q in range(ids.shape[0]):
+            h = b["user_history"][q][(b["user_history_mask"][q] > 0) & (b["user_history"][q] != 0)]
+            ranked.append(ids[q].cpu().tolist()); hists.append(set(h.cpu().tolist())); targets.append(int(b["item_id"][q]))
+    assert got == pytest.approx(R.hit_rate_filtered(ranked, hists, targets, k))
+    assert 0.0 < got < 1.0

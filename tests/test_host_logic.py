@@ -125,3 +125,25 @@ def test_bench_reference_arm_prints_exactly_one_json_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert d["value"] > 0
+
+
+def test_history_filter_matches_reference_hit_rate_loop():
+    """DSSM.filter_history_hits (batched tensor form) == the reference's per-user Python loop (oracle.hit_rate_filtered),
+    incl. empty histories, histories holding the target, duplicates, and candidates beyond the k + |hist| window."""
+    import numpy as np
+    from oracle import ref_path as R
+    from news_recsys_b200.model.recall.DSSM.model import DSSM
+    rng = np.random.default_rng(0)
+    for k, H, N in ((10, 12, 60), (3, 5, 20), (1, 1, 5)):
+        Q = 200
+        ranked = np.stack([rng.permutation(N)[: k + H] for _ in range(Q)])
+        lens = rng.integers(0, H + 1, size=Q)
+        hist = np.full((Q, H), -1, dtype=np.int64)
+        for q in range(Q):
+            hist[q, :lens[q]] = rng.integers(0, N, size=lens[q])     # may contain duplicates / the target
+        targets = rng.integers(0, N, size=Q)
+        got = DSSM.filter_history_hits(torch.from_numpy(ranked), torch.from_numpy(hist), torch.from_numpy(targets), k)
+        per_user = [R.hit_rate_filtered([ranked[q]], [set(hist[q][hist[q] >= 0].tolist())], [int(targets[q])], k) for q in range(Q)]
+        assert got.tolist() == [bool(x) for x in per_user]
+        assert float(got.float().mean()) == pytest.approx(
+            R.hit_rate_filtered(ranked, [set(h[h >= 0].tolist()) for h in hist], targets.tolist(), k))
