@@ -138,3 +138,43 @@ def test_errors_follow_the_reference(tmp_path):
     p.write_text("user_id:1 item_id:2\t1 0\nuser_id:1\t1 0\n")
     with pytest.raises(ValueError, match="differ from line 0"):
         compile_feature_file(CFG, str(p), str(tmp_path / "x.nrxf"))
+
+
+def test_large_batches_split_over_threads_equal_small_ones(tmp_path):
+    """With NRX_INGEST_THREADS > 1 a batch of >= 8192 rows is assembled by several host threads (software prefetch on
+    shuffled rows); the result equals the single-thread path used for small batches.  Run in a fresh process: the
+    thread count is read once."""
+    import subprocess, sys, textwrap
+    code = textwrap.dedent(f"""
+        import os, sys
+        os.environ["NRX_INGEST_THREADS"] = "4"
+        sys.path.insert(0, {os.path.dirname(os.path.dirname(os.path.abspath(__file__)))!r})
+        import tests.test_ingest as T, pathlib
+        T._threads_case(pathlib.Path({str(tmp_path)!r}))
+        print("ok")
+    """)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
+    _threads_case(tmp_path)   # and with the default single thread
+
+
+def _threads_case(tmp_path):
+    from news_recsys_b200.ingest import FeatureFile, compile_feature_file
+    rng = np.random.default_rng(2)
+    lines = []
+    for i in range(12000):
+        hist = ",".join(str(int(x)) for x in rng.integers(1, 299, size=int(rng.integers(0, 20))))
+        lines.append(f"user_id:{i % 399} item_id:{(7 * i) % 299} category:{i % 18} subcategory:2 user_click_category:3 "
+                     f"user_history:{hist}\t{i % 2} {1 - i % 2}")
+    (tmp_path / "t.txt").write_text("\n".join(lines) + "\n")
+    compile_feature_file(CFG, str(tmp_path / "t.txt"), str(tmp_path / "t.nrxf"))
+    ff = FeatureFile(str(tmp_path / "t.nrxf"))
+    rows = rng.permutation(12000)[:10000]
+    big = ff.batch(rows=rows)
+    small = [ff.batch(rows=rows[i:i + 2500]) for i in range(0, 10000, 2500)]
+    for k in big:
+        assert torch.equal(big[k], torch.cat([s[k] for s in small])), k
+    seq = ff.batch(start=1000, B=9000)
+    seq_small = [ff.batch(start=1000 + i, B=3000) for i in range(0, 9000, 3000)]
+    for k in seq:
+        assert torch.equal(seq[k], torch.cat([s[k] for s in seq_small])), k
