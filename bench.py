@@ -558,7 +558,9 @@ def main():
         traffic = json.load(open(tpath)).get(args.workload, {}).get(dom)
     roof = {"bound": bound, "achieved": achieved, "peak": peak, "unit": runit, "frac": achieved / peak, "traffic": traffic,
             "kernel": dom, "kernel_us": per_api[dom], "peak_source": peak_src,
-            "algorithmic_per_launch": qty}
+            "algorithmic_per_launch": qty,
+            "note": "dominant C-ABI call on the main stream (a call may be 2 kernels); at this batch every kernel moves a few MB "
+                    "/ a few GFLOP and is launch-latency bound - the same kernels at B up to 1M are in profiles/r1_kernel_sweep_final.json"}
     breakdown = {}
     for k, us in sorted(per_api.items(), key=lambda kv: -kv[1]):
         b_, q_ = alg.get(k, ("hbm", 0))
