@@ -94,3 +94,53 @@ def test_dp_id_exchange_world2():
 
 def test_sharded_topk_merge_equals_global_world2():
     assert _run("_sharded_topk") == {0: True, 1: True}
+
+
+def _dense_dp_step(rank, world):
+    """The scheme of DataParallelTrainer(table_update="dense") with the oracle standing in for the kernels: every rank
+    computes dense gradients (tables included) on ITS half of the batch with a local-mean loss, the flat gradient is
+    averaged across ranks, every rank owns one slice of the flat parameter buffer (same split as K7 / shard_range),
+    runs AdamW on its slice only and the slices are exchanged."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from oracle import ref_path as R
+    from news_recsys_b200.parallel import shard_range
+    from news_recsys_b200.synthetic import mind_config, synth_batch
+    import importlib
+    cfg = mind_config("fm", {"user_id": 50, "item_id": 40, "category": 18, "subcategory": 70, "user_click_category": 18})
+    torch.manual_seed(3)
+    model = importlib.import_module("news_recsys_b200.model.sort.fm.model").FM(cfg)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    full = synth_batch(cfg, 32, seed=9, label_p=0.5)
+    local = {k: v[rank * 16:(rank + 1) * 16] for k, v in full.items()}
+    _, _, grads = R.loss_and_grads("fm", sd, cfg, local)
+    names = sorted(sd)
+    flat_g = torch.cat([grads[k].reshape(-1) for k in names])
+    flat_p = torch.cat([sd[k].reshape(-1) for k in names])
+    pad = (-flat_g.numel()) % 4
+    flat_g = torch.cat([flat_g, torch.zeros(pad)]); flat_p = torch.cat([flat_p, torch.zeros(pad)])
+    dist.all_reduce(flat_g, op=dist.ReduceOp.SUM)
+    flat_g /= world
+    lo, hi = shard_range(flat_g.numel() // 4, rank, world)
+    lo, hi = 4 * lo, 4 * hi
+    new_slice, _, _ = R.adamw_step(flat_p[lo:hi], flat_g[lo:hi], torch.zeros(hi - lo), torch.zeros(hi - lo), 1, 1e-3)
+    parts = [torch.zeros(4 * (shard_range(flat_g.numel() // 4, r, world)[1] - shard_range(flat_g.numel() // 4, r, world)[0]))
+             for r in range(world)]
+    if parts[0].numel() == parts[1].numel():
+        dist.all_gather(parts, new_slice.contiguous())
+    else:   # gloo all_gather needs equal sizes: pad the shorter slice
+        m = max(p.numel() for p in parts)
+        buf = [torch.zeros(m) for _ in range(world)]
+        dist.all_gather(buf, torch.cat([new_slice, torch.zeros(m - new_slice.numel())]))
+        parts = [b[:p.numel()] for b, p in zip(buf, parts)]
+    new_p = torch.cat(parts)
+    # single process on the whole batch
+    _, _, g_full = R.loss_and_grads("fm", sd, cfg, full)
+    ref_g = torch.cat([g_full[k].reshape(-1) for k in names] + [torch.zeros(pad)])
+    ref_p, _, _ = R.adamw_step(flat_p, ref_g, torch.zeros_like(flat_p), torch.zeros_like(flat_p), 1, 1e-3)
+    return bool(torch.allclose(flat_g, ref_g, rtol=1e-5, atol=1e-8) and torch.allclose(new_p, ref_p, rtol=1e-6, atol=1e-8))
+
+
+def test_dense_data_parallel_scheme_equals_single_process():
+    out = _run("_dense_dp_step")
+    assert out == {0: True, 1: True}
