@@ -3,7 +3,7 @@ The reference itself cannot travel to the GPU box, so this times its CPU restate
 PyTorch ops, device-agnostic) with the tensors on the GPU: forward + BCE + backward + torch.optim.AdamW per step, the
 same workload and step definition as bench.py.  A measurement tool (like bench.py's CPU arm), never a product path.
 
-    python tools/eager_gpu_baseline.py [--device cuda] [--steps 50] [--workload deepfm]
+    python tests/tools/eager_gpu_baseline.py [--device cuda] [--steps 50] [--workload deepfm]
 """
 import argparse
 import json
@@ -13,7 +13,7 @@ import time
 
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 from news_recsys_b200.synthetic import synth_batch  # noqa: E402

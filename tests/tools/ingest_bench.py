@@ -2,7 +2,7 @@
 CPU port of the reference loader (oracle.ref_path.datareader_batch == DataReader.__getitem__ + default collate) on the
 same synthetic feature file.  Pure host code: runs anywhere.
 
-    python tools/ingest_bench.py [--rows 200000] [--batch 16384] > profiles/r1_ingest_bench.json
+    python tests/tools/ingest_bench.py [--rows 200000] [--batch 16384] > profiles/r1_ingest_bench.json
 """
 import argparse
 import json
@@ -15,7 +15,7 @@ import numpy as np
 import torch
 import yaml
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from news_recsys_b200.ingest import FeatureFile, compile_feature_file  # noqa: E402
 from news_recsys_b200.trainer import BatchLayout  # noqa: E402
