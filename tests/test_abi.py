@@ -58,6 +58,16 @@ def test_product_path_never_imports_the_oracle():
                 assert "oracle" not in re.sub(r'""".*?"""', "", src, flags=re.S), f"{f} references the oracle"
 
 
+def test_tools_never_import_the_oracle():
+    """Dev tools under tools/ are not allowed to use the oracle either (measurement helpers that time it live in
+    tests/tools)."""
+    tools = os.path.join(ROOT, "tools")
+    for f in os.listdir(tools):
+        if f.endswith(".py"):
+            src = open(os.path.join(tools, f)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f"tools/{f} imports the oracle"
+
+
 def test_ops_fail_loudly_without_cuda():
     import torch
     from news_recsys_b200 import ops
