@@ -72,6 +72,12 @@ const char* nrx_last_error(void);
 int nrx_embed_pool_fwd(const NrxFeat* h_feats, int n_feats, int64_t B,
                        float* out, int64_t out_ld, int32_t* status, nrx_stream_t stream);
 
+/* Same, writing the tower's input operand as well: `image` = bf16 tile image [tile][image_width/8][128][8] of the
+ * concatenated row (the layout nrx_tower_fwd streams with NRX_TOWER_XIMG; its slot inside the tower workspace comes
+ * from nrx_tower_image_layout).  `out` may be NULL when nothing else reads the fp32 concat.  128-bit path only. */
+int nrx_embed_pool_fwd_img(const NrxFeat* h_feats, int n_feats, int64_t B, float* out, int64_t out_ld,
+                           void* image, int image_width, int32_t* status, nrx_stream_t stream);
+
 /* ---- K3: deterministic sorted-index segment-reduce backward ----------------
  * Replaces aten::embedding_dense_backward behind base_model.py:271 (padding_idx=0
  * rows receive no gradient) plus the backward of the pooling at :278-282.
@@ -245,10 +251,15 @@ typedef struct NrxPeerStep {
   int64_t n;                      /* floats in the flat buffers; multiple of 4, buffers 16-byte aligned */
   const float* d_hparams;         /* {lr, 1-beta1^t, sqrt(1-beta2^t)} on the device (nrx_hparams_step) */
   float beta1, beta2, eps, weight_decay;
+  int32_t* status;                /* optional DEVICE int32: bit 1 (value 2) is OR-ed in when the exchange is dead */
+  uint32_t timeout_ms;            /* spin limit of one flag wait; 0 = 20 s (env NRX_PEER_TIMEOUT_MS overrides) */
+  uint32_t reserved;
 } NrxPeerStep;
 
-/* Returns NRX_OK after the launch; a peer that never arrives makes the kernel give up after ~2 s and set
- * sig[rank][NRX_PEER_SIG_ERR] (read it with nrx_peer_status) instead of hanging the GPU. */
+/* Returns NRX_OK after the launch.  A peer that does not arrive within the limit is FATAL and sticky: the kernel
+ * raises sig[.][NRX_PEER_SIG_ERR] on every rank and bit 1 of `status`, leaves parameters / moments / epochs untouched,
+ * and every later launch on any rank returns at entry (no rank can pair stale flags with new gradients).  The host
+ * must treat it as the end of the run (nrx_peer_status, or the status word it reads back with the loss). */
 enum { NRX_PEER_SIG_ERR = 130 };
 int nrx_adamw_allreduce_peer(const NrxPeerStep* step, nrx_stream_t stream);
 int nrx_peer_status(const uint32_t* sig, int32_t* timed_out, nrx_stream_t stream);  /* synchronises the stream */
@@ -276,6 +287,34 @@ int nrx_tower_pack(const NrxTower* h_tower, int64_t B, int training, void* ws, s
 int nrx_tower_fwd(const NrxTower* h_tower, const float* x, int64_t x_ld, int64_t B,
                   float* y, int64_t y_ld, int training, void* ws, size_t ws_bytes,
                   nrx_stream_t stream);
+/* NRX_TOWER_XIMG: the bf16 tile image of the input (layer 0's operand, see nrx_tower_image_layout) is already in `ws`
+ * — written there by the producing kernel (nrx_embed_pool_fwd_img / nrx_dcn_cross_fwd with an image) — `x` may be NULL. */
+enum { NRX_TOWER_XIMG = 4 };
+
+/* Fused head for towers that end in ONE logit (dims[n_layers] == 1): the last epilogue of the forward computes
+ *   z = sum_t terms[t][b] + tower(x)[b] + bias[0];  prob = sigmoid(z)
+ * and, with a label, the per-sample BCE on probabilities (log clamped at -100: bceLoss, deep/model.py:32-33) and
+ * dL/dlogit of the MEAN loss — the arithmetic of nrx_logit_loss_fwd without the extra launch and the [B] round trip.
+ * Replaces `torch.sigmoid(wide + deep)` (widedeep/model.py:27), `sigmoid(score_fc(x))` (deep/model.py:21,
+ * dcn/model.py:29) followed by F.binary_cross_entropy.  Any output pointer may be NULL. */
+typedef struct NrxTowerHead {
+  const float* terms[4];   /* extra per-sample logit terms [B] (FM / wide logit), added before the tower's */
+  int32_t n_terms;
+  int32_t reserved;
+  const float* bias;       /* [1] or NULL */
+  const float* label;      /* [B * label_stride] or NULL */
+  int64_t label_stride;
+  float* logit;            /* [B] tower logit alone (what y would hold) */
+  float* prob;             /* [B] */
+  float* loss_per_sample;  /* [B] */
+  float* dlogit;           /* [B] */
+} NrxTowerHead;
+int nrx_tower_fwd_head(const NrxTower* h_tower, const float* x, int64_t x_ld, int64_t B,
+                       const NrxTowerHead* h_head, int flags, void* ws, size_t ws_bytes, nrx_stream_t stream);
+
+/* fp32 rows [B, width] -> bf16 tile image [tile][width16/8][128][8] (the operand layout of the tower kernels). */
+int nrx_tower_image_from_rows(const float* x, int64_t x_ld, int64_t B, int width, void* image, nrx_stream_t stream);
+
 /* grad_x (+)= d/dx, grad_w[l] / grad_b[l] = d/dW_l, d/db_l (overwritten). */
 int nrx_tower_bwd(const NrxTower* h_tower, const float* x, int64_t x_ld, int64_t B,
                   const float* grad_y, int64_t gy_ld,
@@ -302,6 +341,10 @@ int nrx_tower_image_layout(const NrxTower* h_tower, int64_t B, int64_t* act_off,
 int nrx_dcn_cross_fwd(const float* x, int64_t ld, int64_t B, int d, int n_layers,
                       const float* const* h_w, const float* const* h_b,
                       float* out, int64_t out_ld, float* dots, nrx_stream_t stream);
+/* Same forward, emitting the bf16 tile image of cat[x, x_L] (width 2d) for the tower; `out` may be NULL. */
+int nrx_dcn_cross_fwd_img(const float* x, int64_t ld, int64_t B, int d, int n_layers,
+                          const float* const* h_w, const float* const* h_b,
+                          float* out, int64_t out_ld, void* image, nrx_stream_t stream);
 int nrx_dcn_cross_bwd(const float* x, int64_t ld, int64_t B, int d, int n_layers,
                       const float* const* h_w, const float* const* h_b,
                       const float* grad_out, int64_t go_ld, const float* dots,

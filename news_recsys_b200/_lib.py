@@ -55,6 +55,7 @@ class NrxPeerStep(C.Structure):
         ("p", C.c_void_p * NRX_MAX_PEERS), ("g", C.c_void_p * NRX_MAX_PEERS), ("sig", C.c_void_p * NRX_MAX_PEERS),
         ("m", C.c_void_p), ("v", C.c_void_p), ("n", C.c_int64), ("d_hparams", C.c_void_p),
         ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("weight_decay", C.c_float),
+        ("status", C.c_void_p), ("timeout_ms", C.c_uint32), ("reserved", C.c_uint32),
     ]
 
 
@@ -71,6 +72,16 @@ class NrxTower(C.Structure):
     ]
 
 
+class NrxTowerHead(C.Structure):
+    _fields_ = [
+        ("terms", C.c_void_p * 4), ("n_terms", C.c_int32), ("reserved", C.c_int32),
+        ("bias", C.c_void_p), ("label", C.c_void_p), ("label_stride", C.c_int64),
+        ("logit", C.c_void_p), ("prob", C.c_void_p), ("loss_per_sample", C.c_void_p), ("dlogit", C.c_void_p),
+    ]
+
+
+TOWER_TRAINING, TOWER_PREPACKED, TOWER_XIMG = 1, 2, 4
+
 _P = C.c_void_p
 _I64 = C.c_int64
 _I32 = C.c_int32
@@ -82,6 +93,7 @@ SIGNATURES = {
     "nrx_version": (C.c_int, []),
     "nrx_last_error": (C.c_char_p, []),
     "nrx_embed_pool_fwd": (C.c_int, [C.POINTER(NrxFeat), C.c_int, _I64, _P, _I64, _P, _P]),
+    "nrx_embed_pool_fwd_img": (C.c_int, [C.POINTER(NrxFeat), C.c_int, _I64, _P, _I64, _P, C.c_int, _P, _P]),
     "nrx_embed_bwd_workspace_bytes": (_SZ, [C.POINTER(NrxFeat), C.c_int, _I64]),
     "nrx_embed_bwd_plan": (C.c_int, [C.POINTER(NrxFeat), C.c_int, _I64, _P, _SZ, _P]),
     "nrx_embed_bwd_apply": (C.c_int, [C.POINTER(NrxFeat), C.c_int, _I64, _P, _I64, C.c_int,
@@ -116,12 +128,15 @@ SIGNATURES = {
     "nrx_tower_workspace_bytes": (_SZ, [C.POINTER(NrxTower), _I64, C.c_int]),
     "nrx_tower_pack": (C.c_int, [C.POINTER(NrxTower), _I64, C.c_int, _P, _SZ, _P]),
     "nrx_tower_fwd": (C.c_int, [C.POINTER(NrxTower), _P, _I64, _I64, _P, _I64, C.c_int, _P, _SZ, _P]),
+    "nrx_tower_fwd_head": (C.c_int, [C.POINTER(NrxTower), _P, _I64, _I64, C.POINTER(NrxTowerHead), C.c_int, _P, _SZ, _P]),
+    "nrx_tower_image_from_rows": (C.c_int, [_P, _I64, _I64, C.c_int, _P, _P]),
     "nrx_tower_bwd": (C.c_int, [C.POINTER(NrxTower), _P, _I64, _I64, _P, _I64, _P, _I64, C.c_int,
                                 C.POINTER(_P), C.POINTER(_P), _P, _SZ, _P]),
     "nrx_tower_bwd_dx": (C.c_int, [C.POINTER(NrxTower), _I64, _P, _I64, _P, _I64, C.c_int, _P, _SZ, _P]),
     "nrx_tower_bwd_dw": (C.c_int, [C.POINTER(NrxTower), _I64, C.POINTER(_P), C.POINTER(_P), _P, _SZ, _P]),
     "nrx_tower_image_layout": (C.c_int, [C.POINTER(NrxTower), _I64, C.POINTER(_I64), C.POINTER(_I32), C.POINTER(_I64), C.POINTER(_I32)]),
     "nrx_dcn_cross_fwd": (C.c_int, [_P, _I64, _I64, C.c_int, C.c_int, C.POINTER(_P), C.POINTER(_P), _P, _I64, _P, _P]),
+    "nrx_dcn_cross_fwd_img": (C.c_int, [_P, _I64, _I64, C.c_int, C.c_int, C.POINTER(_P), C.POINTER(_P), _P, _I64, _P, _P]),
     "nrx_dcn_cross_bwd": (C.c_int, [_P, _I64, _I64, C.c_int, C.c_int, C.POINTER(_P), C.POINTER(_P), _P, _I64, _P,
                                     _P, _I64, C.POINTER(_P), C.POINTER(_P), _P, _SZ, _P]),
     "nrx_dcn_cross_workspace_bytes": (_SZ, [_I64, C.c_int, C.c_int]),
@@ -166,7 +181,8 @@ def load() -> C.CDLL:
 
 
 # kernels of OURS launched per successful API call (library kernels such as the CUB radix sort are not counted)
-KERNELS_PER_CALL = {"nrx_tower_fwd": 2, "nrx_tower_fwd(prepacked)": 1, "nrx_tower_bwd": 3, "nrx_tower_bwd_dw": 2, "nrx_embed_bwd_apply": 2, "nrx_embed_bwd_plan": 2, "nrx_adamw_untouched_rows": 2, "nrx_adamw_untouched_rows_scratch_bytes": 0, "nrx_dcn_cross_bwd": 2,
+KERNELS_PER_CALL = {"nrx_tower_fwd": 3, "nrx_tower_fwd(prepacked)": 2, "nrx_tower_fwd_head": 3, "nrx_tower_fwd_head(prepacked)": 2,
+                    "nrx_tower_fwd(prepacked,ximg)": 1, "nrx_tower_fwd_head(prepacked,ximg)": 1, "nrx_tower_bwd": 3, "nrx_tower_bwd_dw": 2, "nrx_embed_bwd_apply": 2, "nrx_embed_bwd_plan": 2, "nrx_adamw_untouched_rows": 2, "nrx_adamw_untouched_rows_scratch_bytes": 0, "nrx_dcn_cross_bwd": 2,
                     "nrx_embed_bwd_apply(dense)": 2, "nrx_embed_bwd_apply(rowopt)": 2, "nrx_topk_ip": 2,
                     "nrx_topk_search": 5, "nrx_topk_index_build": 1,
                     "nrx_peer_alloc": 0, "nrx_peer_free": 0, "nrx_peer_export": 0, "nrx_peer_open": 0, "nrx_peer_close": 0,

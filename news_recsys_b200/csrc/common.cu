@@ -36,6 +36,14 @@ int sm_count() {
   return cached;
 }
 
+int img_zero_tail(void* image, int Kp, long long B, cudaStream_t st) {
+  if (B % 128 == 0) return NRX_OK;
+  const long long tile = B / 128;
+  cudaError_t e = cudaMemsetAsync((uint8_t*)image + (size_t)tile * Kp * 256, 0, (size_t)Kp * 256, st);
+  if (e != cudaSuccess) { set_error("image tail memset: %s", cudaGetErrorString(e)); return NRX_ELAUNCH; }
+  return NRX_OK;
+}
+
 int make_dfeats(const NrxFeat* feats, int n, long long B, const void* out, long long out_ld, DFeats* d) {
   NRX_REQUIRE(feats != nullptr && n > 0 && n <= NRX_MAX_FEATS, NRX_EINVAL,
               "n_feats=%d outside [1,%d]", n, (int)NRX_MAX_FEATS);

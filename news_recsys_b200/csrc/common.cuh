@@ -68,6 +68,18 @@ __device__ __forceinline__ void adamw_update(float& p, float g, float& m, float&
   p = pi;
 }
 
+__device__ __forceinline__ float sigmoid_f(float z) { return 1.f / (1.f + expf(-z)); }
+
+__device__ __forceinline__ void bce_terms(float p, float y, float invB, float* loss, float* dlogit) {
+  // F.binary_cross_entropy: log clamped at -100; autograd: (p-y)/max(p(1-p),1e-12) then sigmoid' = p(1-p)
+  const float lp = fmaxf(logf(p), -100.f), l1p = fmaxf(logf(1.f - p), -100.f);
+  if (loss) *loss = -(y * lp + (1.f - y) * l1p);
+  if (dlogit) {
+    const float pq = p * (1.f - p);
+    *dlogit = ((p - y) / fmaxf(pq, 1e-12f)) * pq * invB;
+  }
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(NRX_FULL_MASK, v, o);
@@ -104,6 +116,20 @@ struct VecT<1> {
   static __device__ __forceinline__ void add(float& a, float b) { a += b; }
   static __device__ __forceinline__ float div(float a, float d) { return a / d; }
 };
+
+// bf16 tile image of a [B, Kp] operand of the tower kernels: [tile][Kp/8][128 rows][8] — 16 bytes per
+// (row, 8-column chunk).  Stores 4 consecutive columns (col % 4 == 0) of row b.
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  uint32_t d;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+  return d;
+}
+__device__ __forceinline__ void img_store4(uint8_t* __restrict__ img, int Kp, long long b, int col, float4 v) {
+  uint8_t* p = img + (size_t)(b >> 7) * Kp * 256 + (size_t)(col >> 3) * 2048 + (size_t)(b & 127) * 16 + (size_t)(col & 7) * 2;
+  *reinterpret_cast<uint2*>(p) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+}
+// zero the rows of the last tile that lie beyond B (the dW GEMMs contract over all 128 rows of a tile)
+int img_zero_tail(void* image, int Kp, long long B, cudaStream_t st);
 
 static inline int pow2_ceil(int x) {
   int p = 1;

@@ -60,6 +60,60 @@ dcn_cross_fwd_kernel(const float* __restrict__ x, long long ld, long long B, con
   }
 }
 
+// 128-bit variant: lane owns the float4 at columns 4 * (lane + 32 k).  Emits the fp32 concat (optional) and / or the
+// bf16 tile image of cat[x, x_L] that the tower forward streams as its layer-0 operand (nrx_tower_fwd, NRX_TOWER_XIMG).
+template <int NV>
+__global__ void __launch_bounds__(256)
+dcn_cross_fwd_v4_kernel(const float* __restrict__ x, long long ld, long long B, const __grid_constant__ CrossP P,
+                        float* __restrict__ out, long long old, uint8_t* __restrict__ img, int img_kp) {
+  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= B) return;
+  const int d = P.d;
+  float4 x0[NV], xl[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int c = 4 * (lane + 32 * k);
+    x0[k] = c < d ? __ldg(reinterpret_cast<const float4*>(x + row * ld + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    xl[k] = x0[k];
+  }
+  for (int l = 0; l < P.n_layers; ++l) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int c = 4 * (lane + 32 * k);
+      if (c < d) {
+        const float4 w = __ldg(reinterpret_cast<const float4*>(P.w[l] + c));
+        s = fmaf(xl[k].x, w.x, s); s = fmaf(xl[k].y, w.y, s); s = fmaf(xl[k].z, w.z, s); s = fmaf(xl[k].w, w.w, s);
+      }
+    }
+    s = warp_sum(s);
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int c = 4 * (lane + 32 * k);
+      if (c < d) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(P.b[l] + c));
+        xl[k].x = fmaf(x0[k].x, s, b.x + xl[k].x); xl[k].y = fmaf(x0[k].y, s, b.y + xl[k].y);
+        xl[k].z = fmaf(x0[k].z, s, b.z + xl[k].z); xl[k].w = fmaf(x0[k].w, s, b.w + xl[k].w);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int c = 4 * (lane + 32 * k);
+    if (c < d) {
+      if (out != nullptr) {
+        *reinterpret_cast<float4*>(out + row * old + c) = x0[k];
+        *reinterpret_cast<float4*>(out + row * old + d + c) = xl[k];
+      }
+      if (img != nullptr) {
+        img_store4(img, img_kp, row, c, x0[k]);
+        img_store4(img, img_kp, row, d + c, xl[k]);
+      }
+    }
+  }
+}
+
 // partials layout: [block][layer][2 (w,b)][d]
 template <int NC>
 __global__ void __launch_bounds__(256)
@@ -236,4 +290,26 @@ extern "C" int nrx_dcn_cross_bwd(const float* x, int64_t ld, int64_t B, int d, i
   for (int l = 0; l < n_layers; ++l) { G.gw[l] = h_grad_w[l]; G.gb[l] = h_grad_b[l]; }
   dcn_cross_reduce_kernel<<<(n_layers * 2 * d + 255) / 256, 256, 0, st>>>((const float*)ws, blocks, n_layers, d, G);
   return check_launch("dcn_cross_reduce");
+}
+
+// K5 writing the tower's input operand: `image` = bf16 tile image of cat[x, x_L] (width 2d, needs d % 8 == 0 and
+// 16-byte aligned rows / parameters); `out` (fp32 concat) is optional.
+extern "C" int nrx_dcn_cross_fwd_img(const float* x, int64_t ld, int64_t B, int d, int n_layers, const float* const* h_w,
+                                     const float* const* h_b, float* out, int64_t out_ld, void* image, nrx_stream_t stream) {
+  CrossP P;
+  int rc = make_cross(d, n_layers, h_w, h_b, &P);
+  if (rc != NRX_OK) return rc;
+  NRX_REQUIRE((x && image) || B == 0, NRX_EINVAL, "null x / image");
+  NRX_REQUIRE(ld >= d && (!out || out_ld >= 2 * d), NRX_EINVAL, "leading dimension too small");
+  bool ok = d % 8 == 0 && d <= 256 && ld % 4 == 0 && ((uintptr_t)x % 16 == 0) && (!out || (out_ld % 4 == 0 && (uintptr_t)out % 16 == 0));
+  for (int l = 0; l < n_layers; ++l) ok = ok && ((uintptr_t)h_w[l] % 16 == 0) && ((uintptr_t)h_b[l] % 16 == 0);
+  NRX_REQUIRE(ok, NRX_EUNSUPPORTED, "cross image output needs d %% 8 == 0, d <= 256 and 16-byte aligned operands");
+  if (B == 0) return NRX_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  rc = img_zero_tail(image, 2 * d, B, st);
+  if (rc != NRX_OK) return rc;
+  const unsigned blocks = (unsigned)((B + 7) / 8);
+  if (d <= 128) dcn_cross_fwd_v4_kernel<1><<<blocks, 256, 0, st>>>(x, ld, B, P, out, out_ld, (uint8_t*)image, 2 * d);
+  else dcn_cross_fwd_v4_kernel<2><<<blocks, 256, 0, st>>>(x, ld, B, P, out, out_ld, (uint8_t*)image, 2 * d);
+  return check_launch("dcn_cross_fwd_img");
 }

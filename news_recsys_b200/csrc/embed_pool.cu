@@ -20,7 +20,7 @@ namespace nrx {
 template <int V, int SPW>
 __global__ void __launch_bounds__(256)
 embed_pool_fwd_kernel(const __grid_constant__ DFeats P, long long B, float* __restrict__ out, long long ld,
-                      int* __restrict__ status, long long n_sparse_warps) {
+                      int* __restrict__ status, long long n_sparse_warps, uint8_t* __restrict__ img, int img_kp) {
   using VT = VecT<V>;
   using vec_t = typename VT::type;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -51,8 +51,12 @@ embed_pool_fwd_kernel(const __grid_constant__ DFeats P, long long B, float* __re
         }
       }
 #pragma unroll
-      for (int s = 0; s < SPW; ++s)
-        if (b0 + s < B) VT::store(out + (b0 + s) * ld + F.out_col + off, val[s]);
+      for (int s = 0; s < SPW; ++s) {
+        if (b0 + s < B) {
+          if (out != nullptr) VT::store(out + (b0 + s) * ld + F.out_col + off, val[s]);
+          if constexpr (V == 4) { if (img != nullptr) img_store4(img, img_kp, b0 + s, F.out_col + off, val[s]); }
+        }
+      }
     }
   } else {
     const long long item = warp - n_sparse_warps;
@@ -96,7 +100,11 @@ embed_pool_fwd_kernel(const __grid_constant__ DFeats P, long long B, float* __re
         const float msum = warp_sum(msum_lane);
         den = masked ? (msum + 1e-8f) : (float)L;   // base_model.py:281 / :276
       }
-      if (r == 0 && cact) VT::store(out + b * ld + F.out_col + (cbase + c) * V, VT::div(acc, den));
+      if (r == 0 && cact) {
+        const vec_t pooled = VT::div(acc, den);
+        if (out != nullptr) VT::store(out + b * ld + F.out_col + (cbase + c) * V, pooled);
+        if constexpr (V == 4) { if (img != nullptr) img_store4(img, img_kp, b, F.out_col + (cbase + c) * V, pooled); }
+      }
     }
     if (F.inv_den != nullptr && lane == 0) F.inv_den[b] = 1.f / den;
   }
@@ -104,14 +112,15 @@ embed_pool_fwd_kernel(const __grid_constant__ DFeats P, long long B, float* __re
 }
 
 template <int V, int SPW>
-static int launch_fwd(const DFeats& d, long long B, float* out, long long ld, int* status, cudaStream_t st) {
+static int launch_fwd(const DFeats& d, long long B, float* out, long long ld, int* status, cudaStream_t st,
+                      uint8_t* img = nullptr, int img_kp = 0) {
   const long long n_sparse_warps = d.n_sparse ? (B + SPW - 1) / SPW : 0;
   const long long warps = n_sparse_warps + B * d.n_array;
   if (warps == 0) return NRX_OK;
   const int wpb = 8;
   const long long blocks = (warps + wpb - 1) / wpb;
   NRX_REQUIRE(blocks < (1ll << 31), NRX_EUNSUPPORTED, "batch too large for one launch");
-  embed_pool_fwd_kernel<V, SPW><<<(unsigned)blocks, wpb * 32, 0, st>>>(d, B, out, ld, status, n_sparse_warps);
+  embed_pool_fwd_kernel<V, SPW><<<(unsigned)blocks, wpb * 32, 0, st>>>(d, B, out, ld, status, n_sparse_warps, img, img_kp);
   return check_launch("embed_pool_fwd");
 }
 
@@ -132,4 +141,34 @@ extern "C" int nrx_embed_pool_fwd(const NrxFeat* h_feats, int n_feats, int64_t B
   const bool small = B < (long long)sm_count() * 64;
   if (d.vec == 4) return small ? launch_fwd<4, 2>(d, B, out, out_ld, status, st) : launch_fwd<4, 4>(d, B, out, out_ld, status, st);
   return small ? launch_fwd<1, 2>(d, B, out, out_ld, status, st) : launch_fwd<1, 4>(d, B, out, out_ld, status, st);
+}
+
+// K1 writing the tower's input operand directly: besides (or instead of, out == NULL) the fp32 rows, the bf16 tile
+// image [tile][width/8][128][8] that nrx_tower_fwd(..., NRX_TOWER_XIMG) streams — saves the fp32 -> bf16 pass and,
+// for Deep (nobody else reads the fp32 concat in inference), the 4*width B/sample write.  Needs the 128-bit path
+// (every dim / out_col a multiple of 4, 16-byte aligned tables) and width == the concat width, a multiple of 16.
+extern "C" int nrx_embed_pool_fwd_img(const NrxFeat* h_feats, int n_feats, int64_t B, float* out, int64_t out_ld,
+                                      void* image, int image_width, int32_t* status, nrx_stream_t stream) {
+  using namespace nrx;
+  DFeats d;
+  NRX_REQUIRE(image != nullptr || B == 0, NRX_EINVAL, "null image");
+  NRX_REQUIRE(image_width > 0 && image_width % 16 == 0, NRX_EUNSUPPORTED, "image width %d is not a multiple of 16", image_width);
+  int rc = make_dfeats(h_feats, n_feats, B, out != nullptr ? (const void*)out : image, out != nullptr ? out_ld : 4, &d);
+  if (rc != NRX_OK) return rc;
+  NRX_REQUIRE(d.vec == 4, NRX_EUNSUPPORTED, "image output needs the 128-bit path (dims / columns multiples of 4, aligned tables)");
+  int total = 0;
+  for (int i = 0; i < d.n; ++i) {
+    NRX_REQUIRE(d.f[i].out_col + d.f[i].dim <= image_width && (out == nullptr || d.f[i].out_col + d.f[i].dim <= out_ld), NRX_EINVAL,
+                "feature %d overruns the output width", i);
+    total += d.f[i].dim;
+  }
+  NRX_REQUIRE(total == image_width, NRX_EUNSUPPORTED, "features cover %d of %d image columns (pad columns would stay undefined)", total,
+              image_width);
+  if (B == 0) return NRX_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  rc = img_zero_tail(image, image_width, B, st);
+  if (rc != NRX_OK) return rc;
+  const bool small = B < (long long)sm_count() * 64;
+  return small ? launch_fwd<4, 2>(d, B, out, out_ld, status, st, (uint8_t*)image, image_width)
+               : launch_fwd<4, 4>(d, B, out, out_ld, status, st, (uint8_t*)image, image_width);
 }

@@ -148,18 +148,6 @@ static int make_fields(const int32_t* cols, const int32_t* dims, int n, int mode
 }
 
 // ---- gather-fused FM (vec4 path: D % 4 == 0, D/4 a power of two <= 32) ---------------------
-__device__ __forceinline__ float sigmoid_f(float z) { return 1.f / (1.f + expf(-z)); }
-
-__device__ __forceinline__ void bce_terms(float p, float y, float invB, float* loss, float* dlogit) {
-  // F.binary_cross_entropy: log clamped at -100; autograd: (p-y)/max(p(1-p),1e-12) then sigmoid' = p(1-p)
-  const float lp = fmaxf(logf(p), -100.f), l1p = fmaxf(logf(1.f - p), -100.f);
-  if (loss) *loss = -(y * lp + (1.f - y) * l1p);
-  if (dlogit) {
-    const float pq = p * (1.f - p);
-    *dlogit = ((p - y) / fmaxf(pq, 1e-12f)) * pq * invB;
-  }
-}
-
 template <int SPW, bool BWD>
 __global__ void __launch_bounds__(256)
 fm_fused_kernel(const __grid_constant__ DFeats P, long long B, int LPF, const float* __restrict__ bias,

@@ -20,7 +20,7 @@ namespace nrx {
 
 constexpr int kPeerThreads = 256;
 constexpr int kSigA = 0, kSigB = 64, kSigEpoch = 128, kSigBlocks = 129;
-constexpr unsigned long long kSpinLimitNs = 2000000000ull;  // 2 s: a peer that never arrives must not hang the GPU
+constexpr unsigned kDefaultTimeoutMs = 20000;  // a peer that never arrives must not hang the GPU for ever
 
 struct PeerArgs {
   int rank, world;
@@ -32,6 +32,8 @@ struct PeerArgs {
   long long lo4, hi4;  // owned slice in float4 units
   const float* d_hp;
   float b1, b2, eps, wd;
+  int* status;                 // host-visible trainer status word: bit 1 set when this rank gave up on a peer
+  unsigned long long spin_ns;  // spin limit of one flag wait
 };
 
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
@@ -55,15 +57,24 @@ __device__ __forceinline__ unsigned long long now_ns() {
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
-// Spin until *flag >= want (wrap-safe signed distance); false on time-out.
-__device__ __forceinline__ bool wait_flag(const uint32_t* flag, uint32_t want) {
+// Spin until *flag >= want (wrap-safe signed distance); false on time-out or when the sticky error word of this
+// rank's pad is set (a peer that timed out raises it on every rank, so nobody waits out the full limit).
+__device__ __forceinline__ bool wait_flag(const uint32_t* flag, uint32_t want, const uint32_t* err, unsigned long long limit_ns) {
   if ((int32_t)(ld_acquire_sys(flag) - want) >= 0) return true;
   const unsigned long long t0 = now_ns();
   for (unsigned it = 0;; ++it) {
     if ((int32_t)(ld_acquire_sys(flag) - want) >= 0) return true;
-    if ((it & 63u) == 63u && now_ns() - t0 > kSpinLimitNs) return false;
+    if ((it & 63u) == 63u && (now_ns() - t0 > limit_ns || *(const volatile uint32_t*)err != 0u)) return false;
     __nanosleep(32);
   }
+}
+
+// A time-out is FATAL and sticky: the error word is raised on this rank and on every peer, the trainer's status word
+// gets bit 1 (the host raises at its next read-back), and every later launch on any rank returns at entry without
+// touching parameters, moments, flags or epochs — ranks can no longer pair stale flags with new gradients.
+__device__ __forceinline__ void raise_fatal(const PeerArgs& a) {
+  for (int j = 0; j < a.world; ++j) st_relaxed_sys(a.sig[j] + NRX_PEER_SIG_ERR, 1u);
+  if (a.status != nullptr) atomicOr(a.status, 2);
 }
 
 // W = compile-time bound on the world size (loads of all ranks in flight), U = float4 per thread per trip.
@@ -73,18 +84,24 @@ adamw_allreduce_peer_kernel(const __grid_constant__ PeerArgs a) {
   __shared__ int s_flag;
   uint32_t* sig = a.sig[a.rank];
   const int tid = threadIdx.x;
+  if (*(volatile uint32_t*)(sig + NRX_PEER_SIG_ERR) != 0u) {   // dead exchange (sticky): do nothing, keep telling the host
+    if (blockIdx.x == 0 && tid == 0 && a.status != nullptr) atomicOr(a.status, 2);
+    return;
+  }
   const uint32_t epoch = *(volatile uint32_t*)(sig + kSigEpoch) + 1u;  // bumped by the last block, after all read it
   if (tid == 0) s_flag = 0;
   __syncthreads();
   // ---- barrier A ------------------------------------------------------------------------------------
-  // This rank's gradients were written by EARLIER kernels of the stream: the kernel boundary already made them
-  // visible at the L2 the peers read through, so the "ready" flag is a plain system-scope store (no fence: a
-  // MEMBAR.SYS costs microseconds and sits on the critical path of every rank waiting for this flag).
-  if (blockIdx.x == 0 && tid < a.world) st_relaxed_sys(a.sig[tid] + kSigA + a.rank, epoch);
-  if (tid < a.world && !wait_flag(sig + kSigA + tid, epoch)) s_flag = 1;
+  // This rank's gradients were written by EARLIER kernels of the stream.  The flag is a RELEASE store at system scope
+  // (fence.acq_rel.sys + store): together with the peers' acquire loads it orders those writes before the peers'
+  // gradient loads under the PTX memory model, instead of relying on what a kernel boundary happens to flush.  At
+  // kernel entry this rank has no outstanding stores of its own, so the fence is cheap (the costly fences of the first
+  // version sat after the peer stores).
+  if (blockIdx.x == 0 && tid < a.world) st_release_sys(a.sig[tid] + kSigA + a.rank, epoch);
+  if (tid < a.world && !wait_flag(sig + kSigA + tid, epoch, sig + NRX_PEER_SIG_ERR, a.spin_ns)) s_flag = 1;
   __syncthreads();
-  if (s_flag) {  // a peer never arrived: flag it and leave the parameters untouched
-    if (tid == 0) sig[NRX_PEER_SIG_ERR] = 1u;
+  if (s_flag) {  // a peer never arrived: fatal, parameters untouched
+    if (tid == 0) raise_fatal(a);
     return;
   }
   // ---- reduce + AdamW + broadcast over the owned slice ---------------------------------------------
@@ -136,7 +153,7 @@ adamw_allreduce_peer_kernel(const __grid_constant__ PeerArgs a) {
   if (s_flag != 2) return;
   if (tid < a.world) {
     st_release_sys(a.sig[tid] + kSigB + a.rank, epoch);
-    if (!wait_flag(sig + kSigB + tid, epoch)) sig[NRX_PEER_SIG_ERR] = 1u;
+    if (!wait_flag(sig + kSigB + tid, epoch, sig + NRX_PEER_SIG_ERR, a.spin_ns)) raise_fatal(a);
   }
   __syncthreads();
   if (tid == 0) {
@@ -218,6 +235,10 @@ extern "C" int nrx_adamw_allreduce_peer(const NrxPeerStep* s, nrx_stream_t strea
   a.hi4 = a.lo4 + base + (s->rank < rem ? 1 : 0);
   a.d_hp = s->d_hparams;
   a.b1 = s->beta1; a.b2 = s->beta2; a.eps = s->eps; a.wd = s->weight_decay;
+  a.status = s->status;
+  unsigned ms = s->timeout_ms ? s->timeout_ms : kDefaultTimeoutMs;
+  if (const char* e = getenv("NRX_PEER_TIMEOUT_MS")) { const long v = atol(e); if (v > 0) ms = (unsigned)v; }
+  a.spin_ns = (unsigned long long)ms * 1000000ull;
   // Blocks that are not resident yet simply find barrier A already satisfied when they start: the grid needs
   // no co-residency on ITS device, only that every rank's kernel eventually starts on its own device.
   const int U = s->world <= 2 ? 4 : (s->world <= 4 ? 2 : 1);

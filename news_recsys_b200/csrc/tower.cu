@@ -20,41 +20,14 @@
 
 #include <stdlib.h>
 
-#include "common.cuh"
-#include "umma.cuh"
+#include "tower.cuh"
 
 namespace nrx {
 using namespace umma;
 
-static constexpr int kRows = 128;        // rows per tile == UMMA M
-static constexpr int kFwdThreads = 512;  // 16 warps: TMEM lane quadrant = warp % 4, column slice = warp / 4
-static constexpr int kColSplit = kFwdThreads / 128;
-static constexpr int kBiasStride = 256;   // floats of shared memory per layer bias
-static constexpr int kMaxTiny = 4;
-
-struct TowerK {
-  int n_layers, n_mma, tiny;
-  int K[NRX_MAX_LAYERS], N[NRX_MAX_LAYERS], Kp[NRX_MAX_LAYERS], Np[NRX_MAX_LAYERS];
-  const float* w[NRX_MAX_LAYERS];
-  const float* bias[NRX_MAX_LAYERS];
-  unsigned w_off[NRX_MAX_LAYERS], wt_off[NRX_MAX_LAYERS];  // byte offsets inside the W / W^T image blocks
-  unsigned w_bytes, wt_bytes;
-  long long act_off[NRX_MAX_LAYERS];  // ws byte offset of the image of layer l's INPUT (width Kp[l])
-  long long dz_off[NRX_MAX_LAYERS];   // ws byte offset of the image of dL/dz_l (width Np[l])
-  long long wpack_off, wtpack_off, part_off;
-  long long part_layer_off[NRX_MAX_LAYERS];  // float offset of layer l inside one CTA's partial block
-  long long part_stride;                     // floats per CTA
-  int act;
-  float slope;
-  int max_kp;     // widest A operand (activation buffer width)
-  int tmem_cols;
-  long long n_tiles;
-  size_t total_bytes;
-};
-
 static int r16(int x) { return (x + 15) & ~15; }
 
-static int make_tower(const NrxTower* t, long long B, int training, TowerK* k) {
+int make_tower(const NrxTower* t, long long B, int training, TowerK* k) {
   NRX_REQUIRE(t != nullptr, NRX_EINVAL, "null tower");
   NRX_REQUIRE(t->n_layers >= 1 && t->n_layers <= NRX_MAX_LAYERS, NRX_EINVAL, "n_layers=%d outside [1,%d]", t->n_layers,
               (int)NRX_MAX_LAYERS);
@@ -76,12 +49,14 @@ static int make_tower(const NrxTower* t, long long B, int training, TowerK* k) {
     k->Np[l] = r16(k->N[l]);
     k->w[l] = t->w[l];
     k->bias[l] = t->b[l];
-    NRX_REQUIRE(k->Kp[l] <= 240 && k->Np[l] <= 240, NRX_EUNSUPPORTED, "layer %d: widths up to 240 supported (got %d -> %d)", l,
-                k->K[l], k->N[l]);
+    // the first layer is K-streamed by the pipelined forward (tower_fwd.cu): any input width whose weights fit in SMEM
+    NRX_REQUIRE((l == 0 ? k->Kp[l] <= 1024 : k->Kp[l] <= 240) && k->Np[l] <= 240, NRX_EUNSUPPORTED,
+                "layer %d: widths up to 240 supported (got %d -> %d)", l, k->K[l], k->N[l]);
+    if (l == 0 && k->Kp[l] > 240) k->wide0 = 1;
     NRX_REQUIRE(!training || k->Np[l] <= 128, NRX_EUNSUPPORTED, "layer %d: training supports out widths up to 128 (got %d)", l, k->N[l]);
     if (k->Kp[l] > k->max_kp) k->max_kp = k->Kp[l];
     if (l < k->n_mma && k->Np[l] > max_np) max_np = k->Np[l];
-    if (l < k->n_mma && k->Kp[l] > max_np) max_np = k->Kp[l];  // dX accumulators are Kp wide
+    if (l < k->n_mma && k->Kp[l] > max_np && k->Kp[l] <= 240) max_np = k->Kp[l];  // dX accumulators are Kp wide
   }
   for (int l = 0; l + 1 < t->n_layers; ++l)
     NRX_REQUIRE(k->Np[l] == k->Kp[l + 1], NRX_EINVAL, "layer %d out (%d) != layer %d in (%d)", l, k->N[l], l + 1, k->K[l + 1]);
@@ -98,8 +73,10 @@ static int make_tower(const NrxTower* t, long long B, int training, TowerK* k) {
   size_t o = 0;
   k->wpack_off = (long long)o;  o += al(k->w_bytes);
   k->wtpack_off = (long long)o; o += al(k->wt_bytes);
+  // the input image a_0 exists in inference too: it is what the pipelined forward streams
+  k->act_off[0] = (long long)o; o += al((size_t)k->n_tiles * k->Kp[0] * kRows * 2);
   if (training) {
-    for (int l = 0; l < k->n_layers; ++l) { k->act_off[l] = (long long)o; o += al((size_t)k->n_tiles * k->Kp[l] * kRows * 2); }
+    for (int l = 1; l < k->n_layers; ++l) { k->act_off[l] = (long long)o; o += al((size_t)k->n_tiles * k->Kp[l] * kRows * 2); }
     for (int l = 0; l < k->n_layers; ++l) { k->dz_off[l] = (long long)o; o += al((size_t)k->n_tiles * k->Np[l] * kRows * 2); }
     long long p = 0;
     for (int l = 0; l < k->n_layers; ++l) { k->part_layer_off[l] = p; p += (long long)k->N[l] * (k->Kp[l] + 16); }
@@ -150,8 +127,6 @@ tower_pack_kernel(const __grid_constant__ TowerK T, uint8_t* __restrict__ wpack,
   }
 }
 
-__device__ __forceinline__ float act_fwd(float z, float slope) { return z > 0.f ? z : z * slope; }
-__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
 // Issue the K loop of one layer: D[128 x n_cols] = A[128 x Kdim] * B[n_cols x Kdim]^T, both K-major canonical.
 __device__ __forceinline__ void issue_layer_mma(uint32_t tmem, uint32_t a_base, uint32_t b_base, int kdim, int n_cols) {
@@ -913,24 +888,31 @@ extern "C" int nrx_tower_pack(const NrxTower* h_tower, int64_t B, int training, 
   return tower_pack(k, (uint8_t*)ws, (cudaStream_t)stream);
 }
 
-extern "C" int nrx_tower_fwd(const NrxTower* h_tower, const float* x, int64_t x_ld, int64_t B, float* y, int64_t y_ld,
-                             int training, void* ws, size_t ws_bytes, nrx_stream_t stream) {
-  const int prepacked = training & NRX_TOWER_PREPACKED;
-  training &= 1;
+static int tower_fwd_any(const NrxTower* h_tower, const float* x, int64_t x_ld, int64_t B, float* y, int64_t y_ld, int flags,
+                         const NrxTowerHead* head, void* ws, size_t ws_bytes, nrx_stream_t stream) {
+  const int prepacked = flags & NRX_TOWER_PREPACKED;
+  const int ximg = flags & NRX_TOWER_XIMG;
+  const int training = flags & 1;
   TowerK k;
   int rc = make_tower(h_tower, B, training, &k);
   if (rc != NRX_OK) return rc;
   NRX_REQUIRE(ws && ws_bytes >= k.total_bytes, NRX_EWORKSPACE, "workspace %zu < %zu", ws_bytes, k.total_bytes);
-  NRX_REQUIRE((x && y) || B == 0, NRX_EINVAL, "null x / y");
-  NRX_REQUIRE(x_ld >= k.K[0] && y_ld >= k.N[k.n_layers - 1], NRX_EINVAL, "leading dimension too small");
+  NRX_REQUIRE(((x || ximg) && (y || head)) || B == 0, NRX_EINVAL, "null x / y");
+  NRX_REQUIRE((ximg || x_ld >= k.K[0]) && (!y || y_ld >= k.N[k.n_layers - 1]), NRX_EINVAL, "leading dimension too small");
+  NRX_REQUIRE(y || k.tiny, NRX_EINVAL, "y may only be omitted when the tower ends in the fused head");
   if (B == 0) return NRX_OK;
-  const size_t smem = fwd_smem_bytes(k, false);
-  NRX_REQUIRE(smem <= 227 * 1024, NRX_EUNSUPPORTED, "tower needs %zu B of shared memory (> 227 KB)", smem);
   cudaStream_t st = (cudaStream_t)stream;
   if (!prepacked) {
     rc = tower_pack(k, (uint8_t*)ws, st);
     if (rc != NRX_OK) return rc;
   }
+  const char* env3 = getenv("NRX_TOWER_V3");
+  const bool want3 = env3 ? atoi(env3) != 0 : true;
+  if ((want3 || ximg || head || k.wide0) && tower_fwd3_eligible(k))
+    return tower_fwd3_launch(k, ximg ? nullptr : x, x_ld, B, y, y_ld, (uint8_t*)ws, training, head, st);
+  NRX_REQUIRE(!ximg && !head && !k.wide0, NRX_EUNSUPPORTED, "tower shape outside the pipelined forward (image input / fused head / wide first layer need it)");
+  const size_t smem = fwd_smem_bytes(k, false);
+  NRX_REQUIRE(smem <= 227 * 1024, NRX_EUNSUPPORTED, "tower needs %zu B of shared memory (> 227 KB)", smem);
   {
     // large batches: two tile slots per CTA (needs >= 3 tiles per SM to pay, 2 A buffers + 2 accumulators to fit)
     const size_t smem2 = fwd2_smem_bytes(k);
@@ -952,6 +934,17 @@ extern "C" int nrx_tower_fwd(const NrxTower* h_tower, const float* x, int64_t x_
   return check_launch("tower_fwd");
 }
 
+extern "C" int nrx_tower_fwd(const NrxTower* h_tower, const float* x, int64_t x_ld, int64_t B, float* y, int64_t y_ld,
+                             int training, void* ws, size_t ws_bytes, nrx_stream_t stream) {
+  return tower_fwd_any(h_tower, x, x_ld, B, y, y_ld, training, nullptr, ws, ws_bytes, stream);
+}
+
+extern "C" int nrx_tower_fwd_head(const NrxTower* h_tower, const float* x, int64_t x_ld, int64_t B, const NrxTowerHead* h_head,
+                                  int flags, void* ws, size_t ws_bytes, nrx_stream_t stream) {
+  NRX_REQUIRE(h_head != nullptr, NRX_EINVAL, "null head");
+  return tower_fwd_any(h_tower, x, x_ld, B, nullptr, 1, flags, h_head, ws, ws_bytes, stream);
+}
+
 extern "C" int nrx_tower_bwd_dx(const NrxTower* h_tower, int64_t B, const float* grad_y, int64_t gy_ld, float* grad_x,
                                 int64_t gx_ld, int accumulate_gx, void* ws, size_t ws_bytes, nrx_stream_t stream) {
   TowerK k;
@@ -959,6 +952,7 @@ extern "C" int nrx_tower_bwd_dx(const NrxTower* h_tower, int64_t B, const float*
   if (rc != NRX_OK) return rc;
   NRX_REQUIRE(ws && ws_bytes >= k.total_bytes, NRX_EWORKSPACE, "workspace %zu < %zu", ws_bytes, k.total_bytes);
   NRX_REQUIRE(grad_y || B == 0, NRX_EINVAL, "null grad_y");
+  NRX_REQUIRE(!k.wide0, NRX_EUNSUPPORTED, "tower backward: first layer wider than 240 columns (got %d)", k.K[0]);
   NRX_REQUIRE(gy_ld >= k.N[k.n_layers - 1] && (!grad_x || gx_ld >= k.K[0]), NRX_EINVAL, "leading dimension too small");
   if (B == 0) return NRX_OK;
   cudaStream_t st = (cudaStream_t)stream;
@@ -983,6 +977,7 @@ extern "C" int nrx_tower_bwd_dw(const NrxTower* h_tower, int64_t B, float* const
   if (rc != NRX_OK) return rc;
   NRX_REQUIRE(ws && ws_bytes >= k.total_bytes, NRX_EWORKSPACE, "workspace %zu < %zu", ws_bytes, k.total_bytes);
   NRX_REQUIRE(h_grad_w && h_grad_b, NRX_EINVAL, "null gradient pointer arrays");
+  NRX_REQUIRE(!k.wide0, NRX_EUNSUPPORTED, "tower backward: first layer wider than 240 columns (got %d)", k.K[0]);
   if (B == 0) return NRX_OK;
   cudaStream_t st = (cudaStream_t)stream;
   uint8_t* w = (uint8_t*)ws;

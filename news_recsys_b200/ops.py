@@ -112,6 +112,27 @@ def embed_pool_fwd(fb: FeatBinding, out_dim: int, status: Optional[torch.Tensor]
     return out
 
 
+def embed_pool_fwd_img(fb: FeatBinding, out_dim: int, image: torch.Tensor, want_rows: bool = True,
+                       status: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
+    """K1 that also writes the tower's bf16 input image (`image`: the a_0 slot of a prepacked tower workspace, see
+    tower_input_image); returns the fp32 rows, or None with want_rows=False (nothing else reads them)."""
+    out = torch.empty((fb.B, out_dim), dtype=torch.float32, device=fb.device) if want_rows else None
+    lib = L.load()
+    L.check(lib.nrx_embed_pool_fwd_img(fb.arr, fb.n, fb.B, L.ptr(out), out.stride(0) if (out is not None and fb.B) else out_dim,
+                                       image.data_ptr(), out_dim, L.ptr(status), L.stream_ptr(fb.device)), "nrx_embed_pool_fwd_img")
+    return out
+
+
+def embed_img_eligible(fb: FeatBinding, out_dim: int) -> bool:
+    """128-bit K1 path with a concat width the tower can take as is (multiple of 16)."""
+    if out_dim % 16:
+        return False
+    for s, f in zip(fb.specs, fb.arr):
+        if f.dim % 4 or f.row_stride % 4 or f.out_col % 4 or f.table % 16:
+            return False
+    return True
+
+
 class BwdPlan:
     """Sorted-occurrence plan for one batch (nrx_embed_bwd_plan); reusable for any number of applies."""
 
@@ -451,42 +472,111 @@ def tower_prepack(B: int, weights, biases, negative_slope=None, training=False):
     return t, keep, ws, nbytes
 
 
-def tower_fwd(x: torch.Tensor, weights, biases, negative_slope=None, training=False, packed=None):
-    """y = MLP(x) on tensor cores; returns (y, ctx) where ctx carries the workspace for tower_bwd."""
-    _require_cuda(x, "tower input")
-    if x.dtype != torch.float32 or x.stride(-1) != 1:
-        x = x.float().contiguous()
-    B = x.shape[0]
+def tower_head(B: int, device, terms=(), bias=None, label=None, want_loss=True, want_logit=False):
+    """NrxTowerHead + its output tensors: (struct, keepalive, prob, loss_per_sample, dlogit, logit)."""
+    h = L.NrxTowerHead()
+    ts = [t.contiguous().view(-1) for t in terms]
+    if len(ts) > 4:
+        raise L.NrxError("the fused tower head takes at most 4 extra logit terms")
+    h.n_terms = len(ts)
+    for i, t in enumerate(ts):
+        _require_cuda(t, "head term")
+        h.terms[i] = t.data_ptr()
+    prob = torch.empty(B, dtype=torch.float32, device=device)
+    h.prob = prob.data_ptr()
+    keep = list(ts) + [prob]
+    loss = dl = logit = None
+    if bias is not None:
+        h.bias = bias.data_ptr()
+        keep.append(bias)
+    if label is not None:
+        _require_cuda(label, "label")
+        if label.dtype != torch.float32:
+            label = label.float()
+        h.label, h.label_stride = label.data_ptr(), label.stride(0)
+        keep.append(label)
+        if want_loss:
+            loss = torch.empty(B, dtype=torch.float32, device=device)
+            dl = torch.empty(B, dtype=torch.float32, device=device)
+            h.loss_per_sample, h.dlogit = loss.data_ptr(), dl.data_ptr()
+    if want_logit:
+        logit = torch.empty(B, dtype=torch.float32, device=device)
+        h.logit = logit.data_ptr()
+    return h, keep, prob, loss, dl, logit
+
+
+def tower_fwd(x: Optional[torch.Tensor], weights, biases, negative_slope=None, training=False, packed=None, head=None,
+              ximg_rows: Optional[int] = None):
+    """y = MLP(x) on tensor cores; returns (y, ctx) where ctx carries the workspace for tower_bwd.
+
+    head       — an ops.tower_head(...) tuple: the last epilogue also emits sigmoid / BCE / dL/dlogit (y is None then);
+    ximg_rows  — B when the bf16 input image is already in the (prepacked) workspace (x may be None)."""
+    if x is not None:
+        _require_cuda(x, "tower input")
+        if x.dtype != torch.float32 or x.stride(-1) != 1:
+            x = x.float().contiguous()
+    B = x.shape[0] if ximg_rows is None else int(ximg_rows)
     lib = L.load()
-    flags = 1 if training else 0
+    flags = L.TOWER_TRAINING if training else 0
+    tag = ""
     if packed is not None:
         t, keep, ws, nbytes = packed
-        flags |= 2  # NRX_TOWER_PREPACKED
+        flags |= L.TOWER_PREPACKED
+        tag = "(prepacked)"
     else:
         t, keep = _tower_struct(weights, biases, negative_slope)
-        nbytes = int(lib.nrx_tower_workspace_bytes(C.byref(t), B, flags))
+        nbytes = int(lib.nrx_tower_workspace_bytes(C.byref(t), B, flags & 1))
         if nbytes == 0:
             L.check(-2, "nrx_tower_workspace_bytes")
-        ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
-    y = torch.empty((B, t.dims[t.n_layers]), dtype=torch.float32, device=x.device)
-    L.check(lib.nrx_tower_fwd(C.byref(t), x.data_ptr(), x.stride(0), B, y.data_ptr(), y.stride(0), flags,
-                              ws.data_ptr(), nbytes, L.stream_ptr(x.device)),
-            "nrx_tower_fwd(prepacked)" if packed is not None else "nrx_tower_fwd")
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=weights[0].device)
+    if ximg_rows is not None:
+        if packed is None:
+            raise L.NrxError("an input image lives in a prepacked workspace: pass packed=")
+        flags |= L.TOWER_XIMG
+        tag = "(prepacked,ximg)"
+    dev = ws.device
+    xp, xld = (x.data_ptr(), x.stride(0)) if x is not None else (0, 0)
+    if head is not None:
+        L.check(lib.nrx_tower_fwd_head(C.byref(t), xp, xld, B, C.byref(head[0]), flags, ws.data_ptr(), nbytes, L.stream_ptr(dev)),
+                "nrx_tower_fwd_head" + tag)
+        return None, (t, keep, ws, nbytes, x)
+    y = torch.empty((B, t.dims[t.n_layers]), dtype=torch.float32, device=dev)
+    L.check(lib.nrx_tower_fwd(C.byref(t), xp, xld, B, y.data_ptr(), y.stride(0), flags, ws.data_ptr(), nbytes, L.stream_ptr(dev)),
+            "nrx_tower_fwd" + tag)
     return y, (t, keep, ws, nbytes, x)
+
+
+def tower_input_image(packed, B: int) -> torch.Tensor:
+    """The uint8 view of the a_0 image slot inside a prepacked tower workspace (where K1 / K5 write the tower input)."""
+    t, keep, ws, nbytes = packed
+    n = t.n_layers
+    ao, aw = (C.c_int64 * n)(), (C.c_int32 * n)()
+    L.check(L.load().nrx_tower_image_layout(C.byref(t), B, ao, aw, None, None), "nrx_tower_image_layout")
+    nt = (B + 127) // 128
+    return ws[ao[0]: ao[0] + nt * aw[0] * 256]
+
+
+def tower_image_from_rows(x: torch.Tensor, image: torch.Tensor):
+    """fp32 rows [B, width] -> the bf16 tile image (what K1 / K5 write directly on the fused route)."""
+    _require_cuda(x, "rows")
+    x = x.contiguous()
+    L.check(L.load().nrx_tower_image_from_rows(x.data_ptr(), x.stride(0), x.shape[0], x.shape[1], image.data_ptr(),
+                                               L.stream_ptr(x.device)), "nrx_tower_image_from_rows")
 
 
 def tower_bwd(ctx, grad_y: torch.Tensor, need_gx: bool = True):
     t, keep, ws, nbytes, x = ctx
-    B = x.shape[0]
     grad_y = grad_y.contiguous()
+    B = grad_y.shape[0]
     n = t.n_layers
-    gws = [torch.empty((t.dims[i + 1], t.dims[i]), dtype=torch.float32, device=x.device) for i in range(n)]
-    gbs = [torch.empty((t.dims[i + 1],), dtype=torch.float32, device=x.device) for i in range(n)]
-    gx = torch.empty_like(x) if need_gx else None
+    dev = ws.device
+    gws = [torch.empty((t.dims[i + 1], t.dims[i]), dtype=torch.float32, device=dev) for i in range(n)]
+    gbs = [torch.empty((t.dims[i + 1],), dtype=torch.float32, device=dev) for i in range(n)]
+    gx = torch.empty((B, t.dims[0]), dtype=torch.float32, device=dev) if need_gx else None
     lib = L.load()
-    L.check(lib.nrx_tower_bwd(C.byref(t), x.data_ptr(), x.stride(0), B, grad_y.data_ptr(), grad_y.stride(0), L.ptr(gx),
+    L.check(lib.nrx_tower_bwd(C.byref(t), 0, 0, B, grad_y.data_ptr(), grad_y.stride(0), L.ptr(gx),
                               gx.stride(0) if gx is not None else 0, 0, L.ptr_array(gws, L.NRX_MAX_LAYERS),
-                              L.ptr_array(gbs, L.NRX_MAX_LAYERS), ws.data_ptr(), nbytes, L.stream_ptr(x.device)),
+                              L.ptr_array(gbs, L.NRX_MAX_LAYERS), ws.data_ptr(), nbytes, L.stream_ptr(dev)),
             "nrx_tower_bwd")
     return gx, gws, gbs
 
@@ -565,6 +655,24 @@ def dcn_cross_bwd(x, ws, bs, grad_out, need_gx=True):
                                   L.ptr_array(gws), L.ptr_array(gbs), wsb.data_ptr(), nbytes, L.stream_ptr(x.device)),
             "nrx_dcn_cross_bwd")
     return gx, gws, gbs
+
+
+def dcn_cross_fwd_img(x: torch.Tensor, ws: Sequence[torch.Tensor], bs: Sequence[torch.Tensor], image: torch.Tensor):
+    """Cross stack writing cat[x, x_L] straight into the tower's bf16 input image (no fp32 concat)."""
+    _require_cuda(x, "cross input")
+    x = x.contiguous()
+    B, d = x.shape
+    wl = [w.detach().contiguous().view(-1) for w in ws]
+    bl = [b.detach().contiguous().view(-1) for b in bs]
+    lib = L.load()
+    L.check(lib.nrx_dcn_cross_fwd_img(x.data_ptr(), x.stride(0), B, d, len(wl), L.ptr_array(wl), L.ptr_array(bl), None, 0,
+                                      image.data_ptr(), L.stream_ptr(x.device)), "nrx_dcn_cross_fwd_img")
+
+
+def dcn_img_eligible(x: torch.Tensor, ws, bs) -> bool:
+    d = x.shape[1]
+    return (d % 8 == 0 and d <= 256 and x.stride(0) % 4 == 0 and x.data_ptr() % 16 == 0
+            and all(w.data_ptr() % 16 == 0 for w in ws) and all(b.data_ptr() % 16 == 0 for b in bs))
 
 
 class CrossFn(torch.autograd.Function):

@@ -112,9 +112,12 @@ class DataParallelTrainer(FusedTrainer):
     _inline_update = False  # the row update needs the all-gathered gradients of every rank
 
     def __init__(self, model, B: int, kind=None, group=None, use_graph: bool = True, table_update: str = "dense",
-                 exchange: str = "peer", **kw):
+                 exchange: str = "peer", peer_timeout_ms: int = 20000, **kw):
         """exchange (dense mode only): "peer" — K7, gradient all-reduce fused with AdamW over NVLink peer memory,
-        the whole step one CUDA graph, no NCCL on the data path (single node); "nccl" — all-reduce between two graphs."""
+        the whole step one CUDA graph, no NCCL on the data path (single node); "nccl" — all-reduce between two graphs.
+        peer_timeout_ms: how long K7 waits for a peer before it declares the exchange dead.  That is FATAL and sticky
+        (no rank updates anything any more); step() / feed() raise NrxError at their next status read-back."""
+        self.peer_timeout_ms = peer_timeout_ms
         if exchange not in ("peer", "nccl"):
             raise L.NrxError(f"exchange must be 'peer' or 'nccl', got {exchange!r}")
         self.group = group
@@ -184,6 +187,8 @@ class DataParallelTrainer(FusedTrainer):
         st.m, st.v, st.n = self.flat_m.data_ptr(), self.flat_v.data_ptr(), self.n_dense
         st.d_hparams = self.d_hp.data_ptr()
         st.beta1, st.beta2, st.eps, st.weight_decay = self.betas[0], self.betas[1], self.eps, self.wd
+        st.status = self.id_status.data_ptr()    # bit 1: the exchange is dead (read back with the loss, raised by the host)
+        st.timeout_ms = int(self.peer_timeout_ms)
         self._peer_step = st
         dist.barrier(group=self.group)    # every rank has mapped every buffer before the first kernel touches them
         if use_graph:
@@ -195,7 +200,8 @@ class DataParallelTrainer(FusedTrainer):
         L.check(self.lib.nrx_adamw_allreduce_peer(C.byref(self._peer_step), self._sp()), "nrx_adamw_allreduce_peer")
 
     def peer_timed_out(self) -> bool:
-        """True if a K7 launch gave up waiting for a peer (the parameters are then stale, not corrupted)."""
+        """True if a K7 launch gave up waiting for a peer: the exchange is dead on every rank (sticky), parameters and
+        moments were left untouched from that step on.  Synchronises the stream."""
         flag = C.c_int32(0)
         L.check(self.lib.nrx_peer_status(self.sig.data_ptr(), C.byref(flag), self._sp()), "nrx_peer_status")
         return bool(flag.value)
@@ -320,6 +326,7 @@ class ShardedEmbeddingTrainer(FusedTrainer):
         sh = [n for n in model.embedding_tables.keys() if n in self.shards]
         model._table_ids = {n: i for i, n in enumerate(rep + sh)}
         kw.pop("use_graph", None)
+        kw.setdefault("table_update", "sparse")   # every rank updates only the rows it owns (touched rows)
         super().__init__(model, B, kind=kind, use_graph=False, **kw)
         self.fm_fused = False  # the gather is distributed: K1 + field logits instead of the gather-fused FM
         self.id_keys = [key for key, dt, shape, off in self.layout.fields if key != "label"]

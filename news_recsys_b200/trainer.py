@@ -73,11 +73,13 @@ class FusedTrainer:
                      "widedeep": "score_fc.deep_network.network", "dcn": "score_fc.score_fc.network"}
 
     def __init__(self, model, B: int, kind: Optional[str] = None, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01,
-                 use_graph: bool = True, id_dtype=torch.int64, table_update: str = "sparse", dense_impl: str = "flat"):
+                 use_graph: bool = True, id_dtype=torch.int64, table_update: str = "dense", dense_impl: str = "flat"):
         """table_update:
-             "sparse" — fused sparse-row AdamW inside K3: only the rows the batch touched move (lazy rows);
-             "dense"  — the reference's semantics (sort/deep/model.py:55): AdamW with weight decay 0.01 moves every
-                        row of every table every step, touched or not.
+             "dense"  — (default) the reference's semantics (sort/deep/model.py:55): AdamW with weight decay 0.01 moves
+                        every row of every table every step, touched or not;
+             "sparse" — explicit opt-in: fused sparse-row AdamW inside K3, only the rows the batch touched move
+                        (lazy rows) — a different trajectory than the reference's, needed once a dense pass over
+                        the tables per step is unaffordable (BASELINE config 5).
            dense_impl (dense only; bitwise-identical results, tests/test_gpu_trainer.py):
              "flat"   — K3 writes dense table gradients into the same flat buffer as the tower gradients and ONE dense
                         AdamW sweeps every parameter (also what the data-parallel trainer exchanges);
@@ -113,6 +115,11 @@ class FusedTrainer:
         self.layout = BatchLayout(model, B, id_dtype)
         self.blob = torch.zeros(self.layout.nbytes, dtype=torch.uint8, device=self.dev)
         self.batch = self.layout.views(self.blob)
+        # loss and the id-status word share one 8-byte buffer so that feed() reads both back with one copy:
+        # K1 sets the status when an id is outside its table (nn.Embedding would raise; base_model.py:271)
+        self._loss_status = torch.zeros(2, dtype=torch.float32, device=self.dev)
+        self.id_status = self._loss_status[1:2].view(torch.int32)
+        self.fused_input = os.environ.get("NRX_FUSED_INPUT", "1") == "1"
         self.d_step = torch.zeros(1, dtype=torch.int32, device=self.dev)
         self.d_hp = torch.zeros(4, dtype=torch.float32, device=self.dev)
         self._flatten_dense()
@@ -127,7 +134,7 @@ class FusedTrainer:
         self.side2 = torch.cuda.Stream(device=self.dev)
         self.side3 = torch.cuda.Stream(device=self.dev)
         self.side4 = torch.cuda.Stream(device=self.dev)   # untouched-row sweep: from the end of the plan to the end of the step
-        self.loss = torch.zeros(1, dtype=torch.float32, device=self.dev)
+        self.loss = self._loss_status[0:1]
         self.prob = None
         self.graph = None
         self.launches_per_step = None
@@ -179,10 +186,11 @@ class FusedTrainer:
     def _reduce(self, x, scale, out):
         L.check(self.lib.nrx_reduce_f32(x.data_ptr(), x.numel(), scale, out.data_ptr(), self._sp()), "nrx_reduce_f32")
 
-    def _tower(self, x, lin_names, ws_override=None, packed=None):
+    def _tower(self, x, lin_names, ws_override=None, packed=None, head=None, ximg=False):
         ws = ws_override or [self.dense_views[n + ".weight"] for n in lin_names]
         bs = [self.dense_views[n + ".bias"] for n in lin_names]
-        y, tctx = ops.tower_fwd(x, ws, bs, None, training=True, packed=packed)
+        y, tctx = ops.tower_fwd(None if ximg else x, ws, bs, None, training=True, packed=packed, head=head,
+                                ximg_rows=self.B if ximg else None)
         return y, tctx
 
     def _prepack(self, lin_names, main):
@@ -196,8 +204,8 @@ class FusedTrainer:
 
     def _tower_bwd_dx(self, tctx, dl):
         t, keep, ws, nbytes, x = tctx
-        gx = torch.empty_like(x)
-        L.check(self.lib.nrx_tower_bwd_dx(C.byref(t), x.shape[0], dl.data_ptr(), 1, gx.data_ptr(), gx.stride(0), 0,
+        gx = torch.empty((self.B, t.dims[0]), dtype=torch.float32, device=self.dev)
+        L.check(self.lib.nrx_tower_bwd_dx(C.byref(t), self.B, dl.data_ptr(), 1, gx.data_ptr(), gx.stride(0), 0,
                                           ws.data_ptr(), nbytes, self._sp()), "nrx_tower_bwd_dx")
         return gx
 
@@ -205,7 +213,7 @@ class FusedTrainer:
         t, keep, ws, nbytes, x = tctx
         gws = gw_override or [self.grad_views[n + ".weight"] for n in lin_names]
         gbs = [self.grad_views[n + ".bias"] for n in lin_names]
-        L.check(self.lib.nrx_tower_bwd_dw(C.byref(t), x.shape[0], L.ptr_array(gws, L.NRX_MAX_LAYERS),
+        L.check(self.lib.nrx_tower_bwd_dw(C.byref(t), self.B, L.ptr_array(gws, L.NRX_MAX_LAYERS),
                                           L.ptr_array(gbs, L.NRX_MAX_LAYERS), ws.data_ptr(), nbytes, self._sp()),
                 "nrx_tower_bwd_dw")
 
@@ -235,7 +243,7 @@ class FusedTrainer:
 
     def _embed_fwd(self):
         """K1: features [B, ΣD] of the local batch (the row-sharded trainer overrides this with the exchange)."""
-        return ops.embed_pool_fwd(self.fb, self.out_dim)
+        return ops.embed_pool_fwd(self.fb, self.out_dim, status=self.id_status)
 
     # single-GPU trainers apply the sparse-row update inside _fwd_bwd (overlapped with dW); the distributed
     # trainers need the gradient exchange first and keep it in _update
@@ -262,10 +270,23 @@ class FusedTrainer:
         bias = self.dense_views.get("score_fc.bias")
         kind = self.kind
         if self.fm_fused:
-            prob, loss_ps, dl, _ = ops.fm_fused_fwd(fb, bias, label)
+            prob, loss_ps, dl, _ = ops.fm_fused_fwd(fb, bias, label, status=self.id_status)
             gx = ops.fm_fused_bwd(fb, dl, self.out_dim)
         else:
-            x = self._embed_fwd()
+            has_tower = kind in ("deep", "deepfm", "widedeep", "dcn")
+            # the tower streams its input as a bf16 tile image: K1 (Deep / DeepFM) or the cross stack (DCN) write that
+            # image straight into the tower workspace, so the fp32 concat is only materialised where something else
+            # reads it (FM logit, cross stack)
+            img = None
+            if packed is not None and self.fused_input:
+                main.wait_stream(self.side2)   # the workspace (and its packed weights) exists from here on
+                img = ops.tower_input_image(packed, self.B)
+            x_img = (img is not None and kind in ("deep", "deepfm") and ops.embed_img_eligible(fb, self.out_dim)
+                     and type(self)._embed_fwd is FusedTrainer._embed_fwd)
+            if x_img:
+                x = ops.embed_pool_fwd_img(fb, self.out_dim, img, want_rows=(kind != "deep"), status=self.id_status)
+            else:
+                x = self._embed_fwd()
             cols, c = [], 0
             for d in self.dims:
                 cols.append(c)
@@ -283,18 +304,13 @@ class FusedTrainer:
                 field = (wide_cols, [1] * len(wide_cols), L.FIELD_WIDE)
             elif kind == "lr":
                 field = (cols, list(self.dims), L.FIELD_SUM)
-            has_tower = kind in ("deep", "deepfm", "widedeep", "dcn")
             s3 = self.side3
-            if field is not None:
-                if has_tower:  # field logit || tower forward (both only read x)
-                    s3.wait_stream(main)
-                    with torch.cuda.stream(s3):
-                        terms.append(ops.field_logit_fwd(x, field[0], field[1], field[2]))
-                else:
-                    terms.append(ops.field_logit_fwd(x, field[0], field[1], field[2]))
+            if field is not None:   # with a tower: the term feeds the fused head of the tower's last epilogue
+                terms.append(ops.field_logit_fwd(x, field[0], field[1], field[2]))
             if has_tower:
                 lin = self._lin_names(self._TOWER_PREFIX[kind])
                 tin, ws_override = x, None
+                ximg = x_img
                 if kind == "widedeep":  # column selection moved to the weight side (see widedeep/model.py)
                     w0 = self.dense_views[lin[0] + ".weight"]
                     idx = self._wd_idx
@@ -305,14 +321,18 @@ class FusedTrainer:
                 if kind == "dcn":
                     cw = [self.dense_views[f"score_fc.cross_net.cross_net.{i}.w"] for i in range(len(m.score_fc.cross_net.cross_net))]
                     cb = [self.dense_views[f"score_fc.cross_net.cross_net.{i}.b"] for i in range(len(cw))]
-                    tin = ops.dcn_cross_fwd(x, cw, cb)
-                if packed is not None:
+                    if img is not None and ops.dcn_img_eligible(x, cw, cb):
+                        ops.dcn_cross_fwd_img(x, cw, cb, img)
+                        tin, ximg = None, True
+                    else:
+                        tin = ops.dcn_cross_fwd(x, cw, cb)
+                if packed is not None and img is None:
                     main.wait_stream(self.side2)
-                y, tctx = self._tower(tin, lin, ws_override, packed=packed)
-                terms.append(y.view(-1))
-                if field is not None:
-                    main.wait_stream(s3)
-            prob, loss_ps, dl = ops.logit_loss_fwd(terms, bias, label)
+                head = ops.tower_head(self.B, self.dev, terms, bias, label)
+                _, tctx = self._tower(tin, lin, ws_override, packed=packed, head=head, ximg=ximg)
+                prob, loss_ps, dl = head[2], head[3], head[4]
+            else:
+                prob, loss_ps, dl = ops.logit_loss_fwd(terms, bias, label)
             # ---- backward ----
             gx = None
             if tctx is not None:
@@ -480,13 +500,50 @@ class FusedTrainer:
         (device int64[B], e.g. a slice of a device-side permutation) or the contiguous rows [start, start + B)."""
         device_file.assemble(self.layout, self.blob, rows=rows, start=start)
 
+    _STATUS_EVERY = 16   # steps between two asynchronous read-backs of the status word
+
     def step(self) -> torch.Tensor:
-        """Run one training step on the currently loaded batch; returns the (device) mean BCE loss."""
+        """Run one training step on the currently loaded batch; returns the (device) mean BCE loss.
+        Raises NrxError if an EARLIER step flagged an out-of-table id or a dead peer exchange: the status word is read
+        back asynchronously every few steps on a side stream, so the check never stalls the step it follows."""
+        self._poll_status()
         if self.graph is not None:
             self.graph.replay()
         else:
             self._step()
+        self._post_status()
         return self.loss
+
+    def _post_status(self):
+        st = self.__dict__.setdefault("_stat", dict(n=0, stream=None, host=None, done=None, ev=None))
+        st["n"] += 1
+        if st["n"] % self._STATUS_EVERY:
+            return
+        if st["stream"] is None:
+            st["stream"] = torch.cuda.Stream(device=self.dev)
+            st["host"] = torch.zeros(2, dtype=torch.float32).pin_memory()
+            st["ev"], st["done"] = torch.cuda.Event(), torch.cuda.Event()
+        elif not st["done"].query():
+            return   # the previous read-back is still in flight
+        st["ev"].record(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(st["stream"]):
+            st["stream"].wait_event(st["ev"])
+            st["host"].copy_(self._loss_status, non_blocking=True)
+            st["done"].record(st["stream"])
+
+    def _poll_status(self):
+        st = self.__dict__.get("_stat")
+        if st is not None and st["done"] is not None and st["done"].query():
+            self._raise_for_status(int(st["host"].view(torch.int32)[1]))
+
+    @staticmethod
+    def _raise_for_status(bits: int):
+        if bits & 2:
+            raise L.NrxError("the peer-memory gradient exchange (K7) timed out waiting for a rank: the exchange is dead on "
+                             "every rank and no parameter was updated since; restart from the last checkpoint")
+        if bits & 1:
+            raise L.NrxError("a feature id outside its embedding table reached the GPU (vocabulary / config mismatch): "
+                             "the reference's nn.Embedding raises here (base_model.py:271)")
 
     def train_step(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
         self.load_batch(batch)
@@ -512,13 +569,13 @@ class FusedTrainer:
         self.blob.copy_(f["stage"][k], non_blocking=True)
         f["free"][k].record(main)
         self.step()
-        f["loss_host"][k].copy_(self.loss, non_blocking=True)
+        f["loss_host"][k].copy_(self._loss_status, non_blocking=True)
         f["done"][k].record(main)
         prev, f["pending"] = f["pending"], k
         if prev is None:
             return None
         f["done"][prev].synchronize()
-        return float(f["loss_host"][prev])
+        return self._host_loss(f["loss_host"][prev])
 
     def drain(self) -> Optional[float]:
         """Loss of the last fed step (waits for it)."""
@@ -527,14 +584,45 @@ class FusedTrainer:
         if prev is None:
             return None
         f["done"][prev].synchronize()
-        return float(f["loss_host"][prev])
+        return self._host_loss(f["loss_host"][prev])
+
+    @classmethod
+    def _host_loss(cls, buf: torch.Tensor) -> float:
+        cls._raise_for_status(int(buf.view(torch.int32)[1]))
+        return float(buf[0])
+
+    def check_status(self):
+        """Synchronises and raises if any step so far saw an id outside its table (K1's status word) or a dead
+        peer exchange (K7)."""
+        self._raise_for_status(int(self.id_status.item()))
+
+    check_ids = check_status
+
+    # ---- optimizer state (resume) -----------------------------------------------------------------
+    def optimizer_state_dict(self) -> Dict[str, torch.Tensor]:
+        """AdamW moments + step counter (what a Lightning checkpoint of the reference keeps under 'optimizer_states')."""
+        sd = {"step": self.d_step.clone(), "flat_m": self.flat_m.clone(), "flat_v": self.flat_v.clone()}
+        for t in range(L.NRX_MAX_TABLES):
+            if self.m_by_id[t] is not None:
+                sd[f"table_m.{t}"] = self.m_by_id[t].clone()
+                sd[f"table_v.{t}"] = self.v_by_id[t].clone()
+        return sd
+
+    def load_optimizer_state_dict(self, sd: Dict[str, torch.Tensor]):
+        self.d_step.copy_(sd["step"])
+        self.flat_m.copy_(sd["flat_m"])
+        self.flat_v.copy_(sd["flat_v"])
+        for t in range(L.NRX_MAX_TABLES):
+            if self.m_by_id[t] is not None:
+                self.m_by_id[t].copy_(sd[f"table_m.{t}"])
+                self.v_by_id[t].copy_(sd[f"table_v.{t}"])
 
     def _feed_state(self):
         f = getattr(self, "_feed", None)
         if f is None:
             ev = lambda: [torch.cuda.Event(), torch.cuda.Event()]
             f = dict(copy=torch.cuda.Stream(device=self.dev), stage=[torch.empty_like(self.blob) for _ in range(2)],
-                     loss_host=[torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)],
+                     loss_host=[torch.zeros(2, dtype=torch.float32).pin_memory() for _ in range(2)],
                      ready=ev(), free=ev(), done=ev(), i=0, pending=None)
             for e in f["free"]:
                 e.record(torch.cuda.current_stream(self.dev))

@@ -145,13 +145,19 @@ def test_deepfm_matches_oracle_composition(tmp_path):
             assert _cos(params[k].grad, gr) > 0.97, f"deepfm:{k}: cos {_cos(params[k].grad, gr):.4f}"
 
 
-def test_dcn_too_wide_fails_loudly():
-    """DCN + user_history gives a 2d = 288 wide first layer; the SMEM-resident tower supports <= 240 columns
-    (known gaps).  The product path must raise, never fall back."""
+def test_dcn_wide_first_layer_forward():
+    """DCN + user_history gives a 2d = 288 wide first layer.  The pipelined forward K-streams layer 0, so inference
+    matches the reference's golden probabilities; the backward of a > 240-column first layer is not built yet and must
+    raise, never fall back."""
     from news_recsys_b200._lib import NrxError
     g = load("dcn_hist")
     m = _model("dcn", g["cfg_path"])
     m.load_state_dict(g["sd"], strict=True)
     m = m.to(DEV)
-    with pytest.raises(NrxError, match="widths up to 240"):
-        m({k: v.to(DEV) for k, v in g["batch"].items()})
+    batch = {k: v.to(DEV) for k, v in g["batch"].items()}
+    with torch.no_grad():
+        prob = m(batch)
+    torch.testing.assert_close(prob.cpu(), torch.from_numpy(g["z"]["prob"]), rtol=1e-2, atol=2e-3)
+    prob = m(batch)
+    with pytest.raises(NrxError, match="wider than 240"):
+        m.bceLoss(prob, batch["label"][:, 0]).backward()

@@ -84,15 +84,35 @@ def test_peer_step_equals_allreduce_then_adamw(world, n):
 L_ERR = 130  # NRX_PEER_SIG_ERR
 
 
-def test_missing_peer_times_out_instead_of_hanging():
+def test_missing_peer_is_fatal_and_sticky():
+    """A peer that never arrives: the kernel gives up after the limit (no hang), leaves the parameters untouched, raises
+    the error word on EVERY rank and bit 1 of the host-visible status word; every later launch — on the late rank too —
+    returns at entry, so no rank can pair stale flags with new gradients (peer.cu)."""
     L, p0, ranks, hp, steps = _setup(2, 4096)
     lib = L.load()
-    before = ranks[0]["p"].clone()
-    L.check(lib.nrx_adamw_allreduce_peer(C.byref(steps[0]), L.stream_ptr(torch.device(DEV))), "nrx_adamw_allreduce_peer")
+    status = torch.zeros(2, dtype=torch.int32, device=DEV)
+    for r in range(2):
+        steps[r].timeout_ms = 300
+        steps[r].status = status[r:r + 1].data_ptr()
+    before = [ranks[r]["p"].clone() for r in range(2)]
+    sp = L.stream_ptr(torch.device(DEV))
+    L.check(lib.nrx_adamw_allreduce_peer(C.byref(steps[0]), sp), "nrx_adamw_allreduce_peer")   # rank 1 never launches
     flag = C.c_int32(0)
-    L.check(lib.nrx_peer_status(ranks[0]["sig"].data_ptr(), C.byref(flag), L.stream_ptr(torch.device(DEV))), "nrx_peer_status")
+    L.check(lib.nrx_peer_status(ranks[0]["sig"].data_ptr(), C.byref(flag), sp), "nrx_peer_status")
     assert flag.value == 1
-    assert torch.equal(ranks[0]["p"], before)
+    assert int(status[0].item()) & 2
+    assert int(ranks[1]["sig"][L_ERR].item()) == 1, "the error must be raised on the peer as well"
+    assert torch.equal(ranks[0]["p"], before[0])
+    # the late rank arrives now: it must NOT pass barrier A against rank 0's stale flag and update anything
+    epoch1 = int(ranks[1]["sig"][128].item())
+    L.check(lib.nrx_adamw_allreduce_peer(C.byref(steps[1]), sp), "nrx_adamw_allreduce_peer")
+    L.check(lib.nrx_adamw_allreduce_peer(C.byref(steps[0]), sp), "nrx_adamw_allreduce_peer")
+    torch.cuda.synchronize()
+    assert int(status[1].item()) & 2 and int(status[0].item()) & 2
+    for r in range(2):
+        assert torch.equal(ranks[r]["p"], before[r]), f"rank {r}: a dead exchange must not touch the parameters"
+        assert float(ranks[r]["m"].abs().sum()) == 0.0
+    assert int(ranks[1]["sig"][128].item()) == epoch1
 
 
 def test_peer_step_argument_checks():

@@ -52,7 +52,7 @@ def test_fused_step_matches_oracle(kind, hist, graph):
     # every row id 1 is touched in step 0 only for user_id: exercises the lazy-row rule
     ref_sd, ref_losses = _oracle_steps(kind, sd, cfg, batches, cfg["train_hparams"]["lr"])
     model = model.to(DEV)
-    tr = FusedTrainer(model, B, kind=kind, use_graph=graph)
+    tr = FusedTrainer(model, B, kind=kind, use_graph=graph, table_update="sparse")  # the oracle above is the lazy-row rule
     losses = [float(tr.train_step(b).item()) for b in batches]
     bf16 = kind in ("deep", "deepfm", "widedeep", "dcn")
     for a, b in zip(losses, ref_losses):

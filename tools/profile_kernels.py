@@ -135,6 +135,12 @@ def main():
                 fl = 2 * sum(dims_[i] * dims_[i + 1] for i in range(5)) * B
                 rec(f"K4 tower_fwd inference ({nm})", B, timeit(lambda: ops.tower_fwd(x, ws_, bs_, None, training=False), once=a.once), fl, "tensor")
                 rec(f"K4 tower_fwd training ({nm})", B, timeit(lambda: ops.tower_fwd(x, ws_, bs_, None, training=True), once=a.once), fl, "tensor")
+                for tr_ in (False, True):   # the pipelined kernel alone: weights prepacked, bf16 input image in place
+                    packed = ops.tower_prepack(B, ws_, bs_, None, training=tr_)
+                    ops.tower_image_from_rows(x, ops.tower_input_image(packed, B))
+                    rec(f"K4 tower_fwd3 from image, {'training' if tr_ else 'inference'} ({nm})", B,
+                        timeit(lambda: ops.tower_fwd(None, ws_, bs_, None, training=tr_, packed=packed, ximg_rows=B), once=a.once),
+                        fl, "tensor")
                 y, ctx = ops.tower_fwd(x, ws_, bs_, None, training=True)
                 gy = torch.randn(B, 1, device=DEV)
                 rec(f"K4 tower_bwd dx+dw+reduce ({nm})", B, timeit(lambda: ops.tower_bwd(ctx, gy), once=a.once), 2 * fl, "tensor")
