@@ -368,6 +368,12 @@ int nrx_topk_search(const void* index, const float* corpus, int64_t c_ld, int64_
                     const float* queries, int64_t q_ld, int64_t Q, int k, int64_t id_base,
                     float* out_scores, int64_t* out_ids, int32_t* status, void* ws, size_t ws_bytes,
                     nrx_stream_t stream);
+/* Same search, additionally returning the fp64 ordering keys (out_scores64 [Q, k], nullable): what a merge of per-shard
+ * lists must order by to equal one index bit for bit (two rows may differ by less than one fp32 ulp). */
+int nrx_topk_search64(const void* index, const float* corpus, int64_t c_ld, int64_t N, int D,
+                      const float* queries, int64_t q_ld, int64_t Q, int k, int64_t id_base,
+                      float* out_scores, double* out_scores64, int64_t* out_ids, int32_t* status,
+                      void* ws, size_t ws_bytes, nrx_stream_t stream);
 /* One-shot build + search (index lives in `ws`). */
 size_t nrx_topk_ip_workspace_bytes(int64_t Q, int64_t N, int D, int k);
 int nrx_topk_ip(const float* queries, int64_t q_ld, const float* corpus, int64_t c_ld,
@@ -377,6 +383,9 @@ int nrx_topk_ip(const float* queries, int64_t q_ld, const float* corpus, int64_t
 /* Merge `n_lists` per-shard lists [n_lists][Q][k] into the global top-k. */
 int nrx_topk_merge(const float* scores, const int64_t* ids, int n_lists, int64_t Q, int k,
                    float* out_scores, int64_t* out_ids, nrx_stream_t stream);
+/* Merge of per-shard lists that carry the fp64 ordering keys of nrx_topk_search64. */
+int nrx_topk_merge64(const double* scores64, const int64_t* ids, int n_lists, int64_t Q, int k,
+                     float* out_scores, int64_t* out_ids, nrx_stream_t stream);
 /* Row-wise L2 normalisation (faiss.normalize_L2 / F.normalize, DSSM/model.py:69-71). */
 int nrx_l2_normalize(const float* x, int64_t ld, int64_t n, int d, float* y, int64_t y_ld,
                      nrx_stream_t stream);

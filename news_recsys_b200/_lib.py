@@ -144,6 +144,8 @@ SIGNATURES = {
     "nrx_topk_index_build": (C.c_int, [_P, _I64, _I64, C.c_int, _P, _SZ, _P]),
     "nrx_topk_search_workspace_bytes": (_SZ, [_I64, _I64, C.c_int, C.c_int]),
     "nrx_topk_search": (C.c_int, [_P, _P, _I64, _I64, C.c_int, _P, _I64, _I64, C.c_int, _I64, _P, _P, _P, _P, _SZ, _P]),
+    "nrx_topk_search64": (C.c_int, [_P, _P, _I64, _I64, C.c_int, _P, _I64, _I64, C.c_int, _I64, _P, _P, _P, _P, _P, _SZ, _P]),
+    "nrx_topk_merge64": (C.c_int, [_P, _P, C.c_int, _I64, C.c_int, _P, _P, _P]),
     "nrx_topk_ip_workspace_bytes": (_SZ, [_I64, _I64, C.c_int, C.c_int]),
     "nrx_topk_ip": (C.c_int, [_P, _I64, _P, _I64, _I64, _I64, C.c_int, C.c_int, _I64, _P, _P, _P, _SZ, _P]),
     "nrx_topk_merge": (C.c_int, [_P, _P, C.c_int, _I64, C.c_int, _P, _P, _P]),
@@ -184,7 +186,7 @@ def load() -> C.CDLL:
 KERNELS_PER_CALL = {"nrx_tower_fwd": 3, "nrx_tower_fwd(prepacked)": 2, "nrx_tower_fwd_head": 3, "nrx_tower_fwd_head(prepacked)": 2,
                     "nrx_tower_fwd(prepacked,ximg)": 1, "nrx_tower_fwd_head(prepacked,ximg)": 1, "nrx_tower_bwd": 3, "nrx_tower_bwd_dw": 2, "nrx_embed_bwd_apply": 2, "nrx_embed_bwd_plan": 2, "nrx_adamw_untouched_rows": 2, "nrx_adamw_untouched_rows_scratch_bytes": 0, "nrx_dcn_cross_bwd": 2,
                     "nrx_embed_bwd_apply(dense)": 2, "nrx_embed_bwd_apply(rowopt)": 2, "nrx_topk_ip": 2,
-                    "nrx_topk_search": 5, "nrx_topk_index_build": 1,
+                    "nrx_topk_search": 6, "nrx_topk_search64": 6, "nrx_topk_index_build": 1,
                     "nrx_peer_alloc": 0, "nrx_peer_free": 0, "nrx_peer_export": 0, "nrx_peer_open": 0, "nrx_peer_close": 0,
                     "nrx_peer_status": 0, "nrx_ingest_gather_ids": 0, "nrx_ingest_csr_expand": 0, "nrx_ingest_gather_labels": 0,
                     "nrx_tower_workspace_bytes": 0, "nrx_embed_bwd_workspace_bytes": 0, "nrx_tower_image_layout": 0}

@@ -4,22 +4,27 @@
 // Result contract: for every query the k corpus rows with the largest inner product, ordered by
 // (inner product desc, id asc), where the ordering key is the inner product of the fp32 inputs accumulated in
 // fp64 (so near-ties that an fp32 BLAS would order arbitrarily are pinned); returned scores are that value
-// rounded to fp32; ids are corpus positions + id_base; -1 / -FLT_MAX pad when k > N.
+// rounded to fp32 (optionally also the fp64 value, which is what a sharded merge must order by); ids are corpus
+// positions + id_base; -1 / -FLT_MAX pad when k > N.
 //
 // Fast path (tensor cores) with a proof of completeness per query:
 //   index   : corpus packed once to bf16 128-row tile images in the canonical UMMA layout (+ max row norm);
-//   pass A  : S~ = Q C^T on tcgen05 (bf16 in, fp32 accumulate in TMEM), epilogue keeps only the max of each
-//             128-row group -> gmax[tile][query];
-//   theta   : per query the k'-th largest group max (k' > k).  k' distinct rows score >= theta, so theta is a
-//             lower bound of the k'-th best approximate score;
-//   pass B  : the same GEMM, epilogue appends rows with S~ >= theta to the query's candidate list (a few
-//             hundred rows out of N);
+//   sample  : S~ = Q C^T on tcgen05 over every `stride`-th corpus tile (1/8 of the corpus), epilogue keeps the max of
+//             each 32-row group; theta = the ceil(k'/stride)+8-th largest group max (k' = 2k + 64): an ESTIMATE of the
+//             k'-th best approximate score of the whole corpus — its quality only decides how many candidates pass;
+//   scan    : the same GEMM over the WHOLE corpus, once; the epilogue appends rows with S~ >= theta to the query's
+//             candidate list (a few hundred rows out of N);
 //   final   : candidates re-scored exactly (fp64), sorted by (score desc, id asc).  Every row outside the list
 //             has S~ < theta, hence true score < theta + eps (eps = bf16 rounding bound 2^-7.5 |q| max|c|).
 //             If the k-th exact score is >= theta + eps the list provably contains the true top-k.  Otherwise
-//             (or on list overflow) the query is flagged and served by
-//   fallback: an exact fp64 scan of the whole corpus with a block-level streaming top-k.
-// Tensor-bound for Q >= ~256 (2 N D flops per query per pass), HBM-bound (corpus stream) below.
+//             (too few candidates, or list overflow) the query goes on a device-side list for the
+//   fallback: an exact fp64 scan of the corpus with a block-level streaming top-k, several blocks per listed query
+//             (corpus slices) + a merge; with an empty list its fixed grid exits at once.
+// One CTA scans a corpus slice for up to FOUR 128-query tiles: a corpus tile is loaded once per 512 queries (the L2
+// stream drops 4x), and the issuer interleaves the K-steps of two query tiles so that consecutive tcgen05.mma never
+// accumulate into the same TMEM accumulator (back-to-back dependent MMAs are spaced ~105 cycles apart, two
+// independent chains run at ~72 cycles per 128x128x16 MMA: tools/umma_probe2.cu).
+// Tensor-bound for Q >= ~256 (2 N D flops per query), HBM-bound (corpus stream) below.
 #include <float.h>
 
 #include "common.cuh"
@@ -29,18 +34,26 @@ namespace nrx {
 using namespace umma;
 
 static constexpr int kTR = 128;        // corpus rows per tile == UMMA N; queries per tile == UMMA M
-static constexpr int kCap = 2048;      // candidate list capacity per query
-static constexpr int kScanThreads = 320;  // TMA warp + MMA warp + 8 epilogue warps
+static constexpr int kCap = 4096;      // candidate list capacity per query
+static constexpr int kScanThreads = 64 + 512;  // TMA warp + MMA warp + 16 epilogue warps
+static constexpr int kMaxQT = 4;       // query tiles per CTA (4 x 128 TMEM columns)
 static constexpr int kHdrBytes = 256;
+static constexpr int kScanSmem = 232448 - 2048;
 
 struct TopkGeom {
   long long N, Q, n_tiles, n_qtiles, Qp;
   int D, Dp, k, kprime, stages;
-  long long slices;   // corpus slices per query tile (grid.x of the scan)
-  int cap_s;          // candidate capacity per (query, slice): private region, no atomics
+  int nq;             // query tiles per CTA
+  long long n_qgroups;
+  long long slices;   // corpus slices per query group (grid.x of the scan)
+  int stride;         // the sample pass visits every stride-th corpus tile
+  long long n_stiles; // tiles of the sample pass
+  int kprime_s;       // rank of theta among the sample's group maxima
+  int cap_s;          // candidate capacity per (query, slice, column quarter): private region, no atomics
+  int fb_grid, fb_items;   // fallback: fixed grid, capacity of the (query, corpus slice) work list
   size_t tile_bytes, index_bytes;
   // workspace offsets
-  size_t gmax, theta, eps, count, cand, flag, total;
+  size_t gmax, theta, eps, count, cand, flag, flist, fpart, total;
 };
 
 static int make_geom(long long Q, long long N, int D, int k, TopkGeom* g) {
@@ -56,21 +69,38 @@ static int make_geom(long long Q, long long N, int D, int k, TopkGeom* g) {
   g->kprime = 2 * k + 64;
   g->tile_bytes = (size_t)kTR * g->Dp * 2;
   g->index_bytes = kHdrBytes + (size_t)g->n_tiles * g->tile_bytes;
-  g->stages = g->Dp <= 128 ? 4 : 2;
-  g->slices = g->n_qtiles > 0 ? sm_count() / g->n_qtiles : 1;
+  // query tiles per CTA: as many as fit beside >= 2 corpus stages
+  int nq = (int)(kScanSmem / g->tile_bytes) - 2;
+  if (nq > kMaxQT) nq = kMaxQT;
+  if (nq < 1) nq = 1;
+  if (nq > g->n_qtiles) nq = g->n_qtiles > 0 ? (int)g->n_qtiles : 1;
+  g->nq = nq;
+  g->stages = (int)(kScanSmem / g->tile_bytes) - nq;
+  if (g->stages > 4) g->stages = 4;
+  g->n_qgroups = (g->n_qtiles + nq - 1) / nq;
+  g->slices = g->n_qgroups > 0 ? sm_count() / g->n_qgroups : 1;
   if (g->slices < 1) g->slices = 1;
   if (g->slices > g->n_tiles) g->slices = g->n_tiles > 0 ? g->n_tiles : 1;
-  g->cap_s = (int)(kCap / (2 * g->slices));  // regions are per (query, slice, 64-column half)
-  if (g->cap_s < 16) g->cap_s = 16;
+  g->stride = (int)(g->n_tiles / 128);
+  if (g->stride > 8) g->stride = 8;
+  if (g->stride < 1) g->stride = 1;
+  g->n_stiles = (g->n_tiles + g->stride - 1) / g->stride;
+  g->kprime_s = g->stride == 1 ? g->kprime : (g->kprime + g->stride - 1) / g->stride + 8;
+  g->cap_s = (int)(kCap / (4 * g->slices));
+  if (g->cap_s < 12) g->cap_s = 12;
   if (g->cap_s > 512) g->cap_s = 512;
+  g->fb_grid = 2 * sm_count();
+  g->fb_items = (int)(Q > g->fb_grid ? Q : g->fb_grid);
   auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
   size_t o = 0;
-  g->gmax = o;  o += al((size_t)g->n_tiles * 2 * g->Qp * 4);
+  g->gmax = o;  o += al((size_t)g->n_stiles * 4 * g->Qp * 4);
   g->theta = o; o += al((size_t)g->Qp * 4);
   g->eps = o;   o += al((size_t)g->Qp * 4);
-  g->count = o; o += al((size_t)g->Qp * g->slices * 2 * 4);
+  g->count = o; o += al((size_t)g->Qp * g->slices * 4 * 4);
   g->flag = o;  o += al((size_t)g->Qp * 4);
-  g->cand = o;  o += al((size_t)g->Qp * g->slices * 2 * g->cap_s * 4);
+  g->flist = o; o += al((size_t)(g->Qp + 4) * 4);              // [0] = number of listed queries, then their ids
+  g->fpart = o; o += al((size_t)g->fb_items * k * 12);         // fallback partial lists: fp64 score + u32 id
+  g->cand = o;  o += al((size_t)g->Qp * g->slices * 4 * g->cap_s * 4);
   g->total = o;
   return NRX_OK;
 }
@@ -108,42 +138,46 @@ topk_pack_kernel(const float* __restrict__ c, long long ld, long long N, int D, 
   if (lane == 0 && m > 0.f) atomicMax(max_norm_bits, __float_as_uint(sqrtf(m) * 1.0001f));
 }
 
-// ---- the scan (pass A: MODE 0 group maxima, pass B: MODE 1 candidate filter) -------------------------------
+// ---- the scan (MODE 0: group maxima of the sample tiles, MODE 1: candidate filter over every tile) ------------
 template <int MODE>
 __global__ void __launch_bounds__(kScanThreads, 1)
-topk_scan_kernel(const uint8_t* __restrict__ img, long long N, long long n_tiles, int Dp, const float* __restrict__ q,
-                 long long qld, long long Q, int D, long long Qp, int stages, float* __restrict__ gmax,
-                 const float* __restrict__ theta, unsigned* __restrict__ count, unsigned* __restrict__ cand, int cap_s) {
+topk_scan_kernel(const uint8_t* __restrict__ img, long long N, long long n_tiles, int tstride, int Dp, const float* __restrict__ q,
+                 long long qld, long long Q, int D, long long Qp, int nq_max, int stages, float* __restrict__ gmax,
+                 long long n_groups, const float* __restrict__ theta, unsigned* __restrict__ count, unsigned* __restrict__ cand,
+                 int cap_s) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const size_t tile_bytes = (size_t)kTR * Dp * 2;
-  uint8_t* sQ = smem;
-  uint8_t* sC = smem + tile_bytes;
-  __shared__ uint64_t full[4], empty[4], tfull[2], tempty[2];
+  uint8_t* sQ = smem;                                  // [nq][tile image]
+  uint8_t* sC = smem + (size_t)nq_max * tile_bytes;    // [stages][tile image]
+  __shared__ uint64_t full[4], empty[4], tfull[kMaxQT], tempty[kMaxQT];
   __shared__ uint32_t tmem_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const long long q0 = (long long)blockIdx.y * kTR;
-  // corpus slice of this CTA
-  const long long per = (n_tiles + gridDim.x - 1) / gridDim.x;
+  const long long qt0 = (long long)blockIdx.y * nq_max;             // first query tile of this CTA
+  const long long n_qtiles = Qp / kTR;
+  const int nq = (int)(n_qtiles - qt0 < nq_max ? n_qtiles - qt0 : nq_max);
+  // corpus slice of this CTA, in units of visited tiles (tile = visited index * tstride)
+  const long long n_vis = (n_tiles + tstride - 1) / tstride;
+  const long long per = (n_vis + gridDim.x - 1) / gridDim.x;
   const long long t0 = (long long)blockIdx.x * per;
-  const long long t1 = min(t0 + per, n_tiles);
+  const long long t1 = min(t0 + per, n_vis);
 
   if (tid == 0) {
     for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 256); }
+    for (int a = 0; a < kMaxQT; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 16); }
     fence_mbar_init();
   }
-  if (warp == 0) tmem_alloc(&tmem_s, 256u);
-  // query tile: fp32 -> bf16 canonical (rows >= Q are zero)
-  for (int i = tid; i < (Dp / 8) * kTR; i += kScanThreads) {
-    const int r = i % kTR, kc = i / kTR;
-    const long long row = q0 + r;
+  if (warp == 0) tmem_alloc(&tmem_s, 512u);
+  // query tiles: fp32 -> bf16 canonical (rows >= Q are zero)
+  for (int i = tid; i < nq * (Dp / 8) * kTR; i += kScanThreads) {
+    const int r = i % kTR, kc = (i / kTR) % (Dp / 8), a = i / (kTR * (Dp / 8));
+    const long long row = (qt0 + a) * kTR + r;
     float f[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int d = kc * 8 + j;
       f[j] = (row < Q && d < D) ? __ldg(q + row * qld + d) : 0.f;
     }
-    *reinterpret_cast<uint4*>(sQ + canon_off(kTR, r, kc)) =
+    *reinterpret_cast<uint4*>(sQ + (size_t)a * tile_bytes + canon_off(kTR, r, kc)) =
         make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
   }
   fence_async_smem();
@@ -155,99 +189,125 @@ topk_scan_kernel(const uint8_t* __restrict__ img, long long N, long long n_tiles
   if (t1 > t0) {
     if (warp == 0) {
       if (lane == 0) {  // TMA producer
-        uint32_t ph[4] = {0, 0, 0, 0};
-        bool used[4] = {false, false, false, false};
+        uint32_t ph = 0, used = 0;
         int s = 0;
         for (long long t = t0; t < t1; ++t) {
-          if (used[s]) { mbar_wait(&empty[s], ph[s]); ph[s] ^= 1; }
-          used[s] = true;
+          if (used & (1u << s)) { mbar_wait(&empty[s], (ph >> s) & 1u); ph ^= 1u << s; }
+          used |= 1u << s;
           mbar_expect_tx(&full[s], (uint32_t)tile_bytes);
-          bulk_g2s(sC + (size_t)s * tile_bytes, img + (size_t)t * tile_bytes, (uint32_t)tile_bytes, &full[s]);
+          bulk_g2s(sC + (size_t)s * tile_bytes, img + (size_t)(t * tstride) * tile_bytes, (uint32_t)tile_bytes, &full[s]);
           s = (s + 1 == stages) ? 0 : s + 1;
         }
       }
     } else if (warp == 1) {
-      if (lane == 0) {  // MMA issuer
-        const uint32_t idesc = make_idesc_bf16(kTR, kTR);
-        uint32_t fph[4] = {0, 0, 0, 0}, eph[2] = {0, 0};
-        bool aused[2] = {false, false};
-        int s = 0, a = 0;
-        for (long long t = t0; t < t1; ++t) {
-          mbar_wait(&full[s], fph[s]); fph[s] ^= 1;
-          if (aused[a]) { mbar_wait(&tempty[a], eph[a]); eph[a] ^= 1; }
-          aused[a] = true;
-          tc_fence_after();
-          const uint32_t cb = smem_u32(sC + (size_t)s * tile_bytes);
-          for (int k16 = 0; k16 < Dp / 16; ++k16) {
-            const uint64_t ad = make_smem_desc(smem_u32(sQ) + (uint32_t)k16 * 2u * (kTR * 16u), kTR * 16u, 128u);
-            const uint64_t bd = make_smem_desc(cb + (uint32_t)k16 * 2u * (kTR * 16u), kTR * 16u, 128u);
-            mma_bf16_ss(tmem + (uint32_t)a * kTR, ad, bd, idesc, k16 > 0);
-          }
-          mma_commit(&empty[s]);
-          mma_commit(&tfull[a]);
-          s = (s + 1 == stages) ? 0 : s + 1;
-          a ^= 1;
-        }
-      }
-    } else {  // epilogue: 8 warps = 2 per TMEM lane quadrant; thread == (query row, 64-column half of the tile)
-      const int qd = warp & 3;
-      const int half = (warp - 2) >> 2;
-      const int r = qd * 32 + lane;
-      const long long qrow = q0 + r;
-      uint32_t tph[2] = {0, 0};
-      float th = 0.f;
-      if (MODE == 1) th = __ldg(theta + qrow);  // theta is allocated for Qp rows
-      // this thread is the only writer of its (query, slice, half) candidate region: plain stores, register counter
-      unsigned mycnt = 0;
-      const size_t region = ((size_t)qrow * gridDim.x + blockIdx.x) * 2 + half;
-      unsigned* mycand = (MODE == 1) ? cand + region * cap_s : nullptr;
-      int a = 0;
+      // MMA issuer: the whole warp walks the loop in uniform control flow, one elected lane issues (umma.cuh).
+      // Query tiles are issued in pairs whose K-steps alternate between the two accumulators.
+      const uint32_t leader = elect_one_sync() ? 1u : 0u;
+      const uint32_t idesc = make_idesc_bf16(kTR, kTR);
+      uint32_t fph = 0, eph = 0, aused = 0;
+      int s = 0;
+      const uint32_t kstep = (2u * (kTR * 16u)) >> 4;
+      const uint32_t qstep = (uint32_t)(tile_bytes >> 4);
+      const uint64_t qd0 = make_smem_desc(smem_u32(sQ), kTR * 16u, 128u);
       for (long long t = t0; t < t1; ++t) {
-        mbar_wait(&tfull[a], tph[a]); tph[a] ^= 1;
-        tc_fence_after();
-        const long long base = t * kTR + half * 64;
-        const bool tail = base + 64 > N;
-        float v[64];
-        {  // both TMEM loads in flight before the single wait
-          float (&v0)[32] = *reinterpret_cast<float(*)[32]>(&v[0]);
-          float (&v1)[32] = *reinterpret_cast<float(*)[32]>(&v[32]);
-          const uint32_t ta = tmem + ((uint32_t)(qd * 32) << 16) + (uint32_t)(a * kTR + half * 64);
-          tmem_ld32(ta, v0);
-          tmem_ld32(ta + 32u, v1);
-          tmem_ld_wait();
+        mbar_wait(&full[s], (fph >> s) & 1u); fph ^= 1u << s;
+        const uint64_t cd0 = make_smem_desc(smem_u32(sC + (size_t)s * tile_bytes), kTR * 16u, 128u);
+        for (int a0 = 0; a0 < nq; a0 += 2) {
+          const bool two = a0 + 1 < nq;
+          if (aused & (1u << a0)) { mbar_wait(&tempty[a0], (eph >> a0) & 1u); eph ^= 1u << a0; }
+          if (two && (aused & (2u << a0))) { mbar_wait(&tempty[a0 + 1], (eph >> (a0 + 1)) & 1u); eph ^= 2u << a0; }
+          aused |= (two ? 3u : 1u) << a0;
+          tc_fence_after();
+          uint64_t ad = qd0 + (uint64_t)a0 * qstep, bd = cd0;
+          uint32_t accum = 0u;
+          const uint32_t acc0 = tmem + (uint32_t)a0 * kTR;
+          if (two) {
+#pragma unroll 2
+            for (int k16 = 0; k16 < Dp / 16; ++k16) {
+              mma_bf16_ss_if(leader, acc0, ad, bd, idesc, accum);
+              mma_bf16_ss_if(leader, acc0 + kTR, ad + qstep, bd, idesc, accum);
+              ad += kstep; bd += kstep; accum = 1u;
+            }
+            mma_commit_if(leader, &tfull[a0]);
+            mma_commit_if(leader, &tfull[a0 + 1]);
+          } else {
+#pragma unroll 2
+            for (int k16 = 0; k16 < Dp / 16; ++k16) {
+              mma_bf16_ss_if(leader, acc0, ad, bd, idesc, accum);
+              ad += kstep; bd += kstep; accum = 1u;
+            }
+            mma_commit_if(leader, &tfull[a0]);
+          }
         }
-        tc_fence_before();
-        mbar_arrive(&tempty[a]);  // values are in registers: hand the accumulator back before the scan
-        if (tail) {
+        mma_commit_if(leader, &empty[s]);
+        __syncwarp();
+        s = (s + 1 == stages) ? 0 : s + 1;
+      }
+    } else {  // epilogue: 16 warps = (TMEM lane quadrant, 32-column quarter of the tile); thread == query row
+      const int qd = warp & 3;
+      const int cq = (warp - 2) >> 2;
+      const int r = qd * 32 + lane;
+      uint32_t tph = 0;
+      float th[kMaxQT];
+      unsigned mycnt[kMaxQT];
 #pragma unroll
-          for (int j = 0; j < 64; ++j)
-            if (base + j >= N) v[j] = __int_as_float(0xff800000);  // -inf: never admitted, even by theta = -FLT_MAX
-        }
-        float m4[4] = {v[0], v[1], v[2], v[3]};  // four independent max chains
+      for (int a = 0; a < kMaxQT; ++a) {
+        mycnt[a] = 0;
+        th[a] = (MODE == 1 && a < nq) ? __ldg(theta + (qt0 + a) * kTR + r) : 0.f;   // theta is allocated for Qp rows
+      }
+      for (long long t = t0; t < t1; ++t) {
+        const long long base = (t * tstride) * kTR + cq * 32;
+        const bool tail = base + 32 > N;
 #pragma unroll
-        for (int j = 4; j < 64; ++j) m4[j & 3] = fmaxf(m4[j & 3], v[j]);
-        const float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-        if (MODE == 0) {
-          gmax[(qrow * n_tiles + t) * 2 + half] = m;   // groups of 64 corpus rows
-        } else if (m >= th) {  // rare: a few hundred rows out of N pass the threshold
+        for (int a = 0; a < kMaxQT; ++a) {
+          if (a < nq) {
+            mbar_wait(&tfull[a], (tph >> a) & 1u); tph ^= 1u << a;
+            tc_fence_after();
+            float v[32];
+            tmem_ld32(tmem + ((uint32_t)(qd * 32) << 16) + (uint32_t)(a * kTR + cq * 32), v);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[a]);  // values are in registers: hand the accumulator back before the scan
+            if (tail) {
 #pragma unroll
-          for (int j = 0; j < 64; ++j) {
-            if (v[j] >= th) {
-              if (mycnt < (unsigned)cap_s) mycand[mycnt] = (unsigned)(base + j);
-              ++mycnt;
+              for (int j = 0; j < 32; ++j)
+                if (base + j >= N) v[j] = __int_as_float(0xff800000);  // -inf: never admitted, even by theta = -FLT_MAX
+            }
+            float m4[4] = {v[0], v[1], v[2], v[3]};  // four independent max chains
+#pragma unroll
+            for (int j = 4; j < 32; ++j) m4[j & 3] = fmaxf(m4[j & 3], v[j]);
+            const float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+            const long long qrow = (qt0 + a) * kTR + r;
+            if (MODE == 0) {
+              gmax[qrow * n_groups + t * 4 + cq] = m;   // groups of 32 corpus rows
+            } else if (m >= th[a]) {  // rare: a few hundred rows out of N pass the threshold
+              // this thread is the only writer of its (query, slice, quarter) region: plain stores, register counter
+              unsigned* mycand = cand + (((size_t)qrow * gridDim.x + blockIdx.x) * 4 + cq) * cap_s;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                if (v[j] >= th[a]) {
+                  if (mycnt[a] < (unsigned)cap_s) mycand[mycnt[a]] = (unsigned)(base + j);
+                  ++mycnt[a];
+                }
+              }
             }
           }
         }
-        a ^= 1;
       }
-      if (MODE == 1) count[region] = mycnt;
+      if (MODE == 1) {
+#pragma unroll
+        for (int a = 0; a < kMaxQT; ++a)
+          if (a < nq) count[(((size_t)((qt0 + a) * kTR + r)) * gridDim.x + blockIdx.x) * 4 + cq] = mycnt[a];
+      }
     }
   } else if (MODE == 1 && warp >= 2) {  // slice without tiles
-    count[((size_t)(q0 + (warp & 3) * 32 + lane) * gridDim.x + blockIdx.x) * 2 + ((warp - 2) >> 2)] = 0;
+    for (int a = 0; a < nq; ++a)
+      count[(((size_t)((qt0 + a) * kTR + (warp & 3) * 32 + lane)) * gridDim.x + blockIdx.x) * 4 + ((warp - 2) >> 2)] = 0;
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, 256u);
+  if (warp == 0) tmem_dealloc(tmem, 512u);
 }
 
 // ---- theta: k'-th largest group max per query (radix select on order-preserving uint keys) ------------------
@@ -255,15 +315,16 @@ __device__ __forceinline__ unsigned f2key(float f) { unsigned u = __float_as_uin
 __device__ __forceinline__ float key2f(unsigned k) { return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k); }
 
 __global__ void __launch_bounds__(256)
-topk_theta_kernel(const float* __restrict__ gmax, long long n_tiles, long long Qp, long long Q, int kprime,
+topk_theta_kernel(const float* __restrict__ gmax, long long n_tiles /* groups per query */, long long Qp, long long Q, int kprime,
                   const float* __restrict__ q, long long qld, int D, const unsigned* __restrict__ max_norm_bits,
-                  float* __restrict__ theta, float* __restrict__ eps, unsigned* __restrict__ count, int* __restrict__ flag) {
+                  float* __restrict__ theta, float* __restrict__ eps, unsigned* __restrict__ flist, int* __restrict__ flag) {
   __shared__ unsigned hist[256];
   __shared__ unsigned s_prefix, s_remaining;
   __shared__ float s_norm[8];
   const long long qi = blockIdx.x;
   const int tid = threadIdx.x;
   if (tid == 0) flag[qi] = 0;
+  if (qi == 0 && tid == 0) flist[0] = 0u;   // the fallback list of this search starts empty
   if (qi >= Q) { if (tid == 0) { theta[qi] = FLT_MAX; eps[qi] = 0.f; } return; }
   // |q|
   float ss = 0.f;
@@ -347,42 +408,58 @@ __device__ void bitonic_sort(double* s, unsigned* id, int n, int tid, int nthrea
   }
 }
 
+__device__ __forceinline__ void flag_query(long long qi, int* flag, unsigned* flist) {
+  flag[qi] = 1;
+  flist[1 + atomicAdd(flist, 1u)] = (unsigned)qi;
+}
+
 __global__ void __launch_bounds__(256)
 topk_final_kernel(const float* __restrict__ c, long long cld, long long N, int D, const float* __restrict__ q, long long qld,
                   int k, long long id_base, const float* __restrict__ theta, const float* __restrict__ eps,
                   const unsigned* __restrict__ count, const unsigned* __restrict__ cand, int n_slices, int cap_s,
-                  int* __restrict__ flag, float* __restrict__ out_s, long long* __restrict__ out_i) {
+                  int* __restrict__ flag, unsigned* __restrict__ flist, float* __restrict__ out_s, double* __restrict__ out_s64,
+                  long long* __restrict__ out_i) {
   extern __shared__ __align__(16) uint8_t sm_raw[];
   double* s = reinterpret_cast<double*>(sm_raw);              // [kCap]
   unsigned* id = reinterpret_cast<unsigned*>(s + kCap);       // [kCap]
   float* qs = reinterpret_cast<float*>(id + kCap);            // [D]
+  unsigned* s_off = reinterpret_cast<unsigned*>(qs + ((D + 3) & ~3));   // [n_slices]
   const long long qi = blockIdx.x;
   const int tid = threadIdx.x;
-  __shared__ unsigned s_off[320];
-  __shared__ unsigned s_total, s_over;
+  __shared__ unsigned s_total, s_over, s_warp[8];
   const long long kk = k < N ? k : N;
-  if (tid == 0) {  // exclusive scan of the per-slice counts (n_slices <= SM count)
-    unsigned tot = 0, over = 0;
-    for (int sl = 0; sl < n_slices; ++sl) {
-      const unsigned cs = count[qi * n_slices + sl];
-      if (cs > (unsigned)cap_s) over = 1;
-      s_off[sl] = tot;
-      tot += cs < (unsigned)cap_s ? cs : (unsigned)cap_s;
-    }
-    s_total = tot;
-    s_over = over;
+  // exclusive scan of the per-region counts (n_slices = corpus slices x 4 column quarters)
+  unsigned over = 0, run = 0;
+  for (int b0 = 0; b0 < n_slices; b0 += 256) {
+    const int sl = b0 + tid;
+    unsigned cs = sl < n_slices ? count[qi * n_slices + sl] : 0u;
+    if (cs > (unsigned)cap_s) { over = 1; cs = (unsigned)cap_s; }
+    unsigned inc = cs;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(NRX_FULL_MASK, inc, o); if ((tid & 31) >= o) inc += t; }
+    if ((tid & 31) == 31) s_warp[tid >> 5] = inc;
+    __syncthreads();
+    unsigned wbase = 0;
+    for (int w = 0; w < (tid >> 5); ++w) wbase += s_warp[w];
+    if (sl < n_slices) s_off[sl] = run + wbase + inc - cs;
+    unsigned tot = 0;
+    for (int w = 0; w < 8; ++w) tot += s_warp[w];
+    run += tot;
+    __syncthreads();
   }
+  over = __syncthreads_or(over);
+  if (tid == 0) { s_total = run; s_over = over; }
   for (int d = tid; d < D; d += 256) qs[d] = __ldg(q + qi * qld + d);
   __syncthreads();
   const unsigned cnt = s_total;
   if (s_over || cnt > (unsigned)kCap || (long long)cnt < kk) {
-    if (tid == 0) flag[qi] = 1;
+    if (tid == 0) flag_query(qi, flag, flist);
     return;
   }
   int n2 = 1;
   while (n2 < (int)cnt) n2 <<= 1;
   for (int i = (int)cnt + tid; i < n2; i += 256) { id[i] = 0xffffffffu; s[i] = -DBL_MAX; }
-  for (unsigned i = tid; i < cnt; i += 256) {  // all candidates in flight together: slice by binary search
+  for (unsigned i = tid; i < cnt; i += 256) {  // all candidates in flight together: region by binary search
     int lo = 0, hi = n_slices - 1;
     while (lo < hi) {
       const int mid = (lo + hi + 1) >> 1;
@@ -397,77 +474,149 @@ topk_final_kernel(const float* __restrict__ c, long long cld, long long N, int D
   // completeness proof: every row outside the list scores < theta + eps
   const bool ok = (theta[qi] == -FLT_MAX) || (kk == 0) || (s[kk - 1] >= (double)theta[qi] + (double)eps[qi]);
   if (!ok) {
-    if (tid == 0) flag[qi] = 1;
+    if (tid == 0) flag_query(qi, flag, flist);
     return;
   }
   for (int i = tid; i < k; i += 256) {
-    if (i < kk) { out_s[qi * k + i] = (float)s[i]; out_i[qi * k + i] = (long long)id[i] + id_base; }
-    else { out_s[qi * k + i] = -FLT_MAX; out_i[qi * k + i] = -1; }
+    if (i < kk) {
+      out_s[qi * k + i] = (float)s[i];
+      if (out_s64) out_s64[qi * k + i] = s[i];
+      out_i[qi * k + i] = (long long)id[i] + id_base;
+    } else {
+      out_s[qi * k + i] = -FLT_MAX;
+      if (out_s64) out_s64[qi * k + i] = -DBL_MAX;
+      out_i[qi * k + i] = -1;
+    }
   }
 }
 
-// Exact fallback: fp64 scan of the whole corpus, block-level streaming top-k (buffer + periodic bitonic prune).
+// Exact fallback: fp64 scan with a block-level streaming top-k (buffer + periodic bitonic prune).  Fixed grid; the work
+// list is (listed query, corpus slice): S = grid / n_listed slices per query (>= 1), every item leaves its slice's top-k
+// (fp64 score, row) in `part`; topk_exact_merge_kernel combines a query's S lists.  An empty list costs two empty launches.
 static constexpr int kFbCap = 2048;
+__host__ __device__ __forceinline__ int fb_max_slices(int k) { const int m = 4096 / k; return m < 1 ? 1 : (m > 64 ? 64 : m); }
+__device__ __forceinline__ int fb_slices(unsigned n_listed, int grid, int max_items, int k) {
+  if (n_listed == 0) return 1;
+  long long S = grid / (long long)n_listed;
+  if (S < 1) S = 1;
+  if (S > fb_max_slices(k)) S = fb_max_slices(k);
+  while (S > 1 && S * n_listed > (unsigned)max_items) --S;
+  return (int)S;
+}
+
 __global__ void __launch_bounds__(256)
 topk_exact_kernel(const float* __restrict__ c, long long cld, long long N, int D, const float* __restrict__ q, long long qld,
-                  int k, long long id_base, const int* __restrict__ flag, int force, float* __restrict__ out_s,
-                  long long* __restrict__ out_i, int* __restrict__ status) {
+                  int k, const unsigned* __restrict__ flist, int force_Q, int max_items, double* __restrict__ part_s,
+                  unsigned* __restrict__ part_i) {
   extern __shared__ __align__(16) uint8_t sm_raw[];
   double* s = reinterpret_cast<double*>(sm_raw);
   unsigned* id = reinterpret_cast<unsigned*>(s + kFbCap);
   float* qs = reinterpret_cast<float*>(id + kFbCap);
   __shared__ unsigned s_cnt;
   __shared__ double s_th;
-  const long long qi = blockIdx.x;
   const int tid = threadIdx.x;
-  const bool mine = force || flag[qi] != 0;
-  if (status != nullptr && tid == 0) status[qi] = mine && !force ? 1 : 0;
-  if (!mine) return;
-  for (int d = tid; d < D; d += 256) qs[d] = __ldg(q + qi * qld + d);
-  if (tid == 0) { s_cnt = 0; s_th = -DBL_MAX; }
-  __syncthreads();
+  const unsigned n_listed = force_Q > 0 ? (unsigned)force_Q : flist[0];
+  if (n_listed == 0) return;
+  const int S = fb_slices(n_listed, gridDim.x, max_items, k);
+  const long long n_items = (long long)n_listed * S;
   const long long kk = k < N ? k : N;
-  for (long long r0 = 0; r0 < N; r0 += 256) {
-    const long long row = r0 + tid;
-    if (row < N) {
-      const double v = dot64(qs, c + row * cld, D);
-      if (v >= s_th) {
-        const unsigned slot = atomicAdd(&s_cnt, 1u);
-        s[slot] = v;           // slot < kFbCap: pruned whenever fewer than 256 free slots remain
-        id[slot] = (unsigned)row;
+  for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const long long qi = force_Q > 0 ? item / S : (long long)flist[1 + item / S];
+    const int sl = (int)(item % S);
+    const long long r_lo = N * sl / S, r_hi = N * (sl + 1) / S;
+    __syncthreads();
+    for (int d = tid; d < D; d += 256) qs[d] = __ldg(q + qi * qld + d);
+    if (tid == 0) { s_cnt = 0; s_th = -DBL_MAX; }
+    __syncthreads();
+    for (long long r0 = r_lo; r0 < r_hi; r0 += 256) {
+      const long long row = r0 + tid;
+      if (row < r_hi) {
+        const double v = dot64(qs, c + row * cld, D);
+        if (v >= s_th) {
+          const unsigned slot = atomicAdd(&s_cnt, 1u);
+          s[slot] = v;           // slot < kFbCap: pruned whenever fewer than 256 free slots remain
+          id[slot] = (unsigned)row;
+        }
+      }
+      __syncthreads();
+      if (s_cnt > (unsigned)(kFbCap - 256) || r0 + 256 >= r_hi) {
+        const unsigned cnt = s_cnt;
+        for (int i = tid; i < kFbCap; i += 256)
+          if (i >= (int)cnt) { s[i] = -DBL_MAX; id[i] = 0xffffffffu; }
+        __syncthreads();
+        bitonic_sort(s, id, kFbCap, tid, 256);
+        if (tid == 0) {
+          const unsigned keep = cnt < (unsigned)kk ? cnt : (unsigned)kk;
+          s_cnt = keep;
+          s_th = (keep == (unsigned)kk && kk > 0) ? s[kk - 1] : -DBL_MAX;
+        }
+        __syncthreads();
       }
     }
-    __syncthreads();
-    if (s_cnt > (unsigned)(kFbCap - 256) || r0 + 256 >= N) {
-      const unsigned cnt = s_cnt;
-      for (int i = tid; i < kFbCap; i += 256)
-        if (i >= (int)cnt) { s[i] = -DBL_MAX; id[i] = 0xffffffffu; }
+    if (r_hi <= r_lo) {   // empty slice
+      for (int i = tid; i < kFbCap; i += 256) { s[i] = -DBL_MAX; id[i] = 0xffffffffu; }
       __syncthreads();
-      bitonic_sort(s, id, kFbCap, tid, 256);
-      if (tid == 0) {
-        const unsigned keep = cnt < (unsigned)kk ? cnt : (unsigned)kk;
-        s_cnt = keep;
-        s_th = (keep == (unsigned)kk && kk > 0) ? s[kk - 1] : -DBL_MAX;
-      }
-      __syncthreads();
+    }
+    for (int i = tid; i < k; i += 256) {
+      part_s[item * k + i] = s[i];         // sorted; entries past the slice's row count are (-DBL_MAX, 0xffffffff)
+      part_i[item * k + i] = id[i];
     }
   }
-  for (int i = tid; i < k; i += 256) {
-    if (i < kk) { out_s[qi * k + i] = (float)s[i]; out_i[qi * k + i] = (long long)id[i] + id_base; }
-    else { out_s[qi * k + i] = -FLT_MAX; out_i[qi * k + i] = -1; }
+}
+
+__global__ void __launch_bounds__(256)
+topk_exact_merge_kernel(long long N, int k, long long id_base, const unsigned* __restrict__ flist, int force_Q, int exact_grid,
+                        int max_items, const double* __restrict__ part_s, const unsigned* __restrict__ part_i,
+                        float* __restrict__ out_s, double* __restrict__ out_s64, long long* __restrict__ out_i,
+                        int* __restrict__ status) {
+  extern __shared__ __align__(16) uint8_t sm_raw[];
+  const int tid = threadIdx.x;
+  const unsigned n_listed = force_Q > 0 ? (unsigned)force_Q : flist[0];
+  if (n_listed == 0) return;
+  const int S = fb_slices(n_listed, exact_grid, max_items, k);
+  int n2 = 1;
+  while (n2 < S * k) n2 <<= 1;
+  double* s = reinterpret_cast<double*>(sm_raw);          // [n2]
+  unsigned* id = reinterpret_cast<unsigned*>(s + n2);     // [n2]
+  const long long kk = k < N ? k : N;
+  for (long long e = blockIdx.x; e < n_listed; e += gridDim.x) {
+    const long long qi = force_Q > 0 ? e : (long long)flist[1 + e];
+    __syncthreads();
+    for (int i = tid; i < n2; i += 256) {
+      if (i < S * k) { s[i] = part_s[e * S * k + i]; id[i] = part_i[e * S * k + i]; }
+      else { s[i] = -DBL_MAX; id[i] = 0xffffffffu; }
+    }
+    __syncthreads();
+    if (S > 1) bitonic_sort(s, id, n2, tid, 256);
+    for (int i = tid; i < k; i += 256) {
+      if (i < kk) {
+        out_s[qi * k + i] = (float)s[i];
+        if (out_s64) out_s64[qi * k + i] = s[i];
+        out_i[qi * k + i] = (long long)id[i] + id_base;
+      } else {
+        out_s[qi * k + i] = -FLT_MAX;
+        if (out_s64) out_s64[qi * k + i] = -DBL_MAX;
+        out_i[qi * k + i] = -1;
+      }
+    }
+    if (status != nullptr && tid == 0 && force_Q == 0) status[qi] = 1;
   }
 }
 
 // ---- merge of per-shard lists ([n_lists][Q][k]) ----------------------------------------------------------------
+// ST = float: lists carry fp32-rounded scores (two rows whose fp64 scores differ by less than one fp32 ulp then
+// merge in id order); ST = double: the per-shard fp64 ordering keys, the merge equals one index bit for bit.
+template <typename ST>
 __global__ void __launch_bounds__(256)
-topk_merge_kernel(const float* __restrict__ sc, const long long* __restrict__ ids, int n_lists, long long Q, int k,
+topk_merge_kernel(const ST* __restrict__ sc, const long long* __restrict__ ids, int n_lists, long long Q, int k,
                   float* __restrict__ out_s, long long* __restrict__ out_i) {
   extern __shared__ __align__(16) uint8_t sm_raw[];
   const int total = n_lists * k;
   int n2 = 1;
   while (n2 < total) n2 <<= 1;
-  float* s = reinterpret_cast<float*>(sm_raw);
-  long long* id = reinterpret_cast<long long*>(s + n2 + (n2 & 1));
+  long long* id = reinterpret_cast<long long*>(sm_raw);
+  ST* s = reinterpret_cast<ST*>(id + n2);
+  const ST lowest = (ST)(sizeof(ST) == 8 ? -DBL_MAX : -FLT_MAX);
   const long long qi = blockIdx.x;
   const int tid = threadIdx.x;
   for (int i = tid; i < n2; i += 256) {
@@ -475,8 +624,8 @@ topk_merge_kernel(const float* __restrict__ sc, const long long* __restrict__ id
       const int l = i / k, j = i % k;
       s[i] = sc[((long long)l * Q + qi) * k + j];
       id[i] = ids[((long long)l * Q + qi) * k + j];
-      if (id[i] < 0) { s[i] = -FLT_MAX; id[i] = 0x7fffffffffffffffll; }
-    } else { s[i] = -FLT_MAX; id[i] = 0x7fffffffffffffffll; }
+      if (id[i] < 0) { s[i] = lowest; id[i] = 0x7fffffffffffffffll; }
+    } else { s[i] = lowest; id[i] = 0x7fffffffffffffffll; }
   }
   __syncthreads();
   for (int k2 = 2; k2 <= n2; k2 <<= 1)
@@ -488,7 +637,7 @@ topk_merge_kernel(const float* __restrict__ sc, const long long* __restrict__ id
           const bool a_first = s[p] > s[i] || (s[p] == s[i] && id[p] < id[i]);   // p before i
           const bool b_first = s[i] > s[p] || (s[i] == s[p] && id[i] < id[p]);
           if (up ? a_first : b_first) {
-            const float ts = s[i]; s[i] = s[p]; s[p] = ts;
+            const ST ts = s[i]; s[i] = s[p]; s[p] = ts;
             const long long ti = id[i]; id[i] = id[p]; id[p] = ti;
           }
         }
@@ -497,7 +646,7 @@ topk_merge_kernel(const float* __restrict__ sc, const long long* __restrict__ id
     }
   for (int i = tid; i < k; i += 256) {
     const bool pad = i >= total || id[i] == 0x7fffffffffffffffll;
-    out_s[qi * k + i] = pad ? -FLT_MAX : s[i];
+    out_s[qi * k + i] = pad ? -FLT_MAX : (float)s[i];
     out_i[qi * k + i] = pad ? -1 : id[i];
   }
 }
@@ -533,9 +682,9 @@ extern "C" size_t nrx_topk_search_workspace_bytes(int64_t Q, int64_t N, int D, i
   return g.total;
 }
 
-extern "C" int nrx_topk_search(const void* index, const float* corpus, int64_t c_ld, int64_t N, int D, const float* queries,
-                               int64_t q_ld, int64_t Q, int k, int64_t id_base, float* out_scores, int64_t* out_ids,
-                               int32_t* status, void* ws, size_t ws_bytes, nrx_stream_t stream) {
+extern "C" int nrx_topk_search64(const void* index, const float* corpus, int64_t c_ld, int64_t N, int D, const float* queries,
+                                 int64_t q_ld, int64_t Q, int k, int64_t id_base, float* out_scores, double* out_scores64,
+                                 int64_t* out_ids, int32_t* status, void* ws, size_t ws_bytes, nrx_stream_t stream) {
   TopkGeom g;
   int rc = make_geom(Q, N, D, k, &g);
   if (rc != NRX_OK) return rc;
@@ -551,40 +700,65 @@ extern "C" int nrx_topk_search(const void* index, const float* corpus, int64_t c
   float* eps = (float*)(w + g.eps);
   unsigned* count = (unsigned*)(w + g.count);
   int* flag = (int*)(w + g.flag);
+  unsigned* flist = (unsigned*)(w + g.flist);
+  double* part_s = (double*)(w + g.fpart);
+  unsigned* part_i = (unsigned*)(w + g.fpart + (size_t)g.fb_items * k * 8);
   unsigned* cand = (unsigned*)(w + g.cand);
   const uint8_t* img = (const uint8_t*)index + kHdrBytes;
+  if (status != nullptr) {
+    cudaError_t e = cudaMemsetAsync(status, 0, (size_t)Q * sizeof(int32_t), st);
+    NRX_REQUIRE(e == cudaSuccess, NRX_ELAUNCH, "memset: %s", cudaGetErrorString(e));
+  }
   const size_t fb_smem = (size_t)kFbCap * 12 + (size_t)D * 4;
   const bool fast = g.n_tiles >= 4;  // tiny corpora go straight to the exact kernel
   if (fast) {
-    const size_t smem = (size_t)(1 + g.stages) * g.tile_bytes;
+    const size_t smem = (size_t)(g.nq + g.stages) * g.tile_bytes;
     cudaFuncSetAttribute(topk_scan_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(topk_scan_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    NRX_REQUIRE(g.slices <= 160, NRX_EUNSUPPORTED, "more than 160 corpus slices");
-    dim3 grid((unsigned)g.slices, (unsigned)g.n_qtiles);
-    topk_scan_kernel<0><<<grid, kScanThreads, smem, st>>>(img, N, g.n_tiles, g.Dp, queries, q_ld, Q, D, g.Qp, g.stages, gmax,
-                                                          nullptr, nullptr, nullptr, g.cap_s);
-    rc = check_launch("topk_scan<A>");
+    NRX_REQUIRE(g.slices <= 1024, NRX_EUNSUPPORTED, "more than 1024 corpus slices");
+    const long long n_groups = g.n_stiles * 4;
+    // sample: every stride-th tile -> group maxima -> theta
+    long long s_slices = g.slices < g.n_stiles ? g.slices : g.n_stiles;
+    topk_scan_kernel<0><<<dim3((unsigned)s_slices, (unsigned)g.n_qgroups), kScanThreads, smem, st>>>(
+        img, N, g.n_tiles, g.stride, g.Dp, queries, q_ld, Q, D, g.Qp, g.nq, g.stages, gmax, n_groups, nullptr, nullptr, nullptr, g.cap_s);
+    rc = check_launch("topk_scan<sample>");
     if (rc != NRX_OK) return rc;
-    topk_theta_kernel<<<(unsigned)g.Qp, 256, 0, st>>>(gmax, 2 * g.n_tiles /* groups of 64 rows */, g.Qp, Q, g.kprime, queries, q_ld, D, (const unsigned*)index,
-                                                     theta, eps, count, flag);
+    topk_theta_kernel<<<(unsigned)g.Qp, 256, 0, st>>>(gmax, n_groups, g.Qp, Q, g.kprime_s, queries, q_ld, D, (const unsigned*)index, theta,
+                                                     eps, flist, flag);
     rc = check_launch("topk_theta");
     if (rc != NRX_OK) return rc;
-    topk_scan_kernel<1><<<grid, kScanThreads, smem, st>>>(img, N, g.n_tiles, g.Dp, queries, q_ld, Q, D, g.Qp, g.stages, nullptr,
-                                                          theta, count, cand, g.cap_s);
-    rc = check_launch("topk_scan<B>");
+    topk_scan_kernel<1><<<dim3((unsigned)g.slices, (unsigned)g.n_qgroups), kScanThreads, smem, st>>>(
+        img, N, g.n_tiles, 1, g.Dp, queries, q_ld, Q, D, g.Qp, g.nq, g.stages, nullptr, 0, theta, count, cand, g.cap_s);
+    rc = check_launch("topk_scan<filter>");
     if (rc != NRX_OK) return rc;
-    const size_t fsm = (size_t)kCap * 12 + (size_t)D * 4;
+    const int n_regions = (int)(4 * g.slices);
+    const size_t fsm = (size_t)kCap * 12 + (size_t)((D + 3) & ~3) * 4 + (size_t)n_regions * 4;
     cudaFuncSetAttribute(topk_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm);
-    topk_final_kernel<<<(unsigned)Q, 256, fsm, st>>>(corpus, c_ld, N, D, queries, q_ld, k, id_base, theta, eps, count, cand,
-                                                    (int)(2 * g.slices), g.cap_s, flag,
-                                                    out_scores, (long long*)out_ids);
+    topk_final_kernel<<<(unsigned)Q, 256, fsm, st>>>(corpus, c_ld, N, D, queries, q_ld, k, id_base, theta, eps, count, cand, n_regions,
+                                                    g.cap_s, flag, flist, out_scores, out_scores64, (long long*)out_ids);
     rc = check_launch("topk_final");
     if (rc != NRX_OK) return rc;
   }
+  // exact fallback for the listed queries (every query when the corpus is tiny): fixed grid, exits at once on an empty list
   cudaFuncSetAttribute(topk_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fb_smem);
-  topk_exact_kernel<<<(unsigned)Q, 256, fb_smem, st>>>(corpus, c_ld, N, D, queries, q_ld, k, id_base, flag, fast ? 0 : 1, out_scores,
-                                                      (long long*)out_ids, status);
-  return check_launch("topk_exact");
+  topk_exact_kernel<<<(unsigned)g.fb_grid, 256, fb_smem, st>>>(corpus, c_ld, N, D, queries, q_ld, k, flist, fast ? 0 : (int)Q, g.fb_items,
+                                                             part_s, part_i);
+  rc = check_launch("topk_exact");
+  if (rc != NRX_OK) return rc;
+  int n2 = 1;
+  while (n2 < fb_max_slices(k) * k) n2 <<= 1;
+  const size_t msm = (size_t)n2 * 12;
+  cudaFuncSetAttribute(topk_exact_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msm);
+  topk_exact_merge_kernel<<<(unsigned)g.fb_grid, 256, msm, st>>>(N, k, id_base, flist, fast ? 0 : (int)Q, g.fb_grid, g.fb_items, part_s,
+                                                               part_i, out_scores, out_scores64, (long long*)out_ids, status);
+  return check_launch("topk_exact_merge");
+}
+
+extern "C" int nrx_topk_search(const void* index, const float* corpus, int64_t c_ld, int64_t N, int D, const float* queries,
+                               int64_t q_ld, int64_t Q, int k, int64_t id_base, float* out_scores, int64_t* out_ids,
+                               int32_t* status, void* ws, size_t ws_bytes, nrx_stream_t stream) {
+  return nrx_topk_search64(index, corpus, c_ld, N, D, queries, q_ld, Q, k, id_base, out_scores, nullptr, out_ids, status, ws, ws_bytes,
+                           stream);
 }
 
 extern "C" size_t nrx_topk_ip_workspace_bytes(int64_t Q, int64_t N, int D, int k) {
@@ -607,16 +781,27 @@ extern "C" int nrx_topk_ip(const float* queries, int64_t q_ld, const float* corp
                          ws_bytes - ib, stream);
 }
 
-extern "C" int nrx_topk_merge(const float* scores, const int64_t* ids, int n_lists, int64_t Q, int k, float* out_scores,
-                              int64_t* out_ids, nrx_stream_t stream) {
+template <typename ST>
+static int merge_launch(const ST* scores, const int64_t* ids, int n_lists, int64_t Q, int k, float* out_scores, int64_t* out_ids,
+                        nrx_stream_t stream) {
   NRX_REQUIRE(scores && ids && out_scores && out_ids && n_lists >= 1 && k >= 1, NRX_EINVAL, "bad merge arguments");
   NRX_REQUIRE((long long)n_lists * k <= 8192, NRX_EUNSUPPORTED, "merge supports n_lists*k <= 8192");
   if (Q == 0) return NRX_OK;
   int n2 = 1;
   while (n2 < n_lists * k) n2 <<= 1;
-  const size_t smem = (size_t)(n2 + 1) * 4 + (size_t)n2 * 8 + 16;
-  cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  topk_merge_kernel<<<(unsigned)Q, 256, smem, (cudaStream_t)stream>>>(scores, (const long long*)ids, n_lists, Q, k, out_scores,
-                                                                      (long long*)out_ids);
+  const size_t smem = (size_t)n2 * (8 + sizeof(ST));
+  cudaFuncSetAttribute(topk_merge_kernel<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  topk_merge_kernel<ST><<<(unsigned)Q, 256, smem, (cudaStream_t)stream>>>(scores, (const long long*)ids, n_lists, Q, k, out_scores,
+                                                                          (long long*)out_ids);
   return check_launch("topk_merge");
+}
+
+extern "C" int nrx_topk_merge(const float* scores, const int64_t* ids, int n_lists, int64_t Q, int k, float* out_scores,
+                              int64_t* out_ids, nrx_stream_t stream) {
+  return merge_launch<float>(scores, ids, n_lists, Q, k, out_scores, out_ids, stream);
+}
+
+extern "C" int nrx_topk_merge64(const double* scores64, const int64_t* ids, int n_lists, int64_t Q, int k, float* out_scores,
+                                int64_t* out_ids, nrx_stream_t stream) {
+  return merge_launch<double>(scores64, ids, n_lists, Q, k, out_scores, out_ids, stream);
 }

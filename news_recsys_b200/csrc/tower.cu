@@ -138,6 +138,23 @@ __device__ __forceinline__ void issue_layer_mma(uint32_t tmem, uint32_t a_base, 
   }
 }
 
+// Same, called by a WHOLE warp in uniform control flow; `leader` (umma::elect_one_sync) issues.  Keeps the descriptors in
+// uniform registers and avoids the per-thread waterfall the compiler builds around UTCHMMA under `if (tid == 0)`.
+__device__ __forceinline__ void issue_layer_mma_u(uint32_t leader, uint32_t tmem, uint32_t a_base, uint32_t b_base, int kdim, int n_cols) {
+  const uint32_t idesc = make_idesc_bf16(kRows, n_cols);
+  uint64_t ad = make_smem_desc(a_base, kRows * 16u, 128u);
+  uint64_t bd = make_smem_desc(b_base, (uint32_t)n_cols * 16u, 128u);
+  const uint32_t astep = (2u * (kRows * 16u)) >> 4, bstep = (2u * ((uint32_t)n_cols * 16u)) >> 4;
+  uint32_t accum = 0u;
+#pragma unroll 2
+  for (int k16 = 0; k16 < kdim / 16; ++k16) {
+    mma_bf16_ss_if(leader, tmem, ad, bd, idesc, accum);
+    ad += astep;
+    bd += bstep;
+    accum = 1u;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // Forward
 // ------------------------------------------------------------------------------------------------------------
@@ -642,11 +659,13 @@ tower_bwd_dx_kernel(const __grid_constant__ TowerK T, long long B, const float* 
     for (int l = T.n_mma - 1; l >= 0; --l) {
       if (l == 0 && gx == nullptr) break;  // nobody needs dL/dx
       const int Kp = T.Kp[l], K = T.K[l];
-      if (tid == 0) {
+      if (warp == 0) {   // whole warp, uniform control flow; one elected lane issues
+        const uint32_t leader = elect_one_sync() ? 1u : 0u;
         tc_fence_after();
         // D[128 x Kp] = dz_l[128 x Np] * (W^T image: Kp rows, contraction Np)
-        issue_layer_mma(tmem, smem_u32(sA), smem_u32(sW + T.wt_off[l]), T.Np[l], Kp);
-        mma_commit(&mbar);
+        issue_layer_mma_u(leader, tmem, smem_u32(sA), smem_u32(sW + T.wt_off[l]), T.Np[l], Kp);
+        mma_commit_if(leader, &mbar);
+        __syncwarp();
       }
       const uint8_t* aimg = l > 0 ? ws + T.act_off[l] + (size_t)tile * Kp * kRows * 2 : nullptr;
       uint8_t* dzimg = l > 0 ? ws + T.dz_off[l - 1] + (size_t)tile * Kp * kRows * 2 : nullptr;
@@ -778,24 +797,30 @@ tower_bwd_dw_kernel(const __grid_constant__ TowerK T, const uint8_t* __restrict_
           bulk_g2s(sN[s], ws + T.act_off[l] + (size_t)t * bn, bn, &full[s]);
           s ^= 1;
         }
-      } else if (warp == 1 && lane == 0) {  // MMA issuer
+      } else if (warp == 1) {  // MMA issuer: whole warp in uniform control flow, one elected lane issues
+        const uint32_t leader = elect_one_sync() ? 1u : 0u;
         const uint32_t idesc = make_idesc_bf16(128, ncols, 1, 1);
         int s = 0;
         for (long long t = t0; t < t1; ++t) {
           mbar_wait(&full[s], full_phase[s]);
           full_phase[s] ^= 1;
           tc_fence_after();
+          // MN-major: 8-element MN groups are kRows*16 B apart (SBO), 8-row K groups 128 B apart (LBO)
+          uint64_t ad = make_smem_desc(smem_u32(sM[s]), 128u, kRows * 16u);
+          uint64_t bd = make_smem_desc(smem_u32(sN[s]), 128u, kRows * 16u);
+          uint32_t accum = t > t0 ? 1u : 0u;
 #pragma unroll
           for (int k16 = 0; k16 < kRows / 16; ++k16) {
-            // MN-major: 8-element MN groups are kRows*16 B apart (SBO), 8-row K groups 128 B apart (LBO)
-            const uint64_t ad = make_smem_desc(smem_u32(sM[s]) + (uint32_t)k16 * 256u, 128u, kRows * 16u);
-            const uint64_t bd = make_smem_desc(smem_u32(sN[s]) + (uint32_t)k16 * 256u, 128u, kRows * 16u);
-            mma_bf16_ss(tmem, ad, bd, idesc, (t > t0 || k16 > 0) ? 1u : 0u);
+            mma_bf16_ss_if(leader, tmem, ad, bd, idesc, accum);
+            ad += 256u >> 4;
+            bd += 256u >> 4;
+            accum = 1u;
           }
-          mma_commit(&empty[s]);
+          mma_commit_if(leader, &empty[s]);
           s ^= 1;
         }
-        mma_commit(&done);
+        mma_commit_if(leader, &done);
+        __syncwarp();
       }
       mbar_wait(&done, done_phase);
       done_phase ^= 1;

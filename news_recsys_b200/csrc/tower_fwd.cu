@@ -62,15 +62,16 @@ static bool make_fwd3_geom(const TowerK& k, Fwd3Geom* g) {
   g->stage_bytes = mx * kRows * 2;
   unsigned o = (k.w_bytes + 1023) & ~1023u;
   g->off_stage = o;
-  const unsigned fixed = (unsigned)k.n_mma * 128 * 4 + (unsigned)kMaxTiny * 128 * 4 + 2u * 2 * kRows * kMaxTiny * 4;
+  const unsigned nt = k.tiny ? (unsigned)k.N[k.n_layers - 1] : 0u;
+  const unsigned fixed = (unsigned)k.n_mma * 128 * 4 + nt * 128 * 4 + 2u * kRows * nt * 4;
   int ns = ((int)kSmemLimit - (int)o - (int)fixed) / g->stage_bytes;
   if (ns > kF3MaxStages) ns = kF3MaxStages;
   if (ns < 2) return false;
   g->n_stages = ns;
   o += (unsigned)ns * g->stage_bytes;
   g->off_bias = o; o += (unsigned)k.n_mma * 128 * 4;
-  g->off_wt = o;   o += (unsigned)kMaxTiny * 128 * 4;
-  g->off_xch = o;  o += 2u * 2 * kRows * kMaxTiny * 4;
+  g->off_wt = o;   o += nt * 128 * 4;
+  g->off_xch = o;  o += 2u * kRows * nt * 4;
   g->smem_bytes = o;
   return true;
 }
@@ -129,6 +130,45 @@ __device__ __forceinline__ uint32_t bias_act_pack(float z0, float z1, float b0, 
 __device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
 
+// Epilogue arithmetic of one pass over NG 16-column groups held in v[]: fully unrolled, no per-group guards.
+template <bool RELU, int NG>
+__device__ __forceinline__ void hidden_pack(const float (&v)[32], uint32_t (&pk)[16], const float* __restrict__ bias, float slope) {
+  const float4* bp4 = reinterpret_cast<const float4*>(bias);
+#pragma unroll
+  for (int j4 = 0; j4 < 4 * NG; ++j4) {
+    const float4 b4 = bp4[j4];
+    pk[j4 * 2] = bias_act_pack<RELU>(v[j4 * 4], v[j4 * 4 + 1], b4.x, b4.y, slope);
+    pk[j4 * 2 + 1] = bias_act_pack<RELU>(v[j4 * 4 + 2], v[j4 * 4 + 3], b4.z, b4.w, slope);
+  }
+}
+// 2 * NG 16-byte chunks (8 columns each) of this thread's row into the saved tile image
+template <int NG>
+__device__ __forceinline__ void image_store(uint8_t* img, const uint32_t (&pk)[16]) {
+#pragma unroll
+  for (int q4 = 0; q4 < 2 * NG; ++q4)
+    *reinterpret_cast<uint4*>(img + (size_t)q4 * (kRows * 16)) = make_uint4(pk[q4 * 4], pk[q4 * 4 + 1], pk[q4 * 4 + 2], pk[q4 * 4 + 3]);
+}
+// register dot product of the <= 4-wide last layer on the bf16-rounded activations (weights [Nt][128] in shared memory)
+template <int NG>
+__device__ __forceinline__ void tiny_dot(const uint32_t (&pk)[16], const float* __restrict__ wt, int Nt, float (&dot)[kMaxTiny]) {
+#pragma unroll
+  for (int o = 0; o < kMaxTiny; ++o) {
+    if (o < Nt) {
+      const float4* wp4 = reinterpret_cast<const float4*>(wt + o * 128);
+      float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+      for (int j4 = 0; j4 < 4 * NG; ++j4) {
+        const float4 w4 = wp4[j4];
+        a0 = fmaf(bf16_lo(pk[j4 * 2]), w4.x, a0);
+        a1 = fmaf(bf16_hi(pk[j4 * 2]), w4.y, a1);
+        a0 = fmaf(bf16_lo(pk[j4 * 2 + 1]), w4.z, a0);
+        a1 = fmaf(bf16_hi(pk[j4 * 2 + 1]), w4.w, a1);
+      }
+      dot[o] += a0 + a1;
+    }
+  }
+}
+
 struct HeadK {
   const float* terms[4];
   int n_terms;
@@ -142,7 +182,6 @@ struct HeadK {
   int on;
 };
 
-__device__ __forceinline__ void slot_sync(int s) { asm volatile("bar.sync %0, 256;" ::"r"(s + 1) : "memory"); }
 
 template <bool RELU>
 __global__ void __launch_bounds__(kF3Threads, 1)
@@ -153,9 +192,9 @@ tower_fwd3_kernel(const __grid_constant__ TowerK T, const __grid_constant__ Fwd3
   uint8_t* sW = smem;
   uint8_t* sStage = smem + G.off_stage;
   float* sBias = reinterpret_cast<float*>(smem + G.off_bias);  // [n_mma][128]
-  float* sWt = reinterpret_cast<float*>(smem + G.off_wt);      // [kMaxTiny][128] weights of the register-dot layer
-  float* sXch = reinterpret_cast<float*>(smem + G.off_xch);    // [slot][parity][128][kMaxTiny]
-  __shared__ uint64_t wbar, full[kF3MaxStages], empty[kF3MaxStages], acc_full[2], epi_done[2];
+  float* sWt = reinterpret_cast<float*>(smem + G.off_wt);      // [Nt][128] weights of the register-dot layer
+  float* sXch = reinterpret_cast<float*>(smem + G.off_xch);    // [slot][128][Nt]
+  __shared__ uint64_t wbar[NRX_MAX_LAYERS], full[kF3MaxStages], empty[kF3MaxStages], acc_full[2], epi_done[2];
   __shared__ uint32_t tmem_s;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -163,7 +202,7 @@ tower_fwd3_kernel(const __grid_constant__ TowerK T, const __grid_constant__ Fwd3
   const long long n_my = T.n_tiles > blockIdx.x ? (T.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
   if (tid == 0) {
-    mbar_init(&wbar, 1);
+    for (int l = 0; l < NRX_MAX_LAYERS; ++l) mbar_init(&wbar[l], 1);
     for (int s = 0; s < kF3MaxStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&epi_done[s], 8); }
     fence_mbar_init();
@@ -175,9 +214,9 @@ tower_fwd3_kernel(const __grid_constant__ TowerK T, const __grid_constant__ Fwd3
   }
   if (T.tiny) {
     const int Kt = T.K[L - 1], Nt = T.N[L - 1];
-    for (int i = tid; i < kMaxTiny * 128; i += kF3Threads) {
+    for (int i = tid; i < Nt * 128; i += kF3Threads) {
       const int o = i >> 7, c = i & 127;
-      sWt[i] = (o < Nt && c < Kt) ? __ldg(T.w[L - 1] + (long long)o * Kt + c) : 0.f;
+      sWt[i] = c < Kt ? __ldg(T.w[L - 1] + (long long)o * Kt + c) : 0.f;
     }
   }
   tc_fence_before();
@@ -188,8 +227,11 @@ tower_fwd3_kernel(const __grid_constant__ TowerK T, const __grid_constant__ Fwd3
   if (warp == 0) {
     // ===================== producer =====================
     if (lane == 0) {
-      mbar_expect_tx(&wbar, T.w_bytes);
-      for (int l = 0; l < nm; ++l) bulk_g2s(sW + T.w_off[l], wpack + T.w_off[l], (uint32_t)T.Kp[l] * T.Np[l] * 2u, &wbar);
+      for (int l = 0; l < nm; ++l) {   // one barrier per layer: layer 0 starts as soon as ITS weights have landed
+        const uint32_t wb = (uint32_t)T.Kp[l] * T.Np[l] * 2u;
+        mbar_expect_tx(&wbar[l], wb);
+        bulk_g2s(sW + T.w_off[l], wpack + T.w_off[l], wb, &wbar[l]);
+      }
       const uint8_t* ximg = ws + T.act_off[0];
       const size_t tile_bytes = (size_t)T.Kp[0] * kRows * 2;
       int st = 0;
@@ -210,171 +252,174 @@ tower_fwd3_kernel(const __grid_constant__ TowerK T, const __grid_constant__ Fwd3
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      mbar_wait(&wbar, 0);
-      int st = 0;
-      uint32_t fph = 0, dph = 0, slot_used = 0;
-      for (long long j0 = 0; j0 < n_my; j0 += 2) {
-        for (int l = 0; l < nm; ++l) {
-          for (int s = 0; s < 2; ++s) {
-            if (j0 + s >= n_my) continue;
-            // the slot's previous epilogue has drained the accumulator and (l >= 1) published this layer's A operand
-            if (slot_used & (1u << s)) { mbar_wait(&epi_done[s], (dph >> s) & 1u); dph ^= 1u << s; }
-            slot_used |= 1u << s;
-            const uint32_t acc = tmem + (uint32_t)s * kSlotCols;
-            const int Np = T.Np[l];
-            const uint32_t idesc = make_idesc_bf16(kRows, Np);
-            const uint32_t wbase = smem_u32(sW + T.w_off[l]);
-            if (l == 0) {
-              for (int c = 0; c < G.n_chunks; ++c) {
-                mbar_wait(&full[st], (fph >> st) & 1u);
-                fph ^= 1u << st;
-                tc_fence_after();
-                const uint32_t abase = smem_u32(sStage + (size_t)st * G.stage_bytes);
-                const int kc0 = G.chunk_col[c] / 8, n16 = (G.chunk_col[c + 1] - G.chunk_col[c]) / 16;
-                for (int k16 = 0; k16 < n16; ++k16) {
-                  const uint64_t ad = make_smem_desc(abase + (uint32_t)k16 * 2u * (kRows * 16u), kRows * 16u, 128u);
-                  const uint64_t bd = make_smem_desc(wbase + (uint32_t)(kc0 + 2 * k16) * ((uint32_t)Np * 16u), (uint32_t)Np * 16u, 128u);
-                  mma_bf16_ss(acc, ad, bd, idesc, (c > 0 || k16 > 0) ? 1u : 0u);
-                }
-                mma_commit(&empty[st]);
-                st = (st + 1 == G.n_stages) ? 0 : st + 1;
-              }
-            } else {
+    // The whole warp walks the schedule in uniform control flow; one elected lane issues (see umma::elect_one_sync).
+    const uint32_t leader = elect_one_sync() ? 1u : 0u;
+    int st = 0;
+    uint32_t fph = 0, dph = 0, slot_used = 0;
+    for (long long j0 = 0; j0 < n_my; j0 += 2) {
+      for (int l = 0; l < nm; ++l) {
+        if (j0 == 0) mbar_wait(&wbar[l], 0);   // first use of this layer's weights
+        const int Np = T.Np[l];
+        const uint32_t idesc = make_idesc_bf16(kRows, Np);
+        const uint32_t bstep = 2u * (uint32_t)Np * 16u;   // bytes between two K = 16 steps of the weight image
+        const uint64_t bd0 = make_smem_desc(smem_u32(sW + T.w_off[l]), (uint32_t)Np * 16u, 128u);
+        for (int s = 0; s < 2; ++s) {
+          if (j0 + s >= n_my) continue;
+          // the slot's previous epilogue has drained the accumulator and (l >= 1) published this layer's A operand
+          if (slot_used & (1u << s)) { mbar_wait(&epi_done[s], (dph >> s) & 1u); dph ^= 1u << s; }
+          slot_used |= 1u << s;
+          const uint32_t acc = tmem + (uint32_t)s * kSlotCols;
+          if (l == 0) {
+            for (int c = 0; c < G.n_chunks; ++c) {
+              mbar_wait(&full[st], (fph >> st) & 1u);
+              fph ^= 1u << st;
               tc_fence_after();
-              const uint32_t act = acc + 128u;
-              const int n16 = T.Kp[l] / 16;
+              const uint64_t ad0 = make_smem_desc(smem_u32(sStage + (size_t)st * G.stage_bytes), kRows * 16u, 128u);
+              const uint64_t bdc = desc_advance(bd0, (uint32_t)(G.chunk_col[c] / 8) * ((uint32_t)Np * 16u));
+              const int n16 = (G.chunk_col[c + 1] - G.chunk_col[c]) / 16;
+              uint64_t ad = ad0, bd = bdc;
+              uint32_t accum = c > 0 ? 1u : 0u;
+#pragma unroll 2
               for (int k16 = 0; k16 < n16; ++k16) {
-                const uint64_t bd = make_smem_desc(wbase + (uint32_t)k16 * 2u * ((uint32_t)Np * 16u), (uint32_t)Np * 16u, 128u);
-                mma_bf16_ts(acc, act + (uint32_t)k16 * 8u, bd, idesc, k16 > 0 ? 1u : 0u);
+                mma_bf16_ss_if(leader, acc, ad, bd, idesc, accum);
+                ad += (uint64_t)((2u * (kRows * 16u)) >> 4);
+                bd += (uint64_t)(bstep >> 4);
+                accum = 1u;
               }
+              mma_commit_if(leader, &empty[st]);
+              st = (st + 1 == G.n_stages) ? 0 : st + 1;
             }
-            mma_commit(&acc_full[s]);
+          } else {
+            tc_fence_after();
+            const uint32_t act = acc + 128u;
+            const int n16 = T.Kp[l] / 16;
+            uint64_t bd = bd0;
+            uint32_t a = act, accum = 0u;
+#pragma unroll 2
+            for (int k16 = 0; k16 < n16; ++k16) {
+              mma_bf16_ts_if(leader, acc, a, bd, idesc, accum);
+              bd += (uint64_t)(bstep >> 4);
+              a += 8u;
+              accum = 1u;
+            }
           }
+          mma_commit_if(leader, &acc_full[s]);
+          __syncwarp();
         }
       }
     }
   } else {
     // ===================== epilogue =====================
+    // Two groups of 8 warps, one per tile slot; inside a group warp = (TMEM lane quadrant, column half), a thread owns
+    // one row and up to 64 columns of the layer, drained in two passes of 32 (tcgen05.ld.x32 -> 16 FADD2 + 16 F2FP ->
+    // tcgen05.st.x16).  Fewer, fatter warps keep the per-warp bookkeeping (barrier wait, addresses, flags) off the
+    // issue slots: the epilogue of a layer has to fit inside the OTHER slot's MMA time for the tensor pipe to stay busy.
     const int e = warp - 2;
-    const int s = e >> 3;                 // tile slot
+    const int s = e >> 3;                 // tile slot of this warp group
     const int half = (e >> 2) & 1;        // column half of the layer
     const int qd = warp & 3;              // TMEM lane quadrant this warp may touch
     const int r = qd * 32 + lane;
     const uint32_t acc = tmem + (uint32_t)s * kSlotCols + ((uint32_t)(qd * 32) << 16);
     const uint32_t act = acc + 128u;
+    uint64_t* const done_bar = &epi_done[s];
+    uint64_t* const full_bar = &acc_full[s];
     uint32_t aph = 0;
     const int Nt = T.tiny ? T.N[L - 1] : 0;
-    for (long long j = s; j < n_my; j += 2) {
-      const long long tile = blockIdx.x + j * gridDim.x;
-      const long long row = tile * kRows + r;
-      const int par = (int)((j >> 1) & 1);
+    const int n_my_i = (int)n_my;
+    for (int j = s; j < n_my_i; j += 2) {
+      const int tile = (int)blockIdx.x + j * (int)gridDim.x;
+      const long long row = (long long)tile * kRows + r;
       for (int l = 0; l < nm; ++l) {
         const int Np = T.Np[l];
-        const int csplit = ((Np / 2) + 15) & ~15;
-        const int c0 = half ? csplit : 0, c1 = half ? Np : csplit;
-        const int ng = (c1 - c0) >> 4;  // 16-column groups of this thread: 0..4
+        const int csplit = ((Np >> 1) + 15) & ~15;
+        const int c0 = half ? csplit : 0;
+        const int n16 = ((half ? Np : csplit) - c0) >> 4;     // 16-column groups of this thread: 0..4
         const bool is_final = (l == L - 1);
         const bool feeds_tiny = T.tiny && (l == nm - 1);
         const bool to_tmem = (l + 1 < nm);
-        mbar_wait(&acc_full[s], aph);
+        const float* bias_l = sBias + l * 128 + c0;
+        mbar_wait(full_bar, aph);
         aph ^= 1u;
         tc_fence_after();
-        float v[4][16];
-#pragma unroll
-        for (int g = 0; g < 4; ++g)
-          if (g < ng) tmem_ld16(acc + (uint32_t)(c0 + g * 16), v[g]);
-        tmem_ld_wait();
         if (is_final) {
-          // last Linear (no activation) wider than the register-dot limit: fp32 rows out
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&epi_done[s]);
-          if (row < B) {
+          // last Linear (no activation) wider than the register-dot limit: fp32 rows out, 16 columns at a time
+          for (int g = 0; g < n16; ++g) {
+            float v[16];
+            tmem_ld16(acc + (uint32_t)(c0 + g * 16), v);
+            tmem_ld_wait();
+            if (row < B) {
+              const float4* bp4 = reinterpret_cast<const float4*>(bias_l + g * 16);
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              if (g < ng) {
-                const float4* bp4 = reinterpret_cast<const float4*>(sBias + l * 128 + c0 + g * 16);
-#pragma unroll
-                for (int j4 = 0; j4 < 4; ++j4) {
-                  const float4 b4 = bp4[j4];
-                  const int col = c0 + g * 16 + j4 * 4;
-                  const float o0 = v[g][j4 * 4] + b4.x, o1 = v[g][j4 * 4 + 1] + b4.y, o2 = v[g][j4 * 4 + 2] + b4.z,
-                              o3 = v[g][j4 * 4 + 3] + b4.w;
-                  float* dst = y + row * ldy + col;
-                  if (col + 4 <= T.N[l] && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-                    *reinterpret_cast<float4*>(dst) = make_float4(o0, o1, o2, o3);
-                  } else {
-                    if (col < T.N[l]) dst[0] = o0;
-                    if (col + 1 < T.N[l]) dst[1] = o1;
-                    if (col + 2 < T.N[l]) dst[2] = o2;
-                    if (col + 3 < T.N[l]) dst[3] = o3;
-                  }
+              for (int j4 = 0; j4 < 4; ++j4) {
+                const float4 b4 = bp4[j4];
+                const int col = c0 + g * 16 + j4 * 4;
+                const float o0 = v[j4 * 4] + b4.x, o1 = v[j4 * 4 + 1] + b4.y, o2 = v[j4 * 4 + 2] + b4.z, o3 = v[j4 * 4 + 3] + b4.w;
+                float* dst = y + row * ldy + col;
+                if (col + 4 <= T.N[l] && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+                  *reinterpret_cast<float4*>(dst) = make_float4(o0, o1, o2, o3);
+                } else {
+                  if (col < T.N[l]) dst[0] = o0;
+                  if (col + 1 < T.N[l]) dst[1] = o1;
+                  if (col + 2 < T.N[l]) dst[2] = o2;
+                  if (col + 3 < T.N[l]) dst[3] = o3;
                 }
               }
             }
           }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(done_bar);
           continue;
         }
-        // group by group: bias + activation + bf16 pack -> TMEM (next layer's A operand) -> HBM image -> logit dot;
-        // only 8 packed registers are live at a time
-        uint8_t* img = (training && l + 1 < L) ? ws + T.act_off[l + 1] + (size_t)tile * Np * kRows * 2 : nullptr;
+        // hidden layer: two passes of <= 32 columns
+        uint8_t* img = (training && l + 1 < L) ? ws + T.act_off[l + 1] + (size_t)tile * Np * kRows * 2 + canon_off(kRows, r, c0 >> 3)
+                                               : nullptr;
         float dot[kMaxTiny];
 #pragma unroll
         for (int o = 0; o < kMaxTiny; ++o) dot[o] = 0.f;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          if (g < ng) {
-            uint32_t pk[8];
-            const float4* bp4 = reinterpret_cast<const float4*>(sBias + l * 128 + c0 + g * 16);
-#pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4) {
-              const float4 b4 = bp4[j4];
-              pk[j4 * 2] = bias_act_pack<RELU>(v[g][j4 * 4], v[g][j4 * 4 + 1], b4.x, b4.y, T.slope);
-              pk[j4 * 2 + 1] = bias_act_pack<RELU>(v[g][j4 * 4 + 2], v[g][j4 * 4 + 3], b4.z, b4.w, T.slope);
-            }
-            if (to_tmem) tmem_st8(act + (uint32_t)((c0 + g * 16) >> 1), pk);
-            if (img) {
-              const int kc = (c0 + g * 16) >> 3;
-              *reinterpret_cast<uint4*>(img + canon_off(kRows, r, kc)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-              *reinterpret_cast<uint4*>(img + canon_off(kRows, r, kc + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-            }
-            if (feeds_tiny) {
-#pragma unroll
-              for (int o = 0; o < kMaxTiny; ++o) {
-                if (o < Nt) {
-                  const float4* wp4 = reinterpret_cast<const float4*>(sWt + o * 128 + c0 + g * 16);
-                  float acc_o = dot[o];
-#pragma unroll
-                  for (int j4 = 0; j4 < 4; ++j4) {
-                    const float4 w4 = wp4[j4];
-                    acc_o = fmaf(bf16_lo(pk[j4 * 2]), w4.x, acc_o);
-                    acc_o = fmaf(bf16_hi(pk[j4 * 2]), w4.y, acc_o);
-                    acc_o = fmaf(bf16_lo(pk[j4 * 2 + 1]), w4.z, acc_o);
-                    acc_o = fmaf(bf16_hi(pk[j4 * 2 + 1]), w4.w, acc_o);
-                  }
-                  dot[o] = acc_o;
-                }
-              }
-            }
+        for (int pass = 0; pass < 2; ++pass) {
+          const int np = n16 - 2 * pass;       // groups of this pass: <= 0, 1 or >= 2
+          if (np <= 0) continue;
+          float v[32];
+          uint32_t pk[16];
+          const int cp = pass * 32;
+          if (np >= 2) {
+            tmem_ld32(acc + (uint32_t)(c0 + cp), v);
+            tmem_ld_wait();
+            hidden_pack<RELU, 2>(v, pk, bias_l + cp, T.slope);
+            if (to_tmem) tmem_st16(act + (uint32_t)((c0 + cp) >> 1), pk);
+            if (img != nullptr) image_store<2>(img + (size_t)(cp >> 3) * (kRows * 16), pk);
+            if (feeds_tiny) tiny_dot<2>(pk, sWt + c0 + cp, Nt, dot);
+          } else {
+            tmem_ld16(acc + (uint32_t)(c0 + cp), *reinterpret_cast<float(*)[16]>(&v[0]));
+            tmem_ld_wait();
+            hidden_pack<RELU, 1>(v, pk, bias_l + cp, T.slope);
+            if (to_tmem) tmem_st8(act + (uint32_t)((c0 + cp) >> 1), *reinterpret_cast<uint32_t(*)[8]>(&pk[0]));
+            if (img != nullptr) image_store<1>(img + (size_t)(cp >> 3) * (kRows * 16), pk);
+            if (feeds_tiny) tiny_dot<1>(pk, sWt + c0 + cp, Nt, dot);
           }
         }
         if (to_tmem) tmem_st_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&epi_done[s]);   // accumulator drained, next layer's A operand published
+        if (lane == 0) mbar_arrive(done_bar);   // accumulator drained, next layer's A operand published
         if (feeds_tiny) {
-          float* xc = sXch + ((s * 2 + par) * kRows + r) * kMaxTiny;
+          // the two column halves of a row meet in shared memory; half 0 finishes the row.  One buffer per slot is enough:
+          // the slot's next write comes nm layer epilogues later, each of which every warp of the group (half 0 included,
+          // after its reads below) must have passed for the issuer to move on.
+          float* xc = sXch + (size_t)s * kRows * Nt;   // [row][Nt]
           if (half == 1) {
 #pragma unroll
-            for (int o = 0; o < kMaxTiny; ++o) xc[o] = dot[o];
+            for (int o = 0; o < kMaxTiny; ++o)
+              if (o < Nt) xc[r * Nt + o] = dot[o];
           }
-          slot_sync(s);
+          asm volatile("bar.sync %0, 256;" ::"r"(s + 1) : "memory");
           if (half == 0 && row < B) {
 #pragma unroll
             for (int o = 0; o < kMaxTiny; ++o) {
               if (o < Nt) {
-                const float t = dot[o] + xc[o] + __ldg(T.bias[L - 1] + o);
+                const float t = dot[o] + xc[r * Nt + o] + __ldg(T.bias[L - 1] + o);
                 if (y) y[row * ldy + o] = t;
                 if (H.on && o == 0) {
                   if (H.logit) H.logit[row] = t;

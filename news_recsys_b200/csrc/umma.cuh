@@ -134,6 +134,36 @@ __device__ __forceinline__ void mma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, ui
       : "memory");
 }
 
+// Predicated forms for the uniform-control-flow issuer: every lane executes the instruction slot, `issue` (the elected
+// leader) decides whether it issues — no branch around the UTCHMMA.
+__device__ __forceinline__ void mma_bf16_ss_if(uint32_t issue, uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(issue)
+      : "memory");
+}
+__device__ __forceinline__ void mma_bf16_ts_if(uint32_t issue, uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(issue)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit_if(uint32_t issue, uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.ne.b32 q, %1, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar)), "r"(issue)
+      : "memory");
+}
+
 // registers -> TMEM, 32 lanes x 32-bit: thread t of the warp writes TMEM lane (lane_base + t), n consecutive columns
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
   asm volatile(
@@ -148,6 +178,18 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8])
                : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// One leader lane of a fully active warp (deterministic for a given member mask).  The MMA-issuing warp runs its
+// loop in UNIFORM control flow — every lane waits on the barriers and computes the descriptors (uniform registers) —
+// and only the tcgen05.mma / tcgen05.commit instructions are predicated on this: inside `if (lane == 0)` the compiler
+// wraps every UTCHMMA in an ELECT / BRA.U.ANY waterfall with R2UR moves (~100 cycles per MMA, measured).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.b32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+// descriptor of the operand `bytes` further on (start-address field, 16-byte units; operands live below 256 KB)
+__device__ __forceinline__ uint64_t desc_advance(uint64_t d, uint32_t bytes) { return d + (uint64_t)(bytes >> 4); }
 
 // all previously issued MMAs of this thread arrive on `bar` when complete (implies fence::before_thread_sync)
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {

@@ -430,12 +430,13 @@ class ShardedTopk:
         return self.index.search(queries, k)
 
     def search(self, queries: torch.Tensor, k: int):
-        """`queries` must be identical on every rank (replicated)."""
+        """`queries` must be identical on every rank (replicated).  The shards exchange their lists with the
+        fp64 ordering keys, so the merge equals one index bit for bit (rows closer than one fp32 ulp included)."""
         from .retrieval import topk_merge
-        s, i = self.index.search(queries, k)
+        s, i, s64 = self.index.search(queries, k, want_scores64=True)
         Q = s.shape[0]
-        gs = torch.empty((self.world, Q, k), dtype=torch.float32, device=s.device)
+        gs = torch.empty((self.world, Q, k), dtype=torch.float64, device=s.device)
         gi = torch.empty((self.world, Q, k), dtype=torch.int64, device=s.device)
-        dist.all_gather_into_tensor(gs, s, group=self.group)
+        dist.all_gather_into_tensor(gs, s64, group=self.group)
         dist.all_gather_into_tensor(gi, i, group=self.group)
         return topk_merge(gs, gi)

@@ -27,7 +27,8 @@ class TopkIndex:
                                          self.index.data_ptr(), nbytes, L.stream_ptr(corpus.device)), "nrx_topk_index_build")
         self._ws = None
 
-    def search(self, queries: torch.Tensor, k: int, want_status: bool = False):
+    def search(self, queries: torch.Tensor, k: int, want_status: bool = False, want_scores64: bool = False):
+        """-> (scores fp32 [Q,k], ids int64 [Q,k][, status][, scores64]): scores64 are the fp64 ordering keys."""
         q = queries.detach().float().contiguous()
         if not q.is_cuda:
             raise L.NrxError("TopkIndex.search: queries must be CUDA tensors")
@@ -39,20 +40,27 @@ class TopkIndex:
         scores = torch.empty((Q, k), dtype=torch.float32, device=q.device)
         ids = torch.empty((Q, k), dtype=torch.int64, device=q.device)
         status = torch.zeros(max(Q, 1), dtype=torch.int32, device=q.device) if want_status else None
-        L.check(lib.nrx_topk_search(self.index.data_ptr(), self.corpus.data_ptr(), self.corpus.stride(0) if self.N else self.D,
-                                    self.N, self.D, q.data_ptr(), q.stride(0) if Q else self.D, Q, k, self.id_base,
-                                    scores.data_ptr(), ids.data_ptr(), L.ptr(status), self._ws.data_ptr(), self._ws.numel(),
-                                    L.stream_ptr(q.device)), "nrx_topk_search")
-        return (scores, ids, status) if want_status else (scores, ids)
+        s64 = torch.empty((Q, k), dtype=torch.float64, device=q.device) if want_scores64 else None
+        L.check(lib.nrx_topk_search64(self.index.data_ptr(), self.corpus.data_ptr(), self.corpus.stride(0) if self.N else self.D,
+                                      self.N, self.D, q.data_ptr(), q.stride(0) if Q else self.D, Q, k, self.id_base,
+                                      scores.data_ptr(), L.ptr(s64), ids.data_ptr(), L.ptr(status), self._ws.data_ptr(),
+                                      self._ws.numel(), L.stream_ptr(q.device)), "nrx_topk_search64")
+        out = (scores, ids)
+        if want_status:
+            out += (status,)
+        if want_scores64:
+            out += (s64,)
+        return out
 
 
 def topk_merge(scores: torch.Tensor, ids: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-    """[n_lists, Q, k] per-shard lists -> global [Q, k] under (score desc, id asc)."""
+    """[n_lists, Q, k] per-shard lists -> global [Q, k] under (score desc, id asc).  fp64 scores (the ordering keys of
+    search(want_scores64=True)) make the merge equal to one index bit for bit; fp32 scores order near-ties by id."""
     n, Q, k = scores.shape
     scores, ids = scores.contiguous(), ids.contiguous()
     out_s = torch.empty((Q, k), dtype=torch.float32, device=scores.device)
     out_i = torch.empty((Q, k), dtype=torch.int64, device=scores.device)
     lib = L.load()
-    L.check(lib.nrx_topk_merge(scores.data_ptr(), ids.data_ptr(), n, Q, k, out_s.data_ptr(), out_i.data_ptr(),
-                               L.stream_ptr(scores.device)), "nrx_topk_merge")
+    fn, name = (lib.nrx_topk_merge64, "nrx_topk_merge64") if scores.dtype == torch.float64 else (lib.nrx_topk_merge, "nrx_topk_merge")
+    L.check(fn(scores.data_ptr(), ids.data_ptr(), n, Q, k, out_s.data_ptr(), out_i.data_ptr(), L.stream_ptr(scores.device)), name)
     return out_s, out_i

@@ -38,7 +38,7 @@ def test_cfg1_deep_history_b1024_step_matches_oracle():
     with torch.no_grad():
         p = model({k: v.to(DEV) for k, v in batch.items()})
     assert _rel(p, p_ref) < 1e-2
-    tr = FusedTrainer(model, 1024, kind="deep")
+    tr = FusedTrainer(model, 1024, kind="deep", table_update="sparse")
     loss = float(tr.train_step(batch).item())
     assert abs(loss - float(l_ref)) < 1e-2
     # rows that received no gradient must be untouched by the sparse-row update; touched rows must move

@@ -76,12 +76,64 @@ def test_topk_merge_equals_single_index():
     parts = []
     for r in range(4):
         sh = c[r * 10000:(r + 1) * 10000].to(DEV)
-        parts.append(TopkIndex(sh, id_base=r * 10000).search(q.to(DEV), 100))
-    s = torch.stack([p[0] for p in parts])
-    i = torch.stack([p[1] for p in parts])
-    ms, mi = topk_merge(s, i)
-    assert torch.equal(mi.cpu(), ref_i)
+        parts.append(TopkIndex(sh, id_base=r * 10000).search(q.to(DEV), 100, want_scores64=True))
+    for key in (2, 0):   # fp64 ordering keys (what ShardedTopk exchanges) and the fp32 scores
+        s = torch.stack([p[key] for p in parts])
+        i = torch.stack([p[1] for p in parts])
+        ms, mi = topk_merge(s, i)
+        assert torch.equal(mi.cpu(), ref_i)
+        torch.testing.assert_close(ms.cpu(), ref_s, rtol=1e-6, atol=1e-7)
+
+
+def test_topk_sharded_near_ties_at_1m_rows():
+    """BASELINE cfg4 size (N = 1M, D = 128, k = 100), corpus in 8 shards, with pairs of rows in DIFFERENT shards whose fp64
+    scores differ by less than one fp32 ulp and whose id order is the opposite of their score order.  The merged result
+    must equal the single index and the oracle (the fp32 merge ordered such pairs by id)."""
+    from news_recsys_b200.retrieval import TopkIndex, topk_merge
+    g = torch.Generator().manual_seed(9)
+    N, D, k, Qn, G = 1_000_000, 128, 100, 6, 8
+    c = torch.nn.functional.normalize(torch.randn(N, D, generator=g), dim=1)
+    q = torch.nn.functional.normalize(torch.randn(Qn, D, generator=g), dim=1)
+    for j in range(Qn):   # row lo (shard 0) ~ the query; row hi (last shard) = the same row nudged UP by one ulp along q
+        lo, hi = 1000 + j, N - 1000 - j
+        c[lo] = torch.nn.functional.normalize(q[j] + 0.05 * torch.randn(D, generator=g), dim=0)
+        c[hi] = c[lo]
+        e = int(q[j].abs().argmax())
+        c[hi, e] = torch.nextafter(c[lo, e], c[lo, e] + torch.sign(q[j, e]))
+    ties = 0
+    for j in range(Qn):
+        s64 = q[j].double() @ c[[1000 + j, N - 1000 - j]].double().T
+        assert 0 < float(s64[1] - s64[0]) < 6e-8
+        ties += int(float(s64[1].float()) == float(s64[0].float()))
+    assert ties >= 3, "fixture: the pairs must round to the same fp32 score"
+    ref_s, ref_i = R.topk_ip(q, c, k)
+    for j in range(Qn):
+        assert ref_i[j, 0] == N - 1000 - j and ref_i[j, 1] == 1000 + j   # higher id first: score order, not id order
+    qd = q.to(DEV)
+    s1, i1 = TopkIndex(c.to(DEV)).search(qd, k)
+    assert torch.equal(i1.cpu(), ref_i)
+    parts = []
+    for r in range(G):
+        lo, hi = r * N // G, (r + 1) * N // G
+        parts.append(TopkIndex(c[lo:hi].to(DEV), id_base=lo).search(qd, k, want_scores64=True))
+    ms, mi = topk_merge(torch.stack([p[2] for p in parts]), torch.stack([p[1] for p in parts]))
+    assert torch.equal(mi.cpu(), ref_i), "sharded merge differs from the single index"
     torch.testing.assert_close(ms.cpu(), ref_s, rtol=1e-6, atol=1e-7)
+
+
+def test_topk_clustered_corpus_tiled_fallback():
+    """A clustered corpus (every row within 1e-3 of one of 8 centres) makes the bf16 filter useless for most queries:
+    they land on the fallback list and the corpus-sliced exact scan + merge must still return the oracle's lists."""
+    from news_recsys_b200.retrieval import TopkIndex
+    g = torch.Generator().manual_seed(11)
+    centres = torch.nn.functional.normalize(torch.randn(8, 64, generator=g), dim=1)
+    c = centres[torch.randint(0, 8, (60000,), generator=g)] + 1e-3 * torch.randn(60000, 64, generator=g)
+    q = centres[:5] + 0.05 * torch.randn(5, 64, generator=g)
+    ref_s, ref_i = R.topk_ip(q, c, 30)
+    s, i, st = TopkIndex(c.to(DEV)).search(q.to(DEV), 30, want_status=True)
+    assert torch.equal(i.cpu(), ref_i)
+    torch.testing.assert_close(s.cpu(), ref_s, rtol=1e-6, atol=1e-7)
+    assert int(st.sum()) >= 1
 
 
 def test_topk_searcher_api():

@@ -84,33 +84,42 @@ __global__ void __launch_bounds__(128) rate_kernel(int mode, int ncols, int iter
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
-  if (tid == 0) {
+  if (warp == 0) {
+    // the whole warp runs the loop in uniform control flow; one elected lane issues (umma::elect_one_sync)
+    const uint32_t leader = elect_one_sync() ? 1u : 0u;
     const uint32_t idesc = make_idesc_bf16(128, ncols);
+    const uint64_t ad0 = make_smem_desc(smem_u32(sA), 128 * 16, 128);
+    const uint64_t bd0 = make_smem_desc(smem_u32(sB), ncols * 16, 128);
+    const uint32_t bstep = (2u * (uint32_t)ncols * 16u) >> 4, astep = (2u * 128u * 16u) >> 4;
+    const int nacc = mode >= 2 ? mode : 1;
     const long long t0 = clock64();
     // two rounds in flight: round `it` commits to bar[it & 1]; before re-using a barrier wait for its previous phase
     // (an mbarrier may run at most one phase ahead of its waiter)
     for (int it = 0; it < iters; ++it) {
       if (it >= 2) mbar_wait(&bar[it & 1], ((it - 2) >> 1) & 1);
-      for (int k = 0; k < 8; ++k) {
-        const uint64_t bd = make_smem_desc(smem_u32(sB) + k * 2 * (ncols * 16), ncols * 16, 128);
-        if (mode == 0) {
-          const uint64_t ad = make_smem_desc(smem_u32(sA) + k * 2 * (128 * 16), 128 * 16, 128);
-          mma_bf16_ss(tmem, ad, bd, idesc, k > 0);
-        } else if (mode == 1) {
-          mma_bf16_ts(tmem, tmem + 256 + k * 8, bd, idesc, k > 0);
-        } else {
-          // mode 2..: `mode` independent accumulators, round-robin per instruction (is the 128-cycle floor a dependent-
-          // accumulate latency or an issue floor?)
-          const uint64_t ad = make_smem_desc(smem_u32(sA) + k * 2 * (128 * 16), 128 * 16, 128);
-          mma_bf16_ss(tmem + (uint32_t)((k % mode) * ncols), ad, bd, idesc, k >= mode);
+      uint64_t ad = ad0, bd = bd0;
+      uint32_t ta = tmem + 256;
+      if (nacc == 1) {
+#pragma unroll 2
+        for (int k = 0; k < 8; ++k) {
+          if (mode == 0) mma_bf16_ss_if(leader, tmem, ad, bd, idesc, k > 0);
+          else mma_bf16_ts_if(leader, tmem, ta, bd, idesc, k > 0);
+          ad += astep; bd += bstep; ta += 8;
+        }
+      } else {
+        // `nacc` independent accumulators, round-robin per instruction
+#pragma unroll 2
+        for (int k = 0; k < 8; ++k) {
+          mma_bf16_ss_if(leader, tmem + (uint32_t)((k & (nacc - 1)) * ncols), ad, bd, idesc, k >= nacc);
+          ad += astep; bd += bstep;
         }
       }
-      mma_commit(&bar[it & 1]);
+      mma_commit_if(leader, &bar[it & 1]);
     }
     for (int it = iters - 2; it < iters; ++it)
       if (it >= 0) mbar_wait(&bar[it & 1], (it >> 1) & 1);
     const long long t1 = clock64();
-    cycles[blockIdx.x] = t1 - t0;
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
   }
   tc_fence_before();
   __syncthreads();
