@@ -15,6 +15,10 @@ MIND-small table sizes, D = 16, batch 16384.
   cpu_baseline : the oracle port of the reference path (torch CPU, oracle/ref_path.py) on the host cores
   --impl reference : times that same CPU arm as the main line (the reference is pure Python; /root/reference
           does not exist on the GPU box, so the arm is the oracle port — kind "port")
+  legs  : the other BASELINE.json configurations in the same JSON line — cfg3 (DCN, B = 65536, data parallel, weak and
+          strong), cfg1 (Deep + history, B = 1024), cfg5 (WideDeep, 1M / 160k / 10M-row tables, row-sharded at N >= 2),
+          cfg4 (`retrieval`) — each with its own roofline; `eager_gpu`: the eager-PyTorch restatement of the reference
+          step on the same GPU; `parity`: at N > 1, replicas bitwise equal + N-rank vs 1-rank steps
 """
 from __future__ import annotations
 
@@ -55,6 +59,10 @@ def workload_cfg(name):
         return "deep", mind_config("deep", CFG1_ROWS, history_len=50), 1024, "cfg1: Deep + user_history L=50, B=1024"
     if name == "widedeep":
         return "widedeep", mind_config("widedeep", MIND_SMALL_ROWS), 16384, "WideDeep, MIND-small rows, B=16384"
+    if name == "widedeep_large":
+        from news_recsys_b200.synthetic import MIND_LARGE_ROWS
+        return ("widedeep", mind_config("widedeep", MIND_LARGE_ROWS), 16384,
+                "cfg5: WideDeep, 1,000,001 users / 160,001 news / 10,000,000-row hashed table (D 32/32/17), B=16384 per GPU")
     raise SystemExit(f"unknown workload {name}")
 
 
@@ -235,6 +243,9 @@ def algorithmic(kind, cfg, B, table_update="sparse"):
         "nrx_field_logit_bwd": ("hbm", B * (4 * sd + 4 + 8 * sd)),
         "nrx_logit_loss_fwd": ("hbm", B * 24),
         "nrx_tower_fwd": ("tensor", B * tower_flops),
+        "nrx_tower_fwd_head": ("tensor", B * tower_flops),
+        "nrx_embed_pool_fwd_img": ("hbm", B * (k1 - 4 * sd + 2 * sd + (4 * sd if kind != "deep" else 0))),
+        "nrx_dcn_cross_fwd_img": ("hbm", B * (4 * sd + 2 * 2 * sd)),
         "nrx_tower_bwd": ("tensor", 2 * B * tower_flops),
         "nrx_tower_bwd_dx": ("tensor", B * tower_flops),
         "nrx_tower_bwd_dw": ("tensor", B * tower_flops),
@@ -312,7 +323,7 @@ def retrieval_leg(dev, world, rank, dist, quick):
     if rank != 0:
         return None
     hbm_peak, tf_peak, peak_src = peaks()
-    flops = 2.0 * Q * N * D  # algorithmic: one inner product per (query, corpus row); the implementation scans twice
+    flops = 2.0 * Q * N * D  # algorithmic: one inner product per (query, corpus row); the implementation scans 1 + 1/8 times
     achieved = flops / (ms * 1e-3) / 1e12
     out = {"metric": "DSSM top-100 retrieval queries/s (1M x 128 corpus)", "value": Q / (ms * 1e-3), "unit": "queries/s",
            "ms_per_search": ms, "scaling": "strong (corpus sharded N/G per GPU)",
@@ -321,19 +332,250 @@ def retrieval_leg(dev, world, rank, dist, quick):
            "e2e": {"value": Q / (e2e_ms * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": Q * D * 4, "d2h_bytes_per_step": Q * K * 12},
            "index_build_s": build_s, "fallback_queries": fb,
            "roofline": {"bound": "tensor", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
-                        "traffic": None, "kernel": "nrx_topk_search (2 x topk_scan + theta + final)", "peak_source": peak_src,
+                        "traffic": None, "kernel": "nrx_topk_search (query pack + sample scan of 1/8 of the tiles + theta + one full filter scan + final)", "peak_source": peak_src,
                         "algorithmic_per_launch": flops}}
     if world == 1 and not quick:
+        # what faiss-cpu's IndexFlatIP does: blocked fp32 sgemm + top-k selection (no sort of the whole row); the oracle's
+        # own definition (fp64 scores + stable sort, oracle/ref_path.py topk_ip) is timed next to it for reference
         from oracle import ref_path as R
-        cq = queries[0][:32].cpu()
-        cc = corpus.cpu()
         torch.set_num_threads(os.cpu_count() or 1)
+        cc = corpus.cpu()
+        nq_cpu = 256
+        cq = queries[0][:nq_cpu].cpu()
         t0 = time.perf_counter()
-        R.topk_ip(cq, cc, K, chunk=32)
+        for a in range(0, nq_cpu, 64):
+            torch.topk(cq[a:a + 64] @ cc.T, K, dim=1)
         dt = time.perf_counter() - t0
-        out["cpu_baseline"] = {"value": 32 / dt, "unit": "queries/s", "cores": torch.get_num_threads(), "kind": "port",
-                               "sample": "32 queries against the full 1M x 128 corpus (oracle/ref_path.py topk_ip: fp64 scores + stable sort)"}
+        t0 = time.perf_counter()
+        R.topk_ip(cq[:16], cc, K, chunk=16)
+        dt64 = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": nq_cpu / dt, "unit": "queries/s", "cores": torch.get_num_threads(), "kind": "port",
+                               "sample": f"{nq_cpu} queries against the full 1M x 128 corpus: fp32 sgemm (blocks of 64 queries) + "
+                                         "torch.topk, the faiss-cpu IndexFlatIP algorithm (reference TopKSearcher.py:77); near-ties "
+                                         "are NOT pinned by it",
+                               "oracle_fp64_stable_sort_queries_per_s": 16 / dt64}
     return out
+
+
+# ------------------------------------------------------------------------------------------------------------
+# legs: the other BASELINE configurations, measured with the same rules as the headline (device pool > L2 or a working
+# set > L2, CUDA events around exactly K steps, max over ranks), each with the roofline of its dominant call
+# ------------------------------------------------------------------------------------------------------------
+def _pools(trainer, cfg, B, rank, dev, seed0=4242):
+    from news_recsys_b200.synthetic import synth_batch
+    blob_bytes = trainer.layout.nbytes
+    host = []
+    for i in range(4):
+        hb = torch.empty(blob_bytes, dtype=torch.uint8).pin_memory()
+        trainer.layout.pack(synth_batch(cfg, B, seed=seed0 + rank * 100003 + i), hb)
+        host.append(hb)
+    n_dev = max(4, min(96, int(160e6 // blob_bytes) + 1))
+    pool = torch.empty((n_dev, blob_bytes), dtype=torch.uint8, device=dev)
+    for i in range(n_dev):
+        pool[i].copy_(host[i % len(host)])
+    torch.cuda.synchronize()
+    return host, pool
+
+
+def _roofline(prof_trainer, pool, kind, cfg, B, table_update, workload, quick):
+    per_api, launches_per_step = profile_apis(prof_trainer, pool, n=2 if quick else 6)
+    alg = algorithmic(kind, cfg, B, table_update)
+    hbm_peak, tf_peak, peak_src = peaks()
+    forked = {"nrx_embed_bwd_plan", "nrx_hparams_step", "nrx_tower_pack"}
+    if kind in ("deep", "deepfm", "widedeep", "dcn"):
+        forked |= {"nrx_field_logit_bwd", "nrx_reduce2_f32", "nrx_reduce_f32"}
+        if table_update == "sparse":
+            forked.add("nrx_adamw_dense_dev")
+    dom = max((k for k in per_api if k not in forked), key=lambda k: per_api[k])
+    bound, qty = alg.get(dom, ("hbm", 0))
+    dur_s = per_api[dom] * 1e-6
+    if bound == "hbm":
+        achieved, peak, runit = qty / dur_s / 1e9, hbm_peak, "GB/s"
+    else:
+        achieved, peak, runit = qty / dur_s / 1e12, tf_peak, "TFLOP/s"
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(workload, {}).get(dom)
+    roof = {"bound": bound, "achieved": achieved, "peak": peak, "unit": runit, "frac": achieved / peak, "traffic": traffic,
+            "kernel": dom, "kernel_us": per_api[dom], "peak_source": peak_src, "algorithmic_per_launch": qty}
+    breakdown = {}
+    for k, us in sorted(per_api.items(), key=lambda kv: -kv[1]):
+        b_, q_ = alg.get(k, ("hbm", 0))
+        a_ = (q_ / (us * 1e-6) / 1e9) if b_ == "hbm" else (q_ / (us * 1e-6) / 1e12)
+        breakdown[k] = {"us_per_step": round(us, 2), "stream": "forked" if k in forked else "main", "bound": b_,
+                        "achieved": round(a_, 1), "frac": round(a_ / (hbm_peak if b_ == "hbm" else tf_peak), 4)}
+    return roof, breakdown, launches_per_step
+
+
+def train_leg(workload, dev, world, rank, dist, steps, warmup, mode, B=None, table_update="dense", quick=False, scaling="weak"):
+    """One training workload on all ranks.  mode: "dp" (FusedTrainer at N = 1, DataParallelTrainer above) or "sharded"
+    (FusedTrainer at N = 1, ShardedEmbeddingTrainer above).  Returns the leg's dict on rank 0, None elsewhere."""
+    from news_recsys_b200.trainer import FusedTrainer
+    kind, cfg, B0, wl_desc = workload_cfg(workload)
+    B = B or B0
+    torch.manual_seed(42)
+    model = model_class(kind)(cfg).to(dev)
+    if world == 1:
+        trainer = FusedTrainer(model, B, kind=kind, table_update=table_update)
+    elif mode == "dp":
+        from news_recsys_b200.parallel import DataParallelTrainer
+        trainer = DataParallelTrainer(model, B, kind=kind, table_update=table_update)
+    else:
+        from news_recsys_b200.parallel import ShardedEmbeddingTrainer
+        trainer = ShardedEmbeddingTrainer(model, B, kind=kind)
+    host, pool = _pools(trainer, cfg, B, rank, dev)
+    n_pool = pool.shape[0]
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(warmup, 3)):
+        trainer.load_blob(pool[i % n_pool])
+        trainer.step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        trainer.load_blob(pool[(i + 3) % n_pool])
+        trainer.step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    final_loss = float(trainer.loss.item())
+    for i in range(3):
+        trainer.feed(host[i % len(host)])
+    trainer.drain()
+    barrier()
+    e_steps = min(steps, 100)
+    t0 = time.perf_counter()
+    for i in range(e_steps):
+        trainer.feed(host[i % len(host)])
+    trainer.drain()
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    barrier()
+    exch = None
+    if world > 1 and mode == "sharded":
+        exch = trainer.exchange_bandwidth(iters=10)
+    t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = float(t[0]), float(t[1])
+    out = None
+    if rank == 0:
+        blob_bytes = trainer.layout.nbytes
+        out = {"metric": f"train samples/s ({wl_desc})", "value": world * B * steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
+               "batch_per_gpu": B, "global_batch": world * B, "steps": steps, "warmup": max(warmup, 3), "ms_per_step": ms / steps,
+               "scaling": scaling, "table_update": trainer.table_update,
+               "trainer": type(trainer).__name__,
+               "e2e": {"value": world * B * e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": blob_bytes,
+                       "d2h_bytes_per_step": 8, "steps": e_steps},
+               "l2": f"inputs rotate over a {n_pool}-slot device pool ({n_pool * blob_bytes / 1e6:.0f} MB)", "final_loss": final_loss}
+        if exch is not None:
+            out["exchange"] = exch
+        prof = trainer
+        if world > 1:
+            if workload == "widedeep_large":
+                prof = None   # a private replica of the 1.3 GB tables only for per-call timing is not worth its memory traffic
+            else:
+                torch.manual_seed(42)
+                prof = FusedTrainer(model_class(kind)(cfg).to(dev), B, kind=kind, table_update=trainer.table_update)
+        if prof is not None:
+            roof, breakdown, lps = _roofline(prof, pool, kind, cfg, B, trainer.table_update, workload, quick)
+            out["roofline"], out["launches_per_step"] = roof, lps
+            out["kernels"] = {k: v for k, v in list(breakdown.items())[:6]}
+    del trainer, pool
+    torch.cuda.empty_cache()
+    return out
+
+
+def eager_gpu_leg(workload, dev, steps=30, warmup=5):
+    """the reference's step as eager PyTorch ops ON THE SAME GPU (the CPU restatement oracle/ref_path.py
+    with its tensors on the device; the reference itself is pure PyTorch and cannot travel to the GPU box).  This is the
+    competitor that matters — a measurement leg like cpu_baseline, never a product path."""
+    from oracle import ref_path as R
+    from news_recsys_b200.synthetic import synth_batch
+    kind, cfg, B, desc = workload_cfg(workload)
+    torch.manual_seed(42)
+    model = model_class(kind)(cfg)
+    leaf = {k: v.detach().clone().to(dev).requires_grad_(True) for k, v in model.state_dict().items()}
+    opt = torch.optim.AdamW(list(leaf.values()), lr=cfg["train_hparams"]["lr"], betas=(0.9, 0.999))
+    batches = [{k: v.to(dev) for k, v in synth_batch(cfg, B, seed=1000 + i).items()} for i in range(4)]
+
+    def step(b):
+        opt.zero_grad(set_to_none=True)
+        loss = R.bce(R.model_forward(kind, leaf, cfg, b, dcn_materialise=False), b["label"][:, 0])
+        loss.backward()
+        opt.step()
+        return loss
+
+    for i in range(warmup):
+        step(batches[i % 4])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        step(batches[i % 4])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"value": B / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps, "batch": B, "workload": desc,
+            "what": "eager PyTorch restatement of the reference step (fwd + BCE + bwd + torch.optim.AdamW) on this GPU, fp32, "
+                    "DCN cross in its algebraically fused form (the reference's [B,d,d] form is slower still)"}
+
+
+def parity_leg(dev, world, rank, dist):
+    """N > 1: (1) replicas bitwise equal after data-parallel steps; (2) 3 steps at N ranks x B == 3 steps at 1 rank x N*B
+    (tolerances of tests/test_gpu_multi.py: fp32 FM 1e-5 relative, bf16-tower DeepFM 2.5e-3 absolute)."""
+    from news_recsys_b200.parallel import DataParallelTrainer
+    from news_recsys_b200.synthetic import mind_config, synth_batch
+    from news_recsys_b200.trainer import FusedTrainer
+    rows = {"user_id": 3001, "item_id": 2001, "category": 18, "subcategory": 270, "user_click_category": 18}
+    res = {}
+    ok = True
+    for kind in ("fm", "deepfm"):
+        cfg = mind_config(kind, rows)
+        Bs = 256
+        torch.manual_seed(7)
+        model = model_class(kind)(cfg).to(dev)
+        tr = DataParallelTrainer(model, Bs, kind=kind, table_update="dense")
+        for s in range(3):
+            full = synth_batch(cfg, Bs * world, seed=900 + s, label_p=0.5)
+            tr.train_step({k: v[rank * Bs:(rank + 1) * Bs] for k, v in full.items()})
+        torch.cuda.synchronize()
+        tr.check_status()
+        chk = tr.flat_p.view(torch.int32).to(torch.int64).sum().view(1)
+        allc = [torch.zeros_like(chk) for _ in range(world)]
+        dist.all_gather(allc, chk)
+        equal = all(int(c) == int(allc[0]) for c in allc)
+        maxdiff = None
+        if rank == 0:
+            torch.manual_seed(7)
+            ref_model = model_class(kind)(cfg).to(dev)
+            ref = FusedTrainer(ref_model, Bs * world, kind=kind, table_update="dense")
+            for s in range(3):
+                ref.train_step(synth_batch(cfg, Bs * world, seed=900 + s, label_p=0.5))
+            torch.cuda.synchronize()
+            sd, rsd = model.state_dict(), ref_model.state_dict()
+            if kind == "fm":
+                maxdiff = max(float(((sd[k] - rsd[k]).abs() / rsd[k].abs().clamp_min(1e-3)).max()) for k in sd)
+                good = maxdiff <= 1e-4
+            else:
+                maxdiff = max(float((sd[k] - rsd[k]).abs().max()) for k in sd)
+                good = maxdiff <= 2.5e-3
+            ok = ok and good
+        ok = ok and equal
+        res[kind] = {"replicas_bitwise_equal": equal, "n_rank_vs_1_rank_max_diff": maxdiff,
+                     "tolerance": "1e-4 relative (fp32)" if kind == "fm" else "2.5e-3 absolute (bf16 tower, ~2 Adam steps of lr 1e-3)"}
+        del tr
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    res["parity_ok"] = bool(int(flag))
+    res["what"] = "3 data-parallel steps (K7 peer exchange) at N ranks x 256 vs 1 rank x N*256, same batches"
+    return res if rank == 0 else None
 
 
 _OUT = None
@@ -370,6 +612,7 @@ def main():
                          "nccl = NCCL all-reduce between two graphs")
     ap.add_argument("--cpu-steps", type=int, default=0, help="override the CPU arm's step count")
     ap.add_argument("--no-retrieval", action="store_true", help="skip the DSSM top-100 retrieval leg (BASELINE config 4)")
+    ap.add_argument("--no-legs", action="store_true", help="skip the cfg1 / cfg3 / cfg5 / eager-GPU / parity legs")
     ap.add_argument("--quick", action="store_true",
                     help="profiler mode: skip the clock-sampling load loop, shorten the per-API pass and the CPU arm")
     args = ap.parse_args()
@@ -382,8 +625,8 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        steps = max(3, min(args.steps, 30))
-        warm = max(1, min(args.warmup, 3))
+        steps = max(3, min(args.steps, 200))     # a CPU step of this workload is ~16 ms: the whole arm stays under a minute
+        warm = max(1, min(args.warmup, 50))
         v, ms, cores = cpu_arm(kind, cfg, B, steps, warm)
         line = {"impl": "reference", "metric": metric, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
                 "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -502,6 +745,24 @@ def main():
     retrieval = None
     if args.workload == "deepfm" and not args.no_retrieval:
         retrieval = retrieval_leg(dev, world, rank, dist, args.quick)
+    legs, parity, eager = {}, None, None
+    if args.workload == "deepfm" and not args.no_legs and not args.quick:
+        lsteps = max(10, min(args.steps, 50))
+        # cfg3: DCN, B = 65536 — data parallel, weak (65536 per GPU) and strong (65536 in total)
+        legs["cfg3_dcn_weak"] = train_leg("dcn", dev, world, rank, dist, lsteps, args.warmup, "dp", quick=args.quick, scaling="weak")
+        if world > 1:
+            legs["cfg3_dcn_strong"] = train_leg("dcn", dev, world, rank, dist, lsteps, args.warmup, "dp", B=65536 // world,
+                                                quick=args.quick, scaling="strong")
+        # cfg1: the reference's own CPU-runnable case (Deep + user_history, B = 1024)
+        legs["cfg1_deep_hist"] = train_leg("deep", dev, world, rank, dist, lsteps, args.warmup, "dp", quick=args.quick, scaling="weak")
+        # cfg5: WideDeep with 1M / 160k / 10M-row tables; lazy sparse-row update (a dense sweep of 1.3 GB of tables per
+        # step is what the reference's optimizer would do); row-sharded tables at N >= 2
+        legs["cfg5_widedeep_sharded"] = train_leg("widedeep_large", dev, world, rank, dist, lsteps, args.warmup, "sharded",
+                                                  table_update="sparse", quick=args.quick, scaling="weak")
+        if world > 1:
+            parity = parity_leg(dev, world, rank, dist)
+        elif rank == 0:
+            eager = {"cfg2_deepfm": eager_gpu_leg("deepfm", dev), "cfg3_dcn": eager_gpu_leg("dcn", dev, steps=10, warmup=3)}
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -542,7 +803,7 @@ def main():
     # concurrently with forward + backward, and are listed in `kernels` with "stream": "forked"
     forked = {"nrx_embed_bwd_plan", "nrx_hparams_step", "nrx_tower_pack"}
     if kind in ("deep", "deepfm", "widedeep", "dcn"):  # these run beside the tower kernels on the third stream
-        forked |= {"nrx_field_logit_fwd", "nrx_field_logit_bwd", "nrx_reduce2_f32", "nrx_reduce_f32"}
+        forked |= {"nrx_field_logit_bwd", "nrx_reduce2_f32", "nrx_reduce_f32"}
         if args.table_update == "sparse":
             forked.add("nrx_adamw_dense_dev")
     dom = max((k for k in per_api if k not in forked), key=lambda k: per_api[k])
@@ -603,6 +864,13 @@ def main():
         line["variants"] = variants
     if retrieval is not None:
         line["retrieval"] = retrieval
+    if legs:
+        line["legs"] = legs
+    if eager is not None:
+        line["eager_gpu"] = eager
+    if parity is not None:
+        line["parity"] = parity
+        line["parity_ok"] = parity["parity_ok"]
     emit(line)
     if dist is not None:
         dist.destroy_process_group()

@@ -203,6 +203,105 @@ dcn_cross_bwd_kernel(const float* __restrict__ x, long long ld, long long B, con
   }
 }
 
+// 128-bit backward: lane owns the float4 at columns 4 * (lane + 32 k); the layer count is a template parameter so that
+// the per-lane state (x_l chain, parameter-gradient accumulators) is exactly LC deep — the generic kernel above sizes
+// every array for 8 layers, which costs registers and occupancy (135 us at B = 65536, d = 112: 13 % of the HBM
+// roofline).  Same arithmetic and the same fixed combination order (rows of a warp in order, warps of a block in
+// order, blocks in order) => bitwise reproducible.
+__device__ __forceinline__ float dot4(const float4& a, const float4& b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w))); }
+__device__ __forceinline__ void axpy4(float4& y, float a, const float4& x) {
+  y.x = fmaf(a, x.x, y.x); y.y = fmaf(a, x.y, y.y); y.z = fmaf(a, x.z, y.z); y.w = fmaf(a, x.w, y.w);
+}
+__device__ __forceinline__ void add4(float4& y, const float4& x) { y.x += x.x; y.y += x.y; y.z += x.z; y.w += x.w; }
+
+template <int NV, int LC>
+__global__ void __launch_bounds__(256)
+dcn_cross_bwd_v4_kernel(const float* __restrict__ x, long long ld, long long B, const __grid_constant__ CrossP P,
+                        const float* __restrict__ go, long long gold, float* __restrict__ gx, long long gxld,
+                        float* __restrict__ partials) {
+  extern __shared__ float sm[];  // [8 warps][LC][2][d]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int d = P.d;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 gw[LC][NV], gb[LC][NV], w[LC][NV], bb[LC][NV];
+#pragma unroll
+  for (int l = 0; l < LC; ++l)
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int c = 4 * (lane + 32 * k);
+      gw[l][k] = z4; gb[l][k] = z4;
+      w[l][k] = c < d ? __ldg(reinterpret_cast<const float4*>(P.w[l] + c)) : z4;
+      bb[l][k] = c < d ? __ldg(reinterpret_cast<const float4*>(P.b[l] + c)) : z4;
+    }
+  const long long warps_total = (long long)gridDim.x * 8;
+  for (long long row = (long long)blockIdx.x * 8 + warp; row < B; row += warps_total) {
+    float4 x0[NV], xs[LC][NV], g[NV], g0[NV];
+    float s[LC];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int c = 4 * (lane + 32 * k);
+      x0[k] = c < d ? __ldg(reinterpret_cast<const float4*>(x + row * ld + c)) : z4;
+      g0[k] = c < d ? __ldg(reinterpret_cast<const float4*>(go + row * gold + c)) : z4;       // d/dx through the concat's first half
+      g[k] = c < d ? __ldg(reinterpret_cast<const float4*>(go + row * gold + d + c)) : z4;    // d/dx_L
+    }
+    // recompute the chain, keeping x_l (input of layer l) and s_l = x_l . w_l
+#pragma unroll
+    for (int l = 0; l < LC; ++l) {
+      float t = 0.f;
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        if (l == 0) xs[l][k] = x0[k];
+        else {
+          xs[l][k].x = fmaf(x0[k].x, s[l - 1], bb[l - 1][k].x + xs[l - 1][k].x);
+          xs[l][k].y = fmaf(x0[k].y, s[l - 1], bb[l - 1][k].y + xs[l - 1][k].y);
+          xs[l][k].z = fmaf(x0[k].z, s[l - 1], bb[l - 1][k].z + xs[l - 1][k].z);
+          xs[l][k].w = fmaf(x0[k].w, s[l - 1], bb[l - 1][k].w + xs[l - 1][k].w);
+        }
+        t += dot4(xs[l][k], w[l][k]);
+      }
+      s[l] = warp_sum(t);
+    }
+#pragma unroll
+    for (int l = LC - 1; l >= 0; --l) {
+      float ds = 0.f;
+#pragma unroll
+      for (int k = 0; k < NV; ++k) ds += dot4(g[k], x0[k]);
+      ds = warp_sum(ds);
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        add4(gb[l][k], g[k]);
+        axpy4(gw[l][k], ds, xs[l][k]);
+        axpy4(g0[k], s[l], g[k]);
+        axpy4(g[k], ds, w[l][k]);
+      }
+    }
+    if (gx != nullptr) {
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        const int c = 4 * (lane + 32 * k);
+        if (c < d) *reinterpret_cast<float4*>(gx + row * gxld + c) = make_float4(g0[k].x + g[k].x, g0[k].y + g[k].y, g0[k].z + g[k].z, g0[k].w + g[k].w);
+      }
+    }
+  }
+  // block combine in warp order
+#pragma unroll
+  for (int l = 0; l < LC; ++l)
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int c = 4 * (lane + 32 * k);
+      if (c < d) {
+        *reinterpret_cast<float4*>(sm + ((warp * LC + l) * 2 + 0) * d + c) = gw[l][k];
+        *reinterpret_cast<float4*>(sm + ((warp * LC + l) * 2 + 1) * d + c) = gb[l][k];
+      }
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < LC * 2 * d; i += blockDim.x) {
+    float t = 0.f;
+    for (int wv = 0; wv < 8; ++wv) t += sm[wv * LC * 2 * d + i];
+    partials[(long long)blockIdx.x * LC * 2 * d + i] = t;
+  }
+}
+
 struct CrossG { float* gw[kMaxCrossLayers]; float* gb[kMaxCrossLayers]; };
 __global__ void __launch_bounds__(256)
 dcn_cross_reduce_kernel(const float* __restrict__ partials, int n_blocks, int Lc, int d, const __grid_constant__ CrossG G) {
@@ -232,7 +331,7 @@ static int make_cross(int d, int n_layers, const float* const* w, const float* c
 
 static int cross_bwd_blocks(long long B) {
   long long blocks = (B + 63) / 64;  // >= 8 rows per warp
-  const long long cap = (long long)sm_count() * 2;
+  const long long cap = (long long)sm_count() * 3;
   if (blocks > cap) blocks = cap;
   return blocks < 1 ? 1 : (int)blocks;
 }
@@ -276,7 +375,18 @@ extern "C" int nrx_dcn_cross_bwd(const float* x, int64_t ld, int64_t B, int d, i
   NRX_REQUIRE(ws && ws_bytes >= need, NRX_EWORKSPACE, "workspace %zu < %zu", ws_bytes, need);
   cudaStream_t st = (cudaStream_t)stream;
   const size_t smem = (size_t)8 * n_layers * 2 * d * sizeof(float);
-  if (d <= 128) {
+  bool v4 = d % 4 == 0 && ld % 4 == 0 && go_ld % 4 == 0 && ((uintptr_t)x % 16 == 0) && ((uintptr_t)grad_out % 16 == 0) && n_layers <= 4 &&
+            (!grad_x || (gx_ld % 4 == 0 && (uintptr_t)grad_x % 16 == 0)) && smem <= 48 * 1024;
+  for (int l = 0; l < n_layers; ++l) v4 = v4 && ((uintptr_t)h_w[l] % 16 == 0) && ((uintptr_t)h_b[l] % 16 == 0);
+  if (v4) {
+#define NRX_CROSS_V4(NV, LC) dcn_cross_bwd_v4_kernel<NV, LC><<<blocks, 256, smem, st>>>(x, ld, B, P, grad_out, go_ld, grad_x, gx_ld, (float*)ws)
+    if (d <= 128) {
+      switch (n_layers) { case 1: NRX_CROSS_V4(1, 1); break; case 2: NRX_CROSS_V4(1, 2); break; case 3: NRX_CROSS_V4(1, 3); break; default: NRX_CROSS_V4(1, 4); }
+    } else {
+      switch (n_layers) { case 1: NRX_CROSS_V4(2, 1); break; case 2: NRX_CROSS_V4(2, 2); break; case 3: NRX_CROSS_V4(2, 3); break; default: NRX_CROSS_V4(2, 4); }
+    }
+#undef NRX_CROSS_V4
+  } else if (d <= 128) {
     if (smem > 48 * 1024) cudaFuncSetAttribute(dcn_cross_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dcn_cross_bwd_kernel<4><<<blocks, 256, smem, st>>>(x, ld, B, P, grad_out, go_ld, grad_x, gx_ld, (float*)ws);
   } else {

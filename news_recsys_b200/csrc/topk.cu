@@ -34,7 +34,7 @@ namespace nrx {
 using namespace umma;
 
 static constexpr int kTR = 128;        // corpus rows per tile == UMMA N; queries per tile == UMMA M
-static constexpr int kCap = 4096;      // candidate list capacity per query
+static constexpr int kCap = 2048;      // candidate list capacity per query (24 KB of shared memory in the final kernel)
 static constexpr int kScanThreads = 64 + 512;  // TMA warp + MMA warp + 16 epilogue warps
 static constexpr int kMaxQT = 4;       // query tiles per CTA (4 x 128 TMEM columns)
 static constexpr int kHdrBytes = 256;
@@ -53,7 +53,7 @@ struct TopkGeom {
   int fb_grid, fb_items;   // fallback: fixed grid, capacity of the (query, corpus slice) work list
   size_t tile_bytes, index_bytes;
   // workspace offsets
-  size_t gmax, theta, eps, count, cand, flag, flist, fpart, total;
+  size_t gmax, theta, eps, count, cand, flag, flist, fpart, qimg, total;
 };
 
 static int make_geom(long long Q, long long N, int D, int k, TopkGeom* g) {
@@ -100,6 +100,7 @@ static int make_geom(long long Q, long long N, int D, int k, TopkGeom* g) {
   g->flag = o;  o += al((size_t)g->Qp * 4);
   g->flist = o; o += al((size_t)(g->Qp + 4) * 4);              // [0] = number of listed queries, then their ids
   g->fpart = o; o += al((size_t)g->fb_items * k * 12);         // fallback partial lists: fp64 score + u32 id
+  g->qimg = o;  o += al((size_t)g->n_qtiles * g->tile_bytes);   // bf16 tile images of the queries (packed once per search)
   g->cand = o;  o += al((size_t)g->Qp * g->slices * 4 * g->cap_s * 4);
   g->total = o;
   return NRX_OK;
@@ -138,18 +139,43 @@ topk_pack_kernel(const float* __restrict__ c, long long ld, long long N, int D, 
   if (lane == 0 && m > 0.f) atomicMax(max_norm_bits, __float_as_uint(sqrtf(m) * 1.0001f));
 }
 
+// ---- queries: fp32 -> bf16 tile images, once per search (both scans bulk-load them) ---------------------------
+__global__ void __launch_bounds__(256)
+topk_qpack_kernel(const float* __restrict__ q, long long ld, long long Q, int D, int Dp, uint8_t* __restrict__ img, long long n_qtiles) {
+  const long long nchunks = n_qtiles * (Dp / 8) * kTR;
+  const bool vec_ok = ((reinterpret_cast<uintptr_t>(q) & 15) == 0) && (ld % 4 == 0) && (D % 8 == 0);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nchunks; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i % kTR);
+    const long long rest = i / kTR;
+    const int kc = (int)(rest % (Dp / 8));
+    const long long tile = rest / (Dp / 8);
+    const long long row = tile * kTR + r;
+    float f[8];
+    if (row < Q && vec_ok && kc * 8 < D) {
+      const float4* src = reinterpret_cast<const float4*>(q + row * ld + kc * 8);
+      const float4 a = __ldg(src), b = __ldg(src + 1);
+      f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = (row < Q && kc * 8 + j < D) ? __ldg(q + row * ld + kc * 8 + j) : 0.f;
+    }
+    *reinterpret_cast<uint4*>(img + (size_t)tile * kTR * Dp * 2 + canon_off(kTR, r, kc)) =
+        make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+  }
+}
+
 // ---- the scan (MODE 0: group maxima of the sample tiles, MODE 1: candidate filter over every tile) ------------
 template <int MODE>
 __global__ void __launch_bounds__(kScanThreads, 1)
-topk_scan_kernel(const uint8_t* __restrict__ img, long long N, long long n_tiles, int tstride, int Dp, const float* __restrict__ q,
-                 long long qld, long long Q, int D, long long Qp, int nq_max, int stages, float* __restrict__ gmax,
+topk_scan_kernel(const uint8_t* __restrict__ img, long long N, long long n_tiles, int tstride, int Dp,
+                 const uint8_t* __restrict__ qimg, long long Qp, int nq_max, int stages, float* __restrict__ gmax,
                  long long n_groups, const float* __restrict__ theta, unsigned* __restrict__ count, unsigned* __restrict__ cand,
                  int cap_s) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const size_t tile_bytes = (size_t)kTR * Dp * 2;
   uint8_t* sQ = smem;                                  // [nq][tile image]
   uint8_t* sC = smem + (size_t)nq_max * tile_bytes;    // [stages][tile image]
-  __shared__ uint64_t full[4], empty[4], tfull[kMaxQT], tempty[kMaxQT];
+  __shared__ uint64_t full[4], empty[4], tfull[kMaxQT], tempty[kMaxQT], qbar;
   __shared__ uint32_t tmem_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long qt0 = (long long)blockIdx.y * nq_max;             // first query tile of this CTA
@@ -164,23 +190,10 @@ topk_scan_kernel(const uint8_t* __restrict__ img, long long N, long long n_tiles
   if (tid == 0) {
     for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int a = 0; a < kMaxQT; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 16); }
+    mbar_init(&qbar, 1);
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(&tmem_s, 512u);
-  // query tiles: fp32 -> bf16 canonical (rows >= Q are zero)
-  for (int i = tid; i < nq * (Dp / 8) * kTR; i += kScanThreads) {
-    const int r = i % kTR, kc = (i / kTR) % (Dp / 8), a = i / (kTR * (Dp / 8));
-    const long long row = (qt0 + a) * kTR + r;
-    float f[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int d = kc * 8 + j;
-      f[j] = (row < Q && d < D) ? __ldg(q + row * qld + d) : 0.f;
-    }
-    *reinterpret_cast<uint4*>(sQ + (size_t)a * tile_bytes + canon_off(kTR, r, kc)) =
-        make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
-  }
-  fence_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -188,7 +201,9 @@ topk_scan_kernel(const uint8_t* __restrict__ img, long long N, long long n_tiles
 
   if (t1 > t0) {
     if (warp == 0) {
-      if (lane == 0) {  // TMA producer
+      if (lane == 0) {  // TMA producer: the query tile images first (packed once per search), then the corpus stream
+        mbar_expect_tx(&qbar, (uint32_t)(nq * tile_bytes));
+        for (int a = 0; a < nq; ++a) bulk_g2s(sQ + (size_t)a * tile_bytes, qimg + (size_t)(qt0 + a) * tile_bytes, (uint32_t)tile_bytes, &qbar);
         uint32_t ph = 0, used = 0;
         int s = 0;
         for (long long t = t0; t < t1; ++t) {
@@ -209,6 +224,7 @@ topk_scan_kernel(const uint8_t* __restrict__ img, long long N, long long n_tiles
       const uint32_t kstep = (2u * (kTR * 16u)) >> 4;
       const uint32_t qstep = (uint32_t)(tile_bytes >> 4);
       const uint64_t qd0 = make_smem_desc(smem_u32(sQ), kTR * 16u, 128u);
+      mbar_wait(&qbar, 0);
       for (long long t = t0; t < t1; ++t) {
         mbar_wait(&full[s], (fph >> s) & 1u); fph ^= 1u << s;
         const uint64_t cd0 = make_smem_desc(smem_u32(sC + (size_t)s * tile_bytes), kTR * 16u, 128u);
@@ -282,14 +298,18 @@ topk_scan_kernel(const uint8_t* __restrict__ img, long long N, long long n_tiles
             if (MODE == 0) {
               gmax[qrow * n_groups + t * 4 + cq] = m;   // groups of 32 corpus rows
             } else if (m >= th[a]) {  // rare: a few hundred rows out of N pass the threshold
-              // this thread is the only writer of its (query, slice, quarter) region: plain stores, register counter
-              unsigned* mycand = cand + (((size_t)qrow * gridDim.x + blockIdx.x) * 4 + cq) * cap_s;
+              // this thread is the only writer of its (query, slice, quarter) region: plain stores, register counter.
+              // Kept compact (hit mask + bit loop instead of 32 unrolled tests): the unrolled form made the epilogue
+              // larger than the instruction cache (28 % of the stall samples were instruction fetch).
+              unsigned hits = 0;
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                if (v[j] >= th[a]) {
-                  if (mycnt[a] < (unsigned)cap_s) mycand[mycnt[a]] = (unsigned)(base + j);
-                  ++mycnt[a];
-                }
+              for (int j = 0; j < 32; ++j) hits |= (v[j] >= th[a] ? 1u : 0u) << j;
+              unsigned* mycand = cand + (((size_t)qrow * gridDim.x + blockIdx.x) * 4 + cq) * cap_s;
+              while (hits) {
+                const int j = __ffs(hits) - 1;
+                hits &= hits - 1;
+                if (mycnt[a] < (unsigned)cap_s) mycand[mycnt[a]] = (unsigned)(base + j);
+                ++mycnt[a];
               }
             }
           }
@@ -314,6 +334,7 @@ topk_scan_kernel(const uint8_t* __restrict__ img, long long N, long long n_tiles
 __device__ __forceinline__ unsigned f2key(float f) { unsigned u = __float_as_uint(f); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); }
 __device__ __forceinline__ float key2f(unsigned k) { return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k); }
 
+static constexpr int kThetaStage = 10240;   // group maxima staged in shared memory (40 KB)
 __global__ void __launch_bounds__(256)
 topk_theta_kernel(const float* __restrict__ gmax, long long n_tiles /* groups per query */, long long Qp, long long Q, int kprime,
                   const float* __restrict__ q, long long qld, int D, const unsigned* __restrict__ max_norm_bits,
@@ -342,24 +363,65 @@ topk_theta_kernel(const float* __restrict__ gmax, long long n_tiles /* groups pe
     if (tid == 0) theta[qi] = -FLT_MAX;
     return;
   }
+  // the query's group maxima as order-preserving keys, staged once in shared memory when they fit (4 radix passes)
+  extern __shared__ unsigned s_keys[];
+  const bool staged = n_tiles <= kThetaStage;
+  if (staged) {
+    for (long long t = tid; t < n_tiles; t += 256) s_keys[t] = f2key(__ldg(gmax + qi * n_tiles + t));
+    __syncthreads();
+  }
+  // bytes on which every key agrees need no pass (scores of one query share sign, exponent and often more: the first
+  // pass would hammer ONE histogram bin with every key)
+  unsigned kmin = 0xffffffffu, kmax = 0u;
+  for (long long t = tid; t < n_tiles; t += 256) {
+    const unsigned key = staged ? s_keys[t] : f2key(__ldg(gmax + qi * n_tiles + t));
+    kmin = min(kmin, key);
+    kmax = max(kmax, key);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    kmin = min(kmin, __shfl_xor_sync(NRX_FULL_MASK, kmin, o));
+    kmax = max(kmax, __shfl_xor_sync(NRX_FULL_MASK, kmax, o));
+  }
+  __shared__ unsigned s_mm[16];
+  if ((tid & 31) == 0) { s_mm[tid >> 5] = kmin; s_mm[8 + (tid >> 5)] = kmax; }
+  __syncthreads();
+  for (int w = 0; w < 8; ++w) { kmin = min(kmin, s_mm[w]); kmax = max(kmax, s_mm[8 + w]); }
   unsigned prefix = 0, mask = 0, remaining = (unsigned)kprime;
   for (int shift = 24; shift >= 0; shift -= 8) {
+    if (((kmin ^ kmax) >> shift) == 0u) {   // all keys agree down to this byte
+      prefix |= kmin & (255u << shift);
+      mask |= 255u << shift;
+      continue;
+    }
     hist[tid] = 0;
     __syncthreads();
     for (long long t = tid; t < n_tiles; t += 256) {
-      const unsigned key = f2key(__ldg(gmax + qi * n_tiles + t));
+      const unsigned key = staged ? s_keys[t] : f2key(__ldg(gmax + qi * n_tiles + t));
       if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
     }
     __syncthreads();
-    if (tid == 0) {
-      unsigned acc = 0;
-      int b = 255;
-      for (; b > 0; --b) {
-        if (acc + hist[b] >= remaining) break;
-        acc += hist[b];
+    if (tid < 32) {
+      // bin of the `remaining`-th largest key, bins walked from 255 down: lane L owns bins 255 - 8L .. 248 - 8L
+      unsigned c[8], tot = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { c[j] = hist[255 - 8 * tid - j]; tot += c[j]; }
+      unsigned inc = tot;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(NRX_FULL_MASK, inc, o); if (tid >= o) inc += v; }
+      const unsigned before = inc - tot;                         // keys in the bins above this lane's
+      const bool here = before < remaining && remaining <= inc;  // exactly one lane (remaining <= number of keys)
+      if (here) {
+        unsigned acc = before;
+        int b = 255 - 8 * tid;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (acc + c[j] >= remaining) { b = 255 - 8 * tid - j; break; }
+          acc += c[j];
+        }
+        s_prefix = prefix | ((unsigned)b << shift);
+        s_remaining = remaining - acc;
       }
-      s_prefix = prefix | ((unsigned)b << shift);
-      s_remaining = remaining - acc;
     }
     __syncthreads();
     prefix = s_prefix;
@@ -371,19 +433,65 @@ topk_theta_kernel(const float* __restrict__ gmax, long long n_tiles /* groups pe
 }
 
 // ---- exact scoring + ordering -------------------------------------------------------------------------------
-__device__ __forceinline__ double dot64(const float* __restrict__ qs, const float* __restrict__ row, int D) {
-  // four independent fp64 chains (shorter dependency chain), combined in a fixed order; every path that
-  // scores a row uses this one function, so equal rows always get bit-equal scores
-  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-  int d = 0;
-  for (; d + 4 <= D; d += 4) {
-    s0 = fma((double)qs[d], (double)__ldg(row + d), s0);
-    s1 = fma((double)qs[d + 1], (double)__ldg(row + d + 1), s1);
-    s2 = fma((double)qs[d + 2], (double)__ldg(row + d + 2), s2);
-    s3 = fma((double)qs[d + 3], (double)__ldg(row + d + 3), s3);
+// The ONE exact scoring function (final re-scoring and the fallback scan both use it, so equal rows always get bit-equal
+// scores): a warp scores one row — lane l takes elements 4l .. 4l+3 of every 128-element block (coalesced 16-byte
+// loads), accumulates in fp64, and the lane partials are combined by a fixed xor-shuffle tree.  Every lane returns
+// the same value.  `qs` is the query in shared memory.
+__device__ __forceinline__ double dot64_warp(const float* __restrict__ qs, const float* __restrict__ row, int D, int lane, bool vec) {
+  double s = 0.0;
+  if (vec) {
+    for (int d = lane * 4; d < D; d += 128) {
+      const float4 c = __ldg(reinterpret_cast<const float4*>(row + d));
+      const float4 q = *reinterpret_cast<const float4*>(qs + d);
+      s = fma((double)q.x, (double)c.x, s);
+      s = fma((double)q.y, (double)c.y, s);
+      s = fma((double)q.z, (double)c.z, s);
+      s = fma((double)q.w, (double)c.w, s);
+    }
+  } else {
+    for (int d0 = lane * 4; d0 < D; d0 += 128) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (d0 + j < D) s = fma((double)qs[d0 + j], (double)__ldg(row + d0 + j), s);
+    }
   }
-  for (; d < D; ++d) s0 = fma((double)qs[d], (double)__ldg(row + d), s0);
-  return (s0 + s1) + (s2 + s3);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(NRX_FULL_MASK, s, o);
+  return s;
+}
+// Four rows at once: the four 16-byte loads of a 128-element block are issued before the first FMA (one memory
+// latency per block of four candidates instead of four).  Same per-row arithmetic, bit for bit, as dot64_warp.
+__device__ __forceinline__ void dot64_warp4(const float* __restrict__ qs, const float* const (&row)[4], int D, int lane, bool vec,
+                                            double (&out)[4]) {
+  if (!vec) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) out[u] = dot64_warp(qs, row[u], D, lane, false);
+    return;
+  }
+  double s[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int d = lane * 4; d < D; d += 128) {
+    float4 c[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) c[u] = __ldg(reinterpret_cast<const float4*>(row[u] + d));
+    const float4 q = *reinterpret_cast<const float4*>(qs + d);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      s[u] = fma((double)q.x, (double)c[u].x, s[u]);
+      s[u] = fma((double)q.y, (double)c[u].y, s[u]);
+      s[u] = fma((double)q.z, (double)c[u].z, s[u]);
+      s[u] = fma((double)q.w, (double)c[u].w, s[u]);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) s[u] += __shfl_xor_sync(NRX_FULL_MASK, s[u], o);
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) out[u] = s[u];
+}
+__device__ __forceinline__ bool rows_vec_ok(const float* c, long long cld, int D) {
+  return ((reinterpret_cast<uintptr_t>(c) & 15) == 0) && (cld % 4 == 0) && (D % 4 == 0);
 }
 
 // (score desc, id asc): returns true if a must come before b
@@ -459,15 +567,26 @@ topk_final_kernel(const float* __restrict__ c, long long cld, long long N, int D
   int n2 = 1;
   while (n2 < (int)cnt) n2 <<= 1;
   for (int i = (int)cnt + tid; i < n2; i += 256) { id[i] = 0xffffffffu; s[i] = -DBL_MAX; }
-  for (unsigned i = tid; i < cnt; i += 256) {  // all candidates in flight together: region by binary search
+  for (unsigned i = tid; i < cnt; i += 256) {  // candidate row of list position i: region by binary search
     int lo = 0, hi = n_slices - 1;
     while (lo < hi) {
       const int mid = (lo + hi + 1) >> 1;
       if (s_off[mid] <= i) lo = mid; else hi = mid - 1;
     }
-    const unsigned row = cand[((size_t)qi * n_slices + lo) * cap_s + (i - s_off[lo])];
-    id[i] = row;
-    s[i] = dot64(qs, c + (long long)row * cld, D);
+    id[i] = cand[((size_t)qi * n_slices + lo) * cap_s + (i - s_off[lo])];
+  }
+  __syncthreads();
+  {  // exact scores: one warp per candidate, 4 rows in flight per warp
+    const int warp = tid >> 5, lane = tid & 31;
+    const bool vec = rows_vec_ok(c, cld, D);
+    for (unsigned i0 = (unsigned)warp * 4; i0 < cnt; i0 += 32) {
+      double v[4];
+      const float* rowp[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) rowp[u] = c + (long long)id[min(i0 + u, cnt - 1)] * cld;   // past the end: re-score the last one
+      dot64_warp4(qs, rowp, D, lane, vec, v);
+      if (lane < 4 && i0 + lane < cnt) s[i0 + lane] = lane == 0 ? v[0] : lane == 1 ? v[1] : lane == 2 ? v[2] : v[3];
+    }
   }
   __syncthreads();
   bitonic_sort(s, id, n2, tid, 256);
@@ -528,15 +647,28 @@ topk_exact_kernel(const float* __restrict__ c, long long cld, long long N, int D
     for (int d = tid; d < D; d += 256) qs[d] = __ldg(q + qi * qld + d);
     if (tid == 0) { s_cnt = 0; s_th = -DBL_MAX; }
     __syncthreads();
+    const int warp = tid >> 5, lane = tid & 31;
+    const bool vec = rows_vec_ok(c, cld, D);
     for (long long r0 = r_lo; r0 < r_hi; r0 += 256) {
+      // 256 rows per round: every warp scores 32 rows (one at a time, coalesced), lane u keeps row u's score
+      double mine = 0.0;
+      for (int u = 0; u < 32; u += 4) {
+        const long long rb = r0 + warp * 32 + u;
+        if (rb >= r_hi) break;
+        const float* rowp[4];
+        double v4[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rowp[j] = c + (rb + j < r_hi ? rb + j : r_hi - 1) * cld;
+        dot64_warp4(qs, rowp, D, lane, vec, v4);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (lane == u + j) mine = v4[j];
+      }
       const long long row = r0 + tid;
-      if (row < r_hi) {
-        const double v = dot64(qs, c + row * cld, D);
-        if (v >= s_th) {
-          const unsigned slot = atomicAdd(&s_cnt, 1u);
-          s[slot] = v;           // slot < kFbCap: pruned whenever fewer than 256 free slots remain
-          id[slot] = (unsigned)row;
-        }
+      if (row < r_hi && mine >= s_th) {
+        const unsigned slot = atomicAdd(&s_cnt, 1u);
+        s[slot] = mine;           // slot < kFbCap: pruned whenever fewer than 256 free slots remain
+        id[slot] = (unsigned)row;
       }
       __syncthreads();
       if (s_cnt > (unsigned)(kFbCap - 256) || r0 + 256 >= r_hi) {
@@ -717,18 +849,28 @@ extern "C" int nrx_topk_search64(const void* index, const float* corpus, int64_t
     cudaFuncSetAttribute(topk_scan_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     NRX_REQUIRE(g.slices <= 1024, NRX_EUNSUPPORTED, "more than 1024 corpus slices");
     const long long n_groups = g.n_stiles * 4;
+    uint8_t* qimg = w + g.qimg;
+    {
+      const long long nchunks = g.n_qtiles * (g.Dp / 8) * kTR;
+      long long blocks = (nchunks + 255) / 256;
+      if (blocks > 4LL * sm_count()) blocks = 4LL * sm_count();
+      topk_qpack_kernel<<<(unsigned)blocks, 256, 0, st>>>(queries, q_ld, Q, D, g.Dp, qimg, g.n_qtiles);
+      rc = check_launch("topk_qpack");
+      if (rc != NRX_OK) return rc;
+    }
     // sample: every stride-th tile -> group maxima -> theta
     long long s_slices = g.slices < g.n_stiles ? g.slices : g.n_stiles;
     topk_scan_kernel<0><<<dim3((unsigned)s_slices, (unsigned)g.n_qgroups), kScanThreads, smem, st>>>(
-        img, N, g.n_tiles, g.stride, g.Dp, queries, q_ld, Q, D, g.Qp, g.nq, g.stages, gmax, n_groups, nullptr, nullptr, nullptr, g.cap_s);
+        img, N, g.n_tiles, g.stride, g.Dp, qimg, g.Qp, g.nq, g.stages, gmax, n_groups, nullptr, nullptr, nullptr, g.cap_s);
     rc = check_launch("topk_scan<sample>");
     if (rc != NRX_OK) return rc;
-    topk_theta_kernel<<<(unsigned)g.Qp, 256, 0, st>>>(gmax, n_groups, g.Qp, Q, g.kprime_s, queries, q_ld, D, (const unsigned*)index, theta,
-                                                     eps, flist, flag);
+    const size_t tsm = n_groups <= kThetaStage ? (size_t)n_groups * 4 : 0;
+    topk_theta_kernel<<<(unsigned)g.Qp, 256, tsm, st>>>(gmax, n_groups, g.Qp, Q, g.kprime_s, queries, q_ld, D, (const unsigned*)index, theta,
+                                                       eps, flist, flag);
     rc = check_launch("topk_theta");
     if (rc != NRX_OK) return rc;
     topk_scan_kernel<1><<<dim3((unsigned)g.slices, (unsigned)g.n_qgroups), kScanThreads, smem, st>>>(
-        img, N, g.n_tiles, 1, g.Dp, queries, q_ld, Q, D, g.Qp, g.nq, g.stages, nullptr, 0, theta, count, cand, g.cap_s);
+        img, N, g.n_tiles, 1, g.Dp, qimg, g.Qp, g.nq, g.stages, nullptr, 0, theta, count, cand, g.cap_s);
     rc = check_launch("topk_scan<filter>");
     if (rc != NRX_OK) return rc;
     const int n_regions = (int)(4 * g.slices);

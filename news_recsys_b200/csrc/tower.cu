@@ -983,6 +983,9 @@ extern "C" int nrx_tower_bwd_dx(const NrxTower* h_tower, int64_t B, const float*
   cudaStream_t st = (cudaStream_t)stream;
   uint8_t* w = (uint8_t*)ws;
   {
+    const char* env3 = getenv("NRX_TOWER_DX3");
+    if ((env3 ? atoi(env3) != 0 : true) && tower_dx3_eligible(k, grad_x != nullptr))
+      return tower_dx3_launch(k, B, grad_y, gy_ld, grad_x, gx_ld, accumulate_gx, w, st);
     const size_t smem = fwd_smem_bytes(k, true);
     NRX_REQUIRE(smem <= 227 * 1024, NRX_EUNSUPPORTED, "tower backward needs %zu B of shared memory (> 227 KB)", smem);
     cudaError_t e = cudaFuncSetAttribute(tower_bwd_dx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -46,4 +46,10 @@ bool tower_fwd3_eligible(const TowerK& k);
 int tower_fwd3_launch(const TowerK& k, const float* x, long long ldx, long long B, float* y, long long ldy, uint8_t* ws,
                       int training, const NrxTowerHead* head, cudaStream_t st);
 
+
+// ---- pipelined dX chain (tower_bwd_dx.cu) ----
+bool tower_dx3_eligible(const TowerK& k, bool need_gx);
+int tower_dx3_launch(const TowerK& k, long long B, const float* gy, long long ldgy, float* gx, long long ldgx, int accumulate_gx,
+                     uint8_t* ws, cudaStream_t st);
+
 }  // namespace nrx

@@ -112,6 +112,25 @@ class BaseModel(_Base):
     def _weights(self) -> Dict[str, torch.Tensor]:
         return {k: m.weight for k, m in self.embedding_tables.items()}
 
+    # ---- out-of-table ids: the reference's nn.Embedding raises (base_model.py:271); K1 raises a status bit -----------
+    def _id_status(self, device) -> torch.Tensor:
+        """Persistent int32 status word the gather kernels OR into when an id is outside [0, rows)."""
+        st = getattr(self, "_id_status_buf", None)
+        if st is None or st.device != device:
+            st = torch.zeros(1, dtype=torch.int32, device=device)
+            self._id_status_buf = st
+        return st
+
+    def check_ids(self):
+        """Synchronises and raises if any forward since the last check saw an id outside its embedding table — what the
+        reference's nn.Embedding reports as an IndexError / device assert.  Cheap to call every N steps or with the loss
+        read-back; the flag is sticky until checked."""
+        st = getattr(self, "_id_status_buf", None)
+        if st is not None and int(st.item()) != 0:
+            st.zero_()
+            raise IndexError("a feature id outside its embedding table reached the gather kernel "
+                             "(vocabulary / config mismatch; the reference's nn.Embedding raises here, base_model.py:271)")
+
     def bind_features(self, batch, feature_names, want_inv_den=True):
         """NrxFeat[] for `feature_names` (sorted) of this batch -> (binding, dims, names, out_dim)."""
         names = sorted(list(feature_names))
@@ -129,10 +148,11 @@ class BaseModel(_Base):
             return torch.tensor([]).to(dev), [], []
         tnames = list(self.embedding_tables.keys())
         ws = [self.embedding_tables[t].weight for t in tnames]
+        fb.status = self._id_status(fb.device)
         if torch.is_grad_enabled() and any(w.requires_grad for w in ws):
             x = ops.EmbedPoolFn.apply(fb, out_dim, tnames, *ws)
         else:
-            x = ops.embed_pool_fwd(fb, out_dim)
+            x = ops.embed_pool_fwd(fb, out_dim, status=fb.status)
         return x, dims, names
 
     def get_feature_embedding(self, feature_name: str, feature_value: torch.Tensor) -> torch.Tensor:
@@ -146,7 +166,7 @@ class BaseModel(_Base):
         flat = feature_value.reshape(-1)
         spec = ops.FeatSpec("_v", t, 0, w.shape[1], 1, False, 0)
         fb = ops.FeatBinding([spec], {t: w.detach()}, {"_v": flat}, want_inv_den=False)
-        out = ops.embed_pool_fwd(fb, w.shape[1])
+        out = ops.embed_pool_fwd(fb, w.shape[1], status=self._id_status(w.device))
         return out.view(*feature_value.shape, w.shape[1])
 
     def array_feature_pooling(self, embedding: torch.Tensor, mask: Optional[torch.Tensor] = None) -> torch.Tensor:

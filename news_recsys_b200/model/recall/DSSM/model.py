@@ -92,11 +92,23 @@ class DSSM(BaseModel):
 
     # ---- retrieval (on_train_epoch_end :230-254, hit_rate :209) ---------------------------------------
     @torch.no_grad()
-    def build_item_index(self, item_batches, id_base=0):
-        """Item tower over the corpus (list of batches with the item features) -> normalised vectors -> index."""
+    def build_item_index(self, item_batches, id_base=0, item_key="item_id"):
+        """Item tower over the corpus (list of batches with the item features) -> normalised vectors -> index.
+
+        The reference keeps `idx_item_emb_dic`: corpus position -> item id, filled from the id column of every corpus
+        batch (`on_train_epoch_end`, recall/DSSM/model.py:236-247) and maps search results through it before the history
+        filter / hit test (:212-215).  Same here: the id column (`item_key`) of the corpus batches is collected into
+        `self.index_item_ids` (device int64 [N]) and `retrieve_items()` maps ranked positions through it.  Batches
+        without that column fall back to position + id_base (the identity mapping of an id-ordered corpus)."""
         embs = [ops.l2_normalize(self.item_tower(b)) for b in item_batches]
         self.all_item_embeddings = torch.cat(embs, dim=0)
-        self.index = TopkIndex(self.all_item_embeddings, id_base=id_base)
+        self.index = TopkIndex(self.all_item_embeddings, id_base=0)
+        if all(item_key in b for b in item_batches):
+            self.index_item_ids = torch.cat([b[item_key].reshape(-1).to(self.all_item_embeddings.device, torch.int64) for b in item_batches])
+        else:
+            self.index_item_ids = torch.arange(self.all_item_embeddings.shape[0], device=self.all_item_embeddings.device) + int(id_base)
+        if self.index_item_ids.numel() != self.all_item_embeddings.shape[0]:
+            raise ValueError("build_item_index: the item id column and the corpus disagree on the number of items")
         return self.index
 
     @staticmethod
@@ -128,14 +140,22 @@ class DSSM(BaseModel):
             if history_key + "_mask" in b:
                 hist[b[history_key + "_mask"] == 0] = -1
             hist[hist == 0] = -1                                    # id 0 is padding
-            _, ids = self.retrieve(b, k + hist.shape[1])
+            _, ids = self.retrieve_items(b, k + hist.shape[1])     # ITEM ids (positions mapped through the corpus id column)
             hits += int(self.filter_history_hits(ids, hist, b[target_key], k).sum())
             n += ids.shape[0]
         return hits / n if n > 0 else 0
 
     @torch.no_grad()
+    def retrieve_items(self, batch, k):
+        """(scores [B,k], ITEM ids [B,k]): corpus positions of `retrieve` mapped through the id column collected by
+        build_item_index (the reference's idx_item_emb_dic, :212-215); padding (-1) stays -1."""
+        s, pos = self.retrieve(batch, k)
+        ids = torch.where(pos >= 0, self.index_item_ids[pos.clamp_min(0)], pos)
+        return s, ids
+
+    @torch.no_grad()
     def retrieve(self, batch, k):
-        """(scores [B,k], corpus positions [B,k]) ordered by (inner product desc, id asc)."""
+        """(scores [B,k], corpus positions [B,k]) ordered by (inner product desc, position asc)."""
         if self.index is None:
             raise ValueError("Index not initialized. Call build_item_index first.")
         return self.index.search(ops.l2_normalize(self.user_tower(batch)), k)

@@ -41,16 +41,19 @@ class FM(BaseModel):
     def forward(self, x):
         names = self.user_feature_names | self.item_feature_names
         fb, dims, _, out_dim = self.bind_features(x, names)
+        if fb is None:
+            raise ValueError("FM.forward: none of the model's features is present in the batch")
+        fb.status = self._id_status(fb.device)   # out-of-table ids raise at the next check_ids() (nn.Embedding would raise here)
         tnames = list(self.embedding_tables.keys())
         ws = [self.embedding_tables[t].weight for t in tnames]
         if ops.fm_fused_eligible(fb.specs, self._weights()):
             if torch.is_grad_enabled():
                 return ops.FmFusedFn.apply(fb, out_dim, tnames, self.score_fc.bias, *ws)
-            prob, _, _, _ = ops.fm_fused_fwd(fb, self.score_fc.bias)
+            prob, _, _, _ = ops.fm_fused_fwd(fb, self.score_fc.bias, status=fb.status)
             return prob.view(-1, 1)
         if len(set(dims)) != 1:
             raise RuntimeError("stack expects each tensor to be equal size (FM needs equal field widths, fm/model.py:58)")
-        feats = ops.EmbedPoolFn.apply(fb, out_dim, tnames, *ws) if torch.is_grad_enabled() else ops.embed_pool_fwd(fb, out_dim)
+        feats = ops.EmbedPoolFn.apply(fb, out_dim, tnames, *ws) if torch.is_grad_enabled() else ops.embed_pool_fwd(fb, out_dim, status=fb.status)
         cols, c = [], 0
         for d in dims:
             cols.append(c)

@@ -185,7 +185,7 @@ class EmbedPoolFn(torch.autograd.Function):
         ctx.fb = fb
         ctx.table_names = table_names
         ctx.weights = weights
-        return embed_pool_fwd(fb, out_dim)
+        return embed_pool_fwd(fb, out_dim, status=getattr(fb, "status", None))
 
     @staticmethod
     def backward(ctx, grad_out):
@@ -406,7 +406,7 @@ class FmFusedFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, fb: FeatBinding, out_dim: int, table_names: List[str], bias, *weights):
-        prob, _, _, _ = fm_fused_fwd(fb, bias)
+        prob, _, _, _ = fm_fused_fwd(fb, bias, status=getattr(fb, "status", None))
         ctx.fb, ctx.out_dim, ctx.table_names, ctx.weights = fb, out_dim, table_names, weights
         ctx.save_for_backward(prob)
         return prob.view(-1, 1)

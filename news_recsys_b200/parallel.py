@@ -390,6 +390,29 @@ class ShardedEmbeddingTrainer(FusedTrainer):
         self._update(self.gfb_bwd, self._plan, self.gx_global)
         return self.loss
 
+    def exchange_bytes(self) -> int:
+        """Bytes one rank sends in the forward exchange of one step (reduce-scatter of the [G*B, ΣD] partials: G - 1 blocks)."""
+        return (self.world - 1) * self.B * self.out_dim * 4
+
+    def exchange_bandwidth(self, iters: int = 10) -> dict:
+        """Device-timed bandwidth of the forward exchange alone (same buffers as the step), max over ranks."""
+        for _ in range(2):
+            dist.reduce_scatter_tensor(self.x_local, self.partial, op=dist.ReduceOp.SUM, group=self.group)
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            dist.reduce_scatter_tensor(self.x_local, self.partial, op=dist.ReduceOp.SUM, group=self.group)
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / iters], dtype=torch.float64, device=self.dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        ms = float(t[0])
+        return {"collective": "reduce_scatter(sum) of the [G*B, ΣD] fp32 partial features", "bytes_sent_per_rank": self.exchange_bytes(),
+                "ms": ms, "gb_per_s_per_rank": self.exchange_bytes() / (ms * 1e-3) / 1e9,
+                "nvlink_peak_gb_per_s": 770.0, "note": "770 GB/s = measured peer copy per direction (B200_PROFILING.md)"}
+
     def gather_table(self, name: str) -> torch.Tensor:
         """Full [rows, D] table on every rank (tests / checkpointing)."""
         w = self.model.embedding_tables[name].weight.data

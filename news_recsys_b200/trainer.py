@@ -120,6 +120,9 @@ class FusedTrainer:
         self._loss_status = torch.zeros(2, dtype=torch.float32, device=self.dev)
         self.id_status = self._loss_status[1:2].view(torch.int32)
         self.fused_input = os.environ.get("NRX_FUSED_INPUT", "1") == "1"
+        # asynchronous status read-back (step()): stream, pinned word and events exist before the first step
+        self._stat = dict(n=0, posted=False, stream=torch.cuda.Stream(device=self.dev),
+                          host=torch.zeros(2, dtype=torch.float32).pin_memory(), ev=torch.cuda.Event(), done=torch.cuda.Event())
         self.d_step = torch.zeros(1, dtype=torch.int32, device=self.dev)
         self.d_hp = torch.zeros(4, dtype=torch.float32, device=self.dev)
         self._flatten_dense()
@@ -515,16 +518,13 @@ class FusedTrainer:
         return self.loss
 
     def _post_status(self):
-        st = self.__dict__.setdefault("_stat", dict(n=0, stream=None, host=None, done=None, ev=None))
+        st = self._stat
         st["n"] += 1
         if st["n"] % self._STATUS_EVERY:
             return
-        if st["stream"] is None:
-            st["stream"] = torch.cuda.Stream(device=self.dev)
-            st["host"] = torch.zeros(2, dtype=torch.float32).pin_memory()
-            st["ev"], st["done"] = torch.cuda.Event(), torch.cuda.Event()
-        elif not st["done"].query():
+        if st["posted"] and not st["done"].query():
             return   # the previous read-back is still in flight
+        st["posted"] = True
         st["ev"].record(torch.cuda.current_stream(self.dev))
         with torch.cuda.stream(st["stream"]):
             st["stream"].wait_event(st["ev"])
@@ -532,8 +532,8 @@ class FusedTrainer:
             st["done"].record(st["stream"])
 
     def _poll_status(self):
-        st = self.__dict__.get("_stat")
-        if st is not None and st["done"] is not None and st["done"].query():
+        st = self._stat
+        if st["posted"] and st["done"].query():
             self._raise_for_status(int(st["host"].view(torch.int32)[1]))
 
     @staticmethod

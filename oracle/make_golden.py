@@ -16,6 +16,15 @@ replay through the CUDA path.
 import os
 import sys
 
+# The reference creates its embedding tables while iterating a Python `set` of feature names
+# (src/model/BaseModel/base_model.py:146-164), so the order of the N(0,1) draws — and with it every fixture — depends on
+# the string hash seed.  Pin it: regenerating a fixture then reproduces it byte for byte.  (The fixtures committed in
+# round 1 were written under a random hash seed; they stay as they are — authentic outputs of the reference for the
+# parameters stored next to them — and `--only` regenerates single fixtures without touching the others.)
+if os.environ.get("PYTHONHASHSEED") != "0":
+    os.environ["PYTHONHASHSEED"] = "0"
+    os.execv(sys.executable, [sys.executable] + sys.argv)
+
 import numpy as np
 import torch
 
@@ -68,11 +77,17 @@ def np_sd(sd):
     return {"sd__" + k: v.detach().cpu().numpy().copy() for k, v in sd.items()}
 
 
-def run_model(kind, cls, cfg_name, B=24, with_mask=True, tag=None, opt_steps=0):
+def run_model(kind, cls, cfg_name, B=24, with_mask=True, tag=None, opt_steps=0, table_scale=None):
     path = os.path.join(CFGS, f"train_cf_{cfg_name}.yaml")
     cfg = yaml.safe_load(open(path))
     torch.manual_seed(42)
     model = cls(path)
+    if table_scale is not None:
+        # N(0,1) tables saturate the FM logit (|z| ~ 15: probabilities 1e-7, the BCE clamp does the work); scaled tables
+        # keep sigmoid and its gradient in their informative range
+        with torch.no_grad():
+            for t in model.embedding_tables.values():
+                t.weight.mul_(table_scale)
     # make biases / cross terms non-trivial so the fixture exercises them
     g = torch.Generator().manual_seed(7)
     with torch.no_grad():
@@ -184,22 +199,34 @@ def run_units():
 
 
 def main():
+    import argparse
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default="", help="comma-separated fixture names to (re)generate, e.g. fm_soft")
+    only = set(filter(None, ap.parse_args().only.split(",")))
     from src.model.sort.fm.model import FM
     from src.model.sort.deep.model import Deep
     from src.model.sort.widedeep.model import WideDeep
     from src.model.sort.dcn.model import DCN
     from src.model.sort.lr.model import LR
-    run_model("lr", LR, "lr")
-    run_model("fm", FM, "fm", opt_steps=3)
-    run_model("fm", FM, "fm_hist")
-    run_model("deep", Deep, "deep", opt_steps=3)
-    run_model("deep", Deep, "deep_hist")
-    run_model("deep", Deep, "deep_hist", with_mask=False, tag="deep_hist_nomask")
-    run_model("widedeep", WideDeep, "widedeep")
-    run_model("widedeep", WideDeep, "widedeep_hist")
-    run_model("dcn", DCN, "dcn")
-    run_model("dcn", DCN, "dcn_hist")
-    run_units()
+    jobs = [
+        ("lr", lambda: run_model("lr", LR, "lr")),
+        ("fm", lambda: run_model("fm", FM, "fm", opt_steps=3)),
+        ("fm_hist", lambda: run_model("fm", FM, "fm_hist")),
+        # de-saturated FM fixtures (fm.npz has probabilities ~1e-7, its gradient check mostly sees the clamp)
+        ("fm_soft", lambda: run_model("fm", FM, "fm", tag="fm_soft", opt_steps=3, table_scale=0.3)),
+        ("fm_hist_soft", lambda: run_model("fm", FM, "fm_hist", tag="fm_hist_soft", table_scale=0.3)),
+        ("deep", lambda: run_model("deep", Deep, "deep", opt_steps=3)),
+        ("deep_hist", lambda: run_model("deep", Deep, "deep_hist")),
+        ("deep_hist_nomask", lambda: run_model("deep", Deep, "deep_hist", with_mask=False, tag="deep_hist_nomask")),
+        ("widedeep", lambda: run_model("widedeep", WideDeep, "widedeep")),
+        ("widedeep_hist", lambda: run_model("widedeep", WideDeep, "widedeep_hist")),
+        ("dcn", lambda: run_model("dcn", DCN, "dcn")),
+        ("dcn_hist", lambda: run_model("dcn", DCN, "dcn_hist")),
+        ("units", run_units),
+    ]
+    for name, fn in jobs:
+        if not only or name in only:
+            fn()
 
 
 if __name__ == "__main__":

@@ -17,6 +17,14 @@ the feature-name SETS (:150,:167) which decides the column order of the tower in
 
     python oracle/make_golden_dssm.py        # build container only; writes tests/golden/dssm.npz
 """
+import os as _os
+import sys as _sys
+
+# set iteration order inside the reference depends on the string hash seed: pin it so that regenerating reproduces the fixture
+if _os.environ.get("PYTHONHASHSEED") != "0":
+    _os.environ["PYTHONHASHSEED"] = "0"
+    _os.execv(_sys.executable, [_sys.executable] + _sys.argv)
+
 import os
 import sys
 import types

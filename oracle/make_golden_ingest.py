@@ -6,6 +6,14 @@ src/dataset/DataReader/data_reader.py:57-60) and the batches the reference's OWN
 
     python oracle/make_golden_ingest.py      # build container only
 """
+import os as _os
+import sys as _sys
+
+# set iteration order inside the reference depends on the string hash seed: pin it so that regenerating reproduces the fixture
+if _os.environ.get("PYTHONHASHSEED") != "0":
+    _os.environ["PYTHONHASHSEED"] = "0"
+    _os.execv(_sys.executable, [_sys.executable] + _sys.argv)
+
 import os
 import sys
 

@@ -6,6 +6,14 @@ dict is captured from the method's frame when it returns (`sys.setprofile`) — 
 
     python oracle/make_golden_valmetrics.py      # build container only; writes tests/golden/valmetrics.npz
 """
+import os as _os
+import sys as _sys
+
+# set iteration order inside the reference depends on the string hash seed: pin it so that regenerating reproduces the fixture
+if _os.environ.get("PYTHONHASHSEED") != "0":
+    _os.environ["PYTHONHASHSEED"] = "0"
+    _os.execv(_sys.executable, [_sys.executable] + _sys.argv)
+
 import contextlib
 import io
 import os

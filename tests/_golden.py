@@ -8,7 +8,7 @@ import yaml
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CFGS = os.path.join(GOLD, "configs")
 
-MODEL_FIXTURES = ["lr", "fm", "fm_hist", "deep", "deep_hist", "deep_hist_nomask",
+MODEL_FIXTURES = ["lr", "fm", "fm_hist", "fm_soft", "fm_hist_soft", "deep", "deep_hist", "deep_hist_nomask",
                   "widedeep", "widedeep_hist", "dcn", "dcn_hist"]
 
 

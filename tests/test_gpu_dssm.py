@@ -132,18 +132,24 @@ def test_batched_hit_rate_equals_reference_loop():
     torch.manual_seed(1)
     m = DSSM(cfg, hparams={"out_dim": 16}).to(DEV)
     items = {k: v.to(DEV) for k, v in synth_batch(cfg, 300, seed=2).items()}
-    items["item_id"] = torch.arange(1, 301, device=DEV) % 300     # corpus position p holds item ids 1..299, 0
+    # corpus position p holds item id perm[p] (NOT the identity: the reference maps positions through idx_item_emb_dic,
+    # recall/DSSM/model.py:212-215, filled from the id column of the corpus batches :236-247)
+    perm = torch.randperm(300, generator=torch.Generator().manual_seed(5)).to(DEV) + 1          # ids 1..300
+    items["item_id"] = perm
     m.build_item_index([items])
+    assert torch.equal(m.index_item_ids, perm)
     k = 10
     batches = [{kk: v.to(DEV) for kk, v in synth_batch(cfg, 64, seed=10 + i).items()} for i in range(3)]
     for b in batches:
-        b["item_id"] = torch.randint(0, 300, (64,), device=DEV)    # target = a corpus POSITION (identity id map)
-        b["user_history"] = torch.randint(0, 300, b["user_history"].shape, device=DEV) * (b["user_history_mask"] > 0)
+        b["item_id"] = torch.randint(1, 301, (64,), device=DEV)    # target ITEM id
+        b["user_history"] = torch.randint(1, 301, b["user_history"].shape, device=DEV) * (b["user_history_mask"] > 0)
     got = m.hit_rate(batches, k=k)
     ranked, hists, targets = [], [], []
     for b in batches:
         H = b["user_history"].shape[1]
-        _, ids = m.retrieve(b, k + H)
+        _, pos = m.retrieve(b, k + H)
+        _, ids = m.retrieve_items(b, k + H)
+        assert torch.equal(ids, perm[pos])                          # positions -> item ids
         for q in range(ids.shape[0]):
             h = b["user_history"][q][(b["user_history_mask"][q] > 0) & (b["user_history"][q] != 0)]
             ranked.append(ids[q].cpu().tolist()); hists.append(set(h.cpu().tolist())); targets.append(int(b["item_id"][q]))

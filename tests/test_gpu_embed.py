@@ -34,7 +34,7 @@ def _rel_close(a, b, rtol, what):
     assert err <= rtol, f"{what}: max err / max|ref| = {err:.3e} > {rtol}"
 
 
-@pytest.mark.parametrize("name", ["lr", "fm", "fm_hist", "deep", "deep_hist", "deep_hist_nomask", "widedeep_hist", "dcn_hist"])
+@pytest.mark.parametrize("name", ["lr", "fm", "fm_hist", "fm_soft", "fm_hist_soft", "deep", "deep_hist", "deep_hist_nomask", "widedeep_hist", "dcn_hist"])
 def test_k1_features_match_reference(name):
     """get_embeddings_from_batch: sparse columns bit-exact (pure gather), pooled columns 1e-5."""
     from news_recsys_b200.model.BaseModel.base_model import BaseModel
@@ -187,7 +187,7 @@ def test_k3_fused_row_update(mode):
         torch.testing.assert_close(dt[k].cpu(), exp, rtol=2e-5, atol=1e-6)
 
 
-@pytest.mark.parametrize("name", ["lr", "fm", "fm_hist"])
+@pytest.mark.parametrize("name", ["lr", "fm", "fm_hist", "fm_soft", "fm_hist_soft"])
 def test_model_forward_backward_matches_reference(name):
     """forward(batch), bceLoss and loss.backward() of the drop-in modules vs the reference's own outputs."""
     g = load(name)
@@ -271,3 +271,35 @@ def test_dense_adamw_matches_reference_rule():
     d = ref.to(DEV)
     ops.adamw_dense_(d, gg.to(DEV), torch.zeros(257, device=DEV), torch.zeros(257, device=DEV), 1, 1e-3)
     torch.testing.assert_close(d.cpu(), opt_p.detach(), rtol=1e-5, atol=1e-7)
+
+
+def test_model_and_trainer_raise_on_out_of_table_ids():
+    """an id outside its table must not train silently on zero vectors.  The reference's nn.Embedding raises
+    (base_model.py:271); here K1 raises a sticky status bit that Model.check_ids() / FusedTrainer.check_status() /
+    FusedTrainer.feed() turn into an exception."""
+    from news_recsys_b200._lib import NrxError
+    from news_recsys_b200.model.sort.deep.model import Deep
+    from news_recsys_b200.synthetic import mind_config, synth_batch
+    from news_recsys_b200.trainer import FusedTrainer
+    rows = {"user_id": 300, "item_id": 200, "category": 18, "subcategory": 70, "user_click_category": 18}
+    cfg = mind_config("deep", rows)
+    torch.manual_seed(0)
+    m = Deep(cfg).to(DEV)
+    good = {k: v.to(DEV) for k, v in synth_batch(cfg, 64, seed=1).items()}
+    with torch.no_grad():
+        m(good)
+    m.check_ids()                                   # clean batch: no exception
+    bad = dict(good)
+    bad["item_id"] = good["item_id"].clone()
+    bad["item_id"][5] = 200                         # == rows: one past the table
+    with torch.no_grad():
+        m(bad)
+    with pytest.raises(IndexError):
+        m.check_ids()
+    m.check_ids()                                   # the flag was consumed
+    tr = FusedTrainer(m, 64, kind="deep")
+    tr.train_step({k: v.cpu() for k, v in good.items()})
+    tr.check_status()
+    tr.train_step({k: v.cpu() for k, v in bad.items()})
+    with pytest.raises(NrxError, match="outside its embedding table"):
+        tr.check_status()

@@ -100,7 +100,8 @@ def test_heads_match_reference(name):
         assert params[k].grad is not None, k
         assert params[k].grad.shape == gr.shape
         if gr.abs().max() > 0:
-            assert _cos(params[k].grad, gr) > 0.97, f"{name}:{k}: cos {_cos(params[k].grad, gr):.4f}"
+            # gate set from the measured values (profiles/r2_grad_cosines.json: 0.9909 .. 0.9966 over these fixtures)
+            assert _cos(params[k].grad, gr) > 0.985, f"{name}:{k}: cos {_cos(params[k].grad, gr):.4f}"
     if g["kind"] == "widedeep":  # wide path + bias are pure fp32 kernels
         assert _rel(params["score_fc.bias"].grad, g["grads"]["score_fc.bias"]) < 2e-2
     with torch.no_grad():
@@ -142,7 +143,7 @@ def test_deepfm_matches_oracle_composition(tmp_path):
     params = dict(m.named_parameters())
     for k, gr in g_ref.items():
         if gr.abs().max() > 0:
-            assert _cos(params[k].grad, gr) > 0.97, f"deepfm:{k}: cos {_cos(params[k].grad, gr):.4f}"
+            assert _cos(params[k].grad, gr) > 0.985, f"deepfm:{k}: cos {_cos(params[k].grad, gr):.4f}"
 
 
 def test_dcn_wide_first_layer_forward():

@@ -4,9 +4,11 @@ Precision contract (north_star: 1e-2 relative in bf16):
   * forward vs the fp32 oracle: max-norm relative error <= 1e-2;
   * every backward step (dX chain GEMM + act', dW split-K GEMM, db) vs the oracle evaluated on the SAME saved
     bf16 activations: <= 5e-3 (in practice 0 .. 1 bf16 ulp) — this is the exactness proof of the kernels;
-  * end-to-end gradients vs the fp32 oracle: cosine similarity >= 0.98.  The elementwise gap to fp32 gradients
-    (~5-10 % in L2) is the ReLU/LeakyReLU gate flipping for pre-activations within bf16 noise of zero; a pure
-    PyTorch bf16 emulation of the reference shows the same gap ("bf16 and gradient parity").
+  * end-to-end gradients vs the fp32 oracle: cosine similarity >= 0.985 and relative L2 error <= 0.2 — the gates are set
+    from the measured values (profiles/r2_grad_cosines.json: cosine 0.990 .. 0.998, relative L2 0.05 .. 0.14 over
+    these cases; the kernels are bitwise reproducible, so the margin only covers other seeds).  The elementwise gap to
+    fp32 gradients is the ReLU/LeakyReLU gate flipping for pre-activations within bf16 noise of zero; a pure PyTorch
+    bf16 emulation of the reference shows the same gap ("bf16 and gradient parity").
 """
 import pytest
 import torch
@@ -18,11 +20,18 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 BF16_RTOL = 1e-2
 STEP_TOL = 5e-3
+COS_GATE = 0.985    # measured 0.990 .. 0.998 (profiles/r2_grad_cosines.json)
+REL2_GATE = 0.2     # measured 0.05 .. 0.14
 
 
 def _rel(a, b):
     a, b = a.detach().cpu().double(), b.detach().cpu().double()
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def _rel2(a, b):
+    a, b = a.detach().cpu().double().flatten(), b.detach().cpu().double().flatten()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
 
 
 def _cos(a, b):
@@ -98,10 +107,11 @@ def test_tower_forward_and_stepwise_backward(dims, slope, B):
         assert _rel(gws[l], DZ[l].T @ A[l]) < 1e-4, f"gw[{l}]"
         assert _rel(gbs[l], DZ[l].sum(0)) < 1e-4, f"gb[{l}]"
     # end to end vs fp32
-    assert _cos(gx, xr.grad) > 0.98
+    assert _cos(gx, xr.grad) > COS_GATE and _rel2(gx, xr.grad) < REL2_GATE
     for l in range(L):
-        assert _cos(gws[l], wr[l].grad) > 0.98, f"cos gw[{l}] {_cos(gws[l], wr[l].grad):.4f}"
-        assert _cos(gbs[l], br[l].grad) > 0.98, f"cos gb[{l}] {_cos(gbs[l], br[l].grad):.4f}"
+        assert _cos(gws[l], wr[l].grad) > COS_GATE, f"cos gw[{l}] {_cos(gws[l], wr[l].grad):.4f}"
+        assert _cos(gbs[l], br[l].grad) > COS_GATE, f"cos gb[{l}] {_cos(gbs[l], br[l].grad):.4f}"
+        assert _rel2(gws[l], wr[l].grad) < REL2_GATE and _rel2(gbs[l], br[l].grad) < REL2_GATE
     # bitwise reproducible
     y2, tctx2 = ops.tower_fwd(x.to(DEV), wd, bd, slope, training=True)
     gx2, gws2, gbs2 = ops.tower_bwd(tctx2, gy.to(DEV))
@@ -159,7 +169,7 @@ def test_deep_model_matches_reference(name):
     params = dict(m.named_parameters())
     for k, gr in g["grads"].items():
         assert params[k].grad is not None, k
-        assert _cos(params[k].grad, gr) > 0.98, f"{name}:{k}: cos {_cos(params[k].grad, gr):.4f}"
+        assert _cos(params[k].grad, gr) > COS_GATE, f"{name}:{k}: cos {_cos(params[k].grad, gr):.4f}"
 
 
 @pytest.mark.parametrize("dims,slope", [([112, 128, 128, 128, 64, 1], None), ([80, 128, 64, 16], 0.2), ([64, 128, 128], None)])

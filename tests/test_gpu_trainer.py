@@ -89,7 +89,7 @@ def test_graph_replay_is_deterministic():
 
 
 @pytest.mark.parametrize("impl", ["split", "flat"])
-@pytest.mark.parametrize("name", ["fm", "deep"])
+@pytest.mark.parametrize("name", ["fm", "fm_soft", "deep"])
 def test_dense_mode_matches_reference_adamw_golden(name, impl):
     """table_update="dense" is the reference's optimizer (dense AdamW, wd 0.01, every row every step): three
     fused steps on the fixture batches land on the parameters the REFERENCE itself produced with its own

@@ -45,7 +45,7 @@ def test_dcn_fused_association_within_tolerance():
     torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-6)
 
 
-@pytest.mark.parametrize("name", ["fm", "deep"])
+@pytest.mark.parametrize("name", ["fm", "fm_soft", "deep"])
 def test_adamw_and_schedule_match_reference(name):
     """3 steps of the reference's AdamW + CosinDecayLR (deep/model.py:54-65) replayed with
     the restated update rule on oracle gradients."""
