@@ -746,22 +746,27 @@ def main():
     if args.workload == "deepfm" and not args.no_retrieval:
         retrieval = retrieval_leg(dev, world, rank, dist, args.quick)
     legs, parity, eager = {}, None, None
+    only = set(filter(None, os.environ.get("NRX_BENCH_LEGS", "").split(",")))   # developer filter, e.g. NRX_BENCH_LEGS=cfg5
+    want = lambda name: not only or any(name.startswith(o) for o in only)
     if args.workload == "deepfm" and not args.no_legs and not args.quick:
         lsteps = max(10, min(args.steps, 50))
         # cfg3: DCN, B = 65536 — data parallel, weak (65536 per GPU) and strong (65536 in total)
-        legs["cfg3_dcn_weak"] = train_leg("dcn", dev, world, rank, dist, lsteps, args.warmup, "dp", quick=args.quick, scaling="weak")
-        if world > 1:
+        if want("cfg3"):
+            legs["cfg3_dcn_weak"] = train_leg("dcn", dev, world, rank, dist, lsteps, args.warmup, "dp", quick=args.quick, scaling="weak")
+        if world > 1 and want("cfg3"):
             legs["cfg3_dcn_strong"] = train_leg("dcn", dev, world, rank, dist, lsteps, args.warmup, "dp", B=65536 // world,
                                                 quick=args.quick, scaling="strong")
         # cfg1: the reference's own CPU-runnable case (Deep + user_history, B = 1024)
-        legs["cfg1_deep_hist"] = train_leg("deep", dev, world, rank, dist, lsteps, args.warmup, "dp", quick=args.quick, scaling="weak")
+        if want("cfg1"):
+            legs["cfg1_deep_hist"] = train_leg("deep", dev, world, rank, dist, lsteps, args.warmup, "dp", quick=args.quick, scaling="weak")
         # cfg5: WideDeep with 1M / 160k / 10M-row tables; lazy sparse-row update (a dense sweep of 1.3 GB of tables per
         # step is what the reference's optimizer would do); row-sharded tables at N >= 2
-        legs["cfg5_widedeep_sharded"] = train_leg("widedeep_large", dev, world, rank, dist, lsteps, args.warmup, "sharded",
-                                                  table_update="sparse", quick=args.quick, scaling="weak")
-        if world > 1:
+        if want("cfg5"):
+            legs["cfg5_widedeep_sharded"] = train_leg("widedeep_large", dev, world, rank, dist, lsteps, args.warmup, "sharded",
+                                                      table_update="sparse", quick=args.quick, scaling="weak")
+        if world > 1 and want("parity"):
             parity = parity_leg(dev, world, rank, dist)
-        elif rank == 0:
+        elif world == 1 and rank == 0 and want("eager"):
             eager = {"cfg2_deepfm": eager_gpu_leg("deepfm", dev), "cfg3_dcn": eager_gpu_leg("dcn", dev, steps=10, warmup=3)}
     if rank != 0:
         if dist is not None:

@@ -74,9 +74,12 @@ int nrx_embed_pool_fwd(const NrxFeat* h_feats, int n_feats, int64_t B,
 
 /* Same, writing the tower's input operand as well: `image` = bf16 tile image [tile][image_width/8][128][8] of the
  * concatenated row (the layout nrx_tower_fwd streams with NRX_TOWER_XIMG; its slot inside the tower workspace comes
- * from nrx_tower_image_layout).  `out` may be NULL when nothing else reads the fp32 concat.  128-bit path only. */
+ * from nrx_tower_image_layout).  `out` may be NULL when nothing else reads the fp32 concat.  128-bit path only.
+ * `fm_logit` (optional, [B]): the FM logit of fm/model.py:18-25 over ALL the features (w = column 0, v = the rest,
+ * :48-59), computed in the pooling epilogue — sparse features of equal width only (width/4 a power of two, all fields
+ * within 32 lanes); NRX_EUNSUPPORTED otherwise (use nrx_field_logit_fwd). */
 int nrx_embed_pool_fwd_img(const NrxFeat* h_feats, int n_feats, int64_t B, float* out, int64_t out_ld,
-                           void* image, int image_width, int32_t* status, nrx_stream_t stream);
+                           void* image, int image_width, float* fm_logit, int32_t* status, nrx_stream_t stream);
 
 /* ---- K3: deterministic sorted-index segment-reduce backward ----------------
  * Replaces aten::embedding_dense_backward behind base_model.py:271 (padding_idx=0
@@ -264,6 +267,33 @@ enum { NRX_PEER_SIG_ERR = 130 };
 int nrx_adamw_allreduce_peer(const NrxPeerStep* step, nrx_stream_t stream);
 int nrx_peer_status(const uint32_t* sig, int32_t* timed_out, nrx_stream_t stream);  /* synchronises the stream */
 
+/* Stand-alone barrier over the same signal pads (only rank / world / sig / status / timeout_ms of `step` are read):
+ * every rank's earlier work on its stream, peer stores included, is complete and visible before any rank continues.
+ * Same fatal / sticky time-out rule as K7. */
+int nrx_peer_barrier(const NrxPeerStep* step, nrx_stream_t stream);
+
+/* ---- row-sharded embedding tables over peer memory (ids -> owner gather -> pooled vectors) ------------
+ * The reference keeps every nn.Embedding whole on one GPU (base_model.py:141-166); BASELINE config 5 shards the big
+ * tables by contiguous row ranges.  Rank `rank` stores rows [lo, hi) of a sharded table behind a zero row 0.
+ *   nrx_shard_push — forward: for every sample of EVERY rank (ids all-gathered: [world * B]) whose id this rank owns,
+ *     gather the row and store it straight into that rank's feature matrix h_x[r][b, out_col : +dim] (peer stores):
+ *     each rank receives exactly B * sum(dim) * 4 bytes, no collective, no compaction, no host-known sizes;
+ *   nrx_shard_pull — backward: copy, from every rank's gradient matrix h_g[r], the columns of the samples whose id this
+ *     rank owns (and, for the `h_rep` features of replicated tables, of every sample) into the local [world * B, ld]
+ *     buffer `g_global` (peer loads) — the operand of one nrx_embed_bwd_apply over the global batch.
+ * A barrier (nrx_peer_barrier, or any collective on the stream) must separate a push from the readers of x. */
+typedef struct NrxShardFeat {
+  const float* table;   /* push: local shard [hi - lo + 1, row_stride] fp32, row 0 zero; pull: may equal any non-NULL pointer */
+  const void* ids;      /* global ids of all ranks, [world * B] */
+  int64_t lo, hi;       /* owned row range */
+  int32_t dim, row_stride, out_col, idx_dtype;
+} NrxShardFeat;
+int nrx_shard_push(const NrxShardFeat* h_feats, int n_feats, int rank, int world, int64_t B,
+                   float* const* h_x /* [world] peer-mapped feature matrices */, int64_t ld, nrx_stream_t stream);
+int nrx_shard_pull(const NrxShardFeat* h_feats, int n_feats, const NrxShardFeat* h_rep, int n_rep, int rank, int world,
+                   int64_t B, float* const* h_g /* [world] peer-mapped gradient matrices */, int64_t ld,
+                   float* g_global, nrx_stream_t stream);
+
 /* ---- K4/K5: fused bf16 tower on tcgen05 (MLP utils.py:6-17, DSSM towers
  * recall/DSSM/model.py:26-44, DCN cross dcn_arch.py:14-30,53-70) --------------- */
 enum { NRX_ACT_RELU = 0, NRX_ACT_LEAKY = 1 };
@@ -374,6 +404,30 @@ int nrx_topk_search64(const void* index, const float* corpus, int64_t c_ld, int6
                       const float* queries, int64_t q_ld, int64_t Q, int k, int64_t id_base,
                       float* out_scores, double* out_scores64, int64_t* out_ids, int32_t* status,
                       void* ws, size_t ws_bytes, nrx_stream_t stream);
+/* Sharded search over NVLink peer memory (BASELINE config 4: corpus row-sharded across the GPUs of one node).  2-D:
+ * every rank scans ITS shard for ALL queries (sample -> theta -> one filter scan, the threshold budget shared between the
+ * shards) and ships, per query, its exactly re-scored candidates (<= k, fp64 score + global id) into the inbox of the
+ * query's owner — rank q / ceil(Q / world) — by peer stores; after a flag barrier the owner merges the `world` lists of
+ * its Q / world queries, proves completeness against every shard's bound and writes the result into EVERY rank's output
+ * buffers; a query that cannot be proven is re-scanned exactly by its owner over all shards through peer memory.  No NCCL,
+ * the per-query fixed work (final sort, merge) divides by `world`.  All buffers of NrxTopkPeer come from nrx_peer_alloc
+ * and are mapped with nrx_peer_open; corpus shards are contiguous [n_rows, D] fp32.  Results: out_scores[rank] / out_ids[rank]. */
+typedef struct NrxTopkPeer {
+  int32_t rank, world;
+  const float* corpus[NRX_MAX_PEERS];   /* fp32 shard of every rank */
+  int64_t n_rows[NRX_MAX_PEERS];        /* rows per shard; global id = sum of the preceding shards + local row */
+  void* inbox[NRX_MAX_PEERS];           /* nrx_topk_peer_inbox_bytes(Q, world, k) bytes on every rank */
+  float* out_scores[NRX_MAX_PEERS];     /* [Q, k] on every rank */
+  int64_t* out_ids[NRX_MAX_PEERS];      /* [Q, k] on every rank */
+  uint32_t* sig[NRX_MAX_PEERS];         /* signal pads (NRX_PEER_SIG_WORDS u32), as for K7 */
+  int32_t* status;                      /* optional trainer-style status word (bit 1: dead exchange) */
+  uint32_t timeout_ms;
+  uint32_t reserved;
+} NrxTopkPeer;
+size_t nrx_topk_peer_inbox_bytes(int64_t Q, int world, int k);
+int nrx_topk_search_peer(const void* index, int64_t N_local, int D, const float* queries, int64_t q_ld, int64_t Q, int k,
+                         const NrxTopkPeer* h_peer, int32_t* status /* [Q]: 1 = served by the exact scan (owner only) */,
+                         void* ws, size_t ws_bytes, nrx_stream_t stream);
 /* One-shot build + search (index lives in `ws`). */
 size_t nrx_topk_ip_workspace_bytes(int64_t Q, int64_t N, int D, int k);
 int nrx_topk_ip(const float* queries, int64_t q_ld, const float* corpus, int64_t c_ld,

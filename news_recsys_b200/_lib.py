@@ -59,6 +59,18 @@ class NrxPeerStep(C.Structure):
     ]
 
 
+class NrxShardFeat(C.Structure):
+    _fields_ = [("table", C.c_void_p), ("ids", C.c_void_p), ("lo", C.c_int64), ("hi", C.c_int64),
+                ("dim", C.c_int32), ("row_stride", C.c_int32), ("out_col", C.c_int32), ("idx_dtype", C.c_int32)]
+
+
+class NrxTopkPeer(C.Structure):
+    _fields_ = [("rank", C.c_int32), ("world", C.c_int32),
+                ("corpus", C.c_void_p * NRX_MAX_PEERS), ("n_rows", C.c_int64 * NRX_MAX_PEERS), ("inbox", C.c_void_p * NRX_MAX_PEERS),
+                ("out_scores", C.c_void_p * NRX_MAX_PEERS), ("out_ids", C.c_void_p * NRX_MAX_PEERS), ("sig", C.c_void_p * NRX_MAX_PEERS),
+                ("status", C.c_void_p), ("timeout_ms", C.c_uint32), ("reserved", C.c_uint32)]
+
+
 class NrxIngestCol(C.Structure):
     _fields_ = [("data", C.c_void_p), ("offsets", C.c_void_p), ("L", C.c_int32), ("idx_dtype", C.c_int32),
                 ("out_ids", C.c_void_p), ("out_mask", C.c_void_p)]
@@ -93,7 +105,7 @@ SIGNATURES = {
     "nrx_version": (C.c_int, []),
     "nrx_last_error": (C.c_char_p, []),
     "nrx_embed_pool_fwd": (C.c_int, [C.POINTER(NrxFeat), C.c_int, _I64, _P, _I64, _P, _P]),
-    "nrx_embed_pool_fwd_img": (C.c_int, [C.POINTER(NrxFeat), C.c_int, _I64, _P, _I64, _P, C.c_int, _P, _P]),
+    "nrx_embed_pool_fwd_img": (C.c_int, [C.POINTER(NrxFeat), C.c_int, _I64, _P, _I64, _P, C.c_int, _P, _P, _P]),
     "nrx_embed_bwd_workspace_bytes": (_SZ, [C.POINTER(NrxFeat), C.c_int, _I64]),
     "nrx_embed_bwd_plan": (C.c_int, [C.POINTER(NrxFeat), C.c_int, _I64, _P, _SZ, _P]),
     "nrx_embed_bwd_apply": (C.c_int, [C.POINTER(NrxFeat), C.c_int, _I64, _P, _I64, C.c_int,
@@ -124,6 +136,10 @@ SIGNATURES = {
     "nrx_peer_open": (C.c_int, [C.c_char_p, C.POINTER(_P)]),
     "nrx_peer_close": (C.c_int, [_P]),
     "nrx_adamw_allreduce_peer": (C.c_int, [C.POINTER(NrxPeerStep), _P]),
+    "nrx_peer_barrier": (C.c_int, [C.POINTER(NrxPeerStep), _P]),
+    "nrx_shard_push": (C.c_int, [C.POINTER(NrxShardFeat), C.c_int, C.c_int, C.c_int, _I64, C.POINTER(_P), _I64, _P]),
+    "nrx_shard_pull": (C.c_int, [C.POINTER(NrxShardFeat), C.c_int, C.POINTER(NrxShardFeat), C.c_int, C.c_int, C.c_int, _I64,
+                                 C.POINTER(_P), _I64, _P, _P]),
     "nrx_peer_status": (C.c_int, [_P, C.POINTER(C.c_int32), _P]),
     "nrx_tower_workspace_bytes": (_SZ, [C.POINTER(NrxTower), _I64, C.c_int]),
     "nrx_tower_pack": (C.c_int, [C.POINTER(NrxTower), _I64, C.c_int, _P, _SZ, _P]),
@@ -145,6 +161,8 @@ SIGNATURES = {
     "nrx_topk_search_workspace_bytes": (_SZ, [_I64, _I64, C.c_int, C.c_int]),
     "nrx_topk_search": (C.c_int, [_P, _P, _I64, _I64, C.c_int, _P, _I64, _I64, C.c_int, _I64, _P, _P, _P, _P, _SZ, _P]),
     "nrx_topk_search64": (C.c_int, [_P, _P, _I64, _I64, C.c_int, _P, _I64, _I64, C.c_int, _I64, _P, _P, _P, _P, _P, _SZ, _P]),
+    "nrx_topk_peer_inbox_bytes": (_SZ, [_I64, C.c_int, C.c_int]),
+    "nrx_topk_search_peer": (C.c_int, [_P, _I64, C.c_int, _P, _I64, _I64, C.c_int, C.POINTER(NrxTopkPeer), _P, _P, _SZ, _P]),
     "nrx_topk_merge64": (C.c_int, [_P, _P, C.c_int, _I64, C.c_int, _P, _P, _P]),
     "nrx_topk_ip_workspace_bytes": (_SZ, [_I64, _I64, C.c_int, C.c_int]),
     "nrx_topk_ip": (C.c_int, [_P, _I64, _P, _I64, _I64, _I64, C.c_int, C.c_int, _I64, _P, _P, _P, _SZ, _P]),
@@ -186,7 +204,7 @@ def load() -> C.CDLL:
 KERNELS_PER_CALL = {"nrx_tower_fwd": 3, "nrx_tower_fwd(prepacked)": 2, "nrx_tower_fwd_head": 3, "nrx_tower_fwd_head(prepacked)": 2,
                     "nrx_tower_fwd(prepacked,ximg)": 1, "nrx_tower_fwd_head(prepacked,ximg)": 1, "nrx_tower_bwd": 3, "nrx_tower_bwd_dw": 2, "nrx_embed_bwd_apply": 2, "nrx_embed_bwd_plan": 2, "nrx_adamw_untouched_rows": 2, "nrx_adamw_untouched_rows_scratch_bytes": 0, "nrx_dcn_cross_bwd": 2,
                     "nrx_embed_bwd_apply(dense)": 2, "nrx_embed_bwd_apply(rowopt)": 2, "nrx_topk_ip": 2,
-                    "nrx_topk_search": 6, "nrx_topk_search64": 6, "nrx_topk_index_build": 1,
+                    "nrx_topk_search": 6, "nrx_topk_search64": 6, "nrx_topk_search_peer": 10, "nrx_topk_peer_inbox_bytes": 0, "nrx_topk_index_build": 1,
                     "nrx_peer_alloc": 0, "nrx_peer_free": 0, "nrx_peer_export": 0, "nrx_peer_open": 0, "nrx_peer_close": 0,
                     "nrx_peer_status": 0, "nrx_ingest_gather_ids": 0, "nrx_ingest_csr_expand": 0, "nrx_ingest_gather_labels": 0,
                     "nrx_tower_workspace_bytes": 0, "nrx_embed_bwd_workspace_bytes": 0, "nrx_tower_image_layout": 0}

@@ -20,7 +20,8 @@ namespace nrx {
 template <int V, int SPW>
 __global__ void __launch_bounds__(256)
 embed_pool_fwd_kernel(const __grid_constant__ DFeats P, long long B, float* __restrict__ out, long long ld,
-                      int* __restrict__ status, long long n_sparse_warps, uint8_t* __restrict__ img, int img_kp) {
+                      int* __restrict__ status, long long n_sparse_warps, uint8_t* __restrict__ img, int img_kp,
+                      float* __restrict__ fm_logit, int fm_lpf) {
   using VT = VecT<V>;
   using vec_t = typename VT::type;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -55,6 +56,32 @@ embed_pool_fwd_kernel(const __grid_constant__ DFeats P, long long B, float* __re
         if (b0 + s < B) {
           if (out != nullptr) VT::store(out + (b0 + s) * ld + F.out_col + off, val[s]);
           if constexpr (V == 4) { if (img != nullptr) img_store4(img, img_kp, b0 + s, F.out_col + off, val[s]); }
+        }
+      }
+      if constexpr (V == 4) {
+        // FM logit in the pooling epilogue (fm/model.py:18-25 on the w / v split of :48-59): every field is fm_lpf
+        // lanes wide (column 0 of its first lane = first-order weight), all fields fit one pass of the warp.
+        //   logit = sum_f w_f + 1/2 sum_d [ (sum_f v_fd)^2 - sum_f v_fd^2 ]
+        if (fm_logit != nullptr) {   // warp-uniform; host guarantees sparse_cols <= 32 (single pass) and equal widths
+          const bool live = c < P.sparse_cols;
+          const bool head = live && (off == 0);            // this lane holds columns 0..3 of its field
+#pragma unroll
+          for (int s = 0; s < SPW; ++s) {
+            float4 v = live ? val[s] : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float w = head ? v.x : 0.f;
+            if (head) v.x = 0.f;
+            float q = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;           // sum_f v^2 (lane part)
+            float4 S = v;                                                      // sum over fields of the same 4 dims
+            for (int o = fm_lpf; o < 32; o <<= 1) {
+              S.x += __shfl_xor_sync(NRX_FULL_MASK, S.x, o); S.y += __shfl_xor_sync(NRX_FULL_MASK, S.y, o);
+              S.z += __shfl_xor_sync(NRX_FULL_MASK, S.z, o); S.w += __shfl_xor_sync(NRX_FULL_MASK, S.w, o);
+            }
+            // lanes 0 .. fm_lpf-1 hold every dimension's field sum exactly once
+            float t = (lane < fm_lpf) ? 0.5f * (S.x * S.x + S.y * S.y + S.z * S.z + S.w * S.w) : 0.f;
+            t += w - 0.5f * q;
+            t = warp_sum(t);
+            if (lane == 0 && b0 + s < B) fm_logit[b0 + s] = t;
+          }
         }
       }
     }
@@ -113,14 +140,14 @@ embed_pool_fwd_kernel(const __grid_constant__ DFeats P, long long B, float* __re
 
 template <int V, int SPW>
 static int launch_fwd(const DFeats& d, long long B, float* out, long long ld, int* status, cudaStream_t st,
-                      uint8_t* img = nullptr, int img_kp = 0) {
+                      uint8_t* img = nullptr, int img_kp = 0, float* fm_logit = nullptr, int fm_lpf = 0) {
   const long long n_sparse_warps = d.n_sparse ? (B + SPW - 1) / SPW : 0;
   const long long warps = n_sparse_warps + B * d.n_array;
   if (warps == 0) return NRX_OK;
   const int wpb = 8;
   const long long blocks = (warps + wpb - 1) / wpb;
   NRX_REQUIRE(blocks < (1ll << 31), NRX_EUNSUPPORTED, "batch too large for one launch");
-  embed_pool_fwd_kernel<V, SPW><<<(unsigned)blocks, wpb * 32, 0, st>>>(d, B, out, ld, status, n_sparse_warps, img, img_kp);
+  embed_pool_fwd_kernel<V, SPW><<<(unsigned)blocks, wpb * 32, 0, st>>>(d, B, out, ld, status, n_sparse_warps, img, img_kp, fm_logit, fm_lpf);
   return check_launch("embed_pool_fwd");
 }
 
@@ -145,10 +172,11 @@ extern "C" int nrx_embed_pool_fwd(const NrxFeat* h_feats, int n_feats, int64_t B
 
 // K1 writing the tower's input operand directly: besides (or instead of, out == NULL) the fp32 rows, the bf16 tile
 // image [tile][width/8][128][8] that nrx_tower_fwd(..., NRX_TOWER_XIMG) streams — saves the fp32 -> bf16 pass and,
-// for Deep (nobody else reads the fp32 concat in inference), the 4*width B/sample write.  Needs the 128-bit path
+// for Deep (nobody else reads the fp32 concat in inference), the 4*width B/sample write.  `fm_logit` (optional, [B]):
+// the FM first + second order logit over all features, computed in the same epilogue (DeepFM: north_star item 2).  Needs the 128-bit path
 // (every dim / out_col a multiple of 4, 16-byte aligned tables) and width == the concat width, a multiple of 16.
 extern "C" int nrx_embed_pool_fwd_img(const NrxFeat* h_feats, int n_feats, int64_t B, float* out, int64_t out_ld,
-                                      void* image, int image_width, int32_t* status, nrx_stream_t stream) {
+                                      void* image, int image_width, float* fm_logit, int32_t* status, nrx_stream_t stream) {
   using namespace nrx;
   DFeats d;
   NRX_REQUIRE(image != nullptr || B == 0, NRX_EINVAL, "null image");
@@ -164,11 +192,21 @@ extern "C" int nrx_embed_pool_fwd_img(const NrxFeat* h_feats, int n_feats, int64
   }
   NRX_REQUIRE(total == image_width, NRX_EUNSUPPORTED, "features cover %d of %d image columns (pad columns would stay undefined)", total,
               image_width);
+  int fm_lpf = 0;
+  if (fm_logit != nullptr) {   // FM over ALL features: sparse only, equal widths, one pass of the warp
+    NRX_REQUIRE(d.n_array == 0 && d.n_sparse >= 1, NRX_EUNSUPPORTED, "fused FM logit: sparse (single-id) features only");
+    const int D = d.f[d.sparse_ids[0]].dim;
+    for (int k = 0; k < d.n_sparse; ++k)
+      NRX_REQUIRE(d.f[d.sparse_ids[k]].dim == D, NRX_EUNSUPPORTED, "fused FM logit: fields must have equal widths");
+    fm_lpf = D / 4;
+    NRX_REQUIRE(fm_lpf >= 1 && (fm_lpf & (fm_lpf - 1)) == 0 && d.sparse_cols <= 32, NRX_EUNSUPPORTED,
+                "fused FM logit: width/4 must be a power of two and all fields must fit 32 lanes (got %d x %d)", d.n_sparse, D);
+  }
   if (B == 0) return NRX_OK;
   cudaStream_t st = (cudaStream_t)stream;
   rc = img_zero_tail(image, image_width, B, st);
   if (rc != NRX_OK) return rc;
   const bool small = B < (long long)sm_count() * 64;
-  return small ? launch_fwd<4, 2>(d, B, out, out_ld, status, st, (uint8_t*)image, image_width)
-               : launch_fwd<4, 4>(d, B, out, out_ld, status, st, (uint8_t*)image, image_width);
+  return small ? launch_fwd<4, 2>(d, B, out, out_ld, status, st, (uint8_t*)image, image_width, fm_logit, fm_lpf)
+               : launch_fwd<4, 4>(d, B, out, out_ld, status, st, (uint8_t*)image, image_width, fm_logit, fm_lpf);
 }

@@ -10,7 +10,7 @@
 //      the kernel retires only when this rank's parameters are complete and nobody still reads its gradients.
 // Signal values are a launch counter kept in the pad itself (monotone; never reset by optimizer-state restores).
 // Pad layout (u32 words): [0,16) A flags by source rank, [64,80) B flags, 128 launch counter, 129 block counter,
-// 130 timed-out flag.
+// 130 timed-out flag, [160,176) flags of the stand-alone barrier (nrx_peer_barrier), 192 its launch counter.
 #include <cuda_runtime.h>
 #include <stdlib.h>
 
@@ -19,7 +19,7 @@
 namespace nrx {
 
 constexpr int kPeerThreads = 256;
-constexpr int kSigA = 0, kSigB = 64, kSigEpoch = 128, kSigBlocks = 129;
+constexpr int kSigA = 0, kSigB = 64, kSigEpoch = 128, kSigBlocks = 129, kSigC = 160, kSigEpochC = 192;
 constexpr unsigned kDefaultTimeoutMs = 20000;  // a peer that never arrives must not hang the GPU for ever
 
 struct PeerArgs {
@@ -50,6 +50,11 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
 __device__ __forceinline__ float4 ld_peer(const float4* p) {  // written by another GPU before barrier A
   float4 v;
   asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float ld_peer_f32(const float* p) {
+  float v;
+  asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
   return v;
 }
 __device__ __forceinline__ unsigned long long now_ns() {
@@ -162,6 +167,94 @@ adamw_allreduce_peer_kernel(const __grid_constant__ PeerArgs a) {
   }
 }
 
+
+// ---- stand-alone barrier over the signal pads -------------------------------------------------------------------
+// "Every rank's earlier work on this stream (peer stores included) is complete and visible before any rank's later
+// work starts."  One CTA: fence.sys, release-store the launch counter into every peer's pad, acquire-wait for theirs.
+__global__ void __launch_bounds__(32)
+peer_barrier_kernel(const __grid_constant__ PeerArgs a) {
+  uint32_t* sig = a.sig[a.rank];
+  const int tid = threadIdx.x;
+  if (*(volatile uint32_t*)(sig + NRX_PEER_SIG_ERR) != 0u) {
+    if (tid == 0 && a.status != nullptr) atomicOr(a.status, 2);
+    return;
+  }
+  const uint32_t epoch = *(volatile uint32_t*)(sig + kSigEpochC) + 1u;
+  __syncwarp();
+  bool ok = true;
+  if (tid < a.world) {
+    __threadfence_system();
+    st_release_sys(a.sig[tid] + kSigC + a.rank, epoch);
+    ok = wait_flag(sig + kSigC + tid, epoch, sig + NRX_PEER_SIG_ERR, a.spin_ns);
+  }
+  ok = __all_sync(NRX_FULL_MASK, ok);
+  if (!ok) { if (tid == 0) raise_fatal(a); return; }
+  if (tid == 0) *(volatile uint32_t*)(sig + kSigEpochC) = epoch;
+}
+
+// ---- row-sharded embedding tables: owner-side gather pushed straight into the requesters' feature rows -------------
+// Rank `rank` owns rows [lo, hi) of every sharded table (stored behind a zero row 0).  For every sample of EVERY rank
+// (ids all-gathered, [world * B]) whose id it owns, it reads the row and stores it into that rank's feature matrix
+// x_r[b, out_col : out_col + dim] over NVLink (peer stores) — the "ids -> owner gather -> vectors" exchange of SURVEY
+// §8e without a collective, a compaction or host-known sizes: each rank receives exactly B * sum(dim) * 4 bytes.
+struct ShardFeat {
+  const float* table;     // local shard: [hi - lo + 1, stride], row 0 = zeros
+  const void* ids;        // global ids of all ranks [world * B]
+  long long lo, hi;
+  int dim, stride, out_col, idx32;
+};
+struct ShardArgs {
+  ShardFeat f[NRX_MAX_FEATS];
+  int n, rank, world;
+  long long B;
+  float* x[NRX_MAX_PEERS];        // push: feature matrices of every rank; pull: gradient matrices of every rank
+  long long ld;
+  float* g_global;                // pull: local [world * B, ld] gradient buffer (rows of rank r at r * B)
+};
+
+__global__ void __launch_bounds__(256)
+shard_push_kernel(const __grid_constant__ ShardArgs a) {
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long total = (long long)a.world * a.B;
+  if (warp >= total) return;
+  const int r = (int)(warp / a.B);
+  const long long b = warp % a.B;
+  float* xr = a.x[r] + b * a.ld;
+  for (int i = 0; i < a.n; ++i) {
+    const ShardFeat& F = a.f[i];
+    const long long id = load_idx(F.ids, warp, F.idx32);
+    if (id < F.lo || id >= F.hi) continue;                       // another rank's row (or outside the table: nobody pushes)
+    const float* row = F.table + (id - F.lo + 1) * F.stride;     // global padding id 0 -> shard 0's zeroed row
+    for (int c = lane; c < F.dim; c += 32) xr[F.out_col + c] = __ldg(row + c);
+  }
+}
+
+// Backward: the owner pulls, from every rank's gradient matrix, the rows of the samples whose id it owns into its local
+// [world * B, ld] buffer (peer loads) — the operand of ONE K3 over the global batch with ids masked to the owned rows.
+// `all_cols` features (replicated tables: every rank updates them identically) are pulled for every sample.
+__global__ void __launch_bounds__(256)
+shard_pull_kernel(const __grid_constant__ ShardArgs a, int n_all, const __grid_constant__ ShardArgs rep) {
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long total = (long long)a.world * a.B;
+  if (warp >= total) return;
+  const int r = (int)(warp / a.B);
+  const long long b = warp % a.B;
+  const float* gr = a.x[r] + b * a.ld;
+  float* dst = a.g_global + warp * a.ld;
+  for (int i = 0; i < a.n; ++i) {
+    const ShardFeat& F = a.f[i];
+    const long long id = load_idx(F.ids, warp, F.idx32);
+    if (id < F.lo || id >= F.hi) continue;
+    for (int c = lane; c < F.dim; c += 32) dst[F.out_col + c] = ld_peer_f32(gr + F.out_col + c);
+  }
+  for (int i = 0; i < n_all; ++i) {
+    const ShardFeat& F = rep.f[i];
+    for (int c = lane; c < F.dim; c += 32) dst[F.out_col + c] = ld_peer_f32(gr + F.out_col + c);
+  }
+}
+
 }  // namespace nrx
 
 extern "C" int nrx_peer_alloc(size_t bytes, void** ptr) {
@@ -253,6 +346,77 @@ extern "C" int nrx_adamw_allreduce_peer(const NrxPeerStep* s, nrx_stream_t strea
   else if (s->world <= 8) adamw_allreduce_peer_kernel<8, 1><<<(unsigned)blocks, kPeerThreads, 0, st>>>(a);
   else adamw_allreduce_peer_kernel<16, 1><<<(unsigned)blocks, kPeerThreads, 0, st>>>(a);
   return check_launch("adamw_allreduce_peer");
+}
+
+
+extern "C" int nrx_peer_barrier(const NrxPeerStep* s, nrx_stream_t stream) {
+  using namespace nrx;
+  NRX_REQUIRE(s != nullptr, NRX_EINVAL, "null step");
+  NRX_REQUIRE(s->world >= 1 && s->world <= NRX_MAX_PEERS && s->rank >= 0 && s->rank < s->world, NRX_EINVAL, "bad rank / world");
+  PeerArgs a;
+  memset(&a, 0, sizeof(a));
+  a.rank = s->rank;
+  a.world = s->world;
+  for (int j = 0; j < s->world; ++j) {
+    NRX_REQUIRE(s->sig[j], NRX_EINVAL, "rank %d: null signal pad", j);
+    a.sig[j] = s->sig[j];
+  }
+  a.status = s->status;
+  unsigned ms = s->timeout_ms ? s->timeout_ms : kDefaultTimeoutMs;
+  if (const char* e = getenv("NRX_PEER_TIMEOUT_MS")) { const long v = atol(e); if (v > 0) ms = (unsigned)v; }
+  a.spin_ns = (unsigned long long)ms * 1000000ull;
+  peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(a);
+  return check_launch("peer_barrier");
+}
+
+static int make_shard_args(const NrxShardFeat* feats, int n, int rank, int world, int64_t B, float* const* h_mats, int64_t ld,
+                           nrx::ShardArgs* a) {
+  using namespace nrx;
+  NRX_REQUIRE(n >= 0 && n <= NRX_MAX_FEATS && (feats || n == 0), NRX_EINVAL, "bad feature list");
+  NRX_REQUIRE(world >= 1 && world <= NRX_MAX_PEERS && rank >= 0 && rank < world && B >= 0, NRX_EINVAL, "bad rank / world / B");
+  memset(a, 0, sizeof(*a));
+  a->n = n; a->rank = rank; a->world = world; a->B = B; a->ld = ld;
+  for (int i = 0; i < n; ++i) {
+    const NrxShardFeat& s = feats[i];
+    NRX_REQUIRE(s.table && s.ids && s.dim >= 1 && s.row_stride >= s.dim && s.out_col >= 0 && s.out_col + s.dim <= ld && s.lo <= s.hi,
+                NRX_EINVAL, "sharded feature %d: bad descriptor", i);
+    a->f[i].table = s.table; a->f[i].ids = s.ids; a->f[i].lo = s.lo; a->f[i].hi = s.hi; a->f[i].dim = s.dim;
+    a->f[i].stride = s.row_stride; a->f[i].out_col = s.out_col; a->f[i].idx32 = s.idx_dtype == NRX_IDX_I32;
+  }
+  if (h_mats != nullptr)
+    for (int j = 0; j < world; ++j) {
+      NRX_REQUIRE(h_mats[j], NRX_EINVAL, "rank %d: null matrix", j);
+      a->x[j] = h_mats[j];
+    }
+  return NRX_OK;
+}
+
+extern "C" int nrx_shard_push(const NrxShardFeat* h_feats, int n_feats, int rank, int world, int64_t B, float* const* h_x, int64_t ld,
+                              nrx_stream_t stream) {
+  using namespace nrx;
+  ShardArgs a;
+  int rc = make_shard_args(h_feats, n_feats, rank, world, B, h_x, ld, &a);
+  if (rc != NRX_OK) return rc;
+  if (B == 0 || n_feats == 0) return NRX_OK;
+  const long long warps = (long long)world * B;
+  shard_push_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, (cudaStream_t)stream>>>(a);
+  return check_launch("shard_push");
+}
+
+extern "C" int nrx_shard_pull(const NrxShardFeat* h_feats, int n_feats, const NrxShardFeat* h_rep, int n_rep, int rank, int world,
+                              int64_t B, float* const* h_g, int64_t ld, float* g_global, nrx_stream_t stream) {
+  using namespace nrx;
+  ShardArgs a, rep;
+  int rc = make_shard_args(h_feats, n_feats, rank, world, B, h_g, ld, &a);
+  if (rc != NRX_OK) return rc;
+  rc = make_shard_args(h_rep, n_rep, rank, world, B, nullptr, ld, &rep);
+  if (rc != NRX_OK) return rc;
+  NRX_REQUIRE(g_global != nullptr || B == 0, NRX_EINVAL, "null gradient buffer");
+  a.g_global = g_global;
+  if (B == 0) return NRX_OK;
+  const long long warps = (long long)world * B;
+  shard_pull_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, (cudaStream_t)stream>>>(a, n_rep, rep);
+  return check_launch("shard_pull");
 }
 
 extern "C" int nrx_peer_status(const uint32_t* sig, int32_t* timed_out, nrx_stream_t stream) {

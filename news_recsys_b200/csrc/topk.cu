@@ -56,7 +56,7 @@ struct TopkGeom {
   size_t gmax, theta, eps, count, cand, flag, flist, fpart, qimg, total;
 };
 
-static int make_geom(long long Q, long long N, int D, int k, TopkGeom* g) {
+static int make_geom(long long Q, long long N, int D, int k, TopkGeom* g, int kprime_override = 0) {
   NRX_REQUIRE(N >= 0 && Q >= 0 && D >= 1 && k >= 1, NRX_EINVAL, "bad top-k sizes");
   NRX_REQUIRE(D <= 256, NRX_EUNSUPPORTED, "top-k supports D <= 256 (got %d)", D);
   NRX_REQUIRE(k <= 1024, NRX_EUNSUPPORTED, "top-k supports k <= 1024 (got %d)", k);
@@ -66,7 +66,7 @@ static int make_geom(long long Q, long long N, int D, int k, TopkGeom* g) {
   g->n_tiles = (N + kTR - 1) / kTR;
   g->n_qtiles = (Q + kTR - 1) / kTR;
   g->Qp = g->n_qtiles * kTR;
-  g->kprime = 2 * k + 64;
+  g->kprime = kprime_override > 0 ? kprime_override : 2 * k + 64;
   g->tile_bytes = (size_t)kTR * g->Dp * 2;
   g->index_bytes = kHdrBytes + (size_t)g->n_tiles * g->tile_bytes;
   // query tiles per CTA: as many as fit beside >= 2 corpus stages
@@ -623,8 +623,21 @@ __device__ __forceinline__ int fb_slices(unsigned n_listed, int grid, int max_it
   return (int)S;
 }
 
+// The corpus as up to NRX_MAX_PEERS row segments (one locally; in the sharded peer search: every rank's shard, read over
+// NVLink by the owner of a listed query).  Global row = segment base + local row.
+struct CorpusSegs {
+  const float* c[NRX_MAX_PEERS];
+  long long base[NRX_MAX_PEERS + 1];   // prefix sums of the segment sizes; base[n_seg] = N
+  int n_seg;
+};
+__device__ __forceinline__ const float* seg_row(const CorpusSegs& G, long long row, long long cld) {
+  int g = 0;
+  while (g + 1 < G.n_seg && row >= G.base[g + 1]) ++g;
+  return G.c[g] + (row - G.base[g]) * cld;
+}
+
 __global__ void __launch_bounds__(256)
-topk_exact_kernel(const float* __restrict__ c, long long cld, long long N, int D, const float* __restrict__ q, long long qld,
+topk_exact_kernel(const __grid_constant__ CorpusSegs CS, long long cld, long long N, int D, const float* __restrict__ q, long long qld,
                   int k, const unsigned* __restrict__ flist, int force_Q, int max_items, double* __restrict__ part_s,
                   unsigned* __restrict__ part_i) {
   extern __shared__ __align__(16) uint8_t sm_raw[];
@@ -648,9 +661,10 @@ topk_exact_kernel(const float* __restrict__ c, long long cld, long long N, int D
     if (tid == 0) { s_cnt = 0; s_th = -DBL_MAX; }
     __syncthreads();
     const int warp = tid >> 5, lane = tid & 31;
-    const bool vec = rows_vec_ok(c, cld, D);
+    bool vec = (cld % 4 == 0) && (D % 4 == 0);
+    for (int g = 0; g < CS.n_seg; ++g) vec = vec && ((reinterpret_cast<uintptr_t>(CS.c[g]) & 15) == 0);
     for (long long r0 = r_lo; r0 < r_hi; r0 += 256) {
-      // 256 rows per round: every warp scores 32 rows (one at a time, coalesced), lane u keeps row u's score
+      // 256 rows per round: every warp scores 32 rows (four at a time, coalesced), lane u keeps row u's score
       double mine = 0.0;
       for (int u = 0; u < 32; u += 4) {
         const long long rb = r0 + warp * 32 + u;
@@ -658,7 +672,7 @@ topk_exact_kernel(const float* __restrict__ c, long long cld, long long N, int D
         const float* rowp[4];
         double v4[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) rowp[j] = c + (rb + j < r_hi ? rb + j : r_hi - 1) * cld;
+        for (int j = 0; j < 4; ++j) rowp[j] = seg_row(CS, rb + j < r_hi ? rb + j : r_hi - 1, cld);
         dot64_warp4(qs, rowp, D, lane, vec, v4);
 #pragma unroll
         for (int j = 0; j < 4; ++j)
@@ -696,11 +710,17 @@ topk_exact_kernel(const float* __restrict__ c, long long cld, long long N, int D
   }
 }
 
+struct PeerOuts {   // the result buffers of every rank (peer-mapped); n == 0: write the local out_s / out_i only
+  float* s[NRX_MAX_PEERS];
+  long long* i[NRX_MAX_PEERS];
+  int n;
+};
+
 __global__ void __launch_bounds__(256)
 topk_exact_merge_kernel(long long N, int k, long long id_base, const unsigned* __restrict__ flist, int force_Q, int exact_grid,
                         int max_items, const double* __restrict__ part_s, const unsigned* __restrict__ part_i,
                         float* __restrict__ out_s, double* __restrict__ out_s64, long long* __restrict__ out_i,
-                        int* __restrict__ status) {
+                        int* __restrict__ status, const __grid_constant__ PeerOuts PO) {
   extern __shared__ __align__(16) uint8_t sm_raw[];
   const int tid = threadIdx.x;
   const unsigned n_listed = force_Q > 0 ? (unsigned)force_Q : flist[0];
@@ -721,17 +741,193 @@ topk_exact_merge_kernel(long long N, int k, long long id_base, const unsigned* _
     __syncthreads();
     if (S > 1) bitonic_sort(s, id, n2, tid, 256);
     for (int i = tid; i < k; i += 256) {
-      if (i < kk) {
-        out_s[qi * k + i] = (float)s[i];
-        if (out_s64) out_s64[qi * k + i] = s[i];
-        out_i[qi * k + i] = (long long)id[i] + id_base;
+      const float fs = i < kk ? (float)s[i] : -FLT_MAX;
+      const long long fi = i < kk ? (long long)id[i] + id_base : -1;
+      if (PO.n > 0) {
+        for (int g = 0; g < PO.n; ++g) { PO.s[g][qi * k + i] = fs; PO.i[g][qi * k + i] = fi; }
       } else {
-        out_s[qi * k + i] = -FLT_MAX;
-        if (out_s64) out_s64[qi * k + i] = -DBL_MAX;
-        out_i[qi * k + i] = -1;
+        out_s[qi * k + i] = fs;
+        if (out_s64) out_s64[qi * k + i] = i < kk ? s[i] : -DBL_MAX;
+        out_i[qi * k + i] = fi;
       }
     }
     if (status != nullptr && tid == 0 && force_Q == 0) status[qi] = 1;
+  }
+}
+
+
+// ---- sharded search over peer memory (2-D: every rank scans ITS corpus shard for ALL queries, the owner of a query —
+// rank q / ceil(Q / G) — merges the shards' lists and proves completeness) -------------------------------------------
+// Inbox of an owner: [Qown][G][k] entries {fp64 score, global id}, then counts int32 [Qown][G] (-1: the shard's candidate
+// list overflowed), then bounds float [Qown][G] (theta_g + eps_g: every row of shard g outside its list scores below it).
+struct TopkEntry { double s; long long id; };
+struct PeerInbox {
+  uint8_t* box[NRX_MAX_PEERS];
+  int rank, world;
+  long long q_own;     // queries per owner
+};
+__host__ __device__ __forceinline__ size_t inbox_bytes(long long q_own, int world, int k) {
+  return (size_t)q_own * world * ((size_t)k * sizeof(TopkEntry) + 8);
+}
+__device__ __forceinline__ TopkEntry* inbox_entries(uint8_t* box, long long ql, int g, int world, int k) {
+  return reinterpret_cast<TopkEntry*>(box) + (ql * world + g) * k;
+}
+__device__ __forceinline__ int* inbox_cnt(uint8_t* box, long long q_own, int world, int k) {
+  return reinterpret_cast<int*>(box + (size_t)q_own * world * k * sizeof(TopkEntry));
+}
+__device__ __forceinline__ float* inbox_bound(uint8_t* box, long long q_own, int world, int k) {
+  return reinterpret_cast<float*>(box + (size_t)q_own * world * ((size_t)k * sizeof(TopkEntry) + 4));
+}
+
+// Shard side: exact re-scoring + sort of this shard's candidates of query qi (as topk_final_kernel), then the best
+// min(count, k) go straight into the owner's inbox (peer stores) with the shard's completeness bound.
+__global__ void __launch_bounds__(256)
+topk_final_peer_kernel(const float* __restrict__ c, long long cld, long long N, int D, const float* __restrict__ q, long long qld,
+                       int k, long long id_base, const float* __restrict__ theta, const float* __restrict__ eps,
+                       const unsigned* __restrict__ count, const unsigned* __restrict__ cand, int n_slices, int cap_s,
+                       const __grid_constant__ PeerInbox PB) {
+  extern __shared__ __align__(16) uint8_t sm_raw[];
+  double* s = reinterpret_cast<double*>(sm_raw);              // [kCap]
+  unsigned* id = reinterpret_cast<unsigned*>(s + kCap);       // [kCap]
+  float* qs = reinterpret_cast<float*>(id + kCap);            // [D]
+  unsigned* s_off = reinterpret_cast<unsigned*>(qs + ((D + 3) & ~3));   // [n_slices]
+  const long long qi = blockIdx.x;
+  const int tid = threadIdx.x;
+  __shared__ unsigned s_total, s_over, s_warp[8];
+  const int owner = (int)(qi / PB.q_own);
+  const long long ql = qi % PB.q_own;
+  uint8_t* box = PB.box[owner];
+  unsigned over = 0, run = 0;
+  for (int b0 = 0; b0 < n_slices; b0 += 256) {
+    const int sl = b0 + tid;
+    unsigned cs = sl < n_slices ? count[qi * n_slices + sl] : 0u;
+    if (cs > (unsigned)cap_s) { over = 1; cs = (unsigned)cap_s; }
+    unsigned inc = cs;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(NRX_FULL_MASK, inc, o); if ((tid & 31) >= o) inc += t; }
+    if ((tid & 31) == 31) s_warp[tid >> 5] = inc;
+    __syncthreads();
+    unsigned wbase = 0;
+    for (int w = 0; w < (tid >> 5); ++w) wbase += s_warp[w];
+    if (sl < n_slices) s_off[sl] = run + wbase + inc - cs;
+    unsigned tot = 0;
+    for (int w = 0; w < 8; ++w) tot += s_warp[w];
+    run += tot;
+    __syncthreads();
+  }
+  over = __syncthreads_or(over);
+  if (tid == 0) { s_total = run; s_over = over; }
+  for (int d = tid; d < D; d += 256) qs[d] = __ldg(q + qi * qld + d);
+  __syncthreads();
+  const unsigned cnt = s_total;
+  if (s_over || cnt > (unsigned)kCap) {   // the shard cannot vouch for its list: the owner sends the query to the exact scan
+    if (tid == 0) { inbox_cnt(box, PB.q_own, PB.world, k)[ql * PB.world + PB.rank] = -1; inbox_bound(box, PB.q_own, PB.world, k)[ql * PB.world + PB.rank] = 0.f; }
+    return;
+  }
+  int n2 = 1;
+  while (n2 < (int)cnt) n2 <<= 1;
+  for (int i = (int)cnt + tid; i < n2; i += 256) { id[i] = 0xffffffffu; s[i] = -DBL_MAX; }
+  for (unsigned i = tid; i < cnt; i += 256) {
+    int lo = 0, hi = n_slices - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (s_off[mid] <= i) lo = mid; else hi = mid - 1;
+    }
+    id[i] = cand[((size_t)qi * n_slices + lo) * cap_s + (i - s_off[lo])];
+  }
+  __syncthreads();
+  {
+    const int warp = tid >> 5, lane = tid & 31;
+    const bool vec = rows_vec_ok(c, cld, D);
+    for (unsigned i0 = (unsigned)warp * 4; i0 < cnt; i0 += 32) {
+      double v[4];
+      const float* rowp[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) rowp[u] = c + (long long)id[min(i0 + u, cnt - 1)] * cld;
+      dot64_warp4(qs, rowp, D, lane, vec, v);
+      if (lane < 4 && i0 + lane < cnt) s[i0 + lane] = lane == 0 ? v[0] : lane == 1 ? v[1] : lane == 2 ? v[2] : v[3];
+    }
+  }
+  __syncthreads();
+  if (cnt > 1) bitonic_sort(s, id, n2, tid, 256);
+  const int n_send = (int)cnt < k ? (int)cnt : k;
+  TopkEntry* dst = inbox_entries(box, ql, PB.rank, PB.world, k);
+  for (int i = tid; i < n_send; i += 256) { TopkEntry e; e.s = s[i]; e.id = (long long)id[i] + id_base; dst[i] = e; }
+  if (tid == 0) {
+    inbox_cnt(box, PB.q_own, PB.world, k)[ql * PB.world + PB.rank] = n_send;
+    // rows of this shard outside the list score < theta + eps, or are beaten by k listed rows of the same shard
+    inbox_bound(box, PB.q_own, PB.world, k)[ql * PB.world + PB.rank] =
+        theta[qi] == -FLT_MAX ? -FLT_MAX : (float)((double)theta[qi] + (double)eps[qi]) ;
+  }
+}
+
+// Owner side: merge the G lists of one owned query, prove completeness, publish the result to EVERY rank (peer stores);
+// a query that cannot be proven goes on the owner's fallback list (exact scan over all shards through peer memory).
+__global__ void __launch_bounds__(256)
+topk_owner_merge_kernel(long long Q, long long N_total, int k, const __grid_constant__ PeerInbox PB, unsigned* __restrict__ flist,
+                        int* __restrict__ status, const __grid_constant__ PeerOuts PO) {
+  extern __shared__ __align__(16) uint8_t sm_raw[];
+  const long long ql = blockIdx.x;
+  const long long qi = (long long)PB.rank * PB.q_own + ql;
+  const int tid = threadIdx.x;
+  if (qi >= Q) return;
+  uint8_t* box = PB.box[PB.rank];
+  const int G = PB.world;
+  int n2 = 1;
+  while (n2 < G * k) n2 <<= 1;
+  double* s = reinterpret_cast<double*>(sm_raw);            // [n2]
+  long long* id = reinterpret_cast<long long*>(s + n2);     // [n2]
+  __shared__ int s_bad;
+  __shared__ float s_bound;
+  if (tid == 0) {
+    int bad = 0;
+    float bound = -FLT_MAX;
+    for (int g = 0; g < G; ++g) {
+      const int cg = inbox_cnt(box, PB.q_own, G, k)[ql * G + g];
+      if (cg < 0) bad = 1;
+      bound = fmaxf(bound, inbox_bound(box, PB.q_own, G, k)[ql * G + g]);
+    }
+    s_bad = bad;
+    s_bound = bound;
+  }
+  __syncthreads();
+  const long long kk = k < N_total ? k : N_total;
+  bool ok = !s_bad;
+  if (ok) {
+    for (int i = tid; i < n2; i += 256) {
+      const int g = i / k, j = i % k;
+      const int cg = g < G ? inbox_cnt(box, PB.q_own, G, k)[ql * G + g] : 0;
+      if (g < G && j < cg) { const TopkEntry e = inbox_entries(box, ql, g, G, k)[j]; s[i] = e.s; id[i] = e.id; }
+      else { s[i] = -DBL_MAX; id[i] = 0x7fffffffffffffffll; }
+    }
+    __syncthreads();
+    for (int k2 = 2; k2 <= n2; k2 <<= 1)
+      for (int j = k2 >> 1; j > 0; j >>= 1) {
+        for (int i = tid; i < n2; i += 256) {
+          const int p = i ^ j;
+          if (p > i) {
+            const bool up = ((i & k2) == 0);
+            const bool a_first = s[p] > s[i] || (s[p] == s[i] && id[p] < id[i]);
+            const bool b_first = s[i] > s[p] || (s[i] == s[p] && id[i] < id[p]);
+            if (up ? a_first : b_first) {
+              const double ts = s[i]; s[i] = s[p]; s[p] = ts;
+              const long long ti = id[i]; id[i] = id[p]; id[p] = ti;
+            }
+          }
+        }
+        __syncthreads();
+      }
+    // complete iff the k-th merged score clears every shard's bound (and k real rows exist)
+    ok = kk == 0 || (id[kk - 1] != 0x7fffffffffffffffll && (s_bound == -FLT_MAX || s[kk - 1] >= (double)s_bound));
+  }
+  if (!ok) {
+    if (tid == 0) { flist[1 + atomicAdd(flist, 1u)] = (unsigned)qi; if (status) status[qi] = 1; }
+    return;
+  }
+  for (int i = tid; i < k; i += 256) {
+    const float fs = i < kk ? (float)s[i] : -FLT_MAX;
+    const long long fi = i < kk ? id[i] : -1;
+    for (int g = 0; g < PO.n; ++g) { PO.s[g][qi * k + i] = fs; PO.i[g][qi * k + i] = fi; }
   }
 }
 
@@ -882,8 +1078,13 @@ extern "C" int nrx_topk_search64(const void* index, const float* corpus, int64_t
     if (rc != NRX_OK) return rc;
   }
   // exact fallback for the listed queries (every query when the corpus is tiny): fixed grid, exits at once on an empty list
+  CorpusSegs CS;
+  memset(&CS, 0, sizeof(CS));
+  CS.n_seg = 1; CS.c[0] = corpus; CS.base[0] = 0; CS.base[1] = N;
+  PeerOuts PO;
+  memset(&PO, 0, sizeof(PO));
   cudaFuncSetAttribute(topk_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fb_smem);
-  topk_exact_kernel<<<(unsigned)g.fb_grid, 256, fb_smem, st>>>(corpus, c_ld, N, D, queries, q_ld, k, flist, fast ? 0 : (int)Q, g.fb_items,
+  topk_exact_kernel<<<(unsigned)g.fb_grid, 256, fb_smem, st>>>(CS, c_ld, N, D, queries, q_ld, k, flist, fast ? 0 : (int)Q, g.fb_items,
                                                              part_s, part_i);
   rc = check_launch("topk_exact");
   if (rc != NRX_OK) return rc;
@@ -892,7 +1093,7 @@ extern "C" int nrx_topk_search64(const void* index, const float* corpus, int64_t
   const size_t msm = (size_t)n2 * 12;
   cudaFuncSetAttribute(topk_exact_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msm);
   topk_exact_merge_kernel<<<(unsigned)g.fb_grid, 256, msm, st>>>(N, k, id_base, flist, fast ? 0 : (int)Q, g.fb_grid, g.fb_items, part_s,
-                                                               part_i, out_scores, out_scores64, (long long*)out_ids, status);
+                                                               part_i, out_scores, out_scores64, (long long*)out_ids, status, PO);
   return check_launch("topk_exact_merge");
 }
 
@@ -901,6 +1102,132 @@ extern "C" int nrx_topk_search(const void* index, const float* corpus, int64_t c
                                int32_t* status, void* ws, size_t ws_bytes, nrx_stream_t stream) {
   return nrx_topk_search64(index, corpus, c_ld, N, D, queries, q_ld, Q, k, id_base, out_scores, nullptr, out_ids, status, ws, ws_bytes,
                            stream);
+}
+
+
+// ---- sharded search over peer memory --------------------------------------------------------------------------------
+extern "C" size_t nrx_topk_peer_inbox_bytes(int64_t Q, int world, int k) {
+  if (Q < 0 || world < 1 || k < 1) return 0;
+  const long long q_own = (Q + world - 1) / world;
+  return (inbox_bytes(q_own > 0 ? q_own : 1, world, k) + 255) & ~(size_t)255;
+}
+
+extern "C" int nrx_topk_search_peer(const void* index, int64_t N_local, int D, const float* queries, int64_t q_ld, int64_t Q, int k,
+                                    const NrxTopkPeer* h_peer, int32_t* status, void* ws, size_t ws_bytes, nrx_stream_t stream) {
+  NRX_REQUIRE(h_peer != nullptr, NRX_EINVAL, "null peer descriptor");
+  const int G = h_peer->world, R = h_peer->rank;
+  NRX_REQUIRE(G >= 1 && G <= NRX_MAX_PEERS && R >= 0 && R < G, NRX_EINVAL, "bad rank / world");
+  NRX_REQUIRE((long long)G * k <= 8192, NRX_EUNSUPPORTED, "peer search supports world * k <= 8192");
+  long long N_total = 0, id_base = 0;
+  for (int j = 0; j < G; ++j) {
+    NRX_REQUIRE(h_peer->corpus[j] && h_peer->inbox[j] && h_peer->out_scores[j] && h_peer->out_ids[j] && h_peer->sig[j], NRX_EINVAL,
+                "rank %d: null peer buffer", j);
+    if (j < R) id_base += h_peer->n_rows[j];
+    N_total += h_peer->n_rows[j];
+  }
+  NRX_REQUIRE(h_peer->n_rows[R] == N_local, NRX_EINVAL, "n_rows[rank] != N_local");
+  // per-shard threshold rank: the shards share the k' = 2k + 64 budget (each keeps a slack of its own)
+  TopkGeom g;
+  const int kp = (2 * k + 64 + G - 1) / G + 24;
+  int rc = make_geom(Q, N_local, D, k, &g, kp);
+  if (rc != NRX_OK) return rc;
+  if (Q == 0) return NRX_OK;
+  NRX_REQUIRE(index && queries && q_ld >= D, NRX_EINVAL, "null / bad argument");
+  NRX_REQUIRE(ws && ws_bytes >= g.total, NRX_EWORKSPACE, "workspace %zu < %zu", ws_bytes, g.total);
+  NRX_REQUIRE(N_total < (1ll << 32) - 1, NRX_EUNSUPPORTED, "corpus too large for 32-bit row ids");
+  cudaStream_t st = (cudaStream_t)stream;
+  uint8_t* w = (uint8_t*)ws;
+  float* gmax = (float*)(w + g.gmax);
+  float* theta = (float*)(w + g.theta);
+  float* eps = (float*)(w + g.eps);
+  unsigned* count = (unsigned*)(w + g.count);
+  int* flag = (int*)(w + g.flag);
+  unsigned* flist = (unsigned*)(w + g.flist);
+  double* part_s = (double*)(w + g.fpart);
+  unsigned* part_i = (unsigned*)(w + g.fpart + (size_t)g.fb_items * k * 8);
+  unsigned* cand = (unsigned*)(w + g.cand);
+  uint8_t* qimg = w + g.qimg;
+  const uint8_t* img = (const uint8_t*)index + kHdrBytes;
+  const float* corpus = h_peer->corpus[R];
+  if (status != nullptr) {
+    cudaError_t e = cudaMemsetAsync(status, 0, (size_t)Q * sizeof(int32_t), st);
+    NRX_REQUIRE(e == cudaSuccess, NRX_ELAUNCH, "memset: %s", cudaGetErrorString(e));
+  }
+  PeerInbox PB;
+  memset(&PB, 0, sizeof(PB));
+  PB.rank = R; PB.world = G; PB.q_own = (Q + G - 1) / G;
+  PeerOuts PO;
+  memset(&PO, 0, sizeof(PO));
+  PO.n = G;
+  for (int j = 0; j < G; ++j) { PB.box[j] = (uint8_t*)h_peer->inbox[j]; PO.s[j] = h_peer->out_scores[j]; PO.i[j] = (long long*)h_peer->out_ids[j]; }
+  NrxPeerStep bar;
+  memset(&bar, 0, sizeof(bar));
+  bar.rank = R; bar.world = G; bar.status = h_peer->status; bar.timeout_ms = h_peer->timeout_ms;
+  for (int j = 0; j < G; ++j) bar.sig[j] = h_peer->sig[j];
+
+  const bool fast = g.n_tiles >= 4;
+  const int n_regions = (int)(4 * g.slices);
+  if (fast) {
+    const size_t smem = (size_t)(g.nq + g.stages) * g.tile_bytes;
+    cudaFuncSetAttribute(topk_scan_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(topk_scan_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    NRX_REQUIRE(g.slices <= 1024, NRX_EUNSUPPORTED, "more than 1024 corpus slices");
+    const long long n_groups = g.n_stiles * 4;
+    const long long nchunks = g.n_qtiles * (g.Dp / 8) * kTR;
+    long long blocks = (nchunks + 255) / 256;
+    if (blocks > 4LL * sm_count()) blocks = 4LL * sm_count();
+    topk_qpack_kernel<<<(unsigned)blocks, 256, 0, st>>>(queries, q_ld, Q, D, g.Dp, qimg, g.n_qtiles);
+    long long s_slices = g.slices < g.n_stiles ? g.slices : g.n_stiles;
+    topk_scan_kernel<0><<<dim3((unsigned)s_slices, (unsigned)g.n_qgroups), kScanThreads, smem, st>>>(
+        img, N_local, g.n_tiles, g.stride, g.Dp, qimg, g.Qp, g.nq, g.stages, gmax, n_groups, nullptr, nullptr, nullptr, g.cap_s);
+    const size_t tsm = n_groups <= kThetaStage ? (size_t)n_groups * 4 : 0;
+    topk_theta_kernel<<<(unsigned)g.Qp, 256, tsm, st>>>(gmax, n_groups, g.Qp, Q, g.kprime_s, queries, q_ld, D, (const unsigned*)index, theta,
+                                                       eps, flist, flag);
+    topk_scan_kernel<1><<<dim3((unsigned)g.slices, (unsigned)g.n_qgroups), kScanThreads, smem, st>>>(
+        img, N_local, g.n_tiles, 1, g.Dp, qimg, g.Qp, g.nq, g.stages, nullptr, 0, theta, count, cand, g.cap_s);
+    rc = check_launch("topk_scan(peer)");
+    if (rc != NRX_OK) return rc;
+  } else {
+    // tiny shard: no tensor-core filter — every row is a candidate region-less; tell the owner to scan exactly
+    cudaError_t e = cudaMemsetAsync(count, 0xff, (size_t)g.Qp * g.slices * 4 * 4, st);   // counts > cap_s: "overflow" on purpose
+    NRX_REQUIRE(e == cudaSuccess, NRX_ELAUNCH, "memset: %s", cudaGetErrorString(e));
+    e = cudaMemsetAsync(flist, 0, 16, st);
+    NRX_REQUIRE(e == cudaSuccess, NRX_ELAUNCH, "memset: %s", cudaGetErrorString(e));
+  }
+  const size_t fsm = (size_t)kCap * 12 + (size_t)((D + 3) & ~3) * 4 + (size_t)n_regions * 4;
+  cudaFuncSetAttribute(topk_final_peer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm);
+  topk_final_peer_kernel<<<(unsigned)Q, 256, fsm, st>>>(corpus, D, N_local, D, queries, q_ld, k, id_base, theta, eps, count, cand, n_regions,
+                                                        g.cap_s, PB);
+  rc = check_launch("topk_final_peer");
+  if (rc != NRX_OK) return rc;
+  rc = nrx_peer_barrier(&bar, stream);     // every shard's lists have landed in the owners' inboxes
+  if (rc != NRX_OK) return rc;
+  int n2 = 1;
+  while (n2 < G * k) n2 <<= 1;
+  const size_t osm = (size_t)n2 * 16;
+  cudaFuncSetAttribute(topk_owner_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)osm);
+  topk_owner_merge_kernel<<<(unsigned)PB.q_own, 256, osm, st>>>(Q, N_total, k, PB, flist, status, PO);
+  rc = check_launch("topk_owner_merge");
+  if (rc != NRX_OK) return rc;
+  // listed queries (proof failed / a shard overflowed / tiny shards): exact scan of EVERY shard by the owner, through peer memory
+  CorpusSegs CS;
+  memset(&CS, 0, sizeof(CS));
+  CS.n_seg = G;
+  for (int j = 0; j < G; ++j) { CS.c[j] = h_peer->corpus[j]; CS.base[j + 1] = CS.base[j] + h_peer->n_rows[j]; }
+  const size_t fb_smem = (size_t)kFbCap * 12 + (size_t)D * 4;
+  cudaFuncSetAttribute(topk_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fb_smem);
+  topk_exact_kernel<<<(unsigned)g.fb_grid, 256, fb_smem, st>>>(CS, D, N_total, D, queries, q_ld, k, flist, 0, g.fb_items, part_s, part_i);
+  rc = check_launch("topk_exact(peer)");
+  if (rc != NRX_OK) return rc;
+  int m2 = 1;
+  while (m2 < fb_max_slices(k) * k) m2 <<= 1;
+  const size_t msm = (size_t)m2 * 12;
+  cudaFuncSetAttribute(topk_exact_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msm);
+  topk_exact_merge_kernel<<<(unsigned)g.fb_grid, 256, msm, st>>>(N_total, k, 0, flist, 0, g.fb_grid, g.fb_items, part_s, part_i, nullptr,
+                                                               nullptr, nullptr, nullptr, PO);
+  rc = check_launch("topk_exact_merge(peer)");
+  if (rc != NRX_OK) return rc;
+  return nrx_peer_barrier(&bar, stream);   // every owner's results are in every rank's output buffers
 }
 
 extern "C" size_t nrx_topk_ip_workspace_bytes(int64_t Q, int64_t N, int D, int k) {

@@ -734,15 +734,16 @@ tower_bwd_dx_kernel(const __grid_constant__ TowerK T, long long B, const float* 
 static constexpr int kDwThreads = 128;
 static constexpr int kDwStages = 2;
 static constexpr int kStageM = kRows * 128 * 2;          // dz image zero-extended to 128 columns: 32 KB
-static constexpr int kStageN = kRows * (240 + 16) * 2;   // a image + ones chunk pair: 64 KB
+static constexpr int kStageN = kRows * (240 + 16) * 2;   // a image + ones chunk pair: 64 KB (wider first layers: stage_n argument)
 
 __global__ void __launch_bounds__(kDwThreads, 1)
-tower_bwd_dw_kernel(const __grid_constant__ TowerK T, const uint8_t* __restrict__ ws, float* __restrict__ partials) {
+tower_bwd_dw_kernel(const __grid_constant__ TowerK T, const uint8_t* __restrict__ ws, float* __restrict__ partials, int stage_n,
+                    int tmem_cols) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sM[kDwStages];
   uint8_t* sN[kDwStages];
   for (int s = 0; s < kDwStages; ++s) {
-    sM[s] = smem + (size_t)s * (kStageM + kStageN);
+    sM[s] = smem + (size_t)s * (kStageM + stage_n);
     sN[s] = sM[s] + kStageM;
   }
   __shared__ uint64_t full[kDwStages], empty[kDwStages], done;
@@ -754,7 +755,7 @@ tower_bwd_dw_kernel(const __grid_constant__ TowerK T, const uint8_t* __restrict_
     mbar_init(&done, 1);
     fence_mbar_init();
   }
-  if (warp == 0) tmem_alloc(&tmem_s, 256u);
+  if (warp == 0) tmem_alloc(&tmem_s, (uint32_t)tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -799,7 +800,12 @@ tower_bwd_dw_kernel(const __grid_constant__ TowerK T, const uint8_t* __restrict_
         }
       } else if (warp == 1) {  // MMA issuer: whole warp in uniform control flow, one elected lane issues
         const uint32_t leader = elect_one_sync() ? 1u : 0u;
-        const uint32_t idesc = make_idesc_bf16(128, ncols, 1, 1);
+        // one MMA covers <= 256 output columns: a wider first layer (K + 16 > 256) is issued as two column blocks that
+        // alternate per K step (independent accumulators)
+        const int n1 = ncols <= 256 ? ncols : (((ncols / 2) + 15) & ~15);
+        const int n2 = ncols - n1;
+        const uint32_t idesc = make_idesc_bf16(128, n1, 1, 1);
+        const uint32_t idesc2 = make_idesc_bf16(128, n2 > 0 ? n2 : 16, 1, 1);
         int s = 0;
         for (long long t = t0; t < t1; ++t) {
           mbar_wait(&full[s], full_phase[s]);
@@ -808,10 +814,12 @@ tower_bwd_dw_kernel(const __grid_constant__ TowerK T, const uint8_t* __restrict_
           // MN-major: 8-element MN groups are kRows*16 B apart (SBO), 8-row K groups 128 B apart (LBO)
           uint64_t ad = make_smem_desc(smem_u32(sM[s]), 128u, kRows * 16u);
           uint64_t bd = make_smem_desc(smem_u32(sN[s]), 128u, kRows * 16u);
+          const uint64_t b2off = (uint64_t)(((uint32_t)n1 * 256u) >> 4);   // n1 columns further on in the MN-major operand
           uint32_t accum = t > t0 ? 1u : 0u;
 #pragma unroll
           for (int k16 = 0; k16 < kRows / 16; ++k16) {
             mma_bf16_ss_if(leader, tmem, ad, bd, idesc, accum);
+            if (n2 > 0) mma_bf16_ss_if(leader, tmem + (uint32_t)n1, ad, bd + b2off, idesc2, accum);
             ad += 256u >> 4;
             bd += 256u >> 4;
             accum = 1u;
@@ -841,7 +849,7 @@ tower_bwd_dw_kernel(const __grid_constant__ TowerK T, const uint8_t* __restrict_
     tc_fence_before();
     __syncthreads();
   }
-  if (warp == 0) tmem_dealloc(tmem, 256u);
+  if (warp == 0) tmem_dealloc(tmem, (uint32_t)tmem_cols);
 }
 
 // Backward (3): fixed-order sum of the per-CTA partials -> dW [N,K] (nn.Linear layout) and db [N].
@@ -977,7 +985,8 @@ extern "C" int nrx_tower_bwd_dx(const NrxTower* h_tower, int64_t B, const float*
   if (rc != NRX_OK) return rc;
   NRX_REQUIRE(ws && ws_bytes >= k.total_bytes, NRX_EWORKSPACE, "workspace %zu < %zu", ws_bytes, k.total_bytes);
   NRX_REQUIRE(grad_y || B == 0, NRX_EINVAL, "null grad_y");
-  NRX_REQUIRE(!k.wide0, NRX_EUNSUPPORTED, "tower backward: first layer wider than 240 columns (got %d)", k.K[0]);
+  NRX_REQUIRE(!k.wide0 || tower_dx3_eligible(k, grad_x != nullptr), NRX_EUNSUPPORTED,
+              "tower backward: a first layer wider than 240 columns (got %d) needs the pipelined dX kernel", k.K[0]);
   NRX_REQUIRE(gy_ld >= k.N[k.n_layers - 1] && (!grad_x || gx_ld >= k.K[0]), NRX_EINVAL, "leading dimension too small");
   if (B == 0) return NRX_OK;
   cudaStream_t st = (cudaStream_t)stream;
@@ -1005,12 +1014,14 @@ extern "C" int nrx_tower_bwd_dw(const NrxTower* h_tower, int64_t B, float* const
   if (rc != NRX_OK) return rc;
   NRX_REQUIRE(ws && ws_bytes >= k.total_bytes, NRX_EWORKSPACE, "workspace %zu < %zu", ws_bytes, k.total_bytes);
   NRX_REQUIRE(h_grad_w && h_grad_b, NRX_EINVAL, "null gradient pointer arrays");
-  NRX_REQUIRE(!k.wide0, NRX_EUNSUPPORTED, "tower backward: first layer wider than 240 columns (got %d)", k.K[0]);
   if (B == 0) return NRX_OK;
   cudaStream_t st = (cudaStream_t)stream;
   uint8_t* w = (uint8_t*)ws;
   {
-    const size_t smem = (size_t)kDwStages * (kStageM + kStageN);
+    const int stage_n = k.max_kp <= 240 ? kStageN : kRows * (k.max_kp + 16) * 2;
+    const size_t smem = (size_t)kDwStages * (kStageM + stage_n);
+    NRX_REQUIRE(smem <= 227 * 1024 && k.max_kp + 16 <= 496, NRX_EUNSUPPORTED, "tower dW: first layer of %d columns is too wide", k.K[0]);
+    const int dw_tmem = k.max_kp + 16 <= 256 ? 256 : 512;
     cudaError_t e = cudaFuncSetAttribute(tower_bwd_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     NRX_REQUIRE(e == cudaSuccess, NRX_ELAUNCH, "smem opt-in: %s", cudaGetErrorString(e));
     // >= 4 tiles per CTA so the partial-sum traffic stays small next to the GEMM work
@@ -1021,7 +1032,7 @@ extern "C" int nrx_tower_bwd_dw(const NrxTower* h_tower, int64_t B, float* const
     if (parts < 1) parts = 1;
     const long long per = (k.n_tiles + parts - 1) / parts;
     float* partials = (float*)(w + k.part_off);
-    tower_bwd_dw_kernel<<<dim3((unsigned)parts, (unsigned)k.n_layers), kDwThreads, smem, st>>>(k, w, partials);
+    tower_bwd_dw_kernel<<<dim3((unsigned)parts, (unsigned)k.n_layers), kDwThreads, smem, st>>>(k, w, partials, stage_n, dw_tmem);
     rc = check_launch("tower_bwd_dw");
     if (rc != NRX_OK) return rc;
     PtrPack P;

@@ -113,14 +113,26 @@ def embed_pool_fwd(fb: FeatBinding, out_dim: int, status: Optional[torch.Tensor]
 
 
 def embed_pool_fwd_img(fb: FeatBinding, out_dim: int, image: torch.Tensor, want_rows: bool = True,
-                       status: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
+                       status: Optional[torch.Tensor] = None, fm_logit: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
     """K1 that also writes the tower's bf16 input image (`image`: the a_0 slot of a prepacked tower workspace, see
-    tower_input_image); returns the fp32 rows, or None with want_rows=False (nothing else reads them)."""
+    tower_input_image); returns the fp32 rows, or None with want_rows=False (nothing else reads them).  `fm_logit` [B]:
+    the FM logit over all features, computed in the same epilogue (see fm_epilogue_eligible)."""
     out = torch.empty((fb.B, out_dim), dtype=torch.float32, device=fb.device) if want_rows else None
     lib = L.load()
     L.check(lib.nrx_embed_pool_fwd_img(fb.arr, fb.n, fb.B, L.ptr(out), out.stride(0) if (out is not None and fb.B) else out_dim,
-                                       image.data_ptr(), out_dim, L.ptr(status), L.stream_ptr(fb.device)), "nrx_embed_pool_fwd_img")
+                                       image.data_ptr(), out_dim, L.ptr(fm_logit), L.ptr(status), L.stream_ptr(fb.device)),
+            "nrx_embed_pool_fwd_img")
     return out
+
+
+def fm_epilogue_eligible(fb: FeatBinding, fm_cols, fm_dims) -> bool:
+    """The FM field set is every feature of the binding, all single-id, equal width D with D/4 a power of two, <= 32 lanes."""
+    if any(s.is_array for s in fb.specs) or len(fm_cols) != len(fb.specs):
+        return False
+    d = fb.specs[0].dim
+    if any(s.dim != d for s in fb.specs) or d % 4 or ((d // 4) & (d // 4 - 1)) or len(fb.specs) * (d // 4) > 32:
+        return False
+    return sorted(fm_cols) == sorted(s.out_col for s in fb.specs) and all(x == d for x in fm_dims)
 
 
 def embed_img_eligible(fb: FeatBinding, out_dim: int) -> bool:

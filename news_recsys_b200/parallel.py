@@ -22,7 +22,8 @@ The reference is single-GPU only (`devices=1`, sort/deep/train.py:41-42); everyt
 from __future__ import annotations
 
 import ctypes as C
-from typing import Dict, List, Tuple
+import os
+from typing import Optional, Dict, List, Tuple
 
 import torch
 import torch.distributed as dist
@@ -296,12 +297,27 @@ class ShardedEmbeddingTrainer(FusedTrainer):
       6. K3 over the global batch with the local ids updates exactly the rows this rank owns (not-owned
          occurrences map to the padding sentinel and are skipped); replicated tables see all ids on every
          rank and stay bitwise identical.
-    The exchange moves G*B*ΣD*4 bytes per direction (a reduce-scatter instead of the ids/vectors all-to-all
-    of an owner-compute design): simple and shape-static first, traffic-optimal later."""
+    That exchange (`exchange="reduce_scatter"`) moves (G-1)*B*ΣD*4 bytes per rank and direction whatever the ids are.
+
+    `exchange="peer"` (default when every sharded feature is a single-id feature) is the owner-compute exchange of SURVEY
+    §8e over NVLink peer memory, with no collective on the vectors:
+      1. ids all-gathered (tiny: 8 bytes per id);  K1 gathers the REPLICATED features of the local batch into x;
+      2. `nrx_shard_push`: every rank gathers, for the samples of EVERY rank whose ids it owns, the rows of its shard and
+         stores them straight into the requester's feature matrix x_r[b, cols] (peer stores) — each rank receives exactly
+         B*ΣD_sharded*4 bytes; `nrx_peer_barrier` (flag barrier over the K7 signal pads) publishes x;
+      3. heads forward/backward locally, dense grads all-reduced (AVG) — which also orders every rank's gradient matrix
+         before step 4;
+      4. `nrx_shard_pull`: every owner copies, from every rank's gradient matrix, the columns of the samples whose ids it
+         owns (peer loads; replicated features: all samples) into its local [G*B, ΣD] buffer, and ONE K3 over the global
+         batch with the masked local ids updates exactly the owned rows.
+    Single-id features have exactly one contributor, so x is bit-equal to the single-GPU gather."""
 
     _inline_update = False
 
-    def __init__(self, model, B: int, kind=None, group=None, shard_min_rows: int = 100_000, **kw):
+    def __init__(self, model, B: int, kind=None, group=None, shard_min_rows: int = 100_000, exchange: Optional[str] = None,
+                 peer_timeout_ms: int = 20000, **kw):
+        if exchange not in (None, "peer", "reduce_scatter"):
+            raise L.NrxError(f"exchange must be 'peer' or 'reduce_scatter', got {exchange!r}")
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
@@ -346,21 +362,124 @@ class ShardedEmbeddingTrainer(FusedTrainer):
         for i, s in enumerate(self.gfb_bwd.specs):
             if s.name in self.gfb_fwd.inv_den:
                 self.gfb_bwd.arr[i].inv_den = self.gfb_fwd.inv_den[s.name].data_ptr()
+        self._bar_word = torch.zeros(1, dtype=torch.float32, device=dev)
         self.partial = torch.zeros((G * B, self.out_dim), dtype=torch.float32, device=dev)
         self.x_local = torch.zeros((B, self.out_dim), dtype=torch.float32, device=dev)
         self.gx_global = torch.zeros((G * B, self.out_dim), dtype=torch.float32, device=dev)
         own = torch.zeros(G * B, dtype=torch.bool, device=dev)
         own[self.rank * B:(self.rank + 1) * B] = True
         self._own_rows = own
+        sharded_arrays = [sp.name for sp in self.fb.specs if sp.table in self.shards and sp.is_array]
+        if exchange == "peer" and sharded_arrays:
+            raise L.NrxError(f"exchange='peer' handles single-id features on sharded tables; array features {sharded_arrays} "
+                             "need exchange='reduce_scatter' (owner-side partial pooling over peer memory is not built)")
+        self.exchange = exchange or ("reduce_scatter" if (sharded_arrays or G == 1) else "peer")
+        if self.exchange == "peer":
+            self._init_peer_exchange(peer_timeout_ms)
         self._sharded_ready = True
+        self.graph_a = self.graph_b = None
+        if self.exchange == "peer" and os.environ.get("NRX_SHARDED_GRAPH", "1") == "1":
+            self._capture_sharded()
+
+    def _part_a(self):
+        """Everything between the id all-gather and the dense-gradient all-reduce (graph A)."""
+        self._remap_ids()
+        self._fwd_bwd()
+        torch.mul(self._gx, 1.0 / self.world, out=self.gx_peer)
+
+    def _part_b(self):
+        """Everything after the all-reduce: pull the gradient columns this rank owns, K3 + optimizer (graph B)."""
+        L.check(self.lib.nrx_shard_pull(self._sh_feats, self._n_sh, self._rep_feats, self._n_rep, self.rank, self.world, self.B,
+                                        self._g_ptrs, self.out_dim, self.gx_global.data_ptr(), self._sp()), "nrx_shard_pull")
+        self._update(self.gfb_bwd, self._plan, self.gx_global)
+
+    def _capture_sharded(self):
+        """The step minus its two NCCL calls as two CUDA graphs (the eager step is ~50 launches + their Python: 0.9 ms at
+        cfg5 on 2 GPUs against 0.18 ms for the single-GPU graph).  The peer barrier inside graph A is an ordinary kernel."""
+        snap = self._snapshot()
+        self._gather_ids()
+        self._part_a()                       # warm-up (lazy module loading must not happen inside capture), lockstep on all ranks
+        dist.all_reduce(self.flat_g if self.n_dense > 0 else self._bar_word, op=dist.ReduceOp.AVG, group=self.group)
+        self._part_b()
+        torch.cuda.synchronize(self.dev)
+        self._restore(snap)
+        dist.barrier(group=self.group)
+        ga = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(ga):
+            self._part_a()
+        gb = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gb, pool=ga.pool()):
+            self._part_b()
+        torch.cuda.synchronize(self.dev)
+        self._restore(snap)
+        self.graph_a, self.graph_b = ga, gb
+        dist.barrier(group=self.group)
+
+    # ---- owner-compute exchange over peer memory ---------------------------------------------------------------
+    def _init_peer_exchange(self, timeout_ms: int):
+        G, B, dev = self.world, self.B, self.dev
+        n = B * self.out_dim
+        bx, bg = PeerBuffer(4 * n, dev), PeerBuffer(4 * n, dev)
+        bsig = PeerBuffer(4 * L.NRX_PEER_SIG_WORDS, dev, typestr="<i4")
+        self._peer_keep = [bx, bg, bsig]
+        self.x_peer = bx.tensor().view(B, self.out_dim)
+        self.gx_peer = bg.tensor().view(B, self.out_dim)
+        ptrs = open_peers(self._peer_keep, self.group)     # [x, gx, sig][rank]
+        self._x_ptrs = L.ptr_array(ptrs[0], L.NRX_MAX_PEERS)
+        self._g_ptrs = L.ptr_array(ptrs[1], L.NRX_MAX_PEERS)
+        st = L.NrxPeerStep()
+        st.rank, st.world = self.rank, G
+        for j in range(G):
+            st.sig[j] = ptrs[2][j]
+        st.status = self.id_status.data_ptr()
+        st.timeout_ms = int(timeout_ms)
+        self._barrier_step = st
+        sh = [sp for sp in self.fb.specs if sp.table in self.shards]
+        rep = [sp for sp in self.fb.specs if sp.table not in self.shards]
+        weights = self.model._weights()
+
+        def mk(specs, sharded):
+            arr = (L.NrxShardFeat * max(len(specs), 1))()
+            for i, sp in enumerate(specs):
+                w = weights[sp.table]
+                ids = self.gbatch[sp.name]
+                arr[i].table = w.data_ptr()
+                arr[i].ids = ids.data_ptr()
+                if sharded:
+                    arr[i].lo, arr[i].hi = self.shards[sp.table][0], self.shards[sp.table][1]
+                else:
+                    arr[i].lo, arr[i].hi = 0, w.shape[0]
+                arr[i].dim, arr[i].row_stride, arr[i].out_col = sp.dim, w.stride(0), sp.out_col
+                arr[i].idx_dtype = L.IDX_I32 if ids.dtype == torch.int32 else L.IDX_I64
+            return arr, len(specs)
+
+        self._sh_feats, self._n_sh = mk(sh, True)
+        self._rep_feats, self._n_rep = mk(rep, False)
+        # K1 over the LOCAL batch for the replicated features only, writing their columns of x
+        self._rep_fb = ops.FeatBinding(rep, weights, self.batch, want_inv_den=True) if rep else None
+        if self._rep_fb is not None:    # K3 reads the denominators through the global binding: keep one set (local block)
+            for name, inv in self._rep_fb.inv_den.items():
+                pass
+        dist.barrier(group=self.group)
+
+    def _peer_barrier(self):
+        L.check(self.lib.nrx_peer_barrier(C.byref(self._barrier_step), self._sp()), "nrx_peer_barrier")
 
     def _plan_fb(self):
         return self.gfb_bwd if getattr(self, "_sharded_ready", False) else self.fb
 
     def _exchange_ids(self):
+        self._gather_ids()
+        self._remap_ids()
+
+    def _gather_ids(self):
         with dist._coalescing_manager(group=self.group, device=self.dev, async_ops=False):
             for k in self.id_keys:
                 dist.all_gather_into_tensor(self.gbatch[k], self.batch[k], group=self.group)
+
+    def _remap_ids(self):
+        """Global ids -> the id views K1 / K3 use (static buffers, pure device work: part of the captured graph)."""
+        peer = getattr(self, "exchange", "reduce_scatter") == "peer"
         for s in self.fb.specs:
             g = self.gbatch[s.name]
             if s.table in self.shards:
@@ -368,19 +487,47 @@ class ShardedEmbeddingTrainer(FusedTrainer):
                 local = torch.where((g >= lo) & (g < hi), g - (lo - 1), torch.zeros_like(g))
                 if lo == 0:
                     local = torch.where(g == 0, torch.zeros_like(g), local)  # global pad id stays the pad row
-                self.fbatch[s.name].copy_(local)
+                if not peer:
+                    self.fbatch[s.name].copy_(local)
                 self.bbatch[s.name].copy_(local)
             else:
-                own = self._own_rows if g.dim() == 1 else self._own_rows[:, None]
-                self.fbatch[s.name].copy_(torch.where(own, g, torch.zeros_like(g)))
+                if not peer:
+                    own = self._own_rows if g.dim() == 1 else self._own_rows[:, None]
+                    self.fbatch[s.name].copy_(torch.where(own, g, torch.zeros_like(g)))
                 self.bbatch[s.name].copy_(g)
+        if peer:   # K1 only saw the local block: the masked-mean denominators of the global batch come from the gathered masks
+            for name, inv in self.gfb_bwd.inv_den.items():
+                torch.reciprocal(self.gbatch[name + "_mask"].sum(dim=1) + 1e-8, out=inv)
 
     def _embed_fwd(self):
+        if getattr(self, "exchange", "reduce_scatter") == "peer":
+            if self._rep_fb is not None:   # replicated features of my own samples -> their columns of x
+                L.check(self.lib.nrx_embed_pool_fwd(self._rep_fb.arr, self._rep_fb.n, self.B, self.x_peer.data_ptr(), self.out_dim,
+                                                    self.id_status.data_ptr(), self._sp()), "nrx_embed_pool_fwd")
+            L.check(self.lib.nrx_shard_push(self._sh_feats, self._n_sh, self.rank, self.world, self.B, self._x_ptrs, self.out_dim,
+                                            self._sp()), "nrx_shard_push")
+            self._peer_barrier()           # every owner has written its rows into everybody's x
+            return self.x_peer
         ops_out = ops.embed_pool_fwd(self.gfb_fwd, self.out_dim)  # partial features of the rows this rank owns
         dist.reduce_scatter_tensor(self.x_local, ops_out, op=dist.ReduceOp.SUM, group=self.group)
         return self.x_local
 
     def step(self) -> torch.Tensor:
+        self._poll_status()
+        if self.exchange == "peer":
+            self._gather_ids()                 # all-gather: also orders step N's reads of x / gx before step N + 1's writes
+            if self.graph_a is not None:
+                self.graph_a.replay()
+            else:
+                self._part_a()
+            # the all-reduce of the dense gradients doubles as the barrier "every rank's gx is written"
+            dist.all_reduce(self.flat_g if self.n_dense > 0 else self._bar_word, op=dist.ReduceOp.AVG, group=self.group)
+            if self.graph_b is not None:
+                self.graph_b.replay()
+            else:
+                self._part_b()
+            self._post_status()
+            return self.loss
         self._exchange_ids()
         self._fwd_bwd()
         self._gx.mul_(1.0 / self.world)
@@ -388,6 +535,7 @@ class ShardedEmbeddingTrainer(FusedTrainer):
             dist.all_reduce(self.flat_g, op=dist.ReduceOp.AVG, group=self.group)
         dist.all_gather_into_tensor(self.gx_global, self._gx, group=self.group)
         self._update(self.gfb_bwd, self._plan, self.gx_global)
+        self._post_status()
         return self.loss
 
     def exchange_bytes(self) -> int:
@@ -396,6 +544,8 @@ class ShardedEmbeddingTrainer(FusedTrainer):
 
     def exchange_bandwidth(self, iters: int = 10) -> dict:
         """Device-timed bandwidth of the forward exchange alone (same buffers as the step), max over ranks."""
+        if self.exchange == "peer":
+            return self._peer_exchange_bandwidth(iters)
         for _ in range(2):
             dist.reduce_scatter_tensor(self.x_local, self.partial, op=dist.ReduceOp.SUM, group=self.group)
         torch.cuda.synchronize()
@@ -412,6 +562,28 @@ class ShardedEmbeddingTrainer(FusedTrainer):
         return {"collective": "reduce_scatter(sum) of the [G*B, ΣD] fp32 partial features", "bytes_sent_per_rank": self.exchange_bytes(),
                 "ms": ms, "gb_per_s_per_rank": self.exchange_bytes() / (ms * 1e-3) / 1e9,
                 "nvlink_peak_gb_per_s": 770.0, "note": "770 GB/s = measured peer copy per direction (B200_PROFILING.md)"}
+
+    def _peer_exchange_bandwidth(self, iters: int) -> dict:
+        sharded_cols = sum(sp.dim for sp in self.fb.specs if sp.table in self.shards)
+        recv = self.B * sharded_cols * 4 * (self.world - 1) // self.world   # expected bytes arriving over NVLink (uniform ids)
+        dist.barrier(group=self.group)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            L.check(self.lib.nrx_shard_push(self._sh_feats, self._n_sh, self.rank, self.world, self.B, self._x_ptrs, self.out_dim,
+                                            self._sp()), "nrx_shard_push")
+            self._peer_barrier()
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / iters], dtype=torch.float64, device=self.dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        ms = float(t[0])
+        return {"collective": "nrx_shard_push (owner-side gather stored straight into the requesters' feature rows over NVLink peer "
+                              "memory) + nrx_peer_barrier; no NCCL on the vectors",
+                "bytes_received_per_rank": recv, "bytes_reduce_scatter_would_send": self.exchange_bytes(),
+                "ms": ms, "gb_per_s_per_rank": recv / (ms * 1e-3) / 1e9, "nvlink_peak_gb_per_s": 770.0,
+                "note": "770 GB/s = measured peer copy per direction (B200_PROFILING.md); at this size the exchange is latency-bound"}
 
     def gather_table(self, name: str) -> torch.Tensor:
         """Full [rows, D] table on every rank (tests / checkpointing)."""

@@ -286,29 +286,34 @@ class FusedTrainer:
                 img = ops.tower_input_image(packed, self.B)
             x_img = (img is not None and kind in ("deep", "deepfm") and ops.embed_img_eligible(fb, self.out_dim)
                      and type(self)._embed_fwd is FusedTrainer._embed_fwd)
-            if x_img:
-                x = ops.embed_pool_fwd_img(fb, self.out_dim, img, want_rows=(kind != "deep"), status=self.id_status)
-            else:
-                x = self._embed_fwd()
             cols, c = [], 0
             for d in self.dims:
                 cols.append(c)
                 c += d
             terms, tctx, lin, field = [], None, None, None
             gw_override = None
+            fm_term = None
             if kind in ("fm", "deepfm"):
                 if kind == "deepfm":
                     fcols, fdims = m.fm_fields(self.dims, self.names)
                 else:
                     fcols, fdims = cols, list(self.dims)
                 field = (fcols, fdims, L.FIELD_FM)
-            elif kind == "widedeep":
+                if x_img and ops.fm_epilogue_eligible(fb, fcols, fdims):   # FM logit in K1's epilogue: no separate launch
+                    fm_term = torch.empty(self.B, dtype=torch.float32, device=self.dev)
+            if x_img:
+                x = ops.embed_pool_fwd_img(fb, self.out_dim, img, want_rows=(kind != "deep"), status=self.id_status, fm_logit=fm_term)
+            else:
+                x = self._embed_fwd()
+            if kind == "widedeep":
                 wide_cols, deep_cols = m._split_cols(self.dims, self.names)
                 field = (wide_cols, [1] * len(wide_cols), L.FIELD_WIDE)
             elif kind == "lr":
                 field = (cols, list(self.dims), L.FIELD_SUM)
             s3 = self.side3
-            if field is not None:   # with a tower: the term feeds the fused head of the tower's last epilogue
+            if fm_term is not None:
+                terms.append(fm_term)
+            elif field is not None:   # with a tower: the term feeds the fused head of the tower's last epilogue
                 terms.append(ops.field_logit_fwd(x, field[0], field[1], field[2]))
             if has_tower:
                 lin = self._lin_names(self._TOWER_PREFIX[kind])

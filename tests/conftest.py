@@ -24,3 +24,16 @@ def pytest_collection_modifyitems(config, items):
     for it in items:
         if "gpu" in it.keywords:
             it.add_marker(skip)
+
+
+@pytest.fixture(autouse=True)
+def _seed_everything():
+    """Every test starts from the same torch seed (CPU and CUDA generators): tests that draw inputs without an explicit
+    generator (large-batch tower / FM checks on the device) see the same data on every run, so a tolerance check either
+    always passes or always fails."""
+    try:
+        import torch
+        torch.manual_seed(20261017)
+    except Exception:
+        pass
+    yield

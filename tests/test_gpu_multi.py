@@ -101,7 +101,7 @@ def test_dp2_equals_single_gpu(kind, mode, exchange, tmp_path):
     assert torch.equal(i0, ri)
 
 
-def _sharded_worker(rank, world, port, kind, out_dir):
+def _sharded_worker(rank, world, port, kind, out_dir, exchange=None):
     import sys
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     import importlib
@@ -119,8 +119,10 @@ def _sharded_worker(rank, world, port, kind, out_dir):
     torch.manual_seed(1)
     model = cls(cfg).to(f"cuda:{rank}")
     B = 128
-    tr = ShardedEmbeddingTrainer(model, B, kind=kind, shard_min_rows=100)   # user_id and item_id get sharded
+    tr = ShardedEmbeddingTrainer(model, B, kind=kind, shard_min_rows=100, exchange=exchange)   # user_id and item_id get sharded
     assert set(tr.shards) == {"user_id", "item_id"}
+    # single-id features only (fm): owner-compute exchange over peer memory; a sharded array feature (deep + history): reduce-scatter
+    assert tr.exchange == (exchange or ("peer" if kind == "fm" else "reduce_scatter"))
     assert model.embedding_tables["user_id"].weight.shape[0] < 301          # each rank holds a strict subset
     losses = []
     for s in range(3):
@@ -134,12 +136,13 @@ def _sharded_worker(rank, world, port, kind, out_dir):
             sd[k] = tr.gather_table(k[len("embedding_tables."):-len(".weight")]).cpu()
         else:
             sd[k] = v.detach().cpu()
+    tr.check_status()
     torch.save((sd, losses), os.path.join(out_dir, f"sh_{kind}_{rank}.pt"))
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("kind", ["fm", "deep"])
-def test_row_sharded_tables_equal_single_gpu(kind, tmp_path):
+@pytest.mark.parametrize("kind,exchange", [("fm", None), ("fm", "reduce_scatter"), ("deep", None)])
+def test_row_sharded_tables_equal_single_gpu(kind, exchange, tmp_path):
     """BASELINE config 5 mechanism at test scale: big tables row-sharded over 2 ranks, partial pooling +
     reduce-scatter forward, owner-side sparse-row AdamW backward == the single-GPU trainer on the same
     global batch (single-id fields and their tables: fp32-exact up to summation order 1e-5)."""
@@ -149,7 +152,7 @@ def test_row_sharded_tables_equal_single_gpu(kind, tmp_path):
     import torch.multiprocessing as mp
     from news_recsys_b200.synthetic import mind_config, synth_batch
     from news_recsys_b200.trainer import FusedTrainer
-    mp.spawn(_sharded_worker, args=(2, _free_port(), kind, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_sharded_worker, args=(2, _free_port(), kind, str(tmp_path), exchange), nprocs=2, join=True)
     sd0, l0 = torch.load(tmp_path / f"sh_{kind}_0.pt")
     sd1, l1 = torch.load(tmp_path / f"sh_{kind}_1.pt")
     for k in sd0:

@@ -50,6 +50,7 @@ CASES = [
     ([112, 128, 128, 128, 64, 1], None, 300),      # Deep / WideDeep (deep/model.py:29)
     ([224, 128, 128, 128, 64, 1], None, 1000),     # DCN head (dcn/model.py:36)
     ([144, 128, 128, 128, 64, 1], None, 128),      # cfg1 with user_history
+    ([288, 128, 128, 128, 64, 1], None, 700),      # DCN + user_history: 2d = 288 (K-streamed / column-blocked first layer)
     ([48, 128, 128, 64, 16], 0.2, 513),            # DSSM tower (recall/DSSM/model.py:26-44)
     ([80, 128, 128, 64, 128], 0.2, 257),           # DSSM tower, 128-d output (BASELINE cfg4)
     ([20, 16, 8, 1], None, 77),                    # odd small widths (padding path)
