@@ -276,12 +276,14 @@ def retrieval_leg(dev, world, rank, dist, quick):
     queries = [torch.nn.functional.normalize(torch.randn((Q, D), generator=g, device=dev), dim=1) for _ in range(n_q)]
     torch.cuda.synchronize()
     t0 = time.perf_counter()
+    exchange = os.environ.get("NRX_TOPK_EXCHANGE", "peer")
     if world > 1:
-        index = ShardedTopk(corpus, N)
-        search = lambda q: index.search(q, K)
+        index = ShardedTopk(corpus, N, exchange=exchange)
+        search = (lambda q: index.search_peer_(q, K)) if exchange == "peer" else (lambda q: index.search(q, K))
+        search_api = lambda q: index.search(q, K)
     else:
         index = TopkIndex(corpus)
-        search = lambda q: index.search(q, K)
+        search = search_api = lambda q: index.search(q, K)
     torch.cuda.synchronize()
     build_s = time.perf_counter() - t0
     for i in range(3):
@@ -298,10 +300,36 @@ def retrieval_leg(dev, world, rank, dist, quick):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
     # status: how many queries needed the exact fallback scan (single-GPU index only)
-    fb = None
+    fb, sharded = None, None
     if world == 1:
         _, _, st = index.search(queries[0], K, want_status=True)
         fb = int(st.sum().item())
+    else:
+        # sharded result == the per-shard complete lists merged with their fp64 keys (the round-1 exchange), on every rank
+        s_p, i_p = index.search(queries[0], K)
+        t_fb = torch.tensor([index.exact_fallbacks(Q, K) if exchange == "peer" else 0], dtype=torch.int64, device=dev)
+        other = ShardedTopk(corpus, N, exchange="nccl" if exchange == "peer" else "peer")
+        s_n, i_n = other.search(queries[0], K)
+        same = torch.tensor([int(torch.equal(i_p, i_n) and torch.equal(s_p, s_n))], dtype=torch.int64, device=dev)
+        for i in range(3):
+            other.search(queries[i % n_q], K)
+        torch.cuda.synchronize()
+        dist.barrier()
+        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e2.record()
+        for i in range(iters):
+            other.search_peer_(queries[i % n_q], K) if other.exchange == "peer" else other.search(queries[i % n_q], K)
+        e3.record()
+        torch.cuda.synchronize()
+        t_o = torch.tensor([e2.elapsed_time(e3) / iters], dtype=torch.float64, device=dev)
+        dist.all_reduce(t_fb)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        dist.all_reduce(t_o, op=dist.ReduceOp.MAX)
+        fb = int(t_fb.item())
+        sharded = {"exchange": exchange, "parity_ok": bool(same.item()),
+                   "parity_check": "ids and scores of the peer search == per-shard complete lists all-gathered with fp64 keys and merged, on every rank",
+                   f"ms_per_search_{other.exchange}": float(t_o.item())}
+        del other
     # end to end: pinned host queries -> H2D -> search -> D2H of (scores, ids)
     hq = [q.cpu().pin_memory() for q in queries]
     hs = torch.empty((Q, K), dtype=torch.float32).pin_memory()
@@ -311,7 +339,7 @@ def retrieval_leg(dev, world, rank, dist, quick):
     t0 = time.perf_counter()
     for i in range(iters):
         dq.copy_(hq[i % n_q], non_blocking=True)
-        s_, i_ = search(dq)
+        s_, i_ = search_api(dq)
         hs.copy_(s_, non_blocking=True)
         hi_.copy_(i_, non_blocking=True)
         torch.cuda.synchronize()
@@ -330,7 +358,7 @@ def retrieval_leg(dev, world, rank, dist, quick):
            "config": {"workload": "cfg4: N=1,000,000 x D=128 L2-normalised, k=100, Q=1024 per search", "shards": world,
                       "ordering": "(fp64 inner product desc, id asc), bit-exact vs oracle"},
            "e2e": {"value": Q / (e2e_ms * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": Q * D * 4, "d2h_bytes_per_step": Q * K * 12},
-           "index_build_s": build_s, "fallback_queries": fb,
+           "index_build_s": build_s, "fallback_queries": fb, "sharded": sharded,
            "roofline": {"bound": "tensor", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
                         "traffic": None, "kernel": "nrx_topk_search (query pack + sample scan of 1/8 of the tiles + theta + one full filter scan + final)", "peak_source": peak_src,
                         "algorithmic_per_launch": flops}}

@@ -422,7 +422,7 @@ typedef struct NrxTopkPeer {
   uint32_t* sig[NRX_MAX_PEERS];         /* signal pads (NRX_PEER_SIG_WORDS u32), as for K7 */
   int32_t* status;                      /* optional trainer-style status word (bit 1: dead exchange) */
   uint32_t timeout_ms;
-  uint32_t reserved;
+  uint32_t kprime;                      /* per-shard threshold rank; 0 = ceil((2k + 64) / world) + 24 */
 } NrxTopkPeer;
 size_t nrx_topk_peer_inbox_bytes(int64_t Q, int world, int k);
 int nrx_topk_search_peer(const void* index, int64_t N_local, int D, const float* queries, int64_t q_ld, int64_t Q, int k,

@@ -68,7 +68,7 @@ class NrxTopkPeer(C.Structure):
     _fields_ = [("rank", C.c_int32), ("world", C.c_int32),
                 ("corpus", C.c_void_p * NRX_MAX_PEERS), ("n_rows", C.c_int64 * NRX_MAX_PEERS), ("inbox", C.c_void_p * NRX_MAX_PEERS),
                 ("out_scores", C.c_void_p * NRX_MAX_PEERS), ("out_ids", C.c_void_p * NRX_MAX_PEERS), ("sig", C.c_void_p * NRX_MAX_PEERS),
-                ("status", C.c_void_p), ("timeout_ms", C.c_uint32), ("reserved", C.c_uint32)]
+                ("status", C.c_void_p), ("timeout_ms", C.c_uint32), ("kprime", C.c_uint32)]
 
 
 class NrxIngestCol(C.Structure):

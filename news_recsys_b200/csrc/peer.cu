@@ -264,6 +264,9 @@ extern "C" int nrx_peer_alloc(size_t bytes, void** ptr) {
   NRX_REQUIRE(e == cudaSuccess, NRX_ELAUNCH, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
   e = cudaMemset(*ptr, 0, bytes);
   NRX_REQUIRE(e == cudaSuccess, NRX_ELAUNCH, "cudaMemset: %s", cudaGetErrorString(e));
+  // the zero fill must have LANDED before the handle can reach a peer: a peer's first flag store must not be overwritten
+  e = cudaDeviceSynchronize();
+  NRX_REQUIRE(e == cudaSuccess, NRX_ELAUNCH, "cudaDeviceSynchronize: %s", cudaGetErrorString(e));
   return NRX_OK;
 }
 

@@ -177,7 +177,8 @@ topk_scan_kernel(const uint8_t* __restrict__ img, long long N, long long n_tiles
   uint8_t* sC = smem + (size_t)nq_max * tile_bytes;    // [stages][tile image]
   __shared__ uint64_t full[4], empty[4], tfull[kMaxQT], tempty[kMaxQT], qbar;
   __shared__ uint32_t tmem_s;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(NRX_FULL_MASK, tid >> 5, 0);   // provably warp-uniform: the role branches below are uniform, so ptxas keeps the MMA descriptors in uniform registers
   const long long qt0 = (long long)blockIdx.y * nq_max;             // first query tile of this CTA
   const long long n_qtiles = Qp / kTR;
   const int nq = (int)(n_qtiles - qt0 < nq_max ? n_qtiles - qt0 : nq_max);
@@ -334,6 +335,7 @@ topk_scan_kernel(const uint8_t* __restrict__ img, long long N, long long n_tiles
 __device__ __forceinline__ unsigned f2key(float f) { unsigned u = __float_as_uint(f); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); }
 __device__ __forceinline__ float key2f(unsigned k) { return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k); }
 
+static constexpr int kFinalThreads = 128;   // 8 blocks per SM: Q = 1024 query blocks are ONE wave (256 threads: 4 per SM, two waves)
 static constexpr int kThetaStage = 10240;   // group maxima staged in shared memory (40 KB)
 __global__ void __launch_bounds__(256)
 topk_theta_kernel(const float* __restrict__ gmax, long long n_tiles /* groups per query */, long long Qp, long long Q, int kprime,
@@ -460,13 +462,19 @@ __device__ __forceinline__ double dot64_warp(const float* __restrict__ qs, const
   return s;
 }
 // Four rows at once: the four 16-byte loads of a 128-element block are issued before the first FMA (one memory
-// latency per block of four candidates instead of four).  Same per-row arithmetic, bit for bit, as dot64_warp.
-__device__ __forceinline__ void dot64_warp4(const float* __restrict__ qs, const float* const (&row)[4], int D, int lane, bool vec,
-                                            double (&out)[4]) {
+// latency per block of four candidates instead of four).  Same per-row arithmetic, bit for bit, as dot64_warp: the
+// cross-lane sum is the same xor-butterfly tree (levels 16, 8, 4, 2, 1; fp addition commutes), but the first two levels
+// halve the payload instead of keeping all four rows on every lane — 7 instead of 20 fp64 shuffles per call.
+// Returns the score of row dot64_row_of_lane(lane) (every lane holds one of the four rows).
+__device__ __forceinline__ int dot64_row_of_lane(int lane) { return ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1); }
+__device__ __forceinline__ int dot64_lane_of_row(int u) { return ((u >> 1) << 4) | ((u & 1) << 3); }
+__device__ __forceinline__ double dot64_warp4(const float* __restrict__ qs, const float* const (&row)[4], int D, int lane, bool vec) {
   if (!vec) {
+    double out[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) out[u] = dot64_warp(qs, row[u], D, lane, false);
-    return;
+    const int u = dot64_row_of_lane(lane);
+    return u == 0 ? out[0] : u == 1 ? out[1] : u == 2 ? out[2] : out[3];
   }
   double s[4] = {0.0, 0.0, 0.0, 0.0};
   for (int d = lane * 4; d < D; d += 128) {
@@ -482,13 +490,17 @@ __device__ __forceinline__ void dot64_warp4(const float* __restrict__ qs, const 
       s[u] = fma((double)q.w, (double)c[u].w, s[u]);
     }
   }
+  const bool hi16 = (lane & 16) != 0, hi8 = (lane & 8) != 0;
+  // level 16: lanes 0-15 keep rows 0, 1 and hand rows 2, 3 to their partner (and the other way round)
+  const double k0 = hi16 ? s[2] : s[0], k1 = hi16 ? s[3] : s[1];
+  const double g0 = hi16 ? s[0] : s[2], g1 = hi16 ? s[1] : s[3];
+  const double a0 = k0 + __shfl_xor_sync(NRX_FULL_MASK, g0, 16);
+  const double a1 = k1 + __shfl_xor_sync(NRX_FULL_MASK, g1, 16);
+  // level 8: keep one of the two
+  double b = (hi8 ? a1 : a0) + __shfl_xor_sync(NRX_FULL_MASK, hi8 ? a0 : a1, 8);
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-    for (int u = 0; u < 4; ++u) s[u] += __shfl_xor_sync(NRX_FULL_MASK, s[u], o);
-  }
-#pragma unroll
-  for (int u = 0; u < 4; ++u) out[u] = s[u];
+  for (int o = 4; o > 0; o >>= 1) b += __shfl_xor_sync(NRX_FULL_MASK, b, o);
+  return b;
 }
 __device__ __forceinline__ bool rows_vec_ok(const float* c, long long cld, int D) {
   return ((reinterpret_cast<uintptr_t>(c) & 15) == 0) && (cld % 4 == 0) && (D % 4 == 0);
@@ -521,7 +533,7 @@ __device__ __forceinline__ void flag_query(long long qi, int* flag, unsigned* fl
   flist[1 + atomicAdd(flist, 1u)] = (unsigned)qi;
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kFinalThreads, 8)
 topk_final_kernel(const float* __restrict__ c, long long cld, long long N, int D, const float* __restrict__ q, long long qld,
                   int k, long long id_base, const float* __restrict__ theta, const float* __restrict__ eps,
                   const unsigned* __restrict__ count, const unsigned* __restrict__ cand, int n_slices, int cap_s,
@@ -534,11 +546,11 @@ topk_final_kernel(const float* __restrict__ c, long long cld, long long N, int D
   unsigned* s_off = reinterpret_cast<unsigned*>(qs + ((D + 3) & ~3));   // [n_slices]
   const long long qi = blockIdx.x;
   const int tid = threadIdx.x;
-  __shared__ unsigned s_total, s_over, s_warp[8];
+  __shared__ unsigned s_total, s_over, s_warp[kFinalThreads / 32];
   const long long kk = k < N ? k : N;
   // exclusive scan of the per-region counts (n_slices = corpus slices x 4 column quarters)
   unsigned over = 0, run = 0;
-  for (int b0 = 0; b0 < n_slices; b0 += 256) {
+  for (int b0 = 0; b0 < n_slices; b0 += kFinalThreads) {
     const int sl = b0 + tid;
     unsigned cs = sl < n_slices ? count[qi * n_slices + sl] : 0u;
     if (cs > (unsigned)cap_s) { over = 1; cs = (unsigned)cap_s; }
@@ -551,13 +563,13 @@ topk_final_kernel(const float* __restrict__ c, long long cld, long long N, int D
     for (int w = 0; w < (tid >> 5); ++w) wbase += s_warp[w];
     if (sl < n_slices) s_off[sl] = run + wbase + inc - cs;
     unsigned tot = 0;
-    for (int w = 0; w < 8; ++w) tot += s_warp[w];
+    for (int w = 0; w < kFinalThreads / 32; ++w) tot += s_warp[w];
     run += tot;
     __syncthreads();
   }
   over = __syncthreads_or(over);
   if (tid == 0) { s_total = run; s_over = over; }
-  for (int d = tid; d < D; d += 256) qs[d] = __ldg(q + qi * qld + d);
+  for (int d = tid; d < D; d += kFinalThreads) qs[d] = __ldg(q + qi * qld + d);
   __syncthreads();
   const unsigned cnt = s_total;
   if (s_over || cnt > (unsigned)kCap || (long long)cnt < kk) {
@@ -566,8 +578,8 @@ topk_final_kernel(const float* __restrict__ c, long long cld, long long N, int D
   }
   int n2 = 1;
   while (n2 < (int)cnt) n2 <<= 1;
-  for (int i = (int)cnt + tid; i < n2; i += 256) { id[i] = 0xffffffffu; s[i] = -DBL_MAX; }
-  for (unsigned i = tid; i < cnt; i += 256) {  // candidate row of list position i: region by binary search
+  for (int i = (int)cnt + tid; i < n2; i += kFinalThreads) { id[i] = 0xffffffffu; s[i] = -DBL_MAX; }
+  for (unsigned i = tid; i < cnt; i += kFinalThreads) {  // candidate row of list position i: region by binary search
     int lo = 0, hi = n_slices - 1;
     while (lo < hi) {
       const int mid = (lo + hi + 1) >> 1;
@@ -579,24 +591,23 @@ topk_final_kernel(const float* __restrict__ c, long long cld, long long N, int D
   {  // exact scores: one warp per candidate, 4 rows in flight per warp
     const int warp = tid >> 5, lane = tid & 31;
     const bool vec = rows_vec_ok(c, cld, D);
-    for (unsigned i0 = (unsigned)warp * 4; i0 < cnt; i0 += 32) {
-      double v[4];
+    for (unsigned i0 = (unsigned)warp * 4; i0 < cnt; i0 += 4 * (kFinalThreads / 32)) {
       const float* rowp[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) rowp[u] = c + (long long)id[min(i0 + u, cnt - 1)] * cld;   // past the end: re-score the last one
-      dot64_warp4(qs, rowp, D, lane, vec, v);
-      if (lane < 4 && i0 + lane < cnt) s[i0 + lane] = lane == 0 ? v[0] : lane == 1 ? v[1] : lane == 2 ? v[2] : v[3];
+      const double v = dot64_warp4(qs, rowp, D, lane, vec);
+      if ((lane & 7) == 0 && i0 + dot64_row_of_lane(lane) < cnt) s[i0 + dot64_row_of_lane(lane)] = v;
     }
   }
   __syncthreads();
-  bitonic_sort(s, id, n2, tid, 256);
+  bitonic_sort(s, id, n2, tid, kFinalThreads);
   // completeness proof: every row outside the list scores < theta + eps
   const bool ok = (theta[qi] == -FLT_MAX) || (kk == 0) || (s[kk - 1] >= (double)theta[qi] + (double)eps[qi]);
   if (!ok) {
     if (tid == 0) flag_query(qi, flag, flist);
     return;
   }
-  for (int i = tid; i < k; i += 256) {
+  for (int i = tid; i < k; i += kFinalThreads) {
     if (i < kk) {
       out_s[qi * k + i] = (float)s[i];
       if (out_s64) out_s64[qi * k + i] = s[i];
@@ -670,13 +681,11 @@ topk_exact_kernel(const __grid_constant__ CorpusSegs CS, long long cld, long lon
         const long long rb = r0 + warp * 32 + u;
         if (rb >= r_hi) break;
         const float* rowp[4];
-        double v4[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) rowp[j] = seg_row(CS, rb + j < r_hi ? rb + j : r_hi - 1, cld);
-        dot64_warp4(qs, rowp, D, lane, vec, v4);
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (lane == u + j) mine = v4[j];
+        const double v = dot64_warp4(qs, rowp, D, lane, vec);
+        const double vj = __shfl_sync(NRX_FULL_MASK, v, dot64_lane_of_row(lane & 3));   // lane u + j takes row j
+        if ((lane & ~3) == u) mine = vj;
       }
       const long long row = r0 + tid;
       if (row < r_hi && mine >= s_th) {
@@ -781,7 +790,7 @@ __device__ __forceinline__ float* inbox_bound(uint8_t* box, long long q_own, int
 
 // Shard side: exact re-scoring + sort of this shard's candidates of query qi (as topk_final_kernel), then the best
 // min(count, k) go straight into the owner's inbox (peer stores) with the shard's completeness bound.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kFinalThreads, 8)
 topk_final_peer_kernel(const float* __restrict__ c, long long cld, long long N, int D, const float* __restrict__ q, long long qld,
                        int k, long long id_base, const float* __restrict__ theta, const float* __restrict__ eps,
                        const unsigned* __restrict__ count, const unsigned* __restrict__ cand, int n_slices, int cap_s,
@@ -793,12 +802,12 @@ topk_final_peer_kernel(const float* __restrict__ c, long long cld, long long N, 
   unsigned* s_off = reinterpret_cast<unsigned*>(qs + ((D + 3) & ~3));   // [n_slices]
   const long long qi = blockIdx.x;
   const int tid = threadIdx.x;
-  __shared__ unsigned s_total, s_over, s_warp[8];
+  __shared__ unsigned s_total, s_over, s_warp[kFinalThreads / 32];
   const int owner = (int)(qi / PB.q_own);
   const long long ql = qi % PB.q_own;
   uint8_t* box = PB.box[owner];
   unsigned over = 0, run = 0;
-  for (int b0 = 0; b0 < n_slices; b0 += 256) {
+  for (int b0 = 0; b0 < n_slices; b0 += kFinalThreads) {
     const int sl = b0 + tid;
     unsigned cs = sl < n_slices ? count[qi * n_slices + sl] : 0u;
     if (cs > (unsigned)cap_s) { over = 1; cs = (unsigned)cap_s; }
@@ -811,13 +820,13 @@ topk_final_peer_kernel(const float* __restrict__ c, long long cld, long long N, 
     for (int w = 0; w < (tid >> 5); ++w) wbase += s_warp[w];
     if (sl < n_slices) s_off[sl] = run + wbase + inc - cs;
     unsigned tot = 0;
-    for (int w = 0; w < 8; ++w) tot += s_warp[w];
+    for (int w = 0; w < kFinalThreads / 32; ++w) tot += s_warp[w];
     run += tot;
     __syncthreads();
   }
   over = __syncthreads_or(over);
   if (tid == 0) { s_total = run; s_over = over; }
-  for (int d = tid; d < D; d += 256) qs[d] = __ldg(q + qi * qld + d);
+  for (int d = tid; d < D; d += kFinalThreads) qs[d] = __ldg(q + qi * qld + d);
   __syncthreads();
   const unsigned cnt = s_total;
   if (s_over || cnt > (unsigned)kCap) {   // the shard cannot vouch for its list: the owner sends the query to the exact scan
@@ -826,8 +835,8 @@ topk_final_peer_kernel(const float* __restrict__ c, long long cld, long long N, 
   }
   int n2 = 1;
   while (n2 < (int)cnt) n2 <<= 1;
-  for (int i = (int)cnt + tid; i < n2; i += 256) { id[i] = 0xffffffffu; s[i] = -DBL_MAX; }
-  for (unsigned i = tid; i < cnt; i += 256) {
+  for (int i = (int)cnt + tid; i < n2; i += kFinalThreads) { id[i] = 0xffffffffu; s[i] = -DBL_MAX; }
+  for (unsigned i = tid; i < cnt; i += kFinalThreads) {
     int lo = 0, hi = n_slices - 1;
     while (lo < hi) {
       const int mid = (lo + hi + 1) >> 1;
@@ -839,20 +848,19 @@ topk_final_peer_kernel(const float* __restrict__ c, long long cld, long long N, 
   {
     const int warp = tid >> 5, lane = tid & 31;
     const bool vec = rows_vec_ok(c, cld, D);
-    for (unsigned i0 = (unsigned)warp * 4; i0 < cnt; i0 += 32) {
-      double v[4];
+    for (unsigned i0 = (unsigned)warp * 4; i0 < cnt; i0 += 4 * (kFinalThreads / 32)) {
       const float* rowp[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) rowp[u] = c + (long long)id[min(i0 + u, cnt - 1)] * cld;
-      dot64_warp4(qs, rowp, D, lane, vec, v);
-      if (lane < 4 && i0 + lane < cnt) s[i0 + lane] = lane == 0 ? v[0] : lane == 1 ? v[1] : lane == 2 ? v[2] : v[3];
+      const double v = dot64_warp4(qs, rowp, D, lane, vec);
+      if ((lane & 7) == 0 && i0 + dot64_row_of_lane(lane) < cnt) s[i0 + dot64_row_of_lane(lane)] = v;
     }
   }
   __syncthreads();
-  if (cnt > 1) bitonic_sort(s, id, n2, tid, 256);
+  if (cnt > 1) bitonic_sort(s, id, n2, tid, kFinalThreads);
   const int n_send = (int)cnt < k ? (int)cnt : k;
   TopkEntry* dst = inbox_entries(box, ql, PB.rank, PB.world, k);
-  for (int i = tid; i < n_send; i += 256) { TopkEntry e; e.s = s[i]; e.id = (long long)id[i] + id_base; dst[i] = e; }
+  for (int i = tid; i < n_send; i += kFinalThreads) { TopkEntry e; e.s = s[i]; e.id = (long long)id[i] + id_base; dst[i] = e; }
   if (tid == 0) {
     inbox_cnt(box, PB.q_own, PB.world, k)[ql * PB.world + PB.rank] = n_send;
     // rows of this shard outside the list score < theta + eps, or are beaten by k listed rows of the same shard
@@ -1072,7 +1080,8 @@ extern "C" int nrx_topk_search64(const void* index, const float* corpus, int64_t
     const int n_regions = (int)(4 * g.slices);
     const size_t fsm = (size_t)kCap * 12 + (size_t)((D + 3) & ~3) * 4 + (size_t)n_regions * 4;
     cudaFuncSetAttribute(topk_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm);
-    topk_final_kernel<<<(unsigned)Q, 256, fsm, st>>>(corpus, c_ld, N, D, queries, q_ld, k, id_base, theta, eps, count, cand, n_regions,
+    cudaFuncSetAttribute(topk_final_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    topk_final_kernel<<<(unsigned)Q, kFinalThreads, fsm, st>>>(corpus, c_ld, N, D, queries, q_ld, k, id_base, theta, eps, count, cand, n_regions,
                                                     g.cap_s, flag, flist, out_scores, out_scores64, (long long*)out_ids);
     rc = check_launch("topk_final");
     if (rc != NRX_OK) return rc;
@@ -1128,7 +1137,7 @@ extern "C" int nrx_topk_search_peer(const void* index, int64_t N_local, int D, c
   NRX_REQUIRE(h_peer->n_rows[R] == N_local, NRX_EINVAL, "n_rows[rank] != N_local");
   // per-shard threshold rank: the shards share the k' = 2k + 64 budget (each keeps a slack of its own)
   TopkGeom g;
-  const int kp = (2 * k + 64 + G - 1) / G + 24;
+  const int kp = h_peer->kprime > 0 ? (int)h_peer->kprime : (2 * k + 64 + G - 1) / G + 24;
   int rc = make_geom(Q, N_local, D, k, &g, kp);
   if (rc != NRX_OK) return rc;
   if (Q == 0) return NRX_OK;
@@ -1196,7 +1205,8 @@ extern "C" int nrx_topk_search_peer(const void* index, int64_t N_local, int D, c
   }
   const size_t fsm = (size_t)kCap * 12 + (size_t)((D + 3) & ~3) * 4 + (size_t)n_regions * 4;
   cudaFuncSetAttribute(topk_final_peer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm);
-  topk_final_peer_kernel<<<(unsigned)Q, 256, fsm, st>>>(corpus, D, N_local, D, queries, q_ld, k, id_base, theta, eps, count, cand, n_regions,
+  cudaFuncSetAttribute(topk_final_peer_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  topk_final_peer_kernel<<<(unsigned)Q, kFinalThreads, fsm, st>>>(corpus, D, N_local, D, queries, q_ld, k, id_base, theta, eps, count, cand, n_regions,
                                                         g.cap_s, PB);
   rc = check_launch("topk_final_peer");
   if (rc != NRX_OK) return rc;

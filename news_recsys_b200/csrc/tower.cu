@@ -748,7 +748,8 @@ tower_bwd_dw_kernel(const __grid_constant__ TowerK T, const uint8_t* __restrict_
   }
   __shared__ uint64_t full[kDwStages], empty[kDwStages], done;
   __shared__ uint32_t tmem_s;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(NRX_FULL_MASK, tid >> 5, 0);   // provably warp-uniform: the role branches below are uniform, so ptxas keeps the MMA descriptors in uniform registers
 
   if (tid == 0) {
     for (int s = 0; s < kDwStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -787,17 +788,20 @@ tower_bwd_dw_kernel(const __grid_constant__ TowerK T, const uint8_t* __restrict_
     __syncthreads();
 
     if (t1 > t0) {
-      if (warp == 0 && lane == 0) {  // producer: TMA bulk copies of the two tile images
-        int s = 0;
-        for (long long t = t0; t < t1; ++t) {
-          if (stage_used[s]) { mbar_wait(&empty[s], empty_phase[s]); empty_phase[s] ^= 1; }
-          stage_used[s] = true;
-          const uint32_t bm = (uint32_t)Np * kRows * 2, bn = (uint32_t)Kp * kRows * 2;
-          mbar_expect_tx(&full[s], bm + bn);
-          bulk_g2s(sM[s], ws + T.dz_off[l] + (size_t)t * bm, bm, &full[s]);
-          bulk_g2s(sN[s], ws + T.act_off[l] + (size_t)t * bn, bn, &full[s]);
-          s ^= 1;
+      if (warp == 0) {  // producer: TMA bulk copies of the two tile images (uniform role branch, one lane works)
+        if (lane == 0) {
+          int s = 0;
+          for (long long t = t0; t < t1; ++t) {
+            if (stage_used[s]) { mbar_wait(&empty[s], empty_phase[s]); empty_phase[s] ^= 1; }
+            stage_used[s] = true;
+            const uint32_t bm = (uint32_t)Np * kRows * 2, bn = (uint32_t)Kp * kRows * 2;
+            mbar_expect_tx(&full[s], bm + bn);
+            bulk_g2s(sM[s], ws + T.dz_off[l] + (size_t)t * bm, bm, &full[s]);
+            bulk_g2s(sN[s], ws + T.act_off[l] + (size_t)t * bn, bn, &full[s]);
+            s ^= 1;
+          }
         }
+        __syncwarp();
       } else if (warp == 1) {  // MMA issuer: whole warp in uniform control flow, one elected lane issues
         const uint32_t leader = elect_one_sync() ? 1u : 0u;
         // one MMA covers <= 256 output columns: a wider first layer (K + 16 > 256) is issued as two column blocks that
@@ -806,14 +810,15 @@ tower_bwd_dw_kernel(const __grid_constant__ TowerK T, const uint8_t* __restrict_
         const int n2 = ncols - n1;
         const uint32_t idesc = make_idesc_bf16(128, n1, 1, 1);
         const uint32_t idesc2 = make_idesc_bf16(128, n2 > 0 ? n2 : 16, 1, 1);
-        int s = 0;
+        uint32_t s = 0, fph = full_phase[0] | (full_phase[1] << 1);
+        const uint32_t stage_bytes = (uint32_t)(kStageM + stage_n), sm0 = smem_u32(smem);
         for (long long t = t0; t < t1; ++t) {
-          mbar_wait(&full[s], full_phase[s]);
-          full_phase[s] ^= 1;
+          mbar_wait(&full[s], (fph >> s) & 1u);
+          fph ^= 1u << s;
           tc_fence_after();
           // MN-major: 8-element MN groups are kRows*16 B apart (SBO), 8-row K groups 128 B apart (LBO)
-          uint64_t ad = make_smem_desc(smem_u32(sM[s]), 128u, kRows * 16u);
-          uint64_t bd = make_smem_desc(smem_u32(sN[s]), 128u, kRows * 16u);
+          uint64_t ad = make_smem_desc(sm0 + s * stage_bytes, 128u, kRows * 16u);
+          uint64_t bd = make_smem_desc(sm0 + s * stage_bytes + (uint32_t)kStageM, 128u, kRows * 16u);
           const uint64_t b2off = (uint64_t)(((uint32_t)n1 * 256u) >> 4);   // n1 columns further on in the MN-major operand
           uint32_t accum = t > t0 ? 1u : 0u;
 #pragma unroll
@@ -825,8 +830,9 @@ tower_bwd_dw_kernel(const __grid_constant__ TowerK T, const uint8_t* __restrict_
             accum = 1u;
           }
           mma_commit_if(leader, &empty[s]);
-          s ^= 1;
+          s ^= 1u;
         }
+        full_phase[0] = fph & 1u; full_phase[1] = (fph >> 1) & 1u;
         mma_commit_if(leader, &done);
         __syncwarp();
       }

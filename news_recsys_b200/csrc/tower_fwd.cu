@@ -197,7 +197,8 @@ tower_fwd3_kernel(const __grid_constant__ TowerK T, const __grid_constant__ Fwd3
   __shared__ uint64_t wbar[NRX_MAX_LAYERS], full[kF3MaxStages], empty[kF3MaxStages], acc_full[2], epi_done[2];
   __shared__ uint32_t tmem_s;
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(NRX_FULL_MASK, tid >> 5, 0);   // provably warp-uniform: the role branches below are uniform, so ptxas keeps the MMA descriptors in uniform registers
   const int L = T.n_layers, nm = T.n_mma;
   const long long n_my = T.n_tiles > blockIdx.x ? (T.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 

@@ -609,24 +609,105 @@ class ShardedEmbeddingTrainer(FusedTrainer):
 # --------------------------------------------------------------------------- #
 
 class ShardedTopk:
-    """Corpus rows [lo, hi) of this rank behind one TopkIndex; `search` returns the GLOBAL top-k on every rank."""
+    """Corpus rows [lo, hi) of this rank behind one TopkIndex; `search` returns the GLOBAL top-k on every rank.
 
-    def __init__(self, local_corpus: torch.Tensor, n_total: int, group=None):
+    exchange="peer" (default, single node): `nrx_topk_search_peer` — every rank scans its shard for all queries and ships
+    its exactly re-scored candidates (fp64 score + global id) into the inbox of the query's OWNER over NVLink peer memory;
+    the owner of Q / world queries merges, proves completeness against every shard's bound, re-scans exactly through peer
+    memory what it cannot prove, and stores the result into every rank's output.  No NCCL on the data path, and the
+    per-query work (final sort, merge) divides by the world size.  exchange="nccl": per-shard complete top-k lists,
+    all-gathered with their fp64 keys and merged on every rank (works across nodes; per-query work does not shrink)."""
+
+    def __init__(self, local_corpus: torch.Tensor, n_total: int, group=None, exchange: str = "peer",
+                 peer_timeout_ms: int = 20000, kprime: int = 0):
         from .retrieval import TopkIndex
+        self.kprime = int(kprime)     # per-shard threshold rank of the peer search; 0 = library default
+        if exchange not in ("peer", "nccl"):
+            raise L.NrxError(f"exchange must be 'peer' or 'nccl', got {exchange!r}")
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
+        self.exchange = exchange
+        self.peer_timeout_ms = int(peer_timeout_ms)
+        self.n_total = int(n_total)
         self.lo, self.hi = shard_range(n_total, self.rank, self.world)
         if local_corpus.shape[0] != self.hi - self.lo:
             raise L.NrxError(f"rank {self.rank}: shard has {local_corpus.shape[0]} rows, expected {self.hi - self.lo}")
-        self.index = TopkIndex(local_corpus, id_base=self.lo)
+        if not local_corpus.is_cuda:
+            raise L.NrxError("ShardedTopk: the corpus shard must be a CUDA tensor (no CPU fallback)")
+        self.lib = L.load()
+        self._peer = {}
+        if exchange == "peer":
+            if self.world > L.NRX_MAX_PEERS:
+                raise L.NrxError(f"peer exchange supports at most {L.NRX_MAX_PEERS} ranks")
+            n, d = local_corpus.shape
+            self._cbuf = PeerBuffer(max(n * d * 4, 256), local_corpus.device)
+            shard = self._cbuf.tensor()[: n * d].view(n, d)
+            shard.copy_(local_corpus.detach().float())
+            self._sig = PeerBuffer(4 * L.NRX_PEER_SIG_WORDS, local_corpus.device, typestr="<i4")
+            ptrs = open_peers([self._cbuf, self._sig], group)
+            self._corpus_ptrs, self._sig_ptrs = ptrs[0], ptrs[1]
+            self._status = torch.zeros(1, dtype=torch.int32, device=local_corpus.device)
+            self.index = TopkIndex(shard, id_base=self.lo)
+        else:
+            self.index = TopkIndex(local_corpus, id_base=self.lo)
 
     def search_local(self, queries: torch.Tensor, k: int):
         return self.index.search(queries, k)
 
+    # -- peer path ----------------------------------------------------------------------------------------------
+    def _peer_state(self, Q: int, k: int, dev):
+        """Inbox + result buffers for (Q, k), mapped on every rank (collective: every rank must search the same shapes)."""
+        key = (Q, k)
+        st = self._peer.get(key)
+        if st is not None:
+            return st
+        inbox = PeerBuffer(max(int(self.lib.nrx_topk_peer_inbox_bytes(Q, self.world, k)), 256), dev)
+        out_s = PeerBuffer(max(Q * k * 4, 256), dev)
+        out_i = PeerBuffer(max(Q * k * 8, 256), dev)
+        ptrs = open_peers([inbox, out_s, out_i], self.group)
+        d = L.NrxTopkPeer()
+        d.rank, d.world = self.rank, self.world
+        for j in range(self.world):
+            lo, hi = shard_range(self.n_total, j, self.world)
+            d.corpus[j], d.n_rows[j] = self._corpus_ptrs[j], hi - lo
+            d.inbox[j], d.out_scores[j], d.out_ids[j], d.sig[j] = ptrs[0][j], ptrs[1][j], ptrs[2][j], self._sig_ptrs[j]
+        d.status = self._status.data_ptr()
+        d.timeout_ms = self.peer_timeout_ms
+        d.kprime = self.kprime
+        ws = torch.empty(max(int(self.lib.nrx_topk_search_workspace_bytes(Q, self.index.N, self.index.D, k)), 16),
+                         dtype=torch.uint8, device=dev)
+        st = dict(desc=d, keep=(inbox, out_s, out_i), ws=ws,
+                  out_s=out_s.tensor()[: Q * k].view(Q, k), out_i=out_i.tensor()[: Q * k * 2].view(torch.int64).view(Q, k),
+                  status=torch.zeros(max(Q, 1), dtype=torch.int32, device=dev))
+        self._peer[key] = st
+        return st
+
+    def search_peer_(self, queries: torch.Tensor, k: int):
+        """The peer search without the result copy: returns views of this rank's (re-used) output buffers, valid until the
+        next search of the same (Q, k).  One enqueue, no host synchronisation."""
+        q = queries.detach().float().contiguous()
+        Q = q.shape[0]
+        st = self._peer_state(Q, k, q.device)
+        if Q:
+            L.check(self.lib.nrx_topk_search_peer(self.index.index.data_ptr(), self.index.N, self.index.D, q.data_ptr(), q.stride(0), Q, k,
+                                                  C.byref(st["desc"]), st["status"].data_ptr(), st["ws"].data_ptr(), st["ws"].numel(),
+                                                  L.stream_ptr(q.device)), "nrx_topk_search_peer")
+        return st["out_s"], st["out_i"]
+
+    def exact_fallbacks(self, Q: int, k: int) -> int:
+        """How many of THIS rank's owned queries of the last (Q, k) peer search went through the exact scan."""
+        return int(self._peer[(Q, k)]["status"].sum().item())
+
     def search(self, queries: torch.Tensor, k: int):
-        """`queries` must be identical on every rank (replicated).  The shards exchange their lists with the
-        fp64 ordering keys, so the merge equals one index bit for bit (rows closer than one fp32 ulp included)."""
+        """`queries` must be identical on every rank (replicated).  Scores travel with their fp64 ordering
+        keys on both paths, so the result equals one index over the whole corpus bit for bit (rows closer than one fp32
+        ulp included)."""
+        if self.exchange == "peer":
+            s, i = self.search_peer_(queries, k)
+            if int(self._status.item()) & 2:
+                raise L.NrxError("ShardedTopk: a peer did not arrive within peer_timeout_ms; the exchange is dead")
+            return s.clone(), i.clone()
         from .retrieval import topk_merge
         s, i, s64 = self.index.search(queries, k, want_scores64=True)
         Q = s.shape[0]

@@ -175,3 +175,87 @@ def test_row_sharded_tables_equal_single_gpu(kind, exchange, tmp_path):
             torch.testing.assert_close(sd0[k], ref[k], rtol=1e-5, atol=2e-6, msg=lambda m: f"{k}: {m}")
         else:
             assert float((sd0[k] - ref[k]).abs().max()) <= 2.5e-3, k   # bf16 tower: <= ~2 Adam steps of lr=1e-3
+
+
+# --------------------------------------------------------------------------- sharded retrieval over peer memory
+def _topk_cases():
+    """(name, corpus, queries, k): deterministic, rebuilt identically in the workers and in the checking process."""
+    g = torch.Generator().manual_seed(77)
+    nrm = torch.nn.functional.normalize
+    cases = []
+    c = nrm(torch.randn(200_001, 128, generator=g), dim=1)
+    q = nrm(torch.randn(301, 128, generator=g), dim=1)
+    cases.append(("random", c, q, 100))
+    # near ties across the shards: row `hi` (last shard) is row `lo` (first shard) nudged up by one ulp along q
+    c2 = c.clone()
+    q2 = q[:6].clone()
+    for j in range(6):
+        lo, hi = 500 + j, 200_001 - 500 - j
+        c2[lo] = nrm(q2[j] + 0.05 * torch.randn(128, generator=g), dim=0)
+        c2[hi] = c2[lo]
+        e = int(q2[j].abs().argmax())
+        c2[hi, e] = torch.nextafter(c2[lo, e], c2[lo, e] + torch.sign(q2[j, e]))
+    cases.append(("near_ties", c2, q2, 100))
+    # clustered: 6000 near-copies of the query's neighbourhood overflow the candidate lists -> owner-side exact scan over
+    # BOTH shards through peer memory
+    c3 = nrm(torch.randn(60_000, 64, generator=g), dim=1)
+    q3 = nrm(torch.randn(9, 64, generator=g), dim=1)
+    for j in range(3):
+        rows = torch.randperm(60_000, generator=g)[:6000]
+        c3[rows] = nrm(q3[j] + 0.02 * torch.randn(6000, 64, generator=g), dim=1)
+    cases.append(("clustered", c3, q3, 64))
+    # tiny corpus (no tensor-core filter at all), k larger than a shard, one query
+    cases.append(("tiny", nrm(torch.randn(301, 32, generator=g), dim=1), nrm(torch.randn(1, 32, generator=g), dim=1), 200))
+    cases.append(("k_gt_n", nrm(torch.randn(50, 16, generator=g), dim=1), nrm(torch.randn(5, 16, generator=g), dim=1), 64))
+    return cases
+
+
+def _topk_peer_worker(rank, world, port, out_dir):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import torch.distributed as dist
+    from news_recsys_b200.parallel import ShardedTopk, shard_range
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    out = {}
+    for name, c, q, k in _topk_cases():
+        lo, hi = shard_range(c.shape[0], rank, world)
+        st = ShardedTopk(c[lo:hi].cuda(), c.shape[0], exchange="peer")
+        s1, i1 = st.search(q.cuda(), k)
+        s2, i2 = st.search(q.cuda(), k)          # buffers and signal epochs are re-used
+        assert torch.equal(i1, i2) and torch.equal(s1, s2), name
+        nc = ShardedTopk(c[lo:hi].cuda(), c.shape[0], exchange="nccl")
+        s3, i3 = nc.search(q.cuda(), k)
+        out[name] = (s1.cpu(), i1.cpu(), s3.cpu(), i3.cpu(), st.exact_fallbacks(q.shape[0], k))
+        del st, nc
+    torch.cuda.synchronize()
+    torch.save(out, os.path.join(out_dir, f"topk_peer_{rank}.pt"))
+    dist.destroy_process_group()
+
+
+def test_sharded_topk_over_peer_memory_equals_one_index(tmp_path):
+    """nrx_topk_search_peer on 2 ranks == the oracle on the whole corpus (ids bit-exact, near ties and the exact-scan
+    fallback over peer-mapped shards included) == the NCCL list exchange; every rank holds the full result."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    from oracle import ref_path as R
+    mp.spawn(_topk_peer_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    r0 = torch.load(tmp_path / "topk_peer_0.pt")
+    r1 = torch.load(tmp_path / "topk_peer_1.pt")
+    fallbacks = {}
+    for name, c, q, k in _topk_cases():
+        s0, i0, sn, i_n, f0 = r0[name]
+        s1, i1, _, _, f1 = r1[name]
+        ref_s, ref_i = R.topk_ip(q, c, k)
+        assert torch.equal(i0, i1) and torch.equal(s0, s1), f"{name}: ranks disagree"
+        assert torch.equal(i0, ref_i), f"{name}: peer search differs from the oracle"
+        assert torch.equal(i_n, ref_i), f"{name}: nccl exchange differs from the oracle"
+        kk = min(k, c.shape[0])
+        torch.testing.assert_close(s0[:, :kk], ref_s[:, :kk], rtol=1e-6, atol=1e-7)
+        fallbacks[name] = f0 + f1
+    assert fallbacks["random"] == 0, "the filter path must serve well-separated queries"
+    assert fallbacks["clustered"] >= 3, "the clustered queries must go through the owner-side exact scan"
+    assert fallbacks["tiny"] == 1 and fallbacks["k_gt_n"] == 5
