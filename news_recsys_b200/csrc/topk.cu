@@ -507,11 +507,39 @@ __device__ __forceinline__ bool rows_vec_ok(const float* c, long long cld, int D
 }
 
 // (score desc, id asc): returns true if a must come before b
-__device__ __forceinline__ bool before(double sa, unsigned ia, double sb, unsigned ib) { return sa > sb || (sa == sb && ia < ib); }
+template <typename IdT>
+__device__ __forceinline__ bool before(double sa, IdT ia, double sb, IdT ib) { return sa > sb || (sa == sb && ia < ib); }
 
-__device__ void bitonic_sort(double* s, unsigned* id, int n, int tid, int nthreads) {  // n power of two
-  for (int k2 = 2; k2 <= n; k2 <<= 1) {
-    for (int j = k2 >> 1; j > 0; j >>= 1) {
+// One compare-exchange of the bitonic network done with shuffles: element i = (sv, iv) against element i ^ j (j < 32: the
+// partner sits in the same warp).  Position i keeps the element that sorts first iff (i is the lower index) == (ascending
+// block); equal elements (padding) are interchangeable.
+template <typename IdT>
+__device__ __forceinline__ void bitonic_shfl_step(double& sv, IdT& iv, int i, int j, int k2) {
+  const double ps = __shfl_xor_sync(NRX_FULL_MASK, sv, j);
+  const IdT pi = __shfl_xor_sync(NRX_FULL_MASK, iv, j);
+  const bool want_first = ((i & j) == 0) == ((i & k2) == 0);
+  const bool mine_first = before(sv, iv, ps, pi);
+  if (want_first != mine_first) { sv = ps; iv = pi; }
+}
+
+// Block-wide bitonic sort of n (power of two, >= 32) pairs in shared memory by (score desc, id asc).  Exchange distances
+// below 32 stay inside a warp and run on registers + shuffles with no block barrier (all of k2 <= 32 in ONE pass); only the
+// distances >= 32 go through shared memory.  n = 128: 3 barrier stages instead of 28.  nthreads: a multiple of 32; the
+// caller has synchronised its writes to s / id; the result is visible to the whole block on return.
+template <typename IdT>
+__device__ void bitonic_sort(double* s, IdT* id, int n, int tid, int nthreads) {
+  for (int i = tid; i < n; i += nthreads) {          // k2 = 2 .. 32 entirely in registers
+    double sv = s[i];
+    IdT iv = id[i];
+#pragma unroll
+    for (int k2 = 2; k2 <= 32; k2 <<= 1)
+#pragma unroll
+      for (int j = k2 >> 1; j > 0; j >>= 1) bitonic_shfl_step(sv, iv, i, j, k2);
+    s[i] = sv; id[i] = iv;
+  }
+  __syncthreads();
+  for (int k2 = 64; k2 <= n; k2 <<= 1) {
+    for (int j = k2 >> 1; j >= 32; j >>= 1) {
       for (int i = tid; i < n; i += nthreads) {
         const int p = i ^ j;
         if (p > i) {
@@ -519,12 +547,20 @@ __device__ void bitonic_sort(double* s, unsigned* id, int n, int tid, int nthrea
           const bool sw = up ? before(s[p], id[p], s[i], id[i]) : before(s[i], id[i], s[p], id[p]);
           if (sw) {
             const double ts = s[i]; s[i] = s[p]; s[p] = ts;
-            const unsigned ti = id[i]; id[i] = id[p]; id[p] = ti;
+            const IdT ti = id[i]; id[i] = id[p]; id[p] = ti;
           }
         }
       }
       __syncthreads();
     }
+    for (int i = tid; i < n; i += nthreads) {
+      double sv = s[i];
+      IdT iv = id[i];
+#pragma unroll
+      for (int j = 16; j > 0; j >>= 1) bitonic_shfl_step(sv, iv, i, j, k2);
+      s[i] = sv; id[i] = iv;
+    }
+    __syncthreads();
   }
 }
 
@@ -576,7 +612,7 @@ topk_final_kernel(const float* __restrict__ c, long long cld, long long N, int D
     if (tid == 0) flag_query(qi, flag, flist);
     return;
   }
-  int n2 = 1;
+  int n2 = 32;   // the sort network needs >= one warp of elements
   while (n2 < (int)cnt) n2 <<= 1;
   for (int i = (int)cnt + tid; i < n2; i += kFinalThreads) { id[i] = 0xffffffffu; s[i] = -DBL_MAX; }
   for (unsigned i = tid; i < cnt; i += kFinalThreads) {  // candidate row of list position i: region by binary search
@@ -735,7 +771,7 @@ topk_exact_merge_kernel(long long N, int k, long long id_base, const unsigned* _
   const unsigned n_listed = force_Q > 0 ? (unsigned)force_Q : flist[0];
   if (n_listed == 0) return;
   const int S = fb_slices(n_listed, exact_grid, max_items, k);
-  int n2 = 1;
+  int n2 = 32;   // the sort network needs >= one warp of elements
   while (n2 < S * k) n2 <<= 1;
   double* s = reinterpret_cast<double*>(sm_raw);          // [n2]
   unsigned* id = reinterpret_cast<unsigned*>(s + n2);     // [n2]
@@ -833,7 +869,7 @@ topk_final_peer_kernel(const float* __restrict__ c, long long cld, long long N, 
     if (tid == 0) { inbox_cnt(box, PB.q_own, PB.world, k)[ql * PB.world + PB.rank] = -1; inbox_bound(box, PB.q_own, PB.world, k)[ql * PB.world + PB.rank] = 0.f; }
     return;
   }
-  int n2 = 1;
+  int n2 = 32;   // the sort network needs >= one warp of elements
   while (n2 < (int)cnt) n2 <<= 1;
   for (int i = (int)cnt + tid; i < n2; i += kFinalThreads) { id[i] = 0xffffffffu; s[i] = -DBL_MAX; }
   for (unsigned i = tid; i < cnt; i += kFinalThreads) {
@@ -857,7 +893,7 @@ topk_final_peer_kernel(const float* __restrict__ c, long long cld, long long N, 
     }
   }
   __syncthreads();
-  if (cnt > 1) bitonic_sort(s, id, n2, tid, kFinalThreads);
+  bitonic_sort(s, id, n2, tid, kFinalThreads);
   const int n_send = (int)cnt < k ? (int)cnt : k;
   TopkEntry* dst = inbox_entries(box, ql, PB.rank, PB.world, k);
   for (int i = tid; i < n_send; i += kFinalThreads) { TopkEntry e; e.s = s[i]; e.id = (long long)id[i] + id_base; dst[i] = e; }
@@ -881,7 +917,7 @@ topk_owner_merge_kernel(long long Q, long long N_total, int k, const __grid_cons
   if (qi >= Q) return;
   uint8_t* box = PB.box[PB.rank];
   const int G = PB.world;
-  int n2 = 1;
+  int n2 = 32;   // the sort network needs >= one warp of elements
   while (n2 < G * k) n2 <<= 1;
   double* s = reinterpret_cast<double*>(sm_raw);            // [n2]
   long long* id = reinterpret_cast<long long*>(s + n2);     // [n2]
@@ -909,22 +945,7 @@ topk_owner_merge_kernel(long long Q, long long N_total, int k, const __grid_cons
       else { s[i] = -DBL_MAX; id[i] = 0x7fffffffffffffffll; }
     }
     __syncthreads();
-    for (int k2 = 2; k2 <= n2; k2 <<= 1)
-      for (int j = k2 >> 1; j > 0; j >>= 1) {
-        for (int i = tid; i < n2; i += 256) {
-          const int p = i ^ j;
-          if (p > i) {
-            const bool up = ((i & k2) == 0);
-            const bool a_first = s[p] > s[i] || (s[p] == s[i] && id[p] < id[i]);
-            const bool b_first = s[i] > s[p] || (s[i] == s[p] && id[i] < id[p]);
-            if (up ? a_first : b_first) {
-              const double ts = s[i]; s[i] = s[p]; s[p] = ts;
-              const long long ti = id[i]; id[i] = id[p]; id[p] = ti;
-            }
-          }
-        }
-        __syncthreads();
-      }
+    bitonic_sort(s, id, n2, tid, 256);
     // complete iff the k-th merged score clears every shard's bound (and k real rows exist)
     ok = kk == 0 || (id[kk - 1] != 0x7fffffffffffffffll && (s_bound == -FLT_MAX || s[kk - 1] >= (double)s_bound));
   }
@@ -948,7 +969,7 @@ topk_merge_kernel(const ST* __restrict__ sc, const long long* __restrict__ ids, 
                   float* __restrict__ out_s, long long* __restrict__ out_i) {
   extern __shared__ __align__(16) uint8_t sm_raw[];
   const int total = n_lists * k;
-  int n2 = 1;
+  int n2 = 32;   // the sort network needs >= one warp of elements
   while (n2 < total) n2 <<= 1;
   long long* id = reinterpret_cast<long long*>(sm_raw);
   ST* s = reinterpret_cast<ST*>(id + n2);
@@ -1097,7 +1118,7 @@ extern "C" int nrx_topk_search64(const void* index, const float* corpus, int64_t
                                                              part_s, part_i);
   rc = check_launch("topk_exact");
   if (rc != NRX_OK) return rc;
-  int n2 = 1;
+  int n2 = 32;   // the sort network needs >= one warp of elements
   while (n2 < fb_max_slices(k) * k) n2 <<= 1;
   const size_t msm = (size_t)n2 * 12;
   cudaFuncSetAttribute(topk_exact_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msm);
@@ -1212,7 +1233,7 @@ extern "C" int nrx_topk_search_peer(const void* index, int64_t N_local, int D, c
   if (rc != NRX_OK) return rc;
   rc = nrx_peer_barrier(&bar, stream);     // every shard's lists have landed in the owners' inboxes
   if (rc != NRX_OK) return rc;
-  int n2 = 1;
+  int n2 = 32;   // the sort network needs >= one warp of elements
   while (n2 < G * k) n2 <<= 1;
   const size_t osm = (size_t)n2 * 16;
   cudaFuncSetAttribute(topk_owner_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)osm);
@@ -1229,7 +1250,7 @@ extern "C" int nrx_topk_search_peer(const void* index, int64_t N_local, int D, c
   topk_exact_kernel<<<(unsigned)g.fb_grid, 256, fb_smem, st>>>(CS, D, N_total, D, queries, q_ld, k, flist, 0, g.fb_items, part_s, part_i);
   rc = check_launch("topk_exact(peer)");
   if (rc != NRX_OK) return rc;
-  int m2 = 1;
+  int m2 = 32;   // the sort network needs >= one warp of elements
   while (m2 < fb_max_slices(k) * k) m2 <<= 1;
   const size_t msm = (size_t)m2 * 12;
   cudaFuncSetAttribute(topk_exact_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msm);
@@ -1266,7 +1287,7 @@ static int merge_launch(const ST* scores, const int64_t* ids, int n_lists, int64
   NRX_REQUIRE(scores && ids && out_scores && out_ids && n_lists >= 1 && k >= 1, NRX_EINVAL, "bad merge arguments");
   NRX_REQUIRE((long long)n_lists * k <= 8192, NRX_EUNSUPPORTED, "merge supports n_lists*k <= 8192");
   if (Q == 0) return NRX_OK;
-  int n2 = 1;
+  int n2 = 32;   // the sort network needs >= one warp of elements
   while (n2 < n_lists * k) n2 <<= 1;
   const size_t smem = (size_t)n2 * (8 + sizeof(ST));
   cudaFuncSetAttribute(topk_merge_kernel<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
