@@ -191,7 +191,7 @@ int nrx_ingest_gather_labels(const float* labels, int64_t n_rows, int32_t n_labe
 
 /* Device-resident feature file: the same batch assembled ON THE GPU from device copies of the columns (the whole
  * columnar click log fits HBM), one warp per sample; `d_rows` (device int64[B], nullable) selects shuffled rows, a row
- * outside the file yields an all-padding sample.  All pointers are DEVICE pointers except `h_cols`. */
+ * outside the file yields an all-padding sample and sets bit 2 of `status` (the trainer raises at its next status read).  All pointers are DEVICE pointers except `h_cols`. */
 typedef struct NrxIngestCol {
   const int32_t* data;      /* sparse: ids [n_rows]; array: CSR values */
   const int64_t* offsets;   /* array: CSR offsets [n_rows + 1]; NULL for a sparse column */
@@ -202,7 +202,8 @@ typedef struct NrxIngestCol {
 } NrxIngestCol;
 int nrx_ingest_assemble_device(const NrxIngestCol* h_cols, int n_cols, const float* labels, int32_t n_labels,
                                float* out_labels, int32_t out_ld, int64_t n_rows, const int64_t* d_rows, int64_t row0,
-                               int64_t B, nrx_stream_t stream);
+                               int64_t B, int32_t* status /* nullable device word: bit 2 (value 4) is OR-ed in when a row
+                               index lies outside the file */, nrx_stream_t stream);
 
 /* ---- validation metrics ------------------------------------------------------------------------
  * Per-user AUC / NDCG@k / HR@k / MRR@k, replacing the Python loop of BaseModel.on_validation_epoch_end

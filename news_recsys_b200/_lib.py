@@ -113,7 +113,7 @@ SIGNATURES = {
     "nrx_ingest_gather_ids": (C.c_int, [_P, _I64, _P, _I64, _I64, _P, C.c_int]),
     "nrx_ingest_csr_expand": (C.c_int, [_P, _P, _I64, _P, _I64, _I64, _I32, _P, C.c_int, _P]),
     "nrx_ingest_gather_labels": (C.c_int, [_P, _I64, _I32, _P, _I64, _I64, _P, _I32]),
-    "nrx_ingest_assemble_device": (C.c_int, [C.POINTER(NrxIngestCol), C.c_int, _P, _I32, _P, _I32, _I64, _P, _I64, _I64, _P]),
+    "nrx_ingest_assemble_device": (C.c_int, [C.POINTER(NrxIngestCol), C.c_int, _P, _I32, _P, _I32, _I64, _P, _I64, _I64, _P, _P]),
     "nrx_grouped_rank_metrics": (C.c_int, [_P, _P, _P, _I64, _I32, _P, _P, _P]),
     "nrx_adamw_untouched_rows_scratch_bytes": (_SZ, [C.POINTER(NrxFeat), C.c_int]),
     "nrx_adamw_untouched_rows": (C.c_int, [C.POINTER(NrxFeat), C.c_int, _I64, C.POINTER(_P), C.POINTER(NrxRowOpt), _P, _SZ, _P]),

@@ -145,12 +145,13 @@ struct IngestCols {
 __global__ void __launch_bounds__(256)
 ingest_assemble_kernel(const __grid_constant__ IngestCols C, const float* __restrict__ labels, int n_labels,
                        float* __restrict__ out_labels, int out_ld, long long n_rows, const long long* __restrict__ rows,
-                       long long row0, long long B) {
+                       long long row0, long long B, int* __restrict__ status) {
   const long long b = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (b >= B) return;
   const long long r = rows ? __ldg(rows + b) : row0 + b;
-  const bool ok = r >= 0 && r < n_rows;   // a row outside the file becomes an all-padding sample
+  const bool ok = r >= 0 && r < n_rows;   // a row outside the file becomes an all-padding sample and raises status bit 2
+  if (!ok && lane == 0 && status != nullptr) atomicOr(status, 4);
   for (int c = 0; c < C.n; ++c) {
     if (C.off[c] == nullptr) {
       if (lane == 0) {
@@ -179,7 +180,7 @@ ingest_assemble_kernel(const __grid_constant__ IngestCols C, const float* __rest
 
 extern "C" int nrx_ingest_assemble_device(const NrxIngestCol* h_cols, int n_cols, const float* labels, int32_t n_labels,
                                           float* out_labels, int32_t out_ld, int64_t n_rows, const int64_t* d_rows, int64_t row0,
-                                          int64_t B, nrx_stream_t stream) {
+                                          int64_t B, int32_t* status, nrx_stream_t stream) {
   using namespace nrx;
   NRX_REQUIRE(h_cols && n_cols >= 1 && n_cols <= NRX_MAX_FEATS, NRX_EINVAL, "n_cols=%d outside [1,%d]", n_cols, (int)NRX_MAX_FEATS);
   NRX_REQUIRE(B >= 0 && n_rows >= 0, NRX_EINVAL, "negative sizes");
@@ -198,6 +199,6 @@ extern "C" int nrx_ingest_assemble_device(const NrxIngestCol* h_cols, int n_cols
   if (B == 0) return NRX_OK;
   const long long blocks = (B * 32 + 255) / 256;
   ingest_assemble_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(C, labels, n_labels, out_labels, out_ld, n_rows,
-                                                                           (const long long*)d_rows, row0, B);
+                                                                           (const long long*)d_rows, row0, B, status);
   return check_launch("ingest_assemble");
 }

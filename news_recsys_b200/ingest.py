@@ -324,8 +324,11 @@ class DeviceFeatureFile:
         self.labels = up(ff.labels)
         self.lib = L.load()
 
-    def assemble(self, layout, blob: torch.Tensor, rows: Optional[torch.Tensor] = None, start: int = 0):
-        """Fill `blob` (device uint8, trainer.BatchLayout) with rows `rows` (device int64[B]) or [start, start + B)."""
+    def assemble(self, layout, blob: torch.Tensor, rows: Optional[torch.Tensor] = None, start: int = 0,
+                 status: Optional[torch.Tensor] = None):
+        """Fill `blob` (device uint8, trainer.BatchLayout) with rows `rows` (device int64[B]) or [start, start + B).
+        `status` (device int32[1], optional): bit 2 is set when an element of `rows` lies outside the file (such a sample
+        is assembled as all-padding with label 0; FusedTrainer.load_rows passes its status word and raises)."""
         if blob.device != self.dev or blob.dtype != torch.uint8 or blob.numel() < layout.nbytes:
             raise L.NrxError("assemble() needs a device uint8 blob of at least layout.nbytes bytes on the file's device")
         B = layout.B
@@ -356,5 +359,5 @@ class DeviceFeatureFile:
         ldt, lshape, loff = offs["label"]
         L.check(self.lib.nrx_ingest_assemble_device(arr, len(names), self.labels.data_ptr(), self.n_labels, base + loff, lshape[1],
                                                     self.n_rows, None if rows is None else rows.data_ptr(), int(start), B,
-                                                    L.stream_ptr(self.dev)), "nrx_ingest_assemble_device")
+                                                    L.ptr(status), L.stream_ptr(self.dev)), "nrx_ingest_assemble_device")
         return blob

@@ -34,8 +34,12 @@ class BatchLayout:
     """Byte layout of one batch as a single blob (ids | masks | label) so a step needs ONE copy
     (pinned host -> device, or device pool slot -> static slot)."""
 
-    def __init__(self, model, B: int, id_dtype=torch.int64):
-        self.B = B
+    def __init__(self, model, B: int, id_dtype=torch.int64, n_labels: int = 2):
+        """n_labels: columns of the batch's label tensor (MIND feature files carry 2; the reference accepts any count and
+        its loss reads column 0 only, `deep/model.py:69`)."""
+        if n_labels < 1:
+            raise L.NrxError("n_labels must be >= 1")
+        self.B, self.n_labels = B, int(n_labels)
         names = sorted(model.user_feature_names | model.item_feature_names)
         self.fields = []  # (key, dtype, shape, offset)
         off = 0
@@ -47,7 +51,7 @@ class BatchLayout:
                 self.fields.append((n + "_mask", torch.float32, (B, Lh), off)); off = _align(off + B * Lh * 4)
             else:
                 self.fields.append((n, id_dtype, (B,), off)); off = _align(off + B * isz)
-        self.fields.append(("label", torch.float32, (B, 2), off)); off = _align(off + B * 2 * 4)
+        self.fields.append(("label", torch.float32, (B, self.n_labels), off)); off = _align(off + B * self.n_labels * 4)
         self.nbytes = off
 
     def views(self, blob: torch.Tensor) -> Dict[str, torch.Tensor]:
@@ -63,7 +67,11 @@ class BatchLayout:
     def pack(self, batch: Dict[str, torch.Tensor], blob: torch.Tensor):
         v = self.views(blob)
         for key, dt, shape, off in self.fields:
-            v[key].copy_(batch[key].to(dt).view(*shape))
+            src = batch[key]
+            if key == "label" and src.numel() != self.B * self.n_labels:
+                raise L.NrxError(f"label has {src.numel() // max(self.B, 1)} columns per sample, the layout was built for "
+                                 f"n_labels={self.n_labels} (pass n_labels= to BatchLayout / FusedTrainer)")
+            v[key].copy_(src.to(dt).view(*shape))
         return blob
 
 
@@ -73,8 +81,10 @@ class FusedTrainer:
                      "widedeep": "score_fc.deep_network.network", "dcn": "score_fc.score_fc.network"}
 
     def __init__(self, model, B: int, kind: Optional[str] = None, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01,
-                 use_graph: bool = True, id_dtype=torch.int64, table_update: str = "dense", dense_impl: str = "flat"):
-        """table_update:
+                 use_graph: bool = True, id_dtype=torch.int64, table_update: str = "dense", dense_impl: str = "flat",
+                 n_labels: int = 2):
+        """n_labels: label columns per sample in the batches (the loss reads column 0, as the reference does).
+           table_update:
              "dense"  — (default) the reference's semantics (sort/deep/model.py:55): AdamW with weight decay 0.01 moves
                         every row of every table every step, touched or not;
              "sparse" — explicit opt-in: fused sparse-row AdamW inside K3, only the rows the batch touched move
@@ -112,7 +122,7 @@ class FusedTrainer:
         self.milestones = [int(x) for x in hp.lr_milestones]
         self.betas, self.eps, self.wd = betas, eps, weight_decay
         self.lib = L.load()
-        self.layout = BatchLayout(model, B, id_dtype)
+        self.layout = BatchLayout(model, B, id_dtype, n_labels)
         self.blob = torch.zeros(self.layout.nbytes, dtype=torch.uint8, device=self.dev)
         self.batch = self.layout.views(self.blob)
         # loss and the id-status word share one 8-byte buffer so that feed() reads both back with one copy:
@@ -501,12 +511,16 @@ class FusedTrainer:
 
     def load_batch(self, batch: Dict[str, torch.Tensor]):
         for key, dt, shape, off in self.layout.fields:
-            self.batch[key].copy_(batch[key].to(device=self.dev, dtype=dt).view(*shape), non_blocking=True)
+            src = batch[key]
+            if key == "label" and src.numel() != self.B * self.layout.n_labels:
+                raise L.NrxError(f"label has {src.numel() // max(self.B, 1)} column(s) per sample, this trainer was built for "
+                                 f"n_labels={self.layout.n_labels} (FusedTrainer(..., n_labels=))")
+            self.batch[key].copy_(src.to(device=self.dev, dtype=dt).view(*shape), non_blocking=True)
 
     def load_rows(self, device_file, rows: Optional[torch.Tensor] = None, start: int = 0):
         """Assemble the batch on the GPU from a device-resident feature file (ingest.DeviceFeatureFile): rows `rows`
         (device int64[B], e.g. a slice of a device-side permutation) or the contiguous rows [start, start + B)."""
-        device_file.assemble(self.layout, self.blob, rows=rows, start=start)
+        device_file.assemble(self.layout, self.blob, rows=rows, start=start, status=self.id_status)
 
     _STATUS_EVERY = 16   # steps between two asynchronous read-backs of the status word
 
@@ -546,6 +560,9 @@ class FusedTrainer:
         if bits & 2:
             raise L.NrxError("the peer-memory gradient exchange (K7) timed out waiting for a rank: the exchange is dead on "
                              "every rank and no parameter was updated since; restart from the last checkpoint")
+        if bits & 4:
+            raise L.NrxError("load_rows(): a row index outside the device-resident feature file was requested (the sample was "
+                             "assembled as padding with label 0)")
         if bits & 1:
             raise L.NrxError("a feature id outside its embedding table reached the GPU (vocabulary / config mismatch): "
                              "the reference's nn.Embedding raises here (base_model.py:271)")

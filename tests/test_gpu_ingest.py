@@ -42,9 +42,33 @@ def test_device_assembly_equals_host_pack(files, id_dtype):
     dff.assemble(layout, got, rows=bad)
     v = layout.views(got)
     assert int(v["user_id"][-1]) == 0 and float(v["user_history_mask"][-1].sum()) == 0 and float(v["label"][-1].abs().sum()) == 0
+    st = torch.zeros(1, dtype=torch.int32, device=DEV)
+    dff.assemble(layout, got, rows=bad, status=st)
+    assert int(st.item()) == 4                       # ... and is reported through the status word when one is given
+    dff.assemble(layout, got, rows=torch.arange(48, device=DEV), status=st.zero_())
+    assert int(st.item()) == 0
     from news_recsys_b200._lib import NrxError
     with pytest.raises(NrxError):
         dff.assemble(layout, got, start=180)
+
+
+def test_trainer_raises_on_rows_outside_the_device_file(files):
+    """a shuffled-row index past the end of the device-resident file used to become a silent fake negative."""
+    from news_recsys_b200._lib import NrxError
+    from news_recsys_b200.model.sort.deep.model import Deep
+    from news_recsys_b200.trainer import FusedTrainer
+    ff, dff = files
+    torch.manual_seed(3)
+    tr = FusedTrainer(Deep(CFG).to(DEV), 64, kind="deep", id_dtype=torch.int32)
+    rows = torch.arange(64, device=DEV)
+    tr.load_rows(dff, rows=rows)
+    tr.step()
+    tr.check_status()
+    rows[5] = 200                                    # the file has 200 rows
+    tr.load_rows(dff, rows=rows)
+    tr.step()
+    with pytest.raises(NrxError, match="outside the device-resident feature file"):
+        tr.check_status()
 
 
 def test_training_from_the_device_file_equals_host_fed_training(files):

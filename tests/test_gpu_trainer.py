@@ -211,3 +211,35 @@ def test_int32_ids_equal_int64_ids():
     assert out[torch.int32][0] == out[torch.int64][0]
     for k, v in out[torch.int64][1].items():
         assert torch.equal(out[torch.int32][1][k], v), k
+
+
+@pytest.mark.parametrize("kind", ["deep", "fm"])
+def test_label_column_count_is_free(kind):
+    """ADVICE r1 (low): the reference accepts any number of label columns and its loss reads column 0 (deep/model.py:69);
+    the blob layout used to hard-code (B, 2).  One-column and three-column labels train exactly like two-column ones."""
+    from news_recsys_b200._lib import NrxError
+    from news_recsys_b200.synthetic import mind_config, synth_batch
+    from news_recsys_b200.trainer import FusedTrainer
+    rows = {"user_id": 3000, "item_id": 2000, "category": 18, "subcategory": 70, "user_click_category": 18}
+    cfg = mind_config(kind, rows, history_len=6 if kind == "deep" else 0)
+    batches = [synth_batch(cfg, 256, seed=40 + i, label_p=0.5) for i in range(3)]
+    out = {}
+    for nl in (2, 1, 3):
+        torch.manual_seed(8)
+        model = _cls(kind)(cfg).to(DEV)
+        tr = FusedTrainer(model, 256, kind=kind, n_labels=nl)
+        losses = []
+        for b in batches:
+            b = dict(b)
+            col0 = b["label"][:, :1]
+            b["label"] = col0 if nl == 1 else torch.cat([col0] + [torch.rand(256, 1)] * (nl - 1), dim=1)
+            losses.append(float(tr.train_step(b).item()))
+        out[nl] = (losses, {k: v.detach().clone() for k, v in model.state_dict().items()})
+    for nl in (1, 3):
+        assert out[nl][0] == out[2][0]
+        for k, v in out[2][1].items():
+            assert torch.equal(out[nl][1][k], v), (nl, k)
+    tr = FusedTrainer(_cls(kind)(cfg).to(DEV), 256, kind=kind)          # default n_labels = 2
+    bad = dict(batches[0]); bad["label"] = bad["label"][:, 0]
+    with pytest.raises(NrxError, match="n_labels"):
+        tr.train_step(bad)
