@@ -91,7 +91,10 @@ int nrx_embed_pool_fwd_img(const NrxFeat* h_feats, int n_feats, int64_t B, float
  * and either writes dense per-table gradients (mode DENSE, `grads[t]` is
  * [rows_t, stride_t], zeroed by this call) or applies a fused sparse row update
  * in place (SGD / AdamW on touched rows only). */
-enum { NRX_BWD_DENSE = 0, NRX_BWD_SGD = 1, NRX_BWD_ADAMW = 2 };
+enum { NRX_BWD_DENSE = 0, NRX_BWD_SGD = 1, NRX_BWD_ADAMW = 2,
+       /* OR-ed onto NRX_BWD_DENSE: the caller has already zeroed grads[t] (e.g. with ONE memset over a flat gradient buffer,
+        * early in the step and off its critical path); the call then only writes the touched rows */
+       NRX_BWD_NO_ZERO = 0x100 };
 
 typedef struct NrxRowOpt {
   float lr, beta1, beta2, eps, weight_decay;
@@ -105,6 +108,15 @@ typedef struct NrxRowOpt {
 size_t nrx_embed_bwd_workspace_bytes(const NrxFeat* h_feats, int n_feats, int64_t B);
 int nrx_embed_bwd_plan(const NrxFeat* h_feats, int n_feats, int64_t B,
                        void* ws, size_t ws_bytes, nrx_stream_t stream);
+/* The plan in two enqueues, for callers that schedule its halves around other kernels (the fused trainer runs the chunk
+ * sort beside the pooling kernel and the merge beside the dW GEMMs, so that neither holds SMs the persistent tower
+ * kernels need): SORT then MERGE on the same stream == ALL.  For batches on the device-radix-sort path SORT does
+ * everything and MERGE is a no-op. */
+enum { NRX_PLAN_ALL = 0, NRX_PLAN_SORT = 1, NRX_PLAN_MERGE = 2 };
+int nrx_embed_bwd_plan_stage(const NrxFeat* h_feats, int n_feats, int64_t B, void* ws, size_t ws_bytes, int stage,
+                             nrx_stream_t stream);
+/* 1 when the batch takes the two-kernel path (chunk sort + merge), i.e. when NRX_PLAN_MERGE enqueues a kernel. */
+int nrx_embed_bwd_plan_is_staged(const NrxFeat* h_feats, int n_feats, int64_t B);
 int nrx_embed_bwd_apply(const NrxFeat* h_feats, int n_feats, int64_t B,
                         const float* grad_out, int64_t grad_ld,
                         int mode, float* const* h_grads /* [n_tables] device ptrs, DENSE */,

@@ -23,6 +23,8 @@ NRX_PEER_SIG_WORDS = 256
 POOL_NONE, POOL_MASKED_MEAN, POOL_MEAN = 0, 1, 2
 IDX_I64, IDX_I32 = 0, 1
 BWD_DENSE, BWD_SGD, BWD_ADAMW = 0, 1, 2
+BWD_NO_ZERO = 0x100
+PLAN_ALL, PLAN_SORT, PLAN_MERGE = 0, 1, 2
 FIELD_FM, FIELD_WIDE, FIELD_SUM = 0, 1, 2
 ACT_RELU, ACT_LEAKY = 0, 1
 
@@ -108,6 +110,8 @@ SIGNATURES = {
     "nrx_embed_pool_fwd_img": (C.c_int, [C.POINTER(NrxFeat), C.c_int, _I64, _P, _I64, _P, C.c_int, _P, _P, _P]),
     "nrx_embed_bwd_workspace_bytes": (_SZ, [C.POINTER(NrxFeat), C.c_int, _I64]),
     "nrx_embed_bwd_plan": (C.c_int, [C.POINTER(NrxFeat), C.c_int, _I64, _P, _SZ, _P]),
+    "nrx_embed_bwd_plan_is_staged": (C.c_int, [C.POINTER(NrxFeat), C.c_int, _I64]),
+    "nrx_embed_bwd_plan_stage": (C.c_int, [C.POINTER(NrxFeat), C.c_int, _I64, _P, _SZ, C.c_int, _P]),
     "nrx_embed_bwd_apply": (C.c_int, [C.POINTER(NrxFeat), C.c_int, _I64, _P, _I64, C.c_int,
                                       C.POINTER(_P), C.POINTER(_P), C.POINTER(NrxRowOpt), _P, _SZ, _P]),
     "nrx_ingest_gather_ids": (C.c_int, [_P, _I64, _P, _I64, _I64, _P, C.c_int]),
@@ -202,7 +206,7 @@ def load() -> C.CDLL:
 
 # kernels of OURS launched per successful API call (library kernels such as the CUB radix sort are not counted)
 KERNELS_PER_CALL = {"nrx_tower_fwd": 3, "nrx_tower_fwd(prepacked)": 2, "nrx_tower_fwd_head": 3, "nrx_tower_fwd_head(prepacked)": 2,
-                    "nrx_tower_fwd(prepacked,ximg)": 1, "nrx_tower_fwd_head(prepacked,ximg)": 1, "nrx_tower_bwd": 3, "nrx_tower_bwd_dw": 2, "nrx_embed_bwd_apply": 2, "nrx_embed_bwd_plan": 2, "nrx_adamw_untouched_rows": 2, "nrx_adamw_untouched_rows_scratch_bytes": 0, "nrx_dcn_cross_bwd": 2,
+                    "nrx_tower_fwd(prepacked,ximg)": 1, "nrx_tower_fwd_head(prepacked,ximg)": 1, "nrx_tower_bwd": 3, "nrx_tower_bwd_dw": 2, "nrx_embed_bwd_apply": 2, "nrx_embed_bwd_plan": 2, "nrx_embed_bwd_plan(sort)": 1, "nrx_embed_bwd_plan(merge)": 1, "nrx_embed_bwd_plan_is_staged": 0, "nrx_adamw_untouched_rows": 2, "nrx_adamw_untouched_rows_scratch_bytes": 0, "nrx_dcn_cross_bwd": 2,
                     "nrx_embed_bwd_apply(dense)": 2, "nrx_embed_bwd_apply(rowopt)": 2, "nrx_topk_ip": 2,
                     "nrx_topk_search": 6, "nrx_topk_search64": 6, "nrx_topk_search_peer": 10, "nrx_topk_peer_inbox_bytes": 0, "nrx_topk_index_build": 1,
                     "nrx_peer_alloc": 0, "nrx_peer_free": 0, "nrx_peer_export": 0, "nrx_peer_open": 0, "nrx_peer_close": 0,

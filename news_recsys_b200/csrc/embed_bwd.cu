@@ -605,7 +605,21 @@ extern "C" size_t nrx_embed_bwd_workspace_bytes(const NrxFeat* h_feats, int n_fe
 
 extern "C" int nrx_embed_bwd_plan(const NrxFeat* h_feats, int n_feats, int64_t B, void* ws, size_t ws_bytes,
                                   nrx_stream_t stream) {
+  return nrx_embed_bwd_plan_stage(h_feats, n_feats, B, ws, ws_bytes, NRX_PLAN_ALL, stream);
+}
+
+extern "C" int nrx_embed_bwd_plan_is_staged(const NrxFeat* h_feats, int n_feats, int64_t B) {
   using namespace nrx;
+  DFeats d;
+  if (make_dfeats(h_feats, n_feats, B, nullptr, 0, &d) != NRX_OK || d.n_occ == 0) return 0;
+  SmallPlan sp;
+  return make_small_plan(d, &sp) ? 1 : 0;
+}
+
+extern "C" int nrx_embed_bwd_plan_stage(const NrxFeat* h_feats, int n_feats, int64_t B, void* ws, size_t ws_bytes, int stage,
+                                        nrx_stream_t stream) {
+  using namespace nrx;
+  NRX_REQUIRE(stage == NRX_PLAN_ALL || stage == NRX_PLAN_SORT || stage == NRX_PLAN_MERGE, NRX_EINVAL, "bad plan stage %d", stage);
   DFeats d;
   int rc = make_dfeats(h_feats, n_feats, B, nullptr, 0, &d);
   if (rc != NRX_OK) return rc;
@@ -628,14 +642,18 @@ extern "C" int nrx_embed_bwd_plan(const NrxFeat* h_feats, int n_feats, int64_t B
       NRX_REQUIRE(e == cudaSuccess, NRX_ELAUNCH, "smem opt-in: %s", cudaGetErrorString(e));
       uint32_t* km = (uint32_t*)(w + L.keys_in);
       uint32_t* vm = (uint32_t*)(w + L.vals_in);
-      plan_chunk_sort_kernel<<<sp.total_chunks, kChunkThreads, 0, st>>>(d, sp, km, vm);
-      rc = check_launch("plan_chunk_sort");
-      if (rc != NRX_OK) return rc;
+      if (stage != NRX_PLAN_MERGE) {
+        plan_chunk_sort_kernel<<<sp.total_chunks, kChunkThreads, 0, st>>>(d, sp, km, vm);
+        rc = check_launch("plan_chunk_sort");
+        if (rc != NRX_OK) return rc;
+      }
+      if (stage == NRX_PLAN_SORT) return NRX_OK;
       plan_merge_kernel<<<sp.total_chunks * kChunkItems, kChunkThreads, smem, st>>>(sp, L.row_bits, sentinel, km, vm,
                                                                      (uint32_t*)(w + L.keys_out), (uint32_t*)(w + L.vals_out));
       return check_launch("plan_merge");
     }
   }
+  if (stage == NRX_PLAN_MERGE) return NRX_OK;   // large batches: the device radix sort of the SORT stage is the whole plan
   const unsigned blocks = (unsigned)((d.n_occ + 255) / 256);
   build_keys_kernel<<<blocks, 256, 0, st>>>(d, L.row_bits, sentinel, (uint32_t*)(w + L.keys_in), (uint32_t*)(w + L.vals_in));
   rc = check_launch("build_keys");
@@ -659,7 +677,10 @@ extern "C" int nrx_embed_bwd_apply(const NrxFeat* h_feats, int n_feats, int64_t 
   rc = plan_layout(d, &L);
   if (rc != NRX_OK) return rc;
   NRX_REQUIRE(ws != nullptr && ws_bytes >= L.total, NRX_EWORKSPACE, "workspace %zu < %zu", ws_bytes, L.total);
+  const bool no_zero = (mode & NRX_BWD_NO_ZERO) != 0;
+  mode &= ~NRX_BWD_NO_ZERO;
   NRX_REQUIRE(mode == NRX_BWD_DENSE || mode == NRX_BWD_SGD || mode == NRX_BWD_ADAMW, NRX_EINVAL, "bad mode %d", mode);
+  NRX_REQUIRE(!no_zero || mode == NRX_BWD_DENSE, NRX_EINVAL, "NRX_BWD_NO_ZERO only applies to NRX_BWD_DENSE");
   NRX_REQUIRE(grad_out != nullptr || B == 0, NRX_EINVAL, "null grad_out");
   cudaStream_t st = (cudaStream_t)stream;
 
@@ -684,8 +705,10 @@ extern "C" int nrx_embed_bwd_apply(const NrxFeat* h_feats, int n_feats, int64_t 
     if (mode == NRX_BWD_DENSE) {
       NRX_REQUIRE(h_grads && h_grads[t], NRX_EINVAL, "dense mode: missing grad buffer for table %d", t);
       T.g[t] = h_grads[t];
-      cudaError_t e = cudaMemsetAsync(T.g[t], 0, (size_t)trows[t] * T.stride[t] * sizeof(float), st);
-      NRX_REQUIRE(e == cudaSuccess, NRX_ELAUNCH, "memset: %s", cudaGetErrorString(e));
+      if (!no_zero) {
+        cudaError_t e = cudaMemsetAsync(T.g[t], 0, (size_t)trows[t] * T.stride[t] * sizeof(float), st);
+        NRX_REQUIRE(e == cudaSuccess, NRX_ELAUNCH, "memset: %s", cudaGetErrorString(e));
+      }
     } else {
       NRX_REQUIRE(h_tables && h_tables[t] && h_opt, NRX_EINVAL, "row-update mode: missing table %d / options", t);
       T.w[t] = h_tables[t];

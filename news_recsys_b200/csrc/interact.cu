@@ -130,6 +130,42 @@ field_logit_bwd_kernel(const float* __restrict__ x, long long ld, long long B, c
   }
 }
 
+// FM backward, vector form: equal field widths D (D % 4 == 0), 16-byte aligned rows, n * D / 4 <= 32.  One warp per
+// sample, lane = one float4 of one field (coalesced 16-byte loads / stores, one round trip); S_d is summed over the fields
+// in field order by shuffles (same order as the scalar kernel).  Element 0 of a field is its first-order weight:
+// gradient dlogit, excluded from S (fm/model.py:48-59).
+__global__ void __launch_bounds__(256)
+field_logit_bwd_fm_v4_kernel(const float* __restrict__ x, long long ld, long long B, const __grid_constant__ Fields F, int q,
+                             const float* __restrict__ dlogit, float* __restrict__ gx, long long gld, int accumulate) {
+  const long long b = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (b >= B) return;
+  const int f = lane / q, c = lane - f * q;
+  const bool live = f < F.n;
+  const int col = live ? F.col[f] + 4 * c : 0;
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f), o = v;
+  if (live) {
+    v = __ldg(reinterpret_cast<const float4*>(x + b * ld + col));
+    if (accumulate) o = *reinterpret_cast<const float4*>(gx + b * gld + col);
+  }
+  const float g = __ldg(dlogit + b);
+  float4 S = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int u = 0; u < F.n; ++u) {
+    const int src = c + q * u;
+    S.x += __shfl_sync(NRX_FULL_MASK, v.x, src);
+    S.y += __shfl_sync(NRX_FULL_MASK, v.y, src);
+    S.z += __shfl_sync(NRX_FULL_MASK, v.z, src);
+    S.w += __shfl_sync(NRX_FULL_MASK, v.w, src);
+  }
+  if (!live) return;
+  float4 r;
+  r.x = o.x + (c == 0 ? g : g * (S.x - v.x));
+  r.y = o.y + g * (S.y - v.y);
+  r.z = o.z + g * (S.z - v.z);
+  r.w = o.w + g * (S.w - v.w);
+  *reinterpret_cast<float4*>(gx + b * gld + col) = r;
+}
+
 static int make_fields(const int32_t* cols, const int32_t* dims, int n, int mode, long long ld, Fields* F) {
   NRX_REQUIRE(cols && dims && n > 0 && n <= kMaxFields, NRX_EINVAL, "n_fields=%d outside [1,%d]", n, kMaxFields);
   NRX_REQUIRE(mode == NRX_FIELD_FM || mode == NRX_FIELD_WIDE || mode == NRX_FIELD_SUM, NRX_EINVAL, "bad field mode");
@@ -396,6 +432,17 @@ extern "C" int nrx_field_logit_bwd(const float* x, int64_t ld, int64_t B, const 
   if (rc != NRX_OK) return rc;
   NRX_REQUIRE(x && dlogit && grad_x, NRX_EINVAL, "null pointer");
   if (B == 0) return NRX_OK;
+  if (mode == NRX_FIELD_FM) {
+    const int D = F.dim[0];
+    bool v4 = D % 4 == 0 && (D / 4) * n_fields <= 32 && ld % 4 == 0 && grad_ld % 4 == 0 &&
+              ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(grad_x)) & 15) == 0;
+    for (int i = 0; i < n_fields && v4; ++i) v4 = F.col[i] % 4 == 0;
+    if (v4) {
+      field_logit_bwd_fm_v4_kernel<<<warps_grid(B, 8), 256, 0, (cudaStream_t)stream>>>(x, ld, B, F, D / 4, dlogit, grad_x, grad_ld,
+                                                                                       accumulate);
+      return check_launch("field_logit_bwd(fm v4)");
+    }
+  }
   field_logit_bwd_kernel<<<warps_grid(B, 8), 256, 0, (cudaStream_t)stream>>>(x, ld, B, F, dlogit, grad_x, grad_ld, accumulate);
   return check_launch("field_logit_bwd");
 }

@@ -148,15 +148,22 @@ def embed_img_eligible(fb: FeatBinding, out_dim: int) -> bool:
 class BwdPlan:
     """Sorted-occurrence plan for one batch (nrx_embed_bwd_plan); reusable for any number of applies."""
 
-    def __init__(self, fb: FeatBinding):
+    def __init__(self, fb: FeatBinding, stage: int = L.PLAN_ALL):
+        """stage=L.PLAN_SORT enqueues the first half only; call merge() (on any stream ordered after this one) before the
+        first apply."""
         lib = L.load()
         self.fb = fb
         self.bytes = int(lib.nrx_embed_bwd_workspace_bytes(fb.arr, fb.n, fb.B))
         if self.bytes == 0 and fb.B > 0:
             L.check(-2, "nrx_embed_bwd_workspace_bytes")
         self.ws = torch.empty(max(self.bytes, 16), dtype=torch.uint8, device=fb.device)
-        L.check(lib.nrx_embed_bwd_plan(fb.arr, fb.n, fb.B, self.ws.data_ptr(), self.bytes, L.stream_ptr(fb.device)),
-                "nrx_embed_bwd_plan")
+        L.check(lib.nrx_embed_bwd_plan_stage(fb.arr, fb.n, fb.B, self.ws.data_ptr(), self.bytes, stage, L.stream_ptr(fb.device)),
+                "nrx_embed_bwd_plan" if stage == L.PLAN_ALL else "nrx_embed_bwd_plan(sort)")
+
+    def merge(self):
+        fb = self.fb
+        L.check(L.load().nrx_embed_bwd_plan_stage(fb.arr, fb.n, fb.B, self.ws.data_ptr(), self.bytes, L.PLAN_MERGE,
+                                                  L.stream_ptr(fb.device)), "nrx_embed_bwd_plan(merge)")
 
 
 def embed_bwd_dense(plan: BwdPlan, grad_out: torch.Tensor, table_by_id: Sequence[Optional[torch.Tensor]]):

@@ -135,6 +135,7 @@ class FusedTrainer:
                           host=torch.zeros(2, dtype=torch.float32).pin_memory(), ev=torch.cuda.Event(), done=torch.cuda.Event())
         self.d_step = torch.zeros(1, dtype=torch.int32, device=self.dev)
         self.d_hp = torch.zeros(4, dtype=torch.float32, device=self.dev)
+        self._dense_applied = False
         self._flatten_dense()
         self._table_state()
         self.fb, self.dims, self.names, self.out_dim = model.bind_features(self.batch, model.user_feature_names | model.item_feature_names)
@@ -183,14 +184,21 @@ class FusedTrainer:
         self.m_by_id: List[Optional[torch.Tensor]] = [None] * L.NRX_MAX_TABLES
         self.v_by_id: List[Optional[torch.Tensor]] = [None] * L.NRX_MAX_TABLES
         self.table_grads_by_id: List[Optional[torch.Tensor]] = [None] * L.NRX_MAX_TABLES
+        span = (1 << 62, 0)
         for name, tid in self.model._table_ids.items():
             w = self.model.embedding_tables[name].weight.data
             self.tables_by_id[tid] = w
             if self._flat_tables:   # moments live in the flat buffers
                 self.table_grads_by_id[tid] = self.grad_views[f"embedding_tables.{name}.weight"]
+                e0 = (self.table_grads_by_id[tid].data_ptr() - self.flat_g.data_ptr()) // 4
+                span = (min(span[0], e0), max(span[1], e0 + w.numel()))
             else:
                 self.m_by_id[tid] = torch.zeros_like(w)
                 self.v_by_id[tid] = torch.zeros_like(w)
+        if self._flat_tables:
+            # the tables' gradients as ONE span of the flat buffer (named_parameters lists the tables together); a dense
+            # parameter that happened to sit inside it would merely have its gradient zeroed before it is rewritten
+            self._table_grad_span = self.flat_g[span[0]:span[1]] if span[1] > span[0] else self.flat_g[:0]
 
     # ---- raw op helpers writing into preallocated buffers ------------------------------------------
     def _sp(self):
@@ -275,7 +283,19 @@ class FusedTrainer:
                 self.side4.wait_stream(self.side)
                 with torch.cuda.stream(self.side4):
                     self._sweep_untouched(self._plan_fb())
-            plan = ops.BwdPlan(self._plan_fb())
+            # The plan in two halves when a tower follows: the chunk sort runs beside K1 (neither needs much shared memory);
+            # the merge (64 KB CTAs on every SM) waits until the dX chain has been launched and runs beside the dW GEMMs —
+            # beside the forward it held SMs the persistent tower CTAs were waiting for (8 us of the step's critical path).
+            pfb = self._plan_fb()
+            staged = (self.kind in ("deep", "deepfm", "widedeep", "dcn") and not self.fm_fused
+                      and lib.nrx_embed_bwd_plan_is_staged(pfb.arr, pfb.n, pfb.B) == 1)
+            plan = ops.BwdPlan(self._plan_fb(), L.PLAN_SORT if staged else L.PLAN_ALL)
+            if self._flat_tables:
+                # dense table gradients: K3 writes the touched rows only, the rest must be zero.  ONE fill over the tables'
+                # span of the flat gradient buffer, early in the step and off its critical path (five per-table memsets
+                # inside the apply call used to sit between the backward and the optimizer: ~20 us of the step)
+                self._table_grad_span.zero_()
+        self._dense_applied = False
         packed = None
         if self.kind in ("deep", "deepfm", "dcn"):
             packed = self._prepack(self._lin_names(self._TOWER_PREFIX[self.kind]), main)
@@ -355,18 +375,40 @@ class FusedTrainer:
             gx = None
             if tctx is not None:
                 g_tin = self._tower_bwd_dx(tctx, dl)
-                # the scalar reductions and the field-logit backward only need dl / grad_x: run them on the third
-                # stream while the dW GEMMs (and, for DCN, the cross backward) proceed on the main one
+                merged = None
+                if staged:
+                    # second half of the plan, as soon as the dX chain is out of the way: it shares the machine with the dW
+                    # GEMMs (measured: making dW wait for the merge instead lengthens the step by 2 us — the apply then
+                    # collides with dW, NRX_DW_AFTER_MERGE=1 keeps that order for experiments)
+                    self.side.wait_stream(main)
+                    with torch.cuda.stream(self.side):
+                        plan.merge()
+                        merged = torch.cuda.Event()
+                        merged.record(self.side)
+                        self._loss_and_bias_grad(loss_ps, dl, bias)   # scalar reductions: only the optimizer reads them
+                # the field-logit backward, the table-gradient apply and the scalar reductions only need dl / grad_x: they
+                # run on the third stream while the dW GEMMs (and, for DCN, the cross backward) proceed on the main one
                 s3.wait_stream(main)
                 inline = self._inline_update and kind != "dcn" and not self._flat_tables
+                dense_early = self._flat_tables and kind != "dcn" and type(self)._dense_table_grads is FusedTrainer._dense_table_grads
                 with torch.cuda.stream(s3):
-                    self._loss_and_bias_grad(loss_ps, dl, bias)
                     if field is not None:
                         ops.field_logit_bwd(x, field[0], field[1], field[2], dl, g_tin, accumulate=True)
+                    if inline or dense_early:
+                        if merged is not None:
+                            s3.wait_event(merged)
+                        else:
+                            s3.wait_stream(self.side)
                     if inline:  # grad_x is final here: update the embedding rows while dW is still being computed
-                        s3.wait_stream(self.side)
                         self._apply_rows(self._plan_fb(), plan, g_tin)
                         self._rows_applied = True
+                    elif dense_early:  # likewise for the dense table gradients (the optimizer then only waits for the join)
+                        self._dense_table_grads(self._plan_fb(), plan, g_tin)
+                        self._dense_applied = True
+                    if not staged:
+                        self._loss_and_bias_grad(loss_ps, dl, bias)
+                if merged is not None and os.environ.get("NRX_DW_AFTER_MERGE", "0") == "1":
+                    main.wait_event(merged)
                 self._tower_bwd_dw(tctx, lin, gw_override)
                 if kind == "widedeep":
                     self.grad_views[lin[0] + ".weight"].copy_(gw_override[0].index_select(1, idx))
@@ -424,8 +466,11 @@ class FusedTrainer:
                 "nrx_adamw_untouched_rows")
 
     def _dense_table_grads(self, fb, plan, gx):
-        """K3 dense mode: per-table [rows, D] gradients (zero-filled by the call) written into the flat grad buffer."""
-        L.check(self.lib.nrx_embed_bwd_apply(fb.arr, fb.n, fb.B, gx.data_ptr(), gx.stride(0), L.BWD_DENSE,
+        """K3 dense mode: per-table [rows, D] gradients written into the flat grad buffer (zero-filled at the start of the
+        step); a no-op when _fwd_bwd already ran it beside the dW GEMMs."""
+        if self._dense_applied:
+            return
+        L.check(self.lib.nrx_embed_bwd_apply(fb.arr, fb.n, fb.B, gx.data_ptr(), gx.stride(0), L.BWD_DENSE | L.BWD_NO_ZERO,
                                              L.ptr_array(self.table_grads_by_id, L.NRX_MAX_TABLES), None, None,
                                              plan.ws.data_ptr(), plan.bytes, self._sp()), "nrx_embed_bwd_apply(dense)")
 
