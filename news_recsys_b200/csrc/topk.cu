@@ -907,6 +907,18 @@ topk_final_peer_kernel(const float* __restrict__ c, long long cld, long long N, 
 
 // Owner side: merge the G lists of one owned query, prove completeness, publish the result to EVERY rank (peer stores);
 // a query that cannot be proven goes on the owner's fallback list (exact scan over all shards through peer memory).
+// The lists arrive sorted, so the merge is a RANK merge, not a sort: the final position of an element is its index in its
+// own list plus, for every other list, the number of elements that sort before it (one binary search each; ids are unique
+// across shards, so the order is strict).  8 lists x 100: 23.5 us as a 1024-element bitonic sort, a few us this way.
+__device__ __forceinline__ int count_before(const double* ls, const long long* li, int n, double s, long long id) {
+  int lo = 0, hi = n;   // first index whose element does NOT sort before (s, id)
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (before(ls[mid], li[mid], s, id)) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
 __global__ void __launch_bounds__(256)
 topk_owner_merge_kernel(long long Q, long long N_total, int k, const __grid_constant__ PeerInbox PB, unsigned* __restrict__ flist,
                         int* __restrict__ status, const __grid_constant__ PeerOuts PO) {
@@ -917,45 +929,57 @@ topk_owner_merge_kernel(long long Q, long long N_total, int k, const __grid_cons
   if (qi >= Q) return;
   uint8_t* box = PB.box[PB.rank];
   const int G = PB.world;
-  int n2 = 32;   // the sort network needs >= one warp of elements
-  while (n2 < G * k) n2 <<= 1;
-  double* s = reinterpret_cast<double*>(sm_raw);            // [n2]
-  long long* id = reinterpret_cast<long long*>(s + n2);     // [n2]
-  __shared__ int s_bad;
+  double* s = reinterpret_cast<double*>(sm_raw);                    // [G][k]
+  long long* id = reinterpret_cast<long long*>(s + (size_t)G * k);   // [G][k]
+  double* os = reinterpret_cast<double*>(id + (size_t)G * k);       // [k] merged
+  long long* oi = reinterpret_cast<long long*>(os + k);             // [k]
+  __shared__ int s_cnt[NRX_MAX_PEERS];
+  __shared__ int s_bad, s_total;
   __shared__ float s_bound;
   if (tid == 0) {
-    int bad = 0;
+    int bad = 0, total = 0;
     float bound = -FLT_MAX;
     for (int g = 0; g < G; ++g) {
       const int cg = inbox_cnt(box, PB.q_own, G, k)[ql * G + g];
       if (cg < 0) bad = 1;
+      s_cnt[g] = cg < 0 ? 0 : cg;
+      total += s_cnt[g];
       bound = fmaxf(bound, inbox_bound(box, PB.q_own, G, k)[ql * G + g]);
     }
     s_bad = bad;
+    s_total = total;
     s_bound = bound;
   }
   __syncthreads();
   const long long kk = k < N_total ? k : N_total;
-  bool ok = !s_bad;
+  bool ok = !s_bad && (long long)s_total >= kk;
   if (ok) {
-    for (int i = tid; i < n2; i += 256) {
-      const int g = i / k, j = i % k;
-      const int cg = g < G ? inbox_cnt(box, PB.q_own, G, k)[ql * G + g] : 0;
-      if (g < G && j < cg) { const TopkEntry e = inbox_entries(box, ql, g, G, k)[j]; s[i] = e.s; id[i] = e.id; }
-      else { s[i] = -DBL_MAX; id[i] = 0x7fffffffffffffffll; }
+    for (int i = tid; i < G * k; i += 256) {
+      const int g = i / k, j = i - g * k;
+      if (j < s_cnt[g]) { const TopkEntry e = inbox_entries(box, ql, g, G, k)[j]; s[i] = e.s; id[i] = e.id; }
     }
     __syncthreads();
-    bitonic_sort(s, id, n2, tid, 256);
-    // complete iff the k-th merged score clears every shard's bound (and k real rows exist)
-    ok = kk == 0 || (id[kk - 1] != 0x7fffffffffffffffll && (s_bound == -FLT_MAX || s[kk - 1] >= (double)s_bound));
+    for (int i = tid; i < G * k; i += 256) {
+      const int g = i / k, j = i - g * k;
+      if (j >= s_cnt[g]) continue;
+      const double es = s[i];
+      const long long ei = id[i];
+      int rank = j;
+      for (int g2 = 0; g2 < G && rank < kk; ++g2)
+        if (g2 != g) rank += count_before(s + (size_t)g2 * k, id + (size_t)g2 * k, s_cnt[g2], es, ei);
+      if (rank < kk) { os[rank] = es; oi[rank] = ei; }
+    }
+    __syncthreads();
+    // complete iff the k-th merged score clears every shard's bound
+    ok = kk == 0 || s_bound == -FLT_MAX || os[kk - 1] >= (double)s_bound;
   }
   if (!ok) {
     if (tid == 0) { flist[1 + atomicAdd(flist, 1u)] = (unsigned)qi; if (status) status[qi] = 1; }
     return;
   }
   for (int i = tid; i < k; i += 256) {
-    const float fs = i < kk ? (float)s[i] : -FLT_MAX;
-    const long long fi = i < kk ? id[i] : -1;
+    const float fs = i < kk ? (float)os[i] : -FLT_MAX;
+    const long long fi = i < kk ? oi[i] : -1;
     for (int g = 0; g < PO.n; ++g) { PO.s[g][qi * k + i] = fs; PO.i[g][qi * k + i] = fi; }
   }
 }
@@ -1233,9 +1257,7 @@ extern "C" int nrx_topk_search_peer(const void* index, int64_t N_local, int D, c
   if (rc != NRX_OK) return rc;
   rc = nrx_peer_barrier(&bar, stream);     // every shard's lists have landed in the owners' inboxes
   if (rc != NRX_OK) return rc;
-  int n2 = 32;   // the sort network needs >= one warp of elements
-  while (n2 < G * k) n2 <<= 1;
-  const size_t osm = (size_t)n2 * 16;
+  const size_t osm = ((size_t)G * k + k) * 16;   // the G lists + the merged list, (fp64 score, int64 id) each
   cudaFuncSetAttribute(topk_owner_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)osm);
   topk_owner_merge_kernel<<<(unsigned)PB.q_own, 256, osm, st>>>(Q, N_total, k, PB, flist, status, PO);
   rc = check_launch("topk_owner_merge");

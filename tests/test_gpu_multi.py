@@ -17,6 +17,25 @@ def _free_port():
     return p
 
 
+_RENDEZVOUS_ERRORS = ("address already in use", "eaddrinuse", "connection refused", "connection reset", "socket",
+                      "store", "rendezvous", "ncclsystemerror", "ncclremoteerror", "unhandled system error")
+
+
+def _spawn(fn, args_after_port, nprocs=2):
+    """mp.spawn with a fresh port; ONE retry when the failure is the rendezvous itself (a port picked by _free_port() can
+    be taken again before the workers bind it).  Assertion failures and kernel errors are never retried."""
+    import torch.multiprocessing as mp
+    for attempt in range(2):
+        try:
+            mp.spawn(fn, args=(nprocs, _free_port()) + tuple(args_after_port), nprocs=nprocs, join=True)
+            return
+        except Exception as e:   # ProcessRaisedException carries the worker's traceback as text
+            msg = str(e).lower()
+            if attempt == 0 and "assert" not in msg and "nrxerror" not in msg and any(k in msg for k in _RENDEZVOUS_ERRORS):
+                continue
+            raise
+
+
 def _dp_worker(rank, world, port, kind, out_dir, mode, exchange):
     import sys
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -69,7 +88,7 @@ def test_dp2_equals_single_gpu(kind, mode, exchange, tmp_path):
     from oracle import ref_path as R
     from news_recsys_b200.synthetic import mind_config, synth_batch
     from news_recsys_b200.trainer import FusedTrainer
-    mp.spawn(_dp_worker, args=(2, _free_port(), kind, str(tmp_path), mode, exchange), nprocs=2, join=True)
+    _spawn(_dp_worker, (kind, str(tmp_path), mode, exchange))
     sd0 = torch.load(tmp_path / f"dp_{kind}_0.pt")
     sd1 = torch.load(tmp_path / f"dp_{kind}_1.pt")
     for k in sd0:
@@ -152,7 +171,7 @@ def test_row_sharded_tables_equal_single_gpu(kind, exchange, tmp_path):
     import torch.multiprocessing as mp
     from news_recsys_b200.synthetic import mind_config, synth_batch
     from news_recsys_b200.trainer import FusedTrainer
-    mp.spawn(_sharded_worker, args=(2, _free_port(), kind, str(tmp_path), exchange), nprocs=2, join=True)
+    _spawn(_sharded_worker, (kind, str(tmp_path), exchange))
     sd0, l0 = torch.load(tmp_path / f"sh_{kind}_0.pt")
     sd1, l1 = torch.load(tmp_path / f"sh_{kind}_1.pt")
     for k in sd0:
@@ -242,7 +261,7 @@ def test_sharded_topk_over_peer_memory_equals_one_index(tmp_path):
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
     from oracle import ref_path as R
-    mp.spawn(_topk_peer_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    _spawn(_topk_peer_worker, (str(tmp_path),))
     r0 = torch.load(tmp_path / "topk_peer_0.pt")
     r1 = torch.load(tmp_path / "topk_peer_1.pt")
     fallbacks = {}
