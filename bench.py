@@ -161,7 +161,8 @@ class TimedLib:
 
     def __getattr__(self, name):
         fn = getattr(self._lib, name)
-        if not name.startswith("nrx_") or name.endswith("_bytes") or name in ("nrx_last_error", "nrx_version", "nrx_tower_image_layout"):
+        if not name.startswith("nrx_") or name.endswith("_bytes") or name in ("nrx_last_error", "nrx_version", "nrx_tower_image_layout",
+                                                                                   "nrx_embed_bwd_plan_is_staged"):
             return fn
 
         def timed(*a):
@@ -199,8 +200,9 @@ def profile_apis(trainer, pool, n=10):
         trainer.graph = graph
         trainer._restore(snap)
     agg = {}
+    alias = {"nrx_embed_bwd_plan_stage": "nrx_embed_bwd_plan"}   # the plan enqueued in two halves is still one call of the path
     for name, s, e in rec:
-        agg.setdefault(name, []).append(s.elapsed_time(e) * 1e3)  # us
+        agg.setdefault(alias.get(name, name), []).append(s.elapsed_time(e) * 1e3)  # us
     return {k: sum(v) / len(v) * (len(v) / n) for k, v in agg.items()}, per_step_launches  # us per step per API
 
 
@@ -255,6 +257,14 @@ def algorithmic(kind, cfg, B, table_update="sparse"):
         "nrx_embed_bwd_apply": ("hbm", apply_bytes),
         "nrx_adamw_dense_dev": ("hbm", adamw_bytes),
     }
+
+
+def _retrieval_traffic():
+    """DRAM bytes of one cfg4 search from the committed ncu launch list (profiles/roofline_traffic.json), or None."""
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if not os.path.exists(tpath):
+        return None
+    return json.load(open(tpath)).get("retrieval", {}).get("nrx_topk_search")
 
 
 def retrieval_leg(dev, world, rank, dist, quick):
@@ -360,7 +370,12 @@ def retrieval_leg(dev, world, rank, dist, quick):
            "e2e": {"value": Q / (e2e_ms * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": Q * D * 4, "d2h_bytes_per_step": Q * K * 12},
            "index_build_s": build_s, "fallback_queries": fb, "sharded": sharded,
            "roofline": {"bound": "tensor", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
-                        "traffic": None, "kernel": "nrx_topk_search (query pack + sample scan of 1/8 of the tiles + theta + one full filter scan + final)", "peak_source": peak_src,
+                        "traffic": _retrieval_traffic() if world == 1 else None,
+                        "kernel": ("nrx_topk_search (query pack + sample scan of 1/8 of the tiles + theta + one full filter scan + final)"
+                                   if world == 1 else
+                                   "nrx_topk_search_peer, one CUDA graph per rank (shard scan + shard-side final + flag barrier + "
+                                   "owner-side merge / proof / exact re-scan + flag barrier)"),
+                        "peak_source": peak_src,
                         "algorithmic_per_launch": flops}}
     if world == 1 and not quick:
         # what faiss-cpu's IndexFlatIP does: blocked fp32 sgemm + top-k selection (no sort of the whole row); the oracle's
@@ -854,7 +869,7 @@ def main():
             "kernel": dom, "kernel_us": per_api[dom], "peak_source": peak_src,
             "algorithmic_per_launch": qty,
             "note": "dominant C-ABI call on the main stream (a call may be 2 kernels); at this batch every kernel moves a few MB "
-                    "/ a few GFLOP and is launch-latency bound - the same kernels at B up to 1M are in profiles/r1_kernel_sweep_final.json"}
+                    "/ a few GFLOP and is launch-latency bound - the same kernels at B up to 1M are in profiles/r2_kernel_sweep_final.log"}
     breakdown = {}
     for k, us in sorted(per_api.items(), key=lambda kv: -kv[1]):
         b_, q_ = alg.get(k, ("hbm", 0))

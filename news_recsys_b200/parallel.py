@@ -619,8 +619,9 @@ class ShardedTopk:
     all-gathered with their fp64 keys and merged on every rank (works across nodes; per-query work does not shrink)."""
 
     def __init__(self, local_corpus: torch.Tensor, n_total: int, group=None, exchange: str = "peer",
-                 peer_timeout_ms: int = 20000, kprime: int = 0):
+                 peer_timeout_ms: int = 20000, kprime: int = 0, use_graph: Optional[bool] = None):
         from .retrieval import TopkIndex
+        self.use_graph = (os.environ.get("NRX_TOPK_GRAPH", "1") == "1") if use_graph is None else bool(use_graph)
         self.kprime = int(kprime)     # per-shard threshold rank of the peer search; 0 = library default
         if exchange not in ("peer", "nccl"):
             raise L.NrxError(f"exchange must be 'peer' or 'nccl', got {exchange!r}")
@@ -656,7 +657,7 @@ class ShardedTopk:
         return self.index.search(queries, k)
 
     # -- peer path ----------------------------------------------------------------------------------------------
-    def _peer_state(self, Q: int, k: int, dev):
+    def _peer_state(self, Q: int, k: int, dev, warm_queries: Optional[torch.Tensor] = None):
         """Inbox + result buffers for (Q, k), mapped on every rank (collective: every rank must search the same shapes)."""
         key = (Q, k)
         st = self._peer.get(key)
@@ -679,20 +680,47 @@ class ShardedTopk:
                          dtype=torch.uint8, device=dev)
         st = dict(desc=d, keep=(inbox, out_s, out_i), ws=ws,
                   out_s=out_s.tensor()[: Q * k].view(Q, k), out_i=out_i.tensor()[: Q * k * 2].view(torch.int64).view(Q, k),
-                  status=torch.zeros(max(Q, 1), dtype=torch.int32, device=dev))
+                  status=torch.zeros(max(Q, 1), dtype=torch.int32, device=dev),
+                  q=torch.zeros((max(Q, 1), self.index.D), dtype=torch.float32, device=dev), graph=None)
         self._peer[key] = st
+        if Q and self.use_graph:
+            # One search = 10 kernels + 2 memsets; enqueued one by one through ctypes the HOST is the bottleneck once the
+            # shards are small (8 GPUs: ~120 us of device work per search).  Capture the whole search — flag barriers
+            # included, as K7 does — and replay it: every rank captures the same sequence, so replays pair up like launches.
+            if warm_queries is not None:
+                st["q"].copy_(warm_queries.detach())
+            self._launch_peer(st, Q, k)                 # eager once: lazy module loading must not happen inside capture
+            torch.cuda.synchronize(dev)
+            dist.barrier(group=self.group)
+            g = torch.cuda.CUDAGraph()
+            cs = torch.cuda.Stream(device=dev)
+            cs.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(cs), torch.cuda.graph(g, stream=cs):
+                self._launch_peer(st, Q, k)
+            torch.cuda.current_stream(dev).wait_stream(cs)
+            st["graph"] = g
         return st
+
+    def _launch_peer(self, st, Q: int, k: int):
+        q = st["q"]
+        L.check(self.lib.nrx_topk_search_peer(self.index.index.data_ptr(), self.index.N, self.index.D, q.data_ptr(), q.stride(0), Q, k,
+                                              C.byref(st["desc"]), st["status"].data_ptr(), st["ws"].data_ptr(), st["ws"].numel(),
+                                              L.stream_ptr(q.device)), "nrx_topk_search_peer")
 
     def search_peer_(self, queries: torch.Tensor, k: int):
         """The peer search without the result copy: returns views of this rank's (re-used) output buffers, valid until the
         next search of the same (Q, k).  One enqueue, no host synchronisation."""
-        q = queries.detach().float().contiguous()
-        Q = q.shape[0]
-        st = self._peer_state(Q, k, q.device)
+        Q = queries.shape[0]
+        if not queries.is_cuda:
+            raise L.NrxError("ShardedTopk: queries must be CUDA tensors")
+        st = self._peer_state(Q, k, queries.device, warm_queries=queries)
         if Q:
-            L.check(self.lib.nrx_topk_search_peer(self.index.index.data_ptr(), self.index.N, self.index.D, q.data_ptr(), q.stride(0), Q, k,
-                                                  C.byref(st["desc"]), st["status"].data_ptr(), st["ws"].data_ptr(), st["ws"].numel(),
-                                                  L.stream_ptr(q.device)), "nrx_topk_search_peer")
+            st["q"].copy_(queries.detach(), non_blocking=True)     # the search reads its static query buffer
+            if st["graph"] is not None:
+                st["graph"].replay()
+                L.launch_count += L.KERNELS_PER_CALL["nrx_topk_search_peer"]
+            else:
+                self._launch_peer(st, Q, k)
         return st["out_s"], st["out_i"]
 
     def exact_fallbacks(self, Q: int, k: int) -> int:
