@@ -234,15 +234,30 @@ dcn_cross_bwd_v4_kernel(const float* __restrict__ x, long long ld, long long B, 
       bb[l][k] = c < d ? __ldg(reinterpret_cast<const float4*>(P.b[l] + c)) : z4;
     }
   const long long warps_total = (long long)gridDim.x * 8;
-  for (long long row = (long long)blockIdx.x * 8 + warp; row < B; row += warps_total) {
+  // software pipeline: the three row loads of the NEXT row are in flight while this row's chain is recomputed (one row at
+  // a time left every warp idle for a full memory round trip per row: 1.5 TB/s at B = 65536)
+  float4 nx0[NV], ng[NV], ng0[NV];
+  long long row = (long long)blockIdx.x * 8 + warp;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int c = 4 * (lane + 32 * k);
+    const bool ok = c < d && row < B;
+    nx0[k] = ok ? __ldg(reinterpret_cast<const float4*>(x + row * ld + c)) : z4;
+    ng0[k] = ok ? __ldg(reinterpret_cast<const float4*>(go + row * gold + c)) : z4;       // d/dx through the concat's first half
+    ng[k] = ok ? __ldg(reinterpret_cast<const float4*>(go + row * gold + d + c)) : z4;    // d/dx_L
+  }
+  for (; row < B; row += warps_total) {
     float4 x0[NV], xs[LC][NV], g[NV], g0[NV];
     float s[LC];
+    const long long nrow = row + warps_total;
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
+      x0[k] = nx0[k]; g0[k] = ng0[k]; g[k] = ng[k];
       const int c = 4 * (lane + 32 * k);
-      x0[k] = c < d ? __ldg(reinterpret_cast<const float4*>(x + row * ld + c)) : z4;
-      g0[k] = c < d ? __ldg(reinterpret_cast<const float4*>(go + row * gold + c)) : z4;       // d/dx through the concat's first half
-      g[k] = c < d ? __ldg(reinterpret_cast<const float4*>(go + row * gold + d + c)) : z4;    // d/dx_L
+      const bool ok = c < d && nrow < B;
+      nx0[k] = ok ? __ldg(reinterpret_cast<const float4*>(x + nrow * ld + c)) : z4;
+      ng0[k] = ok ? __ldg(reinterpret_cast<const float4*>(go + nrow * gold + c)) : z4;
+      ng[k] = ok ? __ldg(reinterpret_cast<const float4*>(go + nrow * gold + d + c)) : z4;
     }
     // recompute the chain, keeping x_l (input of layer l) and s_l = x_l . w_l
 #pragma unroll
