@@ -340,6 +340,20 @@ def retrieval_leg(dev, world, rank, dist, quick):
                    "parity_check": "ids and scores of the peer search == per-shard complete lists all-gathered with fp64 keys and merged, on every rank",
                    f"ms_per_search_{other.exchange}": float(t_o.item())}
         del other
+    # single-query latency ("also report Q=1 latency"): one search of one query, device-timed
+    q1_ms = None
+    if world == 1:
+        q1 = queries[0][:1].contiguous()
+        for _ in range(3):
+            search(q1)
+        torch.cuda.synchronize()
+        e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e4.record()
+        for _ in range(iters):
+            search(q1)
+        e5.record()
+        torch.cuda.synchronize()
+        q1_ms = e4.elapsed_time(e5) / iters
     # end to end: pinned host queries -> H2D -> search -> D2H of (scores, ids)
     hq = [q.cpu().pin_memory() for q in queries]
     hs = torch.empty((Q, K), dtype=torch.float32).pin_memory()
@@ -368,7 +382,7 @@ def retrieval_leg(dev, world, rank, dist, quick):
            "config": {"workload": "cfg4: N=1,000,000 x D=128 L2-normalised, k=100, Q=1024 per search", "shards": world,
                       "ordering": "(fp64 inner product desc, id asc), bit-exact vs oracle"},
            "e2e": {"value": Q / (e2e_ms * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": Q * D * 4, "d2h_bytes_per_step": Q * K * 12},
-           "index_build_s": build_s, "fallback_queries": fb, "sharded": sharded,
+           "index_build_s": build_s, "fallback_queries": fb, "sharded": sharded, "q1_latency_ms": q1_ms,
            "roofline": {"bound": "tensor", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
                         "traffic": _retrieval_traffic() if world == 1 else None,
                         "kernel": ("nrx_topk_search (query pack + sample scan of 1/8 of the tiles + theta + one full filter scan + final)"
@@ -844,6 +858,30 @@ def main():
                                               "note": ("lazy rows: fused sparse-row AdamW inside K3, untouched rows do not decay"
                                                        if other == "sparse" else "the reference's dense AdamW over every row")}}
         del tr2
+        # ids both uniform and Zipf(1.05) (heavy-tailed click popularity: many duplicate rows per batch in the
+        # sorted backward).  Same trainer, same timing rules, a second device pool of Zipf batches.
+        from news_recsys_b200.synthetic import synth_batch
+        zpool = torch.empty((n_pool, trainer.layout.nbytes), dtype=torch.uint8, device=dev)
+        zhost = torch.empty(trainer.layout.nbytes, dtype=torch.uint8)
+        for i in range(4):
+            trainer.layout.pack(synth_batch(cfg, B, seed=777 + i, zipf=1.05), zhost)
+            zpool[i::4].copy_(zhost.to(dev).unsqueeze(0).expand(zpool[i::4].shape[0], -1))
+        snap = trainer._snapshot()
+        for i in range(max(args.warmup, 3)):
+            trainer.load_blob(zpool[i % zpool.shape[0]]); trainer.step()
+        torch.cuda.synchronize()
+        v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        v0.record()
+        for i in range(args.steps):
+            trainer.load_blob(zpool[(i + 3) % zpool.shape[0]]); trainer.step()
+        v1.record()
+        torch.cuda.synchronize()
+        zms = v0.elapsed_time(v1)
+        trainer._restore(snap)
+        variants["ids=zipf(1.05)"] = {"value": B * args.steps / (zms * 1e-3), "unit": UNIT, "ms_per_step": zms / args.steps,
+                                      "note": "the headline step on Zipf-distributed ids (the headline draws ids uniformly); "
+                                              f"device pool of {zpool.shape[0]} slots ({zpool.numel() / 1e6:.0f} MB)"}
+        del zpool
     per_api, launches_per_step = profile_apis(prof_trainer, pool, n=2 if args.quick else 10)
     alg = algorithmic(kind, cfg, B, args.table_update)
     hbm_peak, tf_peak, peak_src = peaks()

@@ -1,5 +1,11 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout -s KILL 900 python -m pytest tests/test_gpu_embed.py tests/test_gpu_trainer.py tests/test_gpu_fullsize.py -x -q -m gpu 2>&1 | tail -n 3
-NRX_BENCH_LEGS=cfg1 timeout -s KILL 600 python bench.py --no-retrieval --steps 50 --warmup 5 --cpu-steps 1 2>/dev/null | python -c "
-import json,sys; j=json.loads(sys.stdin.read()); v=j['legs']['cfg1_deep_hist']; print(v['value'], v['ms_per_step']); [print('  ',k,x) for k,x in v['kernels'].items()]"
+timeout -s KILL 900 python bench.py --steps 100 --warmup 10 > gpurun_out/r2_bench_n1_final.json 2> gpurun_out/r2_bench_n1_final.err
+tail -n 3 gpurun_out/r2_bench_n1_final.err
+python - <<'PY'
+import json
+j=json.load(open('gpurun_out/r2_bench_n1_final.json')); r=j['retrieval']
+print(j['n_gpus'], j['value'], j['ms_per_step'], j['e2e']['value'], j['roofline']['kernel'], round(j['roofline']['frac'],4))
+print('  ', {k:(round(v['value']/1e6,1), round(v['ms_per_step'],4)) for k,v in j['legs'].items()}, r['value'], r['ms_per_search'], r['e2e']['value'], r['q1_latency_ms'])
+print(j['variants'])
+PY
