@@ -264,6 +264,136 @@ fm_fused_kernel(const __grid_constant__ DFeats P, long long B, int LPF, const fl
   }
 }
 
+// ---- gather-fused FM, one THREAD per sample (field width D = 4 * NQ <= 32) -----------------------------------------
+// The warp-cooperative kernel above spends ~200 warp instructions per sample (shuffle trees, divergent descriptor reads,
+// 12 of 32 lanes idle at 5 fields x 4 columns): instruction-bound at 0.19 of the HBM peak.  Here a thread keeps S_d of its
+// sample in registers: ids are read coalesced across the warp, every row is four independent 16-byte loads (both
+// sectors of the 64-byte row used), no shuffles, field descriptors are warp-uniform constant reads: ~7 warp instructions
+// per sample.  Backward: the same gather again (L1 / L2 hits), then grad_x rows as 16-byte stores.
+template <int NQ, bool BWD>
+__global__ void __launch_bounds__(128)
+fm_fused_tps_kernel(const __grid_constant__ DFeats P, long long B, const float* __restrict__ bias,
+                    const float* __restrict__ label, long long lstride, float* __restrict__ logit,
+                    float* __restrict__ prob, float* __restrict__ loss, float* __restrict__ dlogit,
+                    const float* __restrict__ dlogit_in, float* __restrict__ gx, long long gld, int* __restrict__ status,
+                    int stage_w4, int stage_col0) {
+  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = b < B;
+  if (!live && !(BWD && stage_w4 > 0)) return;   // staged stores are warp-cooperative: tail threads stay for the copy-out
+  float4 S[NQ];
+#pragma unroll
+  for (int k = 0; k < NQ; ++k) S[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  float first = 0.f, sq = 0.f;
+  bool bad = false;
+  for (int f = 0; f < P.n; ++f) {
+    const DFeat& F = P.f[f];
+    const long long id = live ? load_idx(F.idx, b, F.idx32) : 0;
+    const bool ok = (unsigned long long)id < (unsigned long long)F.rows;
+    bad |= !ok;
+    const float4* row = reinterpret_cast<const float4*>(F.table + (ok ? id : 0) * F.stride);
+    float4 v[NQ];
+#pragma unroll
+    for (int k = 0; k < NQ; ++k) v[k] = ok ? __ldg(row + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (BWD && stage_w4 > 0) {   // keep the rows for the second pass (no second gather)
+      extern __shared__ __align__(16) float4 stage[];
+      float4* keep = stage + (size_t)threadIdx.x * (stage_w4 + 1) + (F.out_col - stage_col0) / 4;
+#pragma unroll
+      for (int k = 0; k < NQ; ++k) keep[k] = v[k];
+    }
+    first += v[0].x;
+    v[0].x = 0.f;   // column 0 is the first-order weight
+#pragma unroll
+    for (int k = 0; k < NQ; ++k) {
+      S[k].x += v[k].x; S[k].y += v[k].y; S[k].z += v[k].z; S[k].w += v[k].w;
+      sq += v[k].x * v[k].x + v[k].y * v[k].y + v[k].z * v[k].z + v[k].w * v[k].w;
+    }
+  }
+  if (!BWD) {
+    float ss = 0.f;
+#pragma unroll
+    for (int k = 0; k < NQ; ++k) ss += S[k].x * S[k].x + S[k].y * S[k].y + S[k].z * S[k].z + S[k].w * S[k].w;
+    const float z = (bias ? __ldg(bias) : 0.f) + first + 0.5f * (ss - sq);
+    if (logit) logit[b] = z;
+    const float p = sigmoid_f(z);
+    if (prob) prob[b] = p;
+    if (label) bce_terms(p, __ldg(label + b * lstride), 1.f / (float)B, loss ? loss + b : nullptr, dlogit ? dlogit + b : nullptr);
+    if (bad && status) atomicOr(status, 1);
+  } else {
+    // grad_x rows: written through shared memory when the fields tile one contiguous column range (stage_w4 > 0), so that
+    // a warp stores its 32 rows as whole 16-byte-per-lane coalesced lines instead of 32 scattered half sectors per store
+    extern __shared__ __align__(16) float4 stage[];   // [128][stage_w4 + 1]
+    const float g = live ? __ldg(dlogit_in + b) : 0.f;
+    for (int f = 0; f < P.n; ++f) {
+      const DFeat& F = P.f[f];
+      float4* dst = stage_w4 > 0 ? stage + (size_t)threadIdx.x * (stage_w4 + 1) + (F.out_col - stage_col0) / 4
+                                 : reinterpret_cast<float4*>(gx + b * gld + F.out_col);
+      bool ok = false;
+      const float4* row = nullptr;
+      if (stage_w4 == 0) {   // no staging buffer: gather the row again (L1 / L2 hit)
+        const long long id = live ? load_idx(F.idx, b, F.idx32) : 0;
+        ok = live && (unsigned long long)id < (unsigned long long)F.rows;
+        row = reinterpret_cast<const float4*>(F.table + (ok ? id : 0) * F.stride);
+      }
+#pragma unroll
+      for (int k = 0; k < NQ; ++k) {
+        float4 v = stage_w4 > 0 ? dst[k] : (ok ? __ldg(row + k) : make_float4(0.f, 0.f, 0.f, 0.f));
+        if (k == 0) v.x = 0.f;   // (unused below: column 0 takes g)
+        float4 o;
+        o.x = (k == 0) ? g : g * (S[k].x - v.x);
+        o.y = g * (S[k].y - v.y); o.z = g * (S[k].z - v.z); o.w = g * (S[k].w - v.w);
+        if (live || stage_w4 > 0) dst[k] = o;
+      }
+    }
+    if (stage_w4 > 0) {
+      __syncwarp();
+      const int lane = threadIdx.x & 31, w0 = threadIdx.x & ~31;      // this warp's 32 rows
+      const long long bw = (long long)blockIdx.x * blockDim.x + w0;
+      for (int i = lane; i < 32 * stage_w4; i += 32) {
+        const int r = i / stage_w4, c = i - r * stage_w4;
+        if (bw + r < B)
+          *reinterpret_cast<float4*>(gx + (bw + r) * gld + stage_col0 + 4 * c) = stage[(size_t)(w0 + r) * (stage_w4 + 1) + c];
+      }
+    }
+  }
+}
+
+template <bool BWD>
+static bool launch_fm_tps(const DFeats& d, long long B, int LPF, const float* bias, const float* label, long long lstride,
+                          float* logit, float* prob, float* loss, float* dlogit, const float* dlogit_in, float* gx, long long gld,
+                          int* status, cudaStream_t st) {
+  if (getenv("NRX_FM_WARP") != nullptr) return false;   // keep the warp-cooperative kernel reachable for A/B runs
+  const unsigned blocks = (unsigned)((B + 127) / 128);
+  // backward: do the fields tile ONE contiguous column range of grad_x?  then rows go out through shared memory
+  int w4 = 0, col0 = 0;
+  size_t smem = 0;
+  if (BWD) {
+    int lo = d.f[0].out_col, hi = lo;
+    bool used[NRX_MAX_FEATS * 32] = {false};
+    for (int i = 0; i < d.n; ++i) lo = d.f[i].out_col < lo ? d.f[i].out_col : lo;
+    bool tiled = true;
+    for (int i = 0; i < d.n && tiled; ++i) {
+      const int q = (d.f[i].out_col - lo) / (4 * LPF);
+      tiled = (d.f[i].out_col - lo) % (4 * LPF) == 0 && q < d.n && !used[q];
+      if (tiled) used[q] = true;
+      hi = d.f[i].out_col + 4 * LPF > hi ? d.f[i].out_col + 4 * LPF : hi;
+    }
+    if (tiled && hi - lo == d.n * 4 * LPF && (size_t)128 * (d.n * LPF + 1) * 16 <= 96 * 1024) {
+      w4 = d.n * LPF; col0 = lo;
+      smem = (size_t)128 * (w4 + 1) * 16;
+    }
+  }
+#define NRX_FM_TPS(NQ) do { if (smem > 48 * 1024) cudaFuncSetAttribute(fm_fused_tps_kernel<NQ, BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    fm_fused_tps_kernel<NQ, BWD><<<blocks, 128, smem, st>>>(d, B, bias, label, lstride, logit, prob, loss, dlogit, dlogit_in, gx, gld, status, w4, col0); } while (0)
+  switch (LPF) {
+    case 1: NRX_FM_TPS(1); return true;
+    case 2: NRX_FM_TPS(2); return true;
+    case 4: NRX_FM_TPS(4); return true;
+    case 8: NRX_FM_TPS(8); return true;
+    default: return false;
+  }
+#undef NRX_FM_TPS
+}
+
 static int fm_fused_check(const DFeats& d, int* LPF) {
   NRX_REQUIRE(d.n_array == 0, NRX_EUNSUPPORTED, "fm_fused: array features go through embed_pool + field_logit");
   const int D = d.f[0].dim;
@@ -458,6 +588,8 @@ extern "C" int nrx_fm_fused_fwd(const NrxFeat* h_feats, int n_feats, int64_t B, 
   if (rc != NRX_OK) return rc;
   if (B == 0) return NRX_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  if (launch_fm_tps<false>(d, B, LPF, bias, label, label_stride, logit, prob, loss_per_sample, dlogit, nullptr, nullptr, 0, status, st))
+    return check_launch("fm_fused_fwd");
   if (B < (long long)sm_count() * 64)
     fm_fused_kernel<2, false><<<warps_grid((B + 1) / 2, 8), 256, 0, st>>>(d, B, LPF, bias, label, label_stride, logit, prob,
                                                                         loss_per_sample, dlogit, nullptr, nullptr, 0, status);
@@ -480,6 +612,8 @@ extern "C" int nrx_fm_fused_bwd(const NrxFeat* h_feats, int n_feats, int64_t B, 
   for (int i = 0; i < d.n; ++i) NRX_REQUIRE(d.f[i].out_col + d.f[i].dim <= grad_ld, NRX_EINVAL, "feature %d overruns grad_ld", i);
   if (B == 0) return NRX_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  if (launch_fm_tps<true>(d, B, LPF, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr, dlogit, grad_x, grad_ld, nullptr, st))
+    return check_launch("fm_fused_bwd");
   if (B < (long long)sm_count() * 64)
     fm_fused_kernel<2, true><<<warps_grid((B + 1) / 2, 8), 256, 0, st>>>(d, B, LPF, nullptr, nullptr, 0, nullptr, nullptr, nullptr,
                                                                        nullptr, dlogit, grad_x, grad_ld, nullptr);
