@@ -712,7 +712,7 @@ def main():
         from news_recsys_b200.parallel import DataParallelTrainer
         trainer = DataParallelTrainer(model, B, kind=kind, table_update=args.table_update, exchange=args.exchange)
     else:
-        trainer = FusedTrainer(model, B, kind=kind, table_update=args.table_update)
+        trainer = FusedTrainer(model, B, kind=kind, table_update=args.table_update, dense_impl=os.environ.get('NRX_DENSE_IMPL', 'flat'))
     # batch pools: device pool > L2 (126 MB) so consecutive steps never find their inputs in L2
     blob_bytes = trainer.layout.nbytes
     n_pool = 8 if args.quick else max(8, int(160e6 // blob_bytes) + 1)  # --quick (profiler runs): few setup kernels

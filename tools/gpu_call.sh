@@ -1,4 +1,6 @@
 #!/bin/bash
-mkdir -p gpurun_out
-timeout -s KILL 900 python -m pytest tests/test_gpu_embed.py tests/test_gpu_models.py tests/test_gpu_trainer.py tests/test_gpu_fullsize.py -x -q -m gpu 2>&1 | tail -n 3
-timeout -s KILL 300 python tools/profile_kernels.py --only fm --sizes 16384,65536,262144,1048576 2>&1 | grep "K2"
+timeout -s KILL 600 python -m pytest tests/test_gpu_trainer.py tests/test_gpu_peer.py -x -q -m gpu 2>&1 | tail -n 2
+for i in 1 2; do
+timeout -s KILL 600 python bench.py --no-legs --no-retrieval --steps 200 --warmup 20 --cpu-steps 1 2>/dev/null | python -c "
+import json,sys; j=json.loads(sys.stdin.read()); print(j['value'], j['ms_per_step'], j['e2e']['value'], j['kernels']['nrx_adamw_dense_dev'])"
+done
