@@ -92,8 +92,14 @@ class DSSM(BaseModel):
 
     # ---- retrieval (on_train_epoch_end :230-254, hit_rate :209) ---------------------------------------
     @torch.no_grad()
-    def build_item_index(self, item_batches, id_base=0, item_key="item_id"):
+    def build_item_index(self, item_batches, id_base=0, item_key="item_id", group=None, n_total=None):
         """Item tower over the corpus (list of batches with the item features) -> normalised vectors -> index.
+
+        Sharded refresh (BASELINE config 4): with `group` (a torch.distributed group of > 1 ranks on one node) every rank
+        passes only ITS contiguous share of the corpus — rows shard_range(n_total, rank, world) in rank order —, runs the
+        item tower over that share and keeps it behind parallel.ShardedTopk (one peer-memory search per query batch, the
+        result identical on every rank and to a single index over the whole corpus); the item-id columns are all-gathered
+        once so that every rank can map global positions to item ids.
 
         The reference keeps `idx_item_emb_dic`: corpus position -> item id, filled from the id column of every corpus
         batch (`on_train_epoch_end`, recall/DSSM/model.py:236-247) and maps search results through it before the history
@@ -102,13 +108,44 @@ class DSSM(BaseModel):
         without that column fall back to position + id_base (the identity mapping of an id-ordered corpus)."""
         embs = [ops.l2_normalize(self.item_tower(b)) for b in item_batches]
         self.all_item_embeddings = torch.cat(embs, dim=0)
-        self.index = TopkIndex(self.all_item_embeddings, id_base=0)
+        dev = self.all_item_embeddings.device
+        n_local = self.all_item_embeddings.shape[0]
         if all(item_key in b for b in item_batches):
-            self.index_item_ids = torch.cat([b[item_key].reshape(-1).to(self.all_item_embeddings.device, torch.int64) for b in item_batches])
+            ids = torch.cat([b[item_key].reshape(-1).to(dev, torch.int64) for b in item_batches])
         else:
-            self.index_item_ids = torch.arange(self.all_item_embeddings.shape[0], device=self.all_item_embeddings.device) + int(id_base)
-        if self.index_item_ids.numel() != self.all_item_embeddings.shape[0]:
+            ids = None
+        if ids is not None and ids.numel() != n_local:
             raise ValueError("build_item_index: the item id column and the corpus disagree on the number of items")
+        world = 1
+        if group is not None:
+            import torch.distributed as dist
+            world = dist.get_world_size(group)
+        if world > 1:
+            import torch.distributed as dist
+            from ....parallel import ShardedTopk, shard_range
+            counts = torch.zeros(world, dtype=torch.int64, device=dev)
+            counts[dist.get_rank(group)] = n_local
+            dist.all_reduce(counts, group=group)
+            total = int(counts.sum().item())
+            if n_total is not None and int(n_total) != total:
+                raise ValueError(f"build_item_index: the shards hold {total} items, n_total says {n_total}")
+            lo, hi = shard_range(total, dist.get_rank(group), world)
+            if hi - lo != n_local:
+                raise ValueError(f"build_item_index: this rank must hold rows [{lo}, {hi}) of the corpus ({hi - lo} items), "
+                                 f"got {n_local} (shards are the contiguous ranges of parallel.shard_range)")
+            self.index = ShardedTopk(self.all_item_embeddings, total, group=group)
+            if ids is None:
+                self.index_item_ids = torch.arange(total, device=dev) + int(id_base)
+            else:   # shard sizes differ by at most one: pad to the largest, gather, cut the padding out again
+                cap = int(counts.max().item())
+                padded = torch.full((cap,), -1, dtype=torch.int64, device=dev)
+                padded[:n_local] = ids
+                allp = torch.empty((world, cap), dtype=torch.int64, device=dev)
+                dist.all_gather_into_tensor(allp, padded, group=group)
+                self.index_item_ids = torch.cat([allp[r, : int(counts[r])] for r in range(world)])
+            return self.index
+        self.index = TopkIndex(self.all_item_embeddings, id_base=0)
+        self.index_item_ids = ids if ids is not None else torch.arange(n_local, device=dev) + int(id_base)
         return self.index
 
     @staticmethod

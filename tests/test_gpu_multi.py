@@ -278,3 +278,63 @@ def test_sharded_topk_over_peer_memory_equals_one_index(tmp_path):
     assert fallbacks["random"] == 0, "the filter path must serve well-separated queries"
     assert fallbacks["clustered"] >= 3, "the clustered queries must go through the owner-side exact scan"
     assert fallbacks["tiny"] == 1 and fallbacks["k_gt_n"] == 5
+
+
+# --------------------------------------------------------------------------- sharded corpus refresh of the DSSM model (f3)
+def _dssm_cfg():
+    from news_recsys_b200.synthetic import mind_config
+    rows = {"user_id": 500, "item_id": 3002, "category": 18, "subcategory": 70, "user_click_category": 18}   # item ids 1..3001
+    return mind_config("deep", rows, history_len=6)
+
+
+def _dssm_sharded_worker(rank, world, port, out_dir):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import torch.distributed as dist
+    from news_recsys_b200.model.recall.DSSM.model import DSSM
+    from news_recsys_b200.parallel import shard_range
+    from news_recsys_b200.synthetic import synth_batch
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = f"cuda:{rank}"
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    cfg = _dssm_cfg()
+    torch.manual_seed(1)
+    m = DSSM(cfg, hparams={"out_dim": 16}).to(dev)
+    N = 3001
+    items = synth_batch(cfg, N, seed=2)
+    items["item_id"] = torch.randperm(N, generator=torch.Generator().manual_seed(5)) + 1    # position -> item id, not identity
+    lo, hi = shard_range(N, rank, world)
+    mine = {k: v[lo:hi].to(dev) for k, v in items.items()}
+    m.build_item_index([mine], group=dist.group.WORLD, n_total=N)
+    users = {k: v.to(dev) for k, v in synth_batch(cfg, 77, seed=11).items()}
+    s, ids = m.retrieve_items(users, 25)
+    torch.save((s.cpu(), ids.cpu(), m.index_item_ids.cpu()), os.path.join(out_dir, f"dssm_sh_{rank}.pt"))
+    dist.destroy_process_group()
+
+
+def test_dssm_sharded_corpus_refresh_equals_single_index(tmp_path):
+    """DSSM.build_item_index(group=...): every rank embeds and indexes only its share of the corpus; retrieve_items over
+    the sharded index == the same model with one index over the whole corpus (item ids bit-equal, position -> id map
+    included), on every rank."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from news_recsys_b200.model.recall.DSSM.model import DSSM
+    from news_recsys_b200.synthetic import synth_batch
+    _spawn(_dssm_sharded_worker, (str(tmp_path),))
+    s0, i0, map0 = torch.load(tmp_path / "dssm_sh_0.pt")
+    s1, i1, map1 = torch.load(tmp_path / "dssm_sh_1.pt")
+    assert torch.equal(i0, i1) and torch.equal(s0, s1) and torch.equal(map0, map1)
+    cfg = _dssm_cfg()
+    torch.manual_seed(1)
+    m = DSSM(cfg, hparams={"out_dim": 16}).cuda()
+    N = 3001
+    items = synth_batch(cfg, N, seed=2)
+    items["item_id"] = torch.randperm(N, generator=torch.Generator().manual_seed(5)) + 1
+    m.build_item_index([{k: v.cuda() for k, v in items.items()}])
+    users = {k: v.cuda() for k, v in synth_batch(cfg, 77, seed=11).items()}
+    s, ids = m.retrieve_items(users, 25)
+    assert torch.equal(map0, m.index_item_ids.cpu())
+    assert torch.equal(i0, ids.cpu())
+    torch.testing.assert_close(s0, s.cpu(), rtol=1e-6, atol=1e-7)
