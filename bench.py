@@ -206,6 +206,17 @@ def profile_apis(trainer, pool, n=10):
     return {k: sum(v) / len(v) * (len(v) / n) for k, v in agg.items()}, per_step_launches  # us per step per API
 
 
+def _binding(flops, nbytes):
+    """(bound, algorithmic quantity) of a tower call: the roofline that BINDS is the one with the larger time floor at
+    the measured peaks.  At these layer widths (<= 224 -> 128 -> 128 -> 128 -> 64 -> 1) a training pass has to move the saved
+    bf16 activation / dz images through HBM: ~50-100 flop per byte, well under the ridge (1725 TF/s / 6.45 TB/s = 267
+    flop/B), so forward-with-save, dX and dW are HBM-bound; only the inference forward is tensor-bound."""
+    hbm_peak, tf_peak, _ = peaks()
+    t_tensor = flops / (tf_peak * 1e12)
+    t_hbm = nbytes / (hbm_peak * 1e9)
+    return ("tensor", flops) if t_tensor >= t_hbm else ("hbm", nbytes)
+
+
 def algorithmic(kind, cfg, B, table_update="sparse"):
     """Algorithmic bytes / flops per launch of each API (formulas in DESIGN.md §Kernels)."""
     emb = cfg["embeddings"]
@@ -229,6 +240,8 @@ def algorithmic(kind, cfg, B, table_update="sparse"):
     mlp_in = {"deep": sd, "deepfm": sd, "dcn": 2 * sd, "widedeep": sd}.get(kind, 0)
     layers = [mlp_in, 128, 128, 128, 64, 1]
     tower_flops = 2 * sum(layers[i] * layers[i + 1] for i in range(5)) if mlp_in else 0
+    # bf16 tile images of the hidden activations a_1..a_4 a TRAINING forward saves (2 bytes per unit); dz images are the same size
+    tower_img_bytes = 2 * sum(layers[1:5]) if mlp_in else 0
     uniq_row_bytes = sum(dims[n] * 4 * 7 for n in names if n not in arr) + sum((feats["array_max_length"][n] / 2) * dims[n] * 4 * 7 for n in arr)
     n_table = sum(emb["embedding_table_size"][t] * emb["embedding_size"][t] for t in emb["embedding_size"])
     n_tower = sum(layers[i] * layers[i + 1] + layers[i + 1] for i in range(5)) if mlp_in else 0
@@ -244,13 +257,15 @@ def algorithmic(kind, cfg, B, table_update="sparse"):
         "nrx_field_logit_fwd": ("hbm", B * (4 * sd + 4)),
         "nrx_field_logit_bwd": ("hbm", B * (4 * sd + 4 + 8 * sd)),
         "nrx_logit_loss_fwd": ("hbm", B * 24),
-        "nrx_tower_fwd": ("tensor", B * tower_flops),
-        "nrx_tower_fwd_head": ("tensor", B * tower_flops),
+        "nrx_tower_fwd": _binding(B * tower_flops, B * (2 * mlp_in + tower_img_bytes)),
+        "nrx_tower_fwd_head": _binding(B * tower_flops, B * (2 * mlp_in + tower_img_bytes + 16)),
         "nrx_embed_pool_fwd_img": ("hbm", B * (k1 - 4 * sd + 2 * sd + (4 * sd if kind != "deep" else 0))),
         "nrx_dcn_cross_fwd_img": ("hbm", B * (4 * sd + 2 * 2 * sd)),
-        "nrx_tower_bwd": ("tensor", 2 * B * tower_flops),
-        "nrx_tower_bwd_dx": ("tensor", B * tower_flops),
-        "nrx_tower_bwd_dw": ("tensor", B * tower_flops),
+        "nrx_tower_bwd": _binding(2 * B * tower_flops, B * (4 * tower_img_bytes + 2 * mlp_in + 4 * mlp_in)),
+        # dX: reads every saved activation image (the act' gates), writes every dz image and grad_x (fp32)
+        "nrx_tower_bwd_dx": _binding(B * tower_flops, B * (2 * tower_img_bytes + 4 * mlp_in)),
+        # dW: reads every a_l image (incl. the input image) and every dz_l image once
+        "nrx_tower_bwd_dw": _binding(B * tower_flops, B * (2 * tower_img_bytes + 2 * mlp_in)),
         "nrx_dcn_cross_fwd": ("hbm", B * 4 * (sd + 2 * sd)),
         "nrx_dcn_cross_bwd": ("hbm", B * 4 * (sd + 2 * sd + sd)),
         "nrx_embed_bwd_plan": ("hbm", B * n_occ * (8 + 8 + 3 * 16)),

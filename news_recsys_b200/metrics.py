@@ -90,8 +90,9 @@ class ValidationMetrics:
         L.check(L.load().nrx_grouped_rank_metrics(ss.data_ptr(), ls.data_ptr(), seg.data_ptr(), U, k, per_user.data_ptr(),
                                                   flags.data_ptr(), L.stream_ptr(dev)), "nrx_grouped_rank_metrics")
         cold_user = torch.zeros(U, dtype=torch.bool, device=dev)
-        if self.warm is not None and self.warm.numel() > 0:
-            cold_user = ~torch.isin(uniq, self.warm.to(dev))
+        if self.warm is not None:   # a NON-EMPTY train set was given (base_model.py:364); ids it does not list are cold, also
+            # when none of its entries parses as a user id (the reference then marks every user cold, :366)
+            cold_user = ~torch.isin(uniq, self.warm.to(dev)) if self.warm.numel() > 0 else torch.ones(U, dtype=torch.bool, device=dev)
         # sample-level views in global score-descending order for the overall AUC / log-loss of each group
         s1, pos1 = s[o1], l[o1] == 1
         inv = torch.searchsorted(uniq, u[o1])

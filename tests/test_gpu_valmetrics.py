@@ -54,6 +54,22 @@ def test_device_metrics_match_oracle_on_random_logs(k):
     _close(vm.compute(), R.validation_metrics(us, ss, ls, k, warm), f"k={k}")
 
 
+def test_train_set_without_numeric_ids_marks_every_user_cold():
+    """a non-empty user_in_train_set none of whose entries is a user id — the reference tests
+    `uid not in set and str(uid) not in set` (base_model.py:364-366), so EVERY user is cold; the device path used to treat
+    the unusable set as absent (every user warm)."""
+    from news_recsys_b200.metrics import ValidationMetrics
+    rng = np.random.default_rng(7)
+    train = {"U12", "abc", "007"}                     # "007" != str(7): not a match either
+    vm = ValidationMetrics(k=10, user_in_train_set=train)
+    u = torch.from_numpy(rng.integers(1, 40, size=2048).astype(np.int64))
+    s = torch.from_numpy(rng.random(2048).astype(np.float32)).view(-1, 1)
+    l = torch.from_numpy((rng.random((2048, 2)) < 0.2).astype(np.float32))
+    vm.update(u.to(DEV), s.to(DEV), l.to(DEV))
+    a, b, c = R.validation_pairs(u, s, l)
+    _close(vm.compute(), R.validation_metrics(a.tolist(), list(b), list(c), 10, train), "non-numeric train set")
+
+
 def test_model_validation_hooks_match_oracle():
     """BaseModel.validation_step / on_validation_epoch_end (same names as the reference) on a Deep model."""
     from news_recsys_b200.model.sort.deep.model import Deep
