@@ -457,6 +457,21 @@ int nrx_topk_merge64(const double* scores64, const int64_t* ids, int n_lists, in
 int nrx_l2_normalize(const float* x, int64_t ld, int64_t n, int d, float* y, int64_t y_ld,
                      nrx_stream_t stream);
 
+/* DSSM training tail, fused (recall/DSSM/model.py:51-73 forward + :92-110 infoNCE_loss): from the RAW tower outputs
+ * user [B, d] and item [B, d] and the negative-sampling permutations (h_perms: host array of n_neg DEVICE pointers to
+ * int64 [B]; negative j of sample b is item perms[j][b]; every list must be a permutation of 0..B-1, as torch.randperm
+ * yields) it computes  u^ = user / max(|user|, 1e-12), likewise the items,  logits [u^.p^, u^.n^_1 ..] / temperature,
+ * loss_per_sample[b] = mask[b] * cross_entropy(logits_b, 0)  (mask nullable = ones; read at mask[b * mask_stride])
+ * and — when the pointers are given — the gradients of  mean_b loss_per_sample[b]  with respect to the RAW user and item
+ * rows (through the normalisations and the gather of the negatives; the item gradient is a deterministic gather over the
+ * inverse permutations, no float atomics).  status (nullable): bit 0 is set when a list was not a permutation.
+ * Two launches.  d <= 256, n_neg <= 7. */
+size_t nrx_dssm_infonce_workspace_bytes(int64_t B, int n_neg);
+int nrx_dssm_infonce(const float* user, int64_t u_ld, const float* item, int64_t i_ld, int64_t B, int d,
+                     const int64_t* const* h_perms, int n_neg, const float* mask, int64_t mask_stride,
+                     float temperature, float* loss_per_sample, float* grad_user, int64_t gu_ld, float* grad_item,
+                     int64_t gi_ld, int32_t* status, void* ws, size_t ws_bytes, nrx_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

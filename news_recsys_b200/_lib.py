@@ -171,6 +171,8 @@ SIGNATURES = {
     "nrx_topk_ip_workspace_bytes": (_SZ, [_I64, _I64, C.c_int, C.c_int]),
     "nrx_topk_ip": (C.c_int, [_P, _I64, _P, _I64, _I64, _I64, C.c_int, C.c_int, _I64, _P, _P, _P, _SZ, _P]),
     "nrx_topk_merge": (C.c_int, [_P, _P, C.c_int, _I64, C.c_int, _P, _P, _P]),
+    "nrx_dssm_infonce_workspace_bytes": (_SZ, [_I64, C.c_int]),
+    "nrx_dssm_infonce": (C.c_int, [_P, _I64, _P, _I64, _I64, C.c_int, _P, C.c_int, _P, _I64, C.c_float, _P, _P, _I64, _P, _I64, _P, _P, _SZ, _P]),
     "nrx_l2_normalize": (C.c_int, [_P, _I64, _I64, C.c_int, _P, _I64, _P]),
 }
 
@@ -206,7 +208,7 @@ def load() -> C.CDLL:
 
 # kernels of OURS launched per successful API call (library kernels such as the CUB radix sort are not counted)
 KERNELS_PER_CALL = {"nrx_tower_fwd": 3, "nrx_tower_fwd(prepacked)": 2, "nrx_tower_fwd_head": 3, "nrx_tower_fwd_head(prepacked)": 2,
-                    "nrx_tower_fwd(prepacked,ximg)": 1, "nrx_tower_fwd_head(prepacked,ximg)": 1, "nrx_tower_bwd": 3, "nrx_tower_bwd_dw": 2, "nrx_embed_bwd_apply": 2, "nrx_embed_bwd_plan": 2, "nrx_embed_bwd_plan(sort)": 1, "nrx_embed_bwd_plan(merge)": 1, "nrx_embed_bwd_plan_is_staged": 0, "nrx_adamw_untouched_rows": 2, "nrx_adamw_untouched_rows_scratch_bytes": 0, "nrx_dcn_cross_bwd": 2,
+                    "nrx_tower_fwd(prepacked,ximg)": 1, "nrx_tower_fwd_head(prepacked,ximg)": 1, "nrx_tower_bwd": 3, "nrx_tower_bwd_dw": 2, "nrx_embed_bwd_apply": 2, "nrx_embed_bwd_plan": 2, "nrx_embed_bwd_plan(sort)": 1, "nrx_embed_bwd_plan(merge)": 1, "nrx_embed_bwd_plan_is_staged": 0, "nrx_dssm_infonce": 2, "nrx_dssm_infonce_workspace_bytes": 0, "nrx_adamw_untouched_rows": 2, "nrx_adamw_untouched_rows_scratch_bytes": 0, "nrx_dcn_cross_bwd": 2,
                     "nrx_embed_bwd_apply(dense)": 2, "nrx_embed_bwd_apply(rowopt)": 2, "nrx_topk_ip": 2,
                     "nrx_topk_search": 6, "nrx_topk_search64": 6, "nrx_topk_search_peer": 10, "nrx_topk_peer_inbox_bytes": 0, "nrx_topk_index_build": 1,
                     "nrx_peer_alloc": 0, "nrx_peer_free": 0, "nrx_peer_export": 0, "nrx_peer_open": 0, "nrx_peer_close": 0,

@@ -86,9 +86,21 @@ class DSSM(BaseModel):
             losses = losses * mask
         return losses.mean()
 
-    def training_step(self, batch, batch_idx=0, neg_perms=None):
-        u, it, neg = self.forward(batch, neg_perms)
-        return self.infoNCE_loss(u, it, neg, mask=batch["label"][:, 1])
+    def training_step(self, batch, batch_idx=0, neg_perms=None, fused=True):
+        """The reference's step (:112-126): forward (:51-73) + infoNCE_loss (:92-110) with mask = label[:, 1].
+        fused=True (default): the normalisations, the negative gather, the loss and their whole backward run as
+        ops.InfoNCEFn (nrx_dssm_infonce, two launches) on the raw tower outputs; fused=False keeps the reference's
+        operator-by-operator form (forward() / infoNCE_loss() remain available with the reference's signatures)."""
+        if not fused:
+            u, it, neg = self.forward(batch, neg_perms)
+            return self.infoNCE_loss(u, it, neg, mask=batch["label"][:, 1])
+        user_raw = self.user_tower(batch)
+        item_raw = self.item_tower(batch)
+        B = item_raw.size(0)
+        if neg_perms is None:  # the reference draws torch.randperm on the CPU generator (:63)
+            neg_perms = [torch.randperm(B) for _ in range(self.hparams_["negative_sample_rate"])]
+        perms = [p.to(item_raw.device) for p in neg_perms]
+        return ops.InfoNCEFn.apply(user_raw, item_raw, batch["label"][:, 1], 0.1, *perms)
 
     # ---- retrieval (on_train_epoch_end :230-254, hit_rate :209) ---------------------------------------
     @torch.no_grad()

@@ -378,6 +378,67 @@ def l2_normalize(x: torch.Tensor) -> torch.Tensor:
 
 
 # --------------------------------------------------------------------------- #
+# DSSM training tail: normalise + in-batch negatives + InfoNCE, fused           #
+# --------------------------------------------------------------------------- #
+
+def dssm_infonce(user: torch.Tensor, item: torch.Tensor, perms: Sequence[torch.Tensor], mask: Optional[torch.Tensor] = None,
+                 temperature: float = 0.1, want_grads: bool = True):
+    """-> (loss_per_sample [B], grad_user [B,d] | None, grad_item [B,d] | None): gradients of mean(loss_per_sample) with
+    respect to the RAW tower outputs `user`, `item` (recall/DSSM/model.py:51-73,92-110 in two launches)."""
+    _require_cuda(user, "user"); _require_cuda(item, "item")
+    user, item = user.detach().float().contiguous(), item.detach().float().contiguous()
+    B, d = user.shape
+    if item.shape != user.shape:
+        raise L.NrxError(f"dssm_infonce: user {tuple(user.shape)} and item {tuple(item.shape)} must have the same shape")
+    dev = user.device
+    perms = [p.to(device=dev, dtype=torch.int64).contiguous() for p in perms]
+    for p in perms:
+        if p.numel() != B:
+            raise L.NrxError("dssm_infonce: every permutation must have B elements")
+    lib = L.load()
+    nbytes = int(lib.nrx_dssm_infonce_workspace_bytes(B, len(perms)))
+    if nbytes == 0:
+        L.check(-2, "nrx_dssm_infonce_workspace_bytes")
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    loss = torch.empty(B, dtype=torch.float32, device=dev)
+    gu = torch.empty_like(user) if want_grads else None
+    gi = torch.empty_like(item) if want_grads else None
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    mptr, mstride = 0, 0
+    if mask is not None:
+        _require_cuda(mask, "mask")
+        mask = mask.detach().float()
+        mptr, mstride = mask.data_ptr(), mask.stride(0) if mask.dim() > 0 else 0
+    L.check(lib.nrx_dssm_infonce(user.data_ptr(), user.stride(0), item.data_ptr(), item.stride(0), B, d,
+                                 L.ptr_array(perms, max(len(perms), 1)), len(perms), mptr, mstride, float(temperature),
+                                 loss.data_ptr(), L.ptr(gu), d, L.ptr(gi), d, status.data_ptr(), ws.data_ptr(), nbytes,
+                                 L.stream_ptr(dev)), "nrx_dssm_infonce")
+    return loss, gu, gi, status
+
+
+class InfoNCEFn(torch.autograd.Function):
+    """mean InfoNCE loss of (raw user rows, raw item rows) with in-batch negatives item[perm_j]; the backward was computed by
+    the forward's two launches and is only scaled here."""
+
+    @staticmethod
+    def forward(ctx, user, item, mask, temperature, *perms):
+        need = user.requires_grad or item.requires_grad
+        loss, gu, gi, status = dssm_infonce(user, item, perms, mask, temperature, want_grads=need)
+        ctx.save_for_backward(*(t for t in (gu, gi) if t is not None))
+        ctx.need = need
+        ctx.status = status
+        ctx.n_perms = len(perms)
+        return loss.mean()
+
+    @staticmethod
+    def backward(ctx, g):
+        if not ctx.need:
+            return (None, None, None, None) + (None,) * ctx.n_perms
+        gu, gi = ctx.saved_tensors
+        return (gu * g, gi * g, None, None) + (None,) * ctx.n_perms
+
+
+# --------------------------------------------------------------------------- #
 # Gather-fused FM (sparse-only, equal widths): BASELINE config 2                #
 # --------------------------------------------------------------------------- #
 

@@ -1,2 +1,2 @@
 #!/bin/bash
-timeout -s KILL 900 python -m pytest tests/test_gpu_multi.py -q -m gpu -k "dssm or peer_memory" 2>&1 | tail -n 15
+timeout -s KILL 900 python -m pytest tests/test_gpu_dssm.py tests/test_gpu_valmetrics.py -x -q -m gpu 2>&1 | tail -n 25

@@ -138,12 +138,16 @@ def main():
                 for tr_ in (False, True):   # the pipelined kernel alone: weights prepacked, bf16 input image in place
                     packed = ops.tower_prepack(B, ws_, bs_, None, training=tr_)
                     ops.tower_image_from_rows(x, ops.tower_input_image(packed, B))
-                    rec(f"K4 tower_fwd3 from image, {'training' if tr_ else 'inference'} ({nm})", B,
-                        timeit(lambda: ops.tower_fwd(None, ws_, bs_, None, training=tr_, packed=packed, ximg_rows=B), once=a.once),
-                        fl, "tensor")
+                    us_ = timeit(lambda: ops.tower_fwd(None, ws_, bs_, None, training=tr_, packed=packed, ximg_rows=B), once=a.once)
+                    rec(f"K4 tower_fwd3 from image, {'training' if tr_ else 'inference'} ({nm})", B, us_, fl, "tensor")
+                    if tr_:   # the binding roofline of a training forward: input image in, every hidden image out
+                        rec(f"K4 tower_fwd3 from image, training ({nm}) [HBM view]", B, us_, B * 2 * (dims_[0] + sum(dims_[1:5])), "hbm")
                 y, ctx = ops.tower_fwd(x, ws_, bs_, None, training=True)
                 gy = torch.randn(B, 1, device=DEV)
-                rec(f"K4 tower_bwd dx+dw+reduce ({nm})", B, timeit(lambda: ops.tower_bwd(ctx, gy), once=a.once), 2 * fl, "tensor")
+                us_ = timeit(lambda: ops.tower_bwd(ctx, gy), once=a.once)
+                rec(f"K4 tower_bwd dx+dw+reduce ({nm})", B, us_, 2 * fl, "tensor")
+                # binding roofline: dX reads the a images, writes the dz images + fp32 grad_x; dW reads a (incl. input) and dz
+                rec(f"K4 tower_bwd dx+dw+reduce ({nm}) [HBM view]", B, us_, B * (4 * 2 * sum(dims_[1:5]) + 2 * dims_[0] + 4 * dims_[0]), "hbm")
     if "topk" in only:
         from news_recsys_b200.retrieval import TopkIndex
         N, D = 1_000_000, 128
