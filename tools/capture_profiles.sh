@@ -23,5 +23,8 @@ ncu -i gpurun_out/r2_full_topk_scan.ncu-rep --page raw --csv > gpurun_out/r2_ncu
 $T 600 ncu --set full --import-source on --clock-control none -k regex:tower_fwd3_kernel -s 2 -c 1 -f -o gpurun_out/r2_full_tower_fwd3_B262144 \
     python tools/profile_kernels.py --only tower --sizes 262144 --once > gpurun_out/ncu_full_fwd3_big.log 2>&1
 ncu -i gpurun_out/r2_full_tower_fwd3_B262144.ncu-rep --page raw --csv > gpurun_out/r2_ncu_full_tower_fwd3_B262144.raw.csv 2>/dev/null
+$T 600 ncu --set full --import-source on --clock-control none -k regex:tower_bwd_dx3_kernel -s 1 -c 1 -f -o gpurun_out/r2_full_tower_dx3_B262144 \
+    python tools/profile_kernels.py --only tower --sizes 262144 --once > gpurun_out/ncu_full_dx3_big.log 2>&1
+ncu -i gpurun_out/r2_full_tower_dx3_B262144.ncu-rep --page raw --csv > gpurun_out/r2_ncu_full_tower_dx3_B262144.raw.csv 2>/dev/null
 $T 900 python tools/profile_kernels.py > gpurun_out/r2_kernel_sweep_final.log 2>&1
 tail -n 60 gpurun_out/r2_kernel_sweep_final.log
