@@ -34,7 +34,6 @@ namespace nrx {
 using namespace umma;
 
 static constexpr int kTR = 128;        // corpus rows per tile == UMMA N; queries per tile == UMMA M
-static constexpr uint32_t kEpiParkNs = 400;   // suspend hint of the epilogue warps' waits on the issuer's commits
 static constexpr int kCap = 2048;      // candidate list capacity per query (24 KB of shared memory in the final kernel)
 static constexpr int kScanThreads = 64 + 512;  // TMA warp + MMA warp + 16 epilogue warps
 static constexpr int kMaxQT = 4;       // query tiles per CTA (4 x 128 TMEM columns)
@@ -279,7 +278,7 @@ topk_scan_kernel(const uint8_t* __restrict__ img, long long N, long long n_tiles
 #pragma unroll
         for (int a = 0; a < kMaxQT; ++a) {
           if (a < nq) {
-            mbar_wait_park(&tfull[a], (tph >> a) & 1u, kEpiParkNs); tph ^= 1u << a;
+            mbar_wait(&tfull[a], (tph >> a) & 1u); tph ^= 1u << a;
             tc_fence_after();
             float v[32];
             tmem_ld32(tmem + ((uint32_t)(qd * 32) << 16) + (uint32_t)(a * kTR + cq * 32), v);

@@ -32,18 +32,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "bra WAIT_%=;\n\t"
       "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
-// Same wait with a suspend-time hint: a waiting warp is parked by the hardware for up to `ns` nanoseconds (or until the
-// phase completes) instead of re-issuing try_wait + branch back to back — for the many epilogue warps that wait on the
-// MMA issuer's commits while sharing its scheduler.
-__device__ __forceinline__ void mbar_wait_park(uint64_t* bar, uint32_t parity, uint32_t ns) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "WAITP_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
-      "@p bra DONEP_%=;\n\t"
-      "bra WAITP_%=;\n\t"
-      "DONEP_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity), "r"(ns) : "memory");
-}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
