@@ -210,7 +210,7 @@ def load() -> C.CDLL:
 KERNELS_PER_CALL = {"nrx_tower_fwd": 3, "nrx_tower_fwd(prepacked)": 2, "nrx_tower_fwd_head": 3, "nrx_tower_fwd_head(prepacked)": 2,
                     "nrx_tower_fwd(prepacked,ximg)": 1, "nrx_tower_fwd_head(prepacked,ximg)": 1, "nrx_tower_bwd": 3, "nrx_tower_bwd_dw": 2, "nrx_embed_bwd_apply": 2, "nrx_embed_bwd_plan": 2, "nrx_embed_bwd_plan(sort)": 1, "nrx_embed_bwd_plan(merge)": 1, "nrx_embed_bwd_plan_is_staged": 0, "nrx_dssm_infonce": 2, "nrx_dssm_infonce_workspace_bytes": 0, "nrx_adamw_untouched_rows": 2, "nrx_adamw_untouched_rows_scratch_bytes": 0, "nrx_dcn_cross_bwd": 2,
                     "nrx_embed_bwd_apply(dense)": 2, "nrx_embed_bwd_apply(rowopt)": 2, "nrx_topk_ip": 2,
-                    "nrx_topk_search": 6, "nrx_topk_search64": 6, "nrx_topk_search_peer": 10, "nrx_topk_peer_inbox_bytes": 0, "nrx_topk_index_build": 1,
+                    "nrx_topk_search": 7, "nrx_topk_search64": 7, "nrx_topk_search_peer": 11, "nrx_topk_peer_inbox_bytes": 0, "nrx_topk_index_build": 1,
                     "nrx_peer_alloc": 0, "nrx_peer_free": 0, "nrx_peer_export": 0, "nrx_peer_open": 0, "nrx_peer_close": 0,
                     "nrx_peer_status": 0, "nrx_ingest_gather_ids": 0, "nrx_ingest_csr_expand": 0, "nrx_ingest_gather_labels": 0,
                     "nrx_tower_workspace_bytes": 0, "nrx_embed_bwd_workspace_bytes": 0, "nrx_tower_image_layout": 0}

@@ -53,7 +53,8 @@ struct TopkGeom {
   int fb_grid, fb_items;   // fallback: fixed grid, capacity of the (query, corpus slice) work list
   size_t tile_bytes, index_bytes;
   // workspace offsets
-  size_t gmax, theta, eps, count, cand, flag, flist, fpart, qimg, total;
+  size_t gmax, theta, eps, count, cand, flag, flist, fpart, qimg, pre_id, pre_sc, total;
+  int split_final;    // rescoring as its own wide kernel (few queries: the per-query final blocks alone leave the machine idle)
 };
 
 static int make_geom(long long Q, long long N, int D, int k, TopkGeom* g, int kprime_override = 0) {
@@ -102,6 +103,15 @@ static int make_geom(long long Q, long long N, int D, int k, TopkGeom* g, int kp
   g->fpart = o; o += al((size_t)g->fb_items * k * 12);         // fallback partial lists: fp64 score + u32 id
   g->qimg = o;  o += al((size_t)g->n_qtiles * g->tile_bytes);   // bf16 tile images of the queries (packed once per search)
   g->cand = o;  o += al((size_t)g->Qp * g->slices * 4 * g->cap_s * 4);
+  // measured (B200, N = 1M, D = 128, k = 100): Q = 1: 97 vs 122 us, Q = 64: 106 vs 129 us, Q = 256: equal, Q = 1024: 397 vs
+  // 344 us — with many queries the per-query blocks already fill the machine and the 16 extra blocks per query only
+  // repeat the region prefix.  NRX_TOPK_FINAL_SPLIT=0/1 forces the choice.
+  const char* fs = getenv("NRX_TOPK_FINAL_SPLIT");
+  g->split_final = fs != nullptr ? (fs[0] == '1') : (Q <= 128);
+  if (g->split_final) {
+    g->pre_id = o; o += al((size_t)g->Qp * kCap * 4);
+    g->pre_sc = o; o += al((size_t)g->Qp * kCap * 8);
+  }
   g->total = o;
   return NRX_OK;
 }
@@ -569,12 +579,81 @@ __device__ __forceinline__ void flag_query(long long qi, int* flag, unsigned* fl
   flist[1 + atomicAdd(flist, 1u)] = (unsigned)qi;
 }
 
+// Exact re-scoring as its own WIDE kernel: grid (chunks, Q).  Inside the per-query final kernel the ~350 candidate rows of
+// a query were fetched by 4 warps in ~22 dependent rounds (one DRAM round trip each); here 16 blocks x 8 warps per query
+// have every row of every query in flight at once (random 512-byte rows: DRAM-bound).  Every block recomputes the query's
+// region offsets (a few hundred counts) and re-scores candidates [chunk * 32 + m * 32 * gridDim.x, +32); the final kernel
+// then only sorts and proves.  Same dot64_warp4 arithmetic as the fused path, bit for bit.  Used for small query batches
+// (make_geom: Q <= 128), where Q blocks of the final kernel cannot fill 148 SMs.
+static constexpr int kRescoreChunks = 16;
+__global__ void __launch_bounds__(256)
+topk_rescore_kernel(const float* __restrict__ c, long long cld, int D, const float* __restrict__ q, long long qld,
+                    const unsigned* __restrict__ count, const unsigned* __restrict__ cand, int n_slices, int cap_s,
+                    unsigned* __restrict__ pre_id, double* __restrict__ pre_sc) {
+  extern __shared__ __align__(16) uint8_t sm_raw[];
+  float* qs = reinterpret_cast<float*>(sm_raw);                           // [D]
+  unsigned* s_off = reinterpret_cast<unsigned*>(qs + ((D + 3) & ~3));     // [n_slices]
+  const long long qi = blockIdx.y;
+  const int tid = threadIdx.x;
+  __shared__ unsigned s_total, s_over, s_warp[8];
+  unsigned over = 0, run = 0;
+  for (int b0 = 0; b0 < n_slices; b0 += 256) {
+    const int sl = b0 + tid;
+    unsigned cs = sl < n_slices ? count[qi * n_slices + sl] : 0u;
+    if (cs > (unsigned)cap_s) { over = 1; cs = (unsigned)cap_s; }
+    unsigned inc = cs;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(NRX_FULL_MASK, inc, o); if ((tid & 31) >= o) inc += t; }
+    if ((tid & 31) == 31) s_warp[tid >> 5] = inc;
+    __syncthreads();
+    unsigned wbase = 0;
+    for (int w = 0; w < (tid >> 5); ++w) wbase += s_warp[w];
+    if (sl < n_slices) s_off[sl] = run + wbase + inc - cs;
+    unsigned tot = 0;
+    for (int w = 0; w < 8; ++w) tot += s_warp[w];
+    run += tot;
+    __syncthreads();
+  }
+  over = __syncthreads_or(over);
+  if (tid == 0) { s_total = run; s_over = over; }
+  for (int d = tid; d < D; d += 256) qs[d] = __ldg(q + qi * qld + d);
+  __syncthreads();
+  const unsigned cnt = s_total;
+  if (s_over || cnt > (unsigned)kCap) return;   // the final kernel sends the query to the exact scan
+  const int warp = tid >> 5, lane = tid & 31;
+  const bool vec = rows_vec_ok(c, cld, D);
+  for (unsigned base = blockIdx.x * 32u; base < cnt; base += gridDim.x * 32u) {
+    const unsigned i0 = base + (unsigned)warp * 4;
+    if (i0 >= cnt) continue;
+    unsigned myid = 0;
+    if (lane < 4) {   // lanes 0..3 look up the four candidate rows of this warp
+      const unsigned i = min(i0 + (unsigned)lane, cnt - 1);   // past the end: re-score the last one
+      int lo = 0, hi = n_slices - 1;
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (s_off[mid] <= i) lo = mid; else hi = mid - 1;
+      }
+      myid = cand[((size_t)qi * n_slices + lo) * cap_s + (i - s_off[lo])];
+    }
+    const float* rowp[4];
+    unsigned ids[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { ids[u] = __shfl_sync(NRX_FULL_MASK, myid, u); rowp[u] = c + (long long)ids[u] * cld; }
+    const double v = dot64_warp4(qs, rowp, D, lane, vec);
+    const int u = dot64_row_of_lane(lane);
+    if ((lane & 7) == 0 && i0 + u < cnt) {
+      pre_sc[(size_t)qi * kCap + i0 + u] = v;
+      pre_id[(size_t)qi * kCap + i0 + u] = u == 0 ? ids[0] : u == 1 ? ids[1] : u == 2 ? ids[2] : ids[3];
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kFinalThreads, 8)
 topk_final_kernel(const float* __restrict__ c, long long cld, long long N, int D, const float* __restrict__ q, long long qld,
                   int k, long long id_base, const float* __restrict__ theta, const float* __restrict__ eps,
                   const unsigned* __restrict__ count, const unsigned* __restrict__ cand, int n_slices, int cap_s,
                   int* __restrict__ flag, unsigned* __restrict__ flist, float* __restrict__ out_s, double* __restrict__ out_s64,
-                  long long* __restrict__ out_i) {
+                  long long* __restrict__ out_i, const unsigned* __restrict__ pre_id, const double* __restrict__ pre_sc) {
   extern __shared__ __align__(16) uint8_t sm_raw[];
   double* s = reinterpret_cast<double*>(sm_raw);              // [kCap]
   unsigned* id = reinterpret_cast<unsigned*>(s + kCap);       // [kCap]
@@ -615,24 +694,28 @@ topk_final_kernel(const float* __restrict__ c, long long cld, long long N, int D
   int n2 = 32;   // the sort network needs >= one warp of elements
   while (n2 < (int)cnt) n2 <<= 1;
   for (int i = (int)cnt + tid; i < n2; i += kFinalThreads) { id[i] = 0xffffffffu; s[i] = -DBL_MAX; }
-  for (unsigned i = tid; i < cnt; i += kFinalThreads) {  // candidate row of list position i: region by binary search
-    int lo = 0, hi = n_slices - 1;
-    while (lo < hi) {
-      const int mid = (lo + hi + 1) >> 1;
-      if (s_off[mid] <= i) lo = mid; else hi = mid - 1;
+  if (pre_id != nullptr) {   // re-scored by topk_rescore_kernel: only fetch (id, fp64 score)
+    for (unsigned i = tid; i < cnt; i += kFinalThreads) { id[i] = pre_id[(size_t)qi * kCap + i]; s[i] = pre_sc[(size_t)qi * kCap + i]; }
+  } else {
+    for (unsigned i = tid; i < cnt; i += kFinalThreads) {  // candidate row of list position i: region by binary search
+      int lo = 0, hi = n_slices - 1;
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (s_off[mid] <= i) lo = mid; else hi = mid - 1;
+      }
+      id[i] = cand[((size_t)qi * n_slices + lo) * cap_s + (i - s_off[lo])];
     }
-    id[i] = cand[((size_t)qi * n_slices + lo) * cap_s + (i - s_off[lo])];
-  }
-  __syncthreads();
-  {  // exact scores: one warp per candidate, 4 rows in flight per warp
-    const int warp = tid >> 5, lane = tid & 31;
-    const bool vec = rows_vec_ok(c, cld, D);
-    for (unsigned i0 = (unsigned)warp * 4; i0 < cnt; i0 += 4 * (kFinalThreads / 32)) {
-      const float* rowp[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) rowp[u] = c + (long long)id[min(i0 + u, cnt - 1)] * cld;   // past the end: re-score the last one
-      const double v = dot64_warp4(qs, rowp, D, lane, vec);
-      if ((lane & 7) == 0 && i0 + dot64_row_of_lane(lane) < cnt) s[i0 + dot64_row_of_lane(lane)] = v;
+    __syncthreads();
+    {  // exact scores: one warp per candidate, 4 rows in flight per warp
+      const int warp = tid >> 5, lane = tid & 31;
+      const bool vec = rows_vec_ok(c, cld, D);
+      for (unsigned i0 = (unsigned)warp * 4; i0 < cnt; i0 += 4 * (kFinalThreads / 32)) {
+        const float* rowp[4];
+  #pragma unroll
+        for (int u = 0; u < 4; ++u) rowp[u] = c + (long long)id[min(i0 + u, cnt - 1)] * cld;   // past the end: re-score the last one
+        const double v = dot64_warp4(qs, rowp, D, lane, vec);
+        if ((lane & 7) == 0 && i0 + dot64_row_of_lane(lane) < cnt) s[i0 + dot64_row_of_lane(lane)] = v;
+      }
     }
   }
   __syncthreads();
@@ -830,7 +913,8 @@ __global__ void __launch_bounds__(kFinalThreads, 8)
 topk_final_peer_kernel(const float* __restrict__ c, long long cld, long long N, int D, const float* __restrict__ q, long long qld,
                        int k, long long id_base, const float* __restrict__ theta, const float* __restrict__ eps,
                        const unsigned* __restrict__ count, const unsigned* __restrict__ cand, int n_slices, int cap_s,
-                       const __grid_constant__ PeerInbox PB) {
+                       const __grid_constant__ PeerInbox PB, const unsigned* __restrict__ pre_id,
+                       const double* __restrict__ pre_sc) {
   extern __shared__ __align__(16) uint8_t sm_raw[];
   double* s = reinterpret_cast<double*>(sm_raw);              // [kCap]
   unsigned* id = reinterpret_cast<unsigned*>(s + kCap);       // [kCap]
@@ -872,24 +956,28 @@ topk_final_peer_kernel(const float* __restrict__ c, long long cld, long long N, 
   int n2 = 32;   // the sort network needs >= one warp of elements
   while (n2 < (int)cnt) n2 <<= 1;
   for (int i = (int)cnt + tid; i < n2; i += kFinalThreads) { id[i] = 0xffffffffu; s[i] = -DBL_MAX; }
-  for (unsigned i = tid; i < cnt; i += kFinalThreads) {
-    int lo = 0, hi = n_slices - 1;
-    while (lo < hi) {
-      const int mid = (lo + hi + 1) >> 1;
-      if (s_off[mid] <= i) lo = mid; else hi = mid - 1;
+  if (pre_id != nullptr) {   // re-scored by topk_rescore_kernel: only fetch (id, fp64 score)
+    for (unsigned i = tid; i < cnt; i += kFinalThreads) { id[i] = pre_id[(size_t)qi * kCap + i]; s[i] = pre_sc[(size_t)qi * kCap + i]; }
+  } else {
+    for (unsigned i = tid; i < cnt; i += kFinalThreads) {
+      int lo = 0, hi = n_slices - 1;
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (s_off[mid] <= i) lo = mid; else hi = mid - 1;
+      }
+      id[i] = cand[((size_t)qi * n_slices + lo) * cap_s + (i - s_off[lo])];
     }
-    id[i] = cand[((size_t)qi * n_slices + lo) * cap_s + (i - s_off[lo])];
-  }
-  __syncthreads();
-  {
-    const int warp = tid >> 5, lane = tid & 31;
-    const bool vec = rows_vec_ok(c, cld, D);
-    for (unsigned i0 = (unsigned)warp * 4; i0 < cnt; i0 += 4 * (kFinalThreads / 32)) {
-      const float* rowp[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) rowp[u] = c + (long long)id[min(i0 + u, cnt - 1)] * cld;
-      const double v = dot64_warp4(qs, rowp, D, lane, vec);
-      if ((lane & 7) == 0 && i0 + dot64_row_of_lane(lane) < cnt) s[i0 + dot64_row_of_lane(lane)] = v;
+    __syncthreads();
+    {
+      const int warp = tid >> 5, lane = tid & 31;
+      const bool vec = rows_vec_ok(c, cld, D);
+      for (unsigned i0 = (unsigned)warp * 4; i0 < cnt; i0 += 4 * (kFinalThreads / 32)) {
+        const float* rowp[4];
+  #pragma unroll
+        for (int u = 0; u < 4; ++u) rowp[u] = c + (long long)id[min(i0 + u, cnt - 1)] * cld;
+        const double v = dot64_warp4(qs, rowp, D, lane, vec);
+        if ((lane & 7) == 0 && i0 + dot64_row_of_lane(lane) < cnt) s[i0 + dot64_row_of_lane(lane)] = v;
+      }
     }
   }
   __syncthreads();
@@ -1124,10 +1212,19 @@ extern "C" int nrx_topk_search64(const void* index, const float* corpus, int64_t
     if (rc != NRX_OK) return rc;
     const int n_regions = (int)(4 * g.slices);
     const size_t fsm = (size_t)kCap * 12 + (size_t)((D + 3) & ~3) * 4 + (size_t)n_regions * 4;
+    unsigned* pre_id = g.split_final ? (unsigned*)(w + g.pre_id) : nullptr;
+    double* pre_sc = g.split_final ? (double*)(w + g.pre_sc) : nullptr;
+    if (g.split_final) {
+      const size_t rsm = (size_t)((D + 3) & ~3) * 4 + (size_t)n_regions * 4;
+      topk_rescore_kernel<<<dim3(kRescoreChunks, (unsigned)Q), 256, rsm, st>>>(corpus, c_ld, D, queries, q_ld, count, cand, n_regions, g.cap_s,
+                                                                               pre_id, pre_sc);
+      rc = check_launch("topk_rescore");
+      if (rc != NRX_OK) return rc;
+    }
     cudaFuncSetAttribute(topk_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm);
     cudaFuncSetAttribute(topk_final_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     topk_final_kernel<<<(unsigned)Q, kFinalThreads, fsm, st>>>(corpus, c_ld, N, D, queries, q_ld, k, id_base, theta, eps, count, cand, n_regions,
-                                                    g.cap_s, flag, flist, out_scores, out_scores64, (long long*)out_ids);
+                                                    g.cap_s, flag, flist, out_scores, out_scores64, (long long*)out_ids, pre_id, pre_sc);
     rc = check_launch("topk_final");
     if (rc != NRX_OK) return rc;
   }
@@ -1251,8 +1348,17 @@ extern "C" int nrx_topk_search_peer(const void* index, int64_t N_local, int D, c
   const size_t fsm = (size_t)kCap * 12 + (size_t)((D + 3) & ~3) * 4 + (size_t)n_regions * 4;
   cudaFuncSetAttribute(topk_final_peer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm);
   cudaFuncSetAttribute(topk_final_peer_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  unsigned* pre_id = (g.split_final && fast) ? (unsigned*)(w + g.pre_id) : nullptr;
+  double* pre_sc = (g.split_final && fast) ? (double*)(w + g.pre_sc) : nullptr;
+  if (pre_id != nullptr) {
+    const size_t rsm = (size_t)((D + 3) & ~3) * 4 + (size_t)n_regions * 4;
+    topk_rescore_kernel<<<dim3(kRescoreChunks, (unsigned)Q), 256, rsm, st>>>(corpus, D, D, queries, q_ld, count, cand, n_regions, g.cap_s,
+                                                                             pre_id, pre_sc);
+    rc = check_launch("topk_rescore(peer)");
+    if (rc != NRX_OK) return rc;
+  }
   topk_final_peer_kernel<<<(unsigned)Q, kFinalThreads, fsm, st>>>(corpus, D, N_local, D, queries, q_ld, k, id_base, theta, eps, count, cand, n_regions,
-                                                        g.cap_s, PB);
+                                                        g.cap_s, PB, pre_id, pre_sc);
   rc = check_launch("topk_final_peer");
   if (rc != NRX_OK) return rc;
   rc = nrx_peer_barrier(&bar, stream);     // every shard's lists have landed in the owners' inboxes

@@ -149,3 +149,23 @@ def test_topk_searcher_api():
     # normalisation is done on the GPU in fp32, so only near-ties may differ: compare score values
     torch.testing.assert_close(torch.tensor(scores), ref_s, rtol=1e-5, atol=1e-6)
     assert ts.search([], normalize=True) == ([], [])
+
+
+@pytest.mark.parametrize("Q", [7, 300])
+def test_split_and_fused_final_agree_bitwise(Q, monkeypatch):
+    """The wide re-scoring kernel (small query batches) and the re-scoring inside the per-query final kernel use the same
+    fp64 arithmetic: identical scores and ids, both equal to the oracle."""
+    from news_recsys_b200.retrieval import TopkIndex
+    g = torch.Generator().manual_seed(31 + Q)
+    c = torch.nn.functional.normalize(torch.randn(150_000, 96, generator=g), dim=1)
+    q = torch.nn.functional.normalize(torch.randn(Q, 96, generator=g), dim=1)
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("NRX_TOPK_FINAL_SPLIT", mode)
+        idx = TopkIndex(c.to(DEV))
+        s, i, s64 = idx.search(q.to(DEV), 50, want_scores64=True)
+        out[mode] = (s.cpu(), i.cpu(), s64.cpu())
+    assert torch.equal(out["0"][1], out["1"][1])
+    assert torch.equal(out["0"][2], out["1"][2]) and torch.equal(out["0"][0], out["1"][0])
+    _, ref_i = R.topk_ip(q, c, 50)
+    assert torch.equal(out["1"][1], ref_i)
