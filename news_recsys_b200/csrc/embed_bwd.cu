@@ -387,6 +387,7 @@ segment_reduce_kernel(const __grid_constant__ DFeats P, const __grid_constant__ 
   long long off = 0;
   float scale = 0.f;
   int dim = 0;
+  bool vec4 = false;
   if (live) {
     const long long p = __ldg(vals + ts + lane);
     int f = 0;
@@ -397,14 +398,23 @@ segment_reduce_kernel(const __grid_constant__ DFeats P, const __grid_constant__ 
     const long long b = (F.L == 1) ? r : r / F.L;
     off = b * gld + F.out_col;
     dim = F.dim;
+    vec4 = ((gld | F.out_col) & 3) == 0 && (reinterpret_cast<uintptr_t>(grad) & 15) == 0;
     if (F.pool == NRX_POOL_NONE) scale = 1.f;
     else if (F.pool == NRX_POOL_MEAN) scale = 1.f / (float)F.L;
     else scale = __ldg(F.mask + r) * __ldg(F.inv_den + b);
   }
   for (int c0 = 0; c0 < max_dim; c0 += CW) {
     float v[CW];
+    if (vec4 && live && c0 + CW <= dim) {   // whole 16-byte quads of this occurrence's gradient row
 #pragma unroll
-    for (int j = 0; j < CW; ++j) v[j] = (live && c0 + j < dim) ? scale * __ldg(grad + off + c0 + j) : 0.f;
+      for (int j = 0; j < CW; j += 4) {
+        const float4 g4 = __ldg(reinterpret_cast<const float4*>(grad + off + c0 + j));
+        v[j] = scale * g4.x; v[j + 1] = scale * g4.y; v[j + 2] = scale * g4.z; v[j + 3] = scale * g4.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < CW; ++j) v[j] = (live && c0 + j < dim) ? scale * __ldg(grad + off + c0 + j) : 0.f;
+    }
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
       const bool take = lane - d >= start;
@@ -484,7 +494,12 @@ static int launch_apply(const DFeats& d, const DTables& T, const PlanLayout& L, 
   float* tail = (float*)(ws + L.tail);
   const int wpb = 4;
   const unsigned blocks = (unsigned)((L.n_tiles + wpb - 1) / wpb);
-  if (d.max_dim <= 16)
+  // Wide rows (D = 32): two passes of 16 columns when the gradient rows can be gathered as 16-byte quads (cfg3: the
+  // 32-column instantiation needs 168+ registers, 16 % of the warp slots resident, every warp waiting on its gather:
+  // 66 -> 54 us); with unaligned rows (cfg5: row width 115) the single 32-column pass stays faster (0.168 vs 0.182 ms/step)
+  bool quads = (gld % 4 == 0) && (reinterpret_cast<uintptr_t>(grad) % 16 == 0);
+  for (int i = 0; i < d.n && quads; ++i) quads = d.f[i].out_col % 4 == 0;
+  if (d.max_dim <= 16 || (quads && getenv("NRX_K3_CW32") == nullptr))
     segment_reduce_kernel<16><<<blocks, wpb * 32, 0, st>>>(d, T, keys, vals, grad, gld, d.n_occ, sentinel, head, tail, L.dp, d.max_dim);
   else
     segment_reduce_kernel<32><<<blocks, wpb * 32, 0, st>>>(d, T, keys, vals, grad, gld, d.n_occ, sentinel, head, tail, L.dp, d.max_dim);
