@@ -6,13 +6,13 @@ What it replaces: the per-step work of Lightning's fit loop around the reference
 :54-65) minus logging and the per-step sklearn AUC.
 
 Differences from the autograd route (model(batch); loss.backward(); torch.optim.AdamW):
-  * embedding tables: `table_update="dense"` reproduces the reference's dense AdamW over whole tables (every row
-    decays and moves every step); `table_update="sparse"` (default of this class) is the fused sparse row AdamW inside
-    K3, rows the batch touched only — see DESIGN.md "optimizer semantics";
+  * embedding tables: `table_update="dense"` (the default) reproduces the reference's dense AdamW over whole tables
+    (every row decays and moves every step); `table_update="sparse"` (explicit opt-in) is the fused sparse row AdamW
+    inside K3, rows the batch touched only — see DESIGN.md "optimizer semantics";
   * all dense parameters live in one flat fp32 buffer and take one nrx_adamw_dense_dev launch;
   * lr / bias-correction scalars are produced on the device (nrx_hparams_step), so the graph replays
-    with no host-written arguments; the sort plan (radix sort of row keys) runs on a forked stream
-    concurrently with the forward.
+    with no host-written arguments; the sort plan runs on a forked stream (its chunk sort beside K1, its merge
+    after the dX chain — DESIGN.md section 4, "Fused training step").
 """
 from __future__ import annotations
 

@@ -1,11 +1,10 @@
 #!/bin/bash
-bash tools/capture_profiles.sh
-python tools/summarize_profiles.py gpurun_out gpurun_out > gpurun_out/summarize.log 2>&1
+mkdir -p gpurun_out
+timeout -s KILL 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 8 --steps 100 --warmup 10 > gpurun_out/r2_bench_n8.json 2> gpurun_out/r2_bench_n8.err
 python - <<'PY'
 import json
-j=json.load(open('gpurun_out/r2_bench_n1_final.json')); r=j['retrieval']
-print(j['n_gpus'], j['value'], j['ms_per_step'], j['e2e']['value'], j['roofline']['kernel'], j['roofline']['bound'], round(j['roofline']['frac'],4), j['roofline']['traffic'])
-print('  ', {k:(round(v['value']/1e6,1), round(v['ms_per_step'],4)) for k,v in j['legs'].items()})
-print('  ', r['value'], r['ms_per_search'], r['e2e']['value'], r['q1_latency_ms'], r['roofline']['frac'])
+j=json.load(open('gpurun_out/r2_bench_n8.json')); r=j['retrieval']
+print(j['n_gpus'], j['value'], j['ms_per_step'], j['e2e']['value'], j['parity']['parity_ok'])
+print('  ', {k:(round(v['value']/1e6,1), round(v['ms_per_step'],4)) for k,v in j['legs'].items()}, r['value'], r['ms_per_search'], r['e2e']['value'], r['sharded'])
 PY
-python -c "import __graft_entry__ as g; g.smoke()"
+tail -n 2 gpurun_out/r2_bench_n8.err
