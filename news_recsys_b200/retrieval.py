@@ -64,3 +64,62 @@ def topk_merge(scores: torch.Tensor, ids: torch.Tensor) -> Tuple[torch.Tensor, t
     fn, name = (lib.nrx_topk_merge64, "nrx_topk_merge64") if scores.dtype == torch.float64 else (lib.nrx_topk_merge, "nrx_topk_merge")
     L.check(fn(scores.data_ptr(), ids.data_ptr(), n, Q, k, out_s.data_ptr(), out_i.data_ptr(), L.stream_ptr(scores.device)), name)
     return out_s, out_i
+
+
+class PipelinedSearch:
+    """Host-fed searches, software-pipelined one deep — the retrieval counterpart of `FusedTrainer.feed()`.
+
+    `submit(host_queries)` (pinned float32 [Q, D]) enqueues the H2D copy of these queries on a copy stream (it overlaps the
+    search submitted by the previous call), the search, and the D2H copy of its (scores, ids) into pinned buffers; it then
+    returns the PREVIOUS submission's results (host tensors, valid until the call after next) or None on the first call.
+    `drain()` returns the last one.  `search_fn(device_queries) -> (scores, ids)` is e.g. `TopkIndex(...).search` with k bound,
+    or `ShardedTopk.search_peer_` (results in re-used buffers: pass copy_out=True so they are cloned before the next search
+    may overwrite them)."""
+
+    def __init__(self, search_fn, Q: int, D: int, k: int, device, copy_out: bool = False):
+        self.fn, self.dev, self.copy_out = search_fn, torch.device(device), copy_out
+        self.copy = torch.cuda.Stream(device=self.dev)
+        self.dq = [torch.empty((Q, D), dtype=torch.float32, device=self.dev) for _ in range(2)]
+        self.hs = [torch.empty((Q, k), dtype=torch.float32).pin_memory() for _ in range(2)]
+        self.hi = [torch.empty((Q, k), dtype=torch.int64).pin_memory() for _ in range(2)]
+        self.ev_in = [torch.cuda.Event() for _ in range(2)]
+        self.ev_done = [torch.cuda.Event() for _ in range(2)]     # search finished: its query slot may be refilled
+        self.ev_out = [torch.cuda.Event() for _ in range(2)]
+        self.keep = [None, None]
+        self.n = 0
+
+    def submit(self, host_queries: torch.Tensor):
+        if not host_queries.is_pinned():
+            raise L.NrxError("PipelinedSearch.submit: queries must be pinned host memory")
+        slot = self.n & 1
+        main = torch.cuda.current_stream(self.dev)
+        with torch.cuda.stream(self.copy):
+            if self.n >= 2:
+                self.copy.wait_event(self.ev_done[slot])           # the search that read this slot two calls ago
+            self.dq[slot].copy_(host_queries, non_blocking=True)
+            self.ev_in[slot].record(self.copy)
+        main.wait_event(self.ev_in[slot])
+        s, i = self.fn(self.dq[slot])[:2]
+        if self.copy_out:
+            s, i = s.clone(), i.clone()
+        self.ev_done[slot].record(main)
+        self.keep[slot] = (s, i)                                   # alive until their D2H has been consumed
+        with torch.cuda.stream(self.copy):
+            self.copy.wait_event(self.ev_done[slot])
+            self.hs[slot].copy_(s, non_blocking=True)
+            self.hi[slot].copy_(i, non_blocking=True)
+            self.ev_out[slot].record(self.copy)
+        prev = None
+        if self.n > 0:
+            p = slot ^ 1
+            self.ev_out[p].synchronize()
+            prev = (self.hs[p], self.hi[p])
+        self.n += 1
+        return prev
+
+    def drain(self):
+        if self.n == 0:
+            return None
+        p = (self.n - 1) & 1
+        self.ev_out[p].synchronize()
+        return self.hs[p], self.hi[p]
