@@ -169,3 +169,27 @@ def test_split_and_fused_final_agree_bitwise(Q, monkeypatch):
     assert torch.equal(out["0"][2], out["1"][2]) and torch.equal(out["0"][0], out["1"][0])
     _, ref_i = R.topk_ip(q, c, 50)
     assert torch.equal(out["1"][1], ref_i)
+
+
+def test_pipelined_host_fed_search_equals_direct_search():
+    """retrieval.PipelinedSearch (H2D of the next queries and D2H of the previous results under the running search) returns,
+    one call late, exactly what a direct search of the same queries returns."""
+    from news_recsys_b200.retrieval import PipelinedSearch, TopkIndex
+    g = torch.Generator().manual_seed(3)
+    c = torch.nn.functional.normalize(torch.randn(40_000, 64, generator=g), dim=1)
+    idx = TopkIndex(c.to(DEV))
+    batches = [torch.nn.functional.normalize(torch.randn(200, 64, generator=g), dim=1).pin_memory() for _ in range(5)]
+    pipe = PipelinedSearch(lambda q: idx.search(q, 30), 200, 64, 30, DEV)
+    got = []
+    for b in batches:
+        r = pipe.submit(b)
+        if r is not None:
+            got.append((r[0].clone(), r[1].clone()))
+    last = pipe.drain()
+    got.append((last[0].clone(), last[1].clone()))
+    assert len(got) == len(batches)
+    for b, (s, i) in zip(batches, got):
+        ds, di = idx.search(b.to(DEV), 30)
+        assert torch.equal(i, di.cpu()) and torch.equal(s, ds.cpu())
+    with pytest.raises(Exception):
+        pipe.submit(torch.randn(200, 64))        # pageable memory is refused
