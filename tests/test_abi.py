@@ -77,3 +77,45 @@ def test_ops_fail_loudly_without_cuda():
     w = torch.randn(10, 16)
     with pytest.raises(NrxError, match="CUDA"):
         ops.FeatBinding([ops.FeatSpec("a", "t", 0, 16, 1, False, 0)], {"t": w}, {"a": torch.tensor([1, 2])})
+
+
+def test_every_struct_layout_matches_the_header_as_compiled_by_gcc(tmp_path):
+    """include/nrx.h is plain C99: gcc compiles it, prints sizeof and every field offset of every struct, and the ctypes
+    mirrors in news_recsys_b200/_lib.py must agree field by field (what a cgo / JNI binding of the same header would see)."""
+    import subprocess
+    from news_recsys_b200 import _lib
+    structs = ["NrxFeat", "NrxRowOpt", "NrxIngestCol", "NrxPeerStep", "NrxShardFeat", "NrxTower", "NrxTowerHead", "NrxTopkPeer"]
+    src = open(os.path.join(ROOT, "include", "nrx.h")).read()
+    declared = re.findall(r"^\} (Nrx[A-Za-z]+);", src, flags=re.M)
+    assert sorted(declared) == sorted(structs), "a struct of nrx.h has no layout check here"
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "nrx.h"', "int main(void) {"]
+    for s in structs:
+        cls = getattr(_lib, s)
+        lines.append(f'  printf("{s} %zu\\n", sizeof({s}));')
+        for name, _ in cls._fields_:
+            lines.append(f'  printf("{s}.{name} %zu\\n", offsetof({s}, {name}));')
+    lines += ["  return 0;", "}"]
+    c = tmp_path / "layout.c"
+    c.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(c), "-o", str(exe)], check=True)
+    out = dict(l.split() for l in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for s in structs:
+        cls = getattr(_lib, s)
+        assert ctypes.sizeof(cls) == int(out[s]), f"sizeof({s}): ctypes {ctypes.sizeof(cls)} != C {out[s]}"
+        for name, _ in cls._fields_:
+            assert getattr(cls, name).offset == int(out[f"{s}.{name}"]), f"{s}.{name}: ctypes offset {getattr(cls, name).offset} != C {out[s + '.' + name]}"
+
+
+def test_ctypes_argument_counts_match_the_header():
+    """Every entry point: the number of parameters in include/nrx.h == len(argtypes) in _lib.SIGNATURES."""
+    from news_recsys_b200 import _lib
+    src = open(os.path.join(ROOT, "include", "nrx.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    bad = []
+    for m in re.finditer(r"\b(nrx_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S):
+        name, params = m.group(1), m.group(2).strip()
+        n = 0 if params in ("", "void") else params.count(",") + 1
+        if name in _lib.SIGNATURES and len(_lib.SIGNATURES[name][1]) != n:
+            bad.append((name, n, len(_lib.SIGNATURES[name][1])))
+    assert not bad, f"(entry point, header params, ctypes params): {bad}"
