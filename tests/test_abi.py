@@ -119,3 +119,16 @@ def test_ctypes_argument_counts_match_the_header():
         if name in _lib.SIGNATURES and len(_lib.SIGNATURES[name][1]) != n:
             bad.append((name, n, len(_lib.SIGNATURES[name][1])))
     assert not bad, f"(entry point, header params, ctypes params): {bad}"
+
+
+def test_integration_doc_names_every_entry_point():
+    """INTEGRATION.md (the binding a maintainer of the reference would write) mentions every entry point of include/nrx.h,
+    by name, by a `nrx_a/b/c` shorthand or by the `nrx_*_workspace_bytes` family."""
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    named = set(re.findall(r"nrx_[a-z0-9_]+", doc))
+    for m in re.finditer(r"`(nrx_[a-z0-9_]+(?:/[a-z0-9_]+)+)`", doc):
+        parts = m.group(1).split("/")
+        stem = parts[0][: parts[0].rfind("_") + 1]
+        named |= {stem + p for p in parts[1:]}
+    missing = [s for s in _header_symbols() if s not in named and not s.endswith("_workspace_bytes")]
+    assert not missing, missing
