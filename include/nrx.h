@@ -417,7 +417,9 @@ int nrx_topk_search64(const void* index, const float* corpus, int64_t c_ld, int6
                       const float* queries, int64_t q_ld, int64_t Q, int k, int64_t id_base,
                       float* out_scores, double* out_scores64, int64_t* out_ids, int32_t* status,
                       void* ws, size_t ws_bytes, nrx_stream_t stream);
-/* Sharded search over NVLink peer memory (BASELINE config 4: corpus row-sharded across the GPUs of one node).  2-D:
+/* Sharded search over NVLink peer memory (BASELINE config 4: corpus row-sharded across the GPUs of one node; the
+ * reference holds the whole corpus in ONE faiss.IndexFlatIP and searches it on the CPU, recall/DSSM/model.py:249-251,
+ * model_utils/TopKSearcher.py:34-47,73-77).  2-D:
  * every rank scans ITS shard for ALL queries (sample -> theta -> one filter scan, the threshold budget shared between the
  * shards) and ships, per query, its exactly re-scored candidates (<= k, fp64 score + global id) into the inbox of the
  * query's owner — rank q / ceil(Q / world) — by peer stores; after a flag barrier the owner merges the `world` lists of
