@@ -121,6 +121,23 @@ def test_dssm_matches_reference_golden():
             continue
         cos = float((g @ r) / (g.norm() * r.norm()).clamp_min(1e-30))
         assert cos > 0.97, f"{name}: cosine {cos:.4f}"
+    # the fused training step (K9: nrx_dssm_infonce on the raw tower outputs) against the SAME reference vectors
+    model.zero_grad()
+    floss = model.training_step(batch, neg_perms=perms, fused=True)
+    assert abs(float(floss.detach()) - float(z["infonce"])) < 2e-2 * max(1.0, abs(float(z["infonce"])))
+    floss.backward()
+    for name, p in model.named_parameters():
+        ref = t("grad__" + name)
+        if name == "user_fc.0.weight":
+            ref = to_sorted(uo, ref)
+        if name == "item_fc.0.weight":
+            ref = to_sorted(io, ref)
+        g = p.grad.detach().cpu().double().flatten()
+        r = ref.double().flatten()
+        if float(r.norm()) == 0:
+            continue
+        cos = float((g @ r) / (g.norm() * r.norm()).clamp_min(1e-30))
+        assert cos > 0.97, f"fused step, {name}: cosine {cos:.4f}"
 
 
 def test_batched_hit_rate_equals_reference_loop():
