@@ -78,7 +78,11 @@ class PipelinedSearch:
 
     def __init__(self, search_fn, Q: int, D: int, k: int, device, copy_out: bool = False):
         self.fn, self.dev, self.copy_out = search_fn, torch.device(device), copy_out
+        # two copy streams: on one, the H2D of search i + 1 would queue behind the D2H of search i - 1, which itself waits
+        # for search i - 1 to finish — the next search could then never start before the previous one had ended AND been
+        # copied out (measured: 398 instead of 340 us per search)
         self.copy = torch.cuda.Stream(device=self.dev)
+        self.copy_out_stream = torch.cuda.Stream(device=self.dev)
         self.dq = [torch.empty((Q, D), dtype=torch.float32, device=self.dev) for _ in range(2)]
         self.hs = [torch.empty((Q, k), dtype=torch.float32).pin_memory() for _ in range(2)]
         self.hi = [torch.empty((Q, k), dtype=torch.int64).pin_memory() for _ in range(2)]
@@ -104,11 +108,11 @@ class PipelinedSearch:
             s, i = s.clone(), i.clone()
         self.ev_done[slot].record(main)
         self.keep[slot] = (s, i)                                   # alive until their D2H has been consumed
-        with torch.cuda.stream(self.copy):
-            self.copy.wait_event(self.ev_done[slot])
+        with torch.cuda.stream(self.copy_out_stream):
+            self.copy_out_stream.wait_event(self.ev_done[slot])
             self.hs[slot].copy_(s, non_blocking=True)
             self.hi[slot].copy_(i, non_blocking=True)
-            self.ev_out[slot].record(self.copy)
+            self.ev_out[slot].record(self.copy_out_stream)
         prev = None
         if self.n > 0:
             p = slot ^ 1
