@@ -145,6 +145,8 @@ class DSSM(BaseModel):
             if hi - lo != n_local:
                 raise ValueError(f"build_item_index: this rank must hold rows [{lo}, {hi}) of the corpus ({hi - lo} items), "
                                  f"got {n_local} (shards are the contiguous ranges of parallel.shard_range)")
+            if getattr(self.index, "close", None) is not None:
+                self.index.close()          # the previous epoch's sharded index: peer buffers are not garbage-collected
             self.index = ShardedTopk(self.all_item_embeddings, total, group=group)
             if ids is None:
                 self.index_item_ids = torch.arange(total, device=dev) + int(id_base)

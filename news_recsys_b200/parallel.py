@@ -81,6 +81,14 @@ class PeerBuffer:
         L.check(self.lib.nrx_peer_export(self.ptr, h), "nrx_peer_export")
         return h.raw
 
+    def free(self):
+        """cudaFree.  Only after every peer has closed its mapping (close_peers + a barrier) and every tensor view of this
+        buffer has been dropped."""
+        if self.ptr:
+            with torch.cuda.device(self.device):
+                L.check(self.lib.nrx_peer_free(self.ptr), "nrx_peer_free")
+            self.ptr = 0
+
 
 def open_peers(bufs: List["PeerBuffer"], group=None) -> List[List[int]]:
     """Exchange the IPC handles of `bufs` (same list on every rank) and map every peer's copy.
@@ -103,6 +111,16 @@ def open_peers(bufs: List["PeerBuffer"], group=None) -> List[List[int]]:
             row.append(int(p.value))
         out.append(row)
     return out
+
+
+def close_peers(ptr_rows: List[List[int]], rank: int, device) -> None:
+    """Unmap what open_peers mapped (every pointer of another rank's buffer)."""
+    lib = L.load()
+    with torch.cuda.device(device):
+        for row in ptr_rows:
+            for j, p in enumerate(row):
+                if j != rank and p:
+                    L.check(lib.nrx_peer_close(p), "nrx_peer_close")
 
 
 # --------------------------------------------------------------------------- #
@@ -648,6 +666,7 @@ class ShardedTopk:
             self._sig = PeerBuffer(4 * L.NRX_PEER_SIG_WORDS, local_corpus.device, typestr="<i4")
             ptrs = open_peers([self._cbuf, self._sig], group)
             self._corpus_ptrs, self._sig_ptrs = ptrs[0], ptrs[1]
+            self._dev = local_corpus.device
             self._status = torch.zeros(1, dtype=torch.int32, device=local_corpus.device)
             self.index = TopkIndex(shard, id_base=self.lo)
         else:
@@ -655,6 +674,29 @@ class ShardedTopk:
 
     def search_local(self, queries: torch.Tensor, k: int):
         return self.index.search(queries, k)
+
+    def close(self):
+        """Collective: unmap the peers' buffers and free this rank's (corpus shard copy, signal pad, and the inbox / result
+        buffers of every (Q, k) searched so far).  The object is unusable afterwards.  Peer buffers are cudaMalloc'd outside
+        torch's allocator and mapped into every peer, so they are NOT released by garbage collection: a service that
+        rebuilds its index (DSSM corpus refresh every epoch) must close the old one — DSSM.build_item_index does."""
+        if self.exchange != "peer" or getattr(self, "_closed", False):
+            return
+        self._closed = True
+        torch.cuda.synchronize(self._dev)
+        dist.barrier(group=self.group)                      # nobody is inside a search any more
+        rows = [self._corpus_ptrs, self._sig_ptrs]
+        own = [self._cbuf, self._sig]
+        for st in self._peer.values():
+            rows += list(st["ptrs"])
+            own += list(st["keep"])
+        close_peers(rows, self.rank, self._dev)
+        torch.cuda.synchronize(self._dev)
+        dist.barrier(group=self.group)                      # every rank has dropped its mappings of my buffers
+        self._peer.clear()
+        self.index = None                                   # the tensor views die before the memory does
+        for b in own:
+            b.free()
 
     # -- peer path ----------------------------------------------------------------------------------------------
     def _peer_state(self, Q: int, k: int, dev, warm_queries: Optional[torch.Tensor] = None):
@@ -678,7 +720,7 @@ class ShardedTopk:
         d.kprime = self.kprime
         ws = torch.empty(max(int(self.lib.nrx_topk_search_workspace_bytes(Q, self.index.N, self.index.D, k)), 16),
                          dtype=torch.uint8, device=dev)
-        st = dict(desc=d, keep=(inbox, out_s, out_i), ws=ws,
+        st = dict(desc=d, keep=(inbox, out_s, out_i), ptrs=ptrs, ws=ws,
                   out_s=out_s.tensor()[: Q * k].view(Q, k), out_i=out_i.tensor()[: Q * k * 2].view(torch.int64).view(Q, k),
                   status=torch.zeros(max(Q, 1), dtype=torch.int32, device=dev),
                   q=torch.zeros((max(Q, 1), self.index.D), dtype=torch.float32, device=dev), graph=None)

@@ -310,6 +310,15 @@ def _dssm_sharded_worker(rank, world, port, out_dir):
     m.build_item_index([mine], group=dist.group.WORLD, n_total=N)
     users = {k: v.to(dev) for k, v in synth_batch(cfg, 77, seed=11).items()}
     s, ids = m.retrieve_items(users, 25)
+    # corpus refresh, epoch after epoch: the previous sharded index is closed (peer buffers unmapped and freed), results stay
+    free = []
+    for _ in range(4):
+        m.build_item_index([mine], group=dist.group.WORLD, n_total=N)
+        s2, ids2 = m.retrieve_items(users, 25)
+        assert torch.equal(ids2, ids) and torch.equal(s2, s)
+        torch.cuda.synchronize()
+        free.append(torch.cuda.mem_get_info()[0])
+    assert free[1] - free[-1] < 16 * 2 ** 20, f"peer buffers leak across refreshes: {[f >> 20 for f in free]} MiB free"
     torch.save((s.cpu(), ids.cpu(), m.index_item_ids.cpu()), os.path.join(out_dir, f"dssm_sh_{rank}.pt"))
     dist.destroy_process_group()
 
